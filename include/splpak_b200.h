@@ -1,0 +1,182 @@
+/*
+ * splpak_b200.h -- C ABI of the B200-native fit-and-evaluate path of splpak.
+ *
+ * This is the drop-in boundary: every entry point below is what the reference's Fortran
+ * module would bind through iso_c_binding (see INTEGRATION.md and fortran/splpak_module.F90).
+ * All arrays are laid out exactly as Fortran passes them (column-major, contiguous):
+ *   xdata(l1xdat, ndata)  -> coordinates of one point are contiguous, stride l1xdat per point
+ *   coef(nodes(1),...,nodes(ndim)) -> dimension 1 fastest
+ * No C++ or torch types cross this boundary: plain pointers, sizes and integer codes.
+ *
+ * Precision: splpak_real is double, or float when the library is built with -DSPLPAK_REAL32
+ * (libsplpak_b200_r32.so), mirroring the reference's -DREAL32 switch (src/splpak.F90:33-41).
+ * REAL128 has no GPU equivalent and is refused at compile time.
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device and returns
+ * SPLPAK_ERR_CUDA (201) when none is usable.
+ *
+ * Error convention (src/splpak.F90:674-686 for the fit, :1155-1161 for evaluation):
+ *   0    no error
+ *   101  ndim < 1 (this library also returns 101 for ndim > 4, which the reference documents
+ *        at :1158 but never checks)
+ *   102  nodes(idim) < 4 for some idim
+ *   103  xmin(idim) == xmax(idim) for some idim
+ *   104  fit: ncf < nodes(1)*...*nodes(ndim);   evaluation: nderiv(idim) outside 0..2
+ *   105  ndata < 1
+ *   106  nwrk too small (nwrk - nwrk1 + 1 < 1, :775-781)
+ *   107  solver failure (too few rows, non-positive pivot, or scratch smaller than
+ *        ((n+5)n+2)/2 as suprls checks at :1443-1454)
+ *   201+ failures that cannot occur in the reference (CUDA, NCCL, bad handle, allocation)
+ * The C ABI returns codes silently; printing ' IERR=nnnnn' + message (cfaerr, :399-407) is
+ * done by the host-side mirror (splpak_type.hpp / the Fortran shim).
+ * Every function returns the same code it stores in *ierror (when it has an ierror argument).
+ */
+#ifndef SPLPAK_B200_H
+#define SPLPAK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef REAL128
+#error "splpak_b200: REAL128 has no GPU equivalent (src/splpak.F90:37-38); build REAL64 or REAL32"
+#endif
+#ifdef SPLPAK_REAL32
+typedef float splpak_real;
+#else
+typedef double splpak_real;
+#endif
+
+#define SPLPAK_OK              0
+#define SPLPAK_ERR_NDIM        101
+#define SPLPAK_ERR_NODES       102
+#define SPLPAK_ERR_RANGE       103
+#define SPLPAK_ERR_NCF         104   /* fit */
+#define SPLPAK_ERR_NDERIV      104   /* evaluation */
+#define SPLPAK_ERR_NDATA       105
+#define SPLPAK_ERR_NWRK        106
+#define SPLPAK_ERR_SOLVER      107
+#define SPLPAK_ERR_CUDA        201
+#define SPLPAK_ERR_NCCL        202
+#define SPLPAK_ERR_HANDLE      203
+#define SPLPAK_ERR_ALLOC       204
+
+typedef struct splpak_b200_fit_s *splpak_b200_fit_t;   /* opaque streaming-fit handle */
+
+/* sizeof(splpak_real) of this build (8, or 4 for the REAL32 library). */
+int splpak_b200_sizeof_real(void);
+/* Static string for a code above (the reference's cfaerr message text for 101..107). */
+const char *splpak_b200_strerror(int code, int evaluation);
+
+/* ------------------------------------------------------------------------------------------
+ * One-shot entry points with HOST arrays: exact replacements for the reference procedures.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces splcw (src/splpak.F90:512-513).  wdata: ndata weights, or wdata[0] < 0 meaning
+ * "all weights 1, other elements not referenced" (:581-588).  work is accepted for signature
+ * compatibility and never touched (the GPU needs no host scratch); nwrk is still checked the way
+ * the reference checks it (106, and the suprls scratch test that maps to 107). */
+int splpak_b200_splcw(int ndim, const splpak_real *xdata, int l1xdat, const splpak_real *ydata,
+                      const splpak_real *wdata, int64_t ndata, const splpak_real *xmin,
+                      const splpak_real *xmax, const int *nodes, splpak_real xtrap,
+                      splpak_real *coef, int64_t ncf, splpak_real *work, int64_t nwrk, int *ierror);
+
+/* Replaces splcc (src/splpak.F90:421-422): splcw with all weights 1. */
+int splpak_b200_splcc(int ndim, const splpak_real *xdata, int l1xdat, const splpak_real *ydata,
+                      int64_t ndata, const splpak_real *xmin, const splpak_real *xmax,
+                      const int *nodes, splpak_real xtrap, splpak_real *coef, int64_t ncf,
+                      splpak_real *work, int64_t nwrk, int *ierror);
+
+/* Replaces splde (src/splpak.F90:1089): one value or partial derivative at one point. */
+splpak_real splpak_b200_splde(int ndim, const splpak_real *x, const int *nderiv,
+                              const splpak_real *coef, const splpak_real *xmin,
+                              const splpak_real *xmax, const int *nodes, int *ierror);
+
+/* Replaces splfe (src/splpak.F90:1258): splde with nderiv = 0. */
+splpak_real splpak_b200_splfe(int ndim, const splpak_real *x, const splpak_real *coef,
+                              const splpak_real *xmin, const splpak_real *xmax, const int *nodes,
+                              int *ierror);
+
+/* Batched splfe/splde: nq points x(l1x, nq), out(nq).  nderiv == NULL means splfe.
+ * (New entry point: the reference evaluates one point per call, :1089/:1258.)  HOST arrays. */
+int splpak_b200_eval(int ndim, const splpak_real *x, int l1x, int64_t nq, const int *nderiv,
+                     const splpak_real *coef, const splpak_real *xmin, const splpak_real *xmax,
+                     const int *nodes, splpak_real *out, int *ierror);
+
+/* Same with x, coef and out already in DEVICE memory (xmin/xmax/nodes/nderiv stay on the host).
+ * stream is a cudaStream_t passed as void* (NULL = default stream); the call is asynchronous. */
+int splpak_b200_eval_device(int ndim, const splpak_real *d_x, int l1x, int64_t nq, const int *nderiv,
+                            const splpak_real *d_coef, const splpak_real *xmin,
+                            const splpak_real *xmax, const int *nodes, splpak_real *d_out,
+                            void *stream, int *ierror);
+
+/* ------------------------------------------------------------------------------------------
+ * Streaming fit handle: create -> add_points (any number of calls, host or device arrays)
+ * -> [all-reduce the partial buffer across ranks] -> compute.  This is the assembly / solve
+ * split the north star names add_points / compute; splcw above is create+add_points+compute.
+ * A handle owns its device buffers and one CUDA stream; use it from one host thread at a time.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Validates ndim/nodes/xmin/xmax in the reference's order (101, 102, 103; :718-750). */
+int splpak_b200_fit_create(int ndim, const splpak_real *xmin, const splpak_real *xmax,
+                           const int *nodes, splpak_real xtrap, splpak_b200_fit_t *handle,
+                           int *ierror);
+
+/* Accumulate n more data points into the normal equations (and the sparse-area histogram when
+ * xtrap != 0).  weighted = 0 ignores w (splcc, or wdata(1) < 0); zero-weight points are skipped
+ * as in :796-800.  HOST arrays; the copy is chunked and overlapped with the kernels. */
+int splpak_b200_fit_add_points(splpak_b200_fit_t h, const splpak_real *x, int l1x,
+                               const splpak_real *y, const splpak_real *w, int weighted, int64_t n);
+/* Same with DEVICE arrays; asynchronous on the handle's stream. */
+int splpak_b200_fit_add_points_device(splpak_b200_fit_t h, const splpak_real *d_x, int l1x,
+                                      const splpak_real *d_y, const splpak_real *d_w, int weighted,
+                                      int64_t n);
+
+/* The partial sums a multi-GPU fit must add across ranks before compute: one contiguous DEVICE
+ * buffer of *count float64 values [G in stencil storage | g | node histogram | totlwt | nrows].
+ * Sum it in place with one all-reduce (NCCL via torch.distributed, or splpak_b200_fit_allreduce). */
+int splpak_b200_fit_partial_buffer(splpak_b200_fit_t h, void **d_ptr, int64_t *count);
+/* In-place ncclAllReduce(sum, float64) of that buffer on the handle's stream; comm is an
+ * ncclComm_t passed as void*.  libnccl.so.2 is loaded lazily; 202 if that or the call fails. */
+int splpak_b200_fit_allreduce(splpak_b200_fit_t h, void *nccl_comm);
+
+/* Add the data-sparse derivative-constraint rows (xtrap != 0), factor and solve.
+ * coef/ncf as in splcw (104 if ncf < ncol); nwrk < 0 skips the reference's workspace checks.
+ * coef is a HOST array. */
+int splpak_b200_fit_compute(splpak_b200_fit_t h, splpak_real *coef, int64_t ncf, int64_t nwrk,
+                            int *ierror);
+/* Same, leaving the coefficients in DEVICE memory (d_coef, ncol values). */
+int splpak_b200_fit_compute_device(splpak_b200_fit_t h, splpak_real *d_coef, int64_t ncf,
+                                   int64_t nwrk, int *ierror);
+
+/* Start a new fit on the same grid (zeroes the partial sums). */
+int splpak_b200_fit_reset(splpak_b200_fit_t h);
+/* cudaStream_t (as void*) the handle launches on. */
+void *splpak_b200_fit_stream(splpak_b200_fit_t h);
+/* Device-time split of everything since create/reset, milliseconds:
+ * ms[0] classify+histogram, ms[1] scan+scatter (binning), ms[2] accumulate, ms[3] constraints,
+ * ms[4] band expand, ms[5] factor, ms[6] back-substitution.  Synchronises the stream. */
+int splpak_b200_fit_timings(splpak_b200_fit_t h, double *ms, int n);
+/* Kernels this handle has launched since create/reset (for bench.py's gpu_launches). */
+int64_t splpak_b200_fit_launch_count(splpak_b200_fit_t h);
+/* Debug/parity access: copy the assembled G (stencil storage, ncol*4^ndim float64), g (ncol),
+ * node histogram (ncol) and [totlwt, nrows] to HOST arrays (any may be NULL). */
+int splpak_b200_fit_get_normal_equations(splpak_b200_fit_t h, double *S, double *g, double *cnt,
+                                         double *totals);
+int splpak_b200_fit_destroy(splpak_b200_fit_t h);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement helpers (used by bench.py for the FP64 roofline denominator; MEASURED_PEAKS.json
+ * has no FP64 entry).
+ * ---------------------------------------------------------------------------------------- */
+/* out[0] = DFMA TFLOP/s, out[1] = DMMA.8x8x4 TFLOP/s, out[2] = device copy GB/s (read+write). */
+int splpak_b200_measure_peaks(double *out, int n);
+/* Total kernels launched by this library in this process. */
+int64_t splpak_b200_total_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLPAK_B200_H */

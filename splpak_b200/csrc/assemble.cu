@@ -1,0 +1,553 @@
+// assemble.cu -- point-sharded assembly of the weighted normal equations for sm_100a.
+//
+// Replaces the data-row loop of splcw (src/splpak.F90:788-855) and the row accumulation of
+// suprls (:1468-1549): instead of one dense ncol-wide row per point pushed through a streaming
+// Householder QR (2*ncol^2 flops per point), each point contributes its <= 4^ndim non-zeros to
+//   G = sum_i (w_i phi_i)(w_i phi_i)^T,   g = sum_i (w_i phi_i)(w_i y_i)
+// and, when xtrap != 0, to the nearest-node weight histogram of :885-907.
+//
+// Pipeline per chunk of points (all on one stream):
+//   1. spl_classify_kernel   one pass over the raw AoS points: window id -> per-window counts,
+//                            nearest-node histogram (with the :899 quirk), totlwt, row count
+//   2. spl_scan_kernel       exclusive scan of the counts -> window segment starts + work items
+//   3. spl_scatter_kernel    second pass: counting-sort scatter of (x.., y, w) records by window
+//   4. spl_items_kernel      work-item table (window, segment of <= CH points)
+//   5. spl_accumulate_kernel persistent CTAs; per work item the window-local block of G is
+//                            accumulated in REGISTERS and flushed once with red.global.add.f64
+//
+// The per-point outer product of a tensor-product basis has only 10^ndim distinct entries
+// (10 symmetric pairs per dimension), not 4^ndim(4^ndim+1)/2: G is symmetric under swapping the row
+// and column index of any single dimension.  The accumulator of a window is therefore the
+// 10 x ... x 10 tensor  M[a_N]..[a_1] = sum_p w^2 prod_d s_d[a_d],  s_d[(i,j)] = b_d[i] b_d[j],
+// which is exactly the "orthant stencil" storage S (common.cuh).  This halves the FP64 work of a
+// plain symmetric rank-1 update (1000 vs 2080 FMAs per point in 3-D).
+//
+// Thread mapping inside a CTA: a "group" of LPG lanes owns the whole accumulator tensor of the
+// window; lane u of the group owns R "outer" index tuples (a_N..a_2) x all 10 a_1, i.e. R*10
+// accumulators, and different groups take different points (K-split), reduced at the end of the
+// work item with warp shuffles + one shared-memory pass.  The right-hand side g rides along as
+// 4^(ndim-1) extra outer tuples whose inner vector is b_1[0..3] instead of s_1[0..9].
+#include "basis.cuh"
+
+// ------------------------------------------------------------------------------------------
+// window id / nearest node
+// ------------------------------------------------------------------------------------------
+template <int NDIM>
+__device__ __forceinline__ unsigned spl_window_key(const GridParams &gp, const real_t *xp) {
+    unsigned key = 0;
+#pragma unroll
+    for (int dd = 0; dd < NDIM; ++dd) {
+        const int d = NDIM - 1 - dd;
+        int ws, ibmn, ibmx;
+        spl_box((double)xp[d], gp.xmin[d], gp.dxin[d], gp.nodes[d], ws, ibmn, ibmx);
+        key = key * (unsigned)gp.nwin[d] + (unsigned)ws;
+    }
+    return key;
+}
+
+// Nearest-node address of :893-902, including the quirk at :899 (a dimension whose index is out of
+// range is skipped in the Horner recurrence instead of discarding the point).
+template <int NDIM>
+__device__ __forceinline__ long long spl_nearest_node(const GridParams &gp, const real_t *xp) {
+    long long iin = 0;
+#pragma unroll
+    for (int dd = 0; dd < NDIM; ++dd) {
+        const int d = NDIM - 1 - dd;
+        const int inmx = gp.nodes[d] - 1;
+        double t = spl_add(spl_mul(gp.dxin[d], spl_sub((double)xp[d], gp.xmin[d])), 0.5);
+        t = fmin(fmax(t, -4.0), (double)inmx + 4.0);
+        const int inidim = __double2int_rz(t);     // Fortran int(): truncation toward zero
+        if (inidim < 0 || inidim > inmx) continue;
+        iin = (long long)(inmx + 1) * iin + inidim;
+    }
+    return iin;
+}
+
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
+                    const real_t *__restrict__ w, int weighted, long long n,
+                    unsigned *__restrict__ wincount, int do_hist, double *__restrict__ cnt,
+                    double *__restrict__ totals) {
+    double tot = 0.0;
+    double rows = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nround = ((n + stride - 1) / stride) * stride;   // uniform trip count per warp
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        unsigned key = 0xffffffffu;
+        double wv = 0.0;
+        if (i < n) {
+            wv = weighted ? (double)w[i] : 1.0;
+            if (wv != 0.0) {
+                const real_t *xp = x + i * (long long)l1x;
+                key = spl_window_key<NDIM>(gp, xp);
+                rows += 1.0;
+                if (do_hist) {
+                    const long long iin = spl_nearest_node<NDIM>(gp, xp);
+                    atomicAdd(cnt + iin, wv);
+                    tot += wv;
+                }
+            }
+        }
+        // warp-aggregated count: one atomic per distinct window in the warp
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key != 0xffffffffu && (threadIdx.x & 31) == (__ffs(peers) - 1))
+            atomicAdd(wincount + key, (unsigned)__popc(peers));
+    }
+    // block reduction of totlwt and the row count
+    __shared__ double s_tot[8], s_rows[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        rows += __shfl_xor_sync(0xffffffffu, rows, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_tot[threadIdx.x >> 5] = tot;
+        s_rows[threadIdx.x >> 5] = rows;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0, r = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+            t += s_tot[k];
+            r += s_rows[k];
+        }
+        if (t != 0.0) atomicAdd(totals + 0, t);
+        if (r != 0.0) atomicAdd(totals + 1, r);
+    }
+}
+
+// Exclusive scan of the window counts (single CTA; nwindows is at most a few 10^5 in practice).
+// winstart[k] = first record of window k, itemstart[k] = first work item of window k,
+// meta[0] = number of work items, meta[1] = number of records; also resets the work counter.
+__global__ void __launch_bounds__(1024)
+spl_scan_kernel(const unsigned *__restrict__ wincount, long long nwindows, unsigned ch,
+                unsigned *__restrict__ winstart, unsigned *__restrict__ itemstart,
+                unsigned *__restrict__ meta) {
+    __shared__ unsigned s_a[1024], s_b[1024];
+    const int t = threadIdx.x;
+    const long long per = (nwindows + 1023) / 1024;
+    const long long lo = (long long)t * per;
+    const long long hi = (lo + per < nwindows) ? lo + per : nwindows;
+    unsigned sa = 0, sb = 0;
+    for (long long k = lo; k < hi; ++k) {
+        const unsigned c = wincount[k];
+        sa += c;
+        sb += (c + ch - 1) / ch;
+    }
+    s_a[t] = sa;
+    s_b[t] = sb;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        unsigned va = 0, vb = 0;
+        if (t >= off) {
+            va = s_a[t - off];
+            vb = s_b[t - off];
+        }
+        __syncthreads();
+        s_a[t] += va;
+        s_b[t] += vb;
+        __syncthreads();
+    }
+    unsigned ra = s_a[t] - sa, rb = s_b[t] - sb;   // exclusive prefix of this strip
+    for (long long k = lo; k < hi; ++k) {
+        const unsigned c = wincount[k];
+        winstart[k] = ra;
+        itemstart[k] = rb;
+        ra += c;
+        rb += (c + ch - 1) / ch;
+    }
+    if (t == 1023) {
+        meta[0] = s_b[1023];
+        meta[1] = s_a[1023];
+        meta[2] = 0;   // work counter for the accumulate kernel
+    }
+}
+
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+spl_scatter_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
+                   const real_t *__restrict__ y, const real_t *__restrict__ w, int weighted,
+                   long long n, const unsigned *__restrict__ winstart,
+                   unsigned *__restrict__ wincursor, double *__restrict__ records) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nround = ((n + stride - 1) / stride) * stride;
+    const unsigned lane = threadIdx.x & 31;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        unsigned key = 0xffffffffu;
+        double wv = 0.0;
+        const real_t *xp = x + i * (long long)l1x;
+        if (i < n) {
+            wv = weighted ? (double)w[i] : 1.0;
+            if (wv != 0.0) key = spl_window_key<NDIM>(gp, xp);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (key != 0xffffffffu && (int)lane == leader)
+            base = atomicAdd(wincursor + key, (unsigned)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (key != 0xffffffffu) {
+            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            const long long pos = (long long)winstart[key] + base + rank;
+            double *r = records + pos * (NDIM + 2);
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) r[d] = (double)xp[d];
+            r[NDIM] = (double)y[i];
+            r[NDIM + 1] = wv;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+spl_items_kernel(const unsigned *__restrict__ wincount, const unsigned *__restrict__ itemstart,
+                 long long nwindows, unsigned ch, unsigned *__restrict__ item_win,
+                 unsigned *__restrict__ item_seg) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nwindows) return;
+    const unsigned c = wincount[k];
+    const unsigned ni = (c + ch - 1) / ch;
+    const unsigned s0 = itemstart[k];
+    for (unsigned s = 0; s < ni; ++s) {
+        item_win[s0 + s] = (unsigned)k;
+        item_seg[s0 + s] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// accumulate
+// ------------------------------------------------------------------------------------------
+
+template <int NDIM> struct AccTraits;
+template <> struct AccTraits<1> { static constexpr int R = 1, LPG = 2,   NT = 256, PB = 256, CH = 16384, RS = 22;  };
+template <> struct AccTraits<2> { static constexpr int R = 4, LPG = 4,   NT = 256, PB = 128, CH = 4096,  RS = 38;  };
+template <> struct AccTraits<3> { static constexpr int R = 4, LPG = 32,  NT = 256, PB = 64,  CH = 8192,  RS = 48;  };
+template <> struct AccTraits<4> { static constexpr int R = 4, LPG = 288, NT = 288, PB = 32,  CH = 4096,  RS = 178; };
+
+template <int NDIM> struct AccDerived {
+    using T = AccTraits<NDIM>;
+    static constexpr int NOUT = spl_ipow(10, NDIM - 1);          // G outer tuples
+    static constexpr int NRO = spl_ipow(4, NDIM - 1);            // rhs outer tuples
+    static constexpr int NGT = (NOUT + T::R - 1) / T::R;         // lanes holding G tuples
+    static constexpr int NRT = (NRO + T::R - 1) / T::R;          // lanes holding rhs tuples
+    static constexpr int NG = T::NT / T::LPG;                    // groups per CTA
+    static constexpr int NW = T::NT / 32;                        // warps per CTA
+    static constexpr int LPGW = T::LPG < 32 ? T::LPG : 32;       // lanes of a group inside one warp
+    static constexpr int OFF_I = 0;                              // s_1[10], b_1[4], 6 zeros
+    static constexpr int OFF_T2 = 20;                            // s_2[10], b_2[4]
+    static constexpr int OFF_H = (NDIM >= 2) ? 34 : 20;          // outer table
+    static constexpr int NH = (NDIM <= 2) ? 2 : (NDIM == 3 ? 14 : 116);
+    static constexpr int OFF_TMP = OFF_H + NH;                   // 4-D only: T4'[14], T3[14]
+    static constexpr int HRHS = (NDIM <= 2) ? 1 : NOUT / 10;     // first rhs entry of H
+    static_assert(NGT + NRT <= T::LPG, "group too small");
+    static_assert(OFF_TMP + (NDIM == 4 ? 28 : 0) <= T::RS, "record stride too small");
+};
+
+template <int NDIM>
+__device__ __forceinline__ void spl_flush_entry(const GridParams &gp, const int *ws, int u, int r,
+                                                int a, double v, double *__restrict__ S,
+                                                double *__restrict__ g) {
+    using D = AccDerived<NDIM>;
+    using T = AccTraits<NDIM>;
+    if (v == 0.0) return;
+    if (u < D::NGT) {
+        int o = u * T::R + r;
+        if (o >= D::NOUT) return;
+        long long node = 0, nstride = 1;
+        int sten = 0, sstride = 1;
+        int ad = a;
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) {
+            int i, j;
+            spl_pair(ad, i, j);
+            node += (long long)(ws[d] + i) * nstride;
+            sten += (j - i) * sstride;
+            nstride *= gp.nodes[d];
+            sstride *= 4;
+            ad = o % 10;
+            o /= 10;
+        }
+        atomicAdd(S + node * gp.nsten + sten, v);
+    } else if (u < D::NGT + D::NRT) {
+        int o = (u - D::NGT) * T::R + r;
+        if (o >= D::NRO || a >= 4) return;
+        long long node = 0, nstride = 1;
+        int id = a;
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) {
+            node += (long long)(ws[d] + id) * nstride;
+            nstride *= gp.nodes[d];
+            id = o % 4;
+            o /= 4;
+        }
+        atomicAdd(g + node, v);
+    }
+}
+
+template <int NDIM>
+__global__ void __launch_bounds__(AccTraits<NDIM>::NT)
+spl_accumulate_kernel(const __grid_constant__ GridParams gp, const double *__restrict__ records,
+                      const unsigned *__restrict__ wincount, const unsigned *__restrict__ winstart,
+                      const unsigned *__restrict__ item_win, const unsigned *__restrict__ item_seg,
+                      unsigned *__restrict__ meta, double *__restrict__ S, double *__restrict__ g) {
+    using T = AccTraits<NDIM>;
+    using D = AccDerived<NDIM>;
+    constexpr int R = T::R, RS = T::RS, PB = T::PB, NT = T::NT;
+    extern __shared__ __align__(16) double smem[];
+    double *s_pts = smem;                       // PB * RS
+    double *s_red = smem + PB * RS;             // LPGW * R * 10 (unused for 4-D)
+    __shared__ unsigned s_item;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int grp = tid / T::LPG;
+    const int u = tid % T::LPG;
+    const bool is_rhs = (u >= D::NGT);
+
+    // per-thread constant table indices
+    int hidx[R], lidx[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (!is_rhs) {
+            const int o = min(u * R + r, D::NOUT - 1);
+            hidx[r] = o / 10;
+            lidx[r] = o % 10;
+        } else {
+            const int o = min((u - D::NGT) * R + r, D::NRO - 1);
+            hidx[r] = D::HRHS + o / 4;
+            lidx[r] = 10 + o % 4;
+        }
+    }
+    const int ibase = D::OFF_I + (is_rhs ? 10 : 0);
+    const unsigned nitems = meta[0];
+
+    for (;;) {
+        __syncthreads();                        // protects s_item, s_pts and s_red reuse
+        if (tid == 0) s_item = atomicAdd(meta + 2, 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= nitems) break;
+        const unsigned win = item_win[item];
+        const unsigned seg = item_seg[item];
+        const unsigned wc = wincount[win];
+        const long long first = (long long)winstart[win] + (long long)seg * T::CH;
+        const int npts = (int)min((unsigned)T::CH, wc - seg * (unsigned)T::CH);
+        int ws[NDIM];
+        {
+            unsigned k = win;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                ws[d] = (int)(k % (unsigned)gp.nwin[d]);
+                k /= (unsigned)gp.nwin[d];
+            }
+        }
+
+        double acc[R][10];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int a = 0; a < 10; ++a) acc[r][a] = 0.0;
+
+        for (int b0 = 0; b0 < npts; b0 += PB) {
+            const int nb = min(PB, npts - b0);
+            if (b0 > 0) __syncthreads();        // previous batch fully consumed
+            // ---- stage: 1-D bases, pair products and outer tables of nb points ----
+            for (int idx = tid; idx < nb * NDIM; idx += NT) {
+                const int p = idx / NDIM;
+                const int d = idx - p * NDIM;
+                const double *rec = records + (first + b0 + p) * (NDIM + 2);
+                double b[4], s[10];
+                int wsd;
+                spl_window_weights(rec[d], gp.xmin[d], gp.dx[d], gp.dxin[d], gp.nodes[d], 0, wsd, b);
+                {
+                    int a = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = i; j < 4; ++j) s[a++] = b[i] * b[j];
+                }
+                double *out = s_pts + p * RS;
+                if (d == 0) {
+#pragma unroll
+                    for (int a = 0; a < 10; ++a) out[D::OFF_I + a] = s[a];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) out[D::OFF_I + 10 + i] = b[i];
+#pragma unroll
+                    for (int i = 14; i < 20; ++i) out[D::OFF_I + i] = 0.0;
+                }
+                if (NDIM >= 2 && d == 1) {
+#pragma unroll
+                    for (int a = 0; a < 10; ++a) out[D::OFF_T2 + a] = s[a];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) out[D::OFF_T2 + 10 + i] = b[i];
+                }
+                if (d == NDIM - 1) {
+                    const double yv = rec[NDIM], wv = rec[NDIM + 1];
+                    const double w2 = wv * wv;             // row = w*phi, rhs = w*y (:806, :837)
+                    const double w2y = w2 * yv;
+                    if (NDIM <= 2) {
+                        out[D::OFF_H + 0] = w2;
+                        out[D::OFF_H + 1] = w2y;
+                    } else if (NDIM == 3) {
+#pragma unroll
+                        for (int a = 0; a < 10; ++a) out[D::OFF_H + a] = w2 * s[a];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) out[D::OFF_H + 10 + i] = w2y * b[i];
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < 10; ++a) out[D::OFF_TMP + a] = w2 * s[a];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) out[D::OFF_TMP + 10 + i] = w2y * b[i];
+                    }
+                }
+                if (NDIM == 4 && d == 2) {
+#pragma unroll
+                    for (int a = 0; a < 10; ++a) out[D::OFF_TMP + 14 + a] = s[a];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) out[D::OFF_TMP + 24 + i] = b[i];
+                }
+            }
+            __syncthreads();
+            if (NDIM == 4) {
+                // H[a4*10+a3] = T4'[a4]*T3[a3];  H[100 + i4*4+i3] = T4'[10+i4]*T3[10+i3]
+                for (int idx = tid; idx < nb * 116; idx += NT) {
+                    const int p = idx / 116;
+                    const int e = idx - p * 116;
+                    double *rec = s_pts + p * RS;
+                    double v;
+                    if (e < 100) v = rec[D::OFF_TMP + e / 10] * rec[D::OFF_TMP + 14 + e % 10];
+                    else v = rec[D::OFF_TMP + 10 + (e - 100) / 4] * rec[D::OFF_TMP + 24 + (e - 100) % 4];
+                    rec[D::OFF_H + e] = v;
+                }
+                __syncthreads();
+            }
+            // ---- accumulate: group grp takes points grp, grp+NG, ... of the batch ----
+            for (int p = grp; p < nb; p += D::NG) {
+                const double *rec = s_pts + p * RS;
+                double in[10];
+#pragma unroll
+                for (int a = 0; a < 10; a += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(rec + ibase + a);
+                    in[a] = v.x;
+                    in[a + 1] = v.y;
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double P = rec[D::OFF_H + hidx[r]];
+                    if (NDIM >= 2) P *= rec[D::OFF_T2 + lidx[r]];
+#pragma unroll
+                    for (int a = 0; a < 10; ++a) acc[r][a] = fma(P, in[a], acc[r][a]);
+                }
+            }
+        }
+
+        // ---- reduce the K-split groups and flush once per work item ----
+        if (T::LPG < 32) {
+#pragma unroll
+            for (int off = T::LPG; off < 32; off <<= 1)
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int a = 0; a < 10; ++a)
+                        acc[r][a] += __shfl_xor_sync(0xffffffffu, acc[r][a], off);
+        }
+        if (D::NG > 1) {
+            for (int w = 0; w < D::NW; ++w) {
+                if (warp == w && lane < D::LPGW) {
+                    const int ul = lane;   // == u for the first group of the warp
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int a = 0; a < 10; ++a) {
+                            double *dst = s_red + (ul * R + r) * 10 + a;
+                            *dst = (w == 0 ? 0.0 : *dst) + acc[r][a];
+                        }
+                }
+                __syncthreads();
+            }
+            for (int idx = tid; idx < (D::NGT + D::NRT) * R * 10; idx += NT) {
+                const int slot = idx / 10;
+                const int a = idx - slot * 10;
+                spl_flush_entry<NDIM>(gp, ws, slot / R, slot % R, a, s_red[idx], S, g);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int a = 0; a < 10; ++a) spl_flush_entry<NDIM>(gp, ws, u, r, a, acc[r][a], S, g);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launch of the chunk pipeline
+// ------------------------------------------------------------------------------------------
+struct AssembleScratch {
+    unsigned *wincount, *winstart, *wincursor, *itemstart, *item_win, *item_seg, *meta;
+    double *records;
+    long long max_items;
+};
+
+int spl_acc_chunk_points(int ndim) {
+    switch (ndim) {
+    case 1: return AccTraits<1>::CH;
+    case 2: return AccTraits<2>::CH;
+    case 3: return AccTraits<3>::CH;
+    default: return AccTraits<4>::CH;
+    }
+}
+
+template <int NDIM>
+static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y,
+                            const real_t *d_w, int weighted, long long n, int do_hist,
+                            const AssembleScratch &sc, double *d_S, double *d_g, double *d_cnt,
+                            double *d_totals, cudaStream_t st, int nsm, cudaEvent_t *ev) {
+    using T = AccTraits<NDIM>;
+    using D = AccDerived<NDIM>;
+    SPL_CUDA_TRY(cudaMemsetAsync(sc.wincount, 0, sizeof(unsigned) * gp.nwindows, st));
+    SPL_CUDA_TRY(cudaMemsetAsync(sc.wincursor, 0, sizeof(unsigned) * gp.nwindows, st));
+    long long nb = (n + 255) / 256;
+    const long long cap = (long long)nsm * 8;
+    const int grid = (int)(nb < cap ? nb : cap);
+
+    if (ev) cudaEventRecord(ev[0], st);
+    spl_classify_kernel<NDIM><<<grid, 256, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.wincount, do_hist,
+                                                    d_cnt, d_totals);
+    if (ev) cudaEventRecord(ev[1], st);
+    spl_scan_kernel<<<1, 1024, 0, st>>>(sc.wincount, gp.nwindows, (unsigned)T::CH, sc.winstart,
+                                        sc.itemstart, sc.meta);
+    spl_scatter_kernel<NDIM><<<grid, 256, 0, st>>>(gp, d_x, l1x, d_y, d_w, weighted, n, sc.winstart,
+                                                   sc.wincursor, sc.records);
+    spl_items_kernel<<<spl_div_up(gp.nwindows, 256), 256, 0, st>>>(sc.wincount, sc.itemstart, gp.nwindows,
+                                                                   (unsigned)T::CH, sc.item_win, sc.item_seg);
+    if (ev) cudaEventRecord(ev[2], st);
+    const size_t smem = sizeof(double) * ((size_t)T::PB * T::RS + (size_t)D::LPGW * T::R * 10);
+    auto kern = spl_accumulate_kernel<NDIM>;
+    SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    SPL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T::NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long agrid = (long long)nsm * per_sm;
+    const long long max_items = gp.nwindows + n / T::CH + 1;
+    if (agrid > max_items) agrid = max_items;
+    kern<<<(unsigned)agrid, T::NT, smem, st>>>(gp, sc.records, sc.wincount, sc.winstart, sc.item_win,
+                                               sc.item_seg, sc.meta, d_S, d_g);
+    if (ev) cudaEventRecord(ev[3], st);
+    g_spl_launches += 5;
+    SPL_CUDA_TRY(cudaGetLastError());
+    return SPLPAK_OK;
+}
+
+int spl_assemble_chunk(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y,
+                       const real_t *d_w, int weighted, long long n, int do_hist,
+                       const AssembleScratch &sc, double *d_S, double *d_g, double *d_cnt,
+                       double *d_totals, cudaStream_t st, int nsm, cudaEvent_t *ev) {
+    switch (gp.ndim) {
+    case 1: return assemble_chunk_t<1>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 2: return assemble_chunk_t<2>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 3: return assemble_chunk_t<3>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 4: return assemble_chunk_t<4>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    }
+    return SPLPAK_ERR_NDIM;
+}

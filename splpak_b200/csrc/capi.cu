@@ -1,0 +1,728 @@
+// capi.cu -- the C ABI of include/splpak_b200.h: argument validation in the reference's order,
+// device-memory ownership, host<->device staging, and the launch sequences of the kernels in
+// eval.cu / assemble.cu / solve.cu.  There is no CPU fallback anywhere in this file: without a
+// usable CUDA device every compute entry point returns SPLPAK_ERR_CUDA.
+#include <dlfcn.h>
+#include <new>
+#include <string.h>
+
+#include "common.cuh"
+
+unsigned long long g_spl_launches = 0;
+
+// ---- kernels' host launchers (other translation units) ----
+struct AssembleScratch {
+    unsigned *wincount, *winstart, *wincursor, *itemstart, *item_win, *item_seg, *meta;
+    double *records;
+    long long max_items;
+};
+int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, int l1x, long long nq,
+                    const double *d_coef, long long ncol_padded, real_t *d_out, cudaStream_t stream,
+                    int nsm, size_t smem_optin);
+int spl_acc_chunk_points(int ndim);
+int spl_assemble_chunk(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y,
+                       const real_t *d_w, int weighted, long long n, int do_hist,
+                       const AssembleScratch &sc, double *d_S, double *d_g, double *d_cnt,
+                       double *d_totals, cudaStream_t st, int nsm, cudaEvent_t *ev);
+int spl_constraints_launch(const GridParams &gp, double xtrap, const double *d_cnt,
+                           const double *d_totals_in, double *d_S, double *d_totals_out,
+                           cudaStream_t st, int nsm);
+long long spl_band_lda(int bw);
+int spl_half_bandwidth(const GridParams &gp);
+int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, double *d_y, int *d_fail,
+                     cudaStream_t st, int nsm, cudaEvent_t *ev);
+int spl_measure_peaks_impl(double *out, int n);
+
+// ------------------------------------------------------------------------------------------
+// small conversion kernels
+// ------------------------------------------------------------------------------------------
+__global__ void spl_to_double_kernel(const real_t *__restrict__ in, double *__restrict__ out,
+                                     long long n, long long npad) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += stride)
+        out[i] = (i < n) ? (double)in[i] : 0.0;
+}
+__global__ void spl_from_double_kernel(const double *__restrict__ in, real_t *__restrict__ out,
+                                       long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (real_t)in[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// device context
+// ------------------------------------------------------------------------------------------
+struct DeviceInfo {
+    int ok = 0, dev = 0, nsm = SPL_NSM_DEFAULT;
+    size_t smem_optin = 0;
+};
+static int get_device(DeviceInfo &di) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
+        cudaGetLastError();
+        return SPLPAK_ERR_CUDA;
+    }
+    SPL_CUDA_TRY(cudaGetDevice(&di.dev));
+    cudaDeviceProp p;
+    SPL_CUDA_TRY(cudaGetDeviceProperties(&p, di.dev));
+    di.nsm = p.multiProcessorCount;
+    di.smem_optin = p.sharedMemPerBlockOptin;
+    di.ok = 1;
+    return SPLPAK_OK;
+}
+
+// Grid validation shared by fit and evaluation, in the reference's order
+// (fit :718-750, evaluation :1168-1198).  nderiv != NULL adds the 104 check of :1190.
+static int make_grid(int ndim, const real_t *xmin, const real_t *xmax, const int *nodes,
+                     const int *nderiv, GridParams &gp, int *soft104) {
+    memset(&gp, 0, sizeof(gp));
+    if (soft104) *soft104 = 0;
+    if (ndim < 1 || ndim > SPL_MAXDIM) return SPLPAK_ERR_NDIM;
+    gp.ndim = ndim;
+    gp.ncol = 1;
+    gp.nwindows = 1;
+    gp.nsten = 1;
+    for (int d = 0; d < ndim; ++d) {
+        const int nod = nodes[d];
+        if (nod < 4) return SPLPAK_ERR_NODES;
+        const real_t xrng = xmax[d] - xmin[d];
+        if (xrng == (real_t)0) return SPLPAK_ERR_RANGE;
+        if (nderiv && soft104 && (nderiv[d] < 0 || nderiv[d] > 2)) *soft104 = 1;   // no return, :1190-1194
+        // working-precision arithmetic exactly as :747-748, then widened
+        const real_t dx = xrng / (real_t)(nod - 1);
+        const real_t dxin = (real_t)1.0 / dx;
+        gp.nodes[d] = nod;
+        gp.nwin[d] = nod - 3;
+        gp.xmin[d] = (double)xmin[d];
+        gp.dx[d] = (double)dx;
+        gp.dxin[d] = (double)dxin;
+        gp.ncol *= nod;
+        gp.nwindows *= (nod - 3);
+        gp.nsten *= 4;
+    }
+    for (int d = ndim; d < SPL_MAXDIM; ++d) {
+        gp.nodes[d] = 4;
+        gp.nwin[d] = 1;
+        gp.dx[d] = 1.0;
+        gp.dxin[d] = 1.0;
+    }
+    return SPLPAK_OK;
+}
+
+extern "C" int splpak_b200_sizeof_real(void) { return (int)sizeof(real_t); }
+
+extern "C" const char *splpak_b200_strerror(int code, int evaluation) {
+    if (evaluation) {
+        switch (code) {   // src/splpak.F90:1170-1193
+        case 0: return "";
+        case 101: return " splfe or splde - NDIM is less than 1";
+        case 102: return " splfe or splde - NODES(IDIM) is less than  4for some IDIM";
+        case 103: return " splfe or splde - XMIN(IDIM) = XMAX(IDIM) for some IDIM";
+        case 104: return " splde - NDERIV(IDIM) IS less than 0 or greater than 2 for some IDIM";
+        }
+    } else {
+        switch (code) {   // src/splpak.F90:720-779, :852
+        case 0: return "";
+        case 101: return " splcc or splcw - NDIM is less than 1";
+        case 102: return " splcc or splcw - NODES(IDIM) is less than 4 for some IDIM";
+        case 103: return " splcc or splcw - XMIN(IDIM) equals XMAX(IDIM) for some IDIM";
+        case 104: return " splcc or splcw - NCF (size of COEF) is too small";
+        case 105: return " splcc or splcw - Ndata Is less than 1";
+        case 106: return " splcc or splcw - NWRK (size of WORK) is too small";
+        case 107: return " splcc or splcw - suprls failure (this usually indicates insufficient input data)";
+        }
+    }
+    switch (code) {
+    case SPLPAK_ERR_CUDA: return " splpak_b200 - CUDA failure (no usable device, or a runtime error)";
+    case SPLPAK_ERR_NCCL: return " splpak_b200 - NCCL failure";
+    case SPLPAK_ERR_HANDLE: return " splpak_b200 - invalid handle or argument";
+    case SPLPAK_ERR_ALLOC: return " splpak_b200 - device allocation failed";
+    }
+    return " splpak_b200 - unknown error";
+}
+
+// ------------------------------------------------------------------------------------------
+// evaluation
+// ------------------------------------------------------------------------------------------
+static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const int *nderiv,
+                            const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
+                            real_t *d_out, cudaStream_t st) {
+    const long long npad = (gp.ncol + 1) & ~1LL;
+    const double *coef64 = nullptr;
+    double *tmp = nullptr;
+    const bool direct = sizeof(real_t) == sizeof(double) && (gp.ncol % 2 == 0) &&
+                        ((uintptr_t)d_coef % 16 == 0);
+    if (direct) {
+        coef64 = reinterpret_cast<const double *>(d_coef);
+    } else {
+        SPL_CUDA_TRY(cudaMallocAsync((void **)&tmp, sizeof(double) * npad, st));
+        spl_to_double_kernel<<<spl_div_up(npad, 256), 256, 0, st>>>(d_coef, tmp, gp.ncol, npad);
+        ++g_spl_launches;
+        coef64 = tmp;
+    }
+    int rc = spl_eval_launch(gp, nderiv, d_x, l1x, nq, coef64, npad, d_out, st, di.nsm, di.smem_optin);
+    if (tmp) cudaFreeAsync(tmp, st);
+    return rc;
+}
+
+extern "C" int splpak_b200_eval_device(int ndim, const real_t *d_x, int l1x, int64_t nq,
+                                       const int *nderiv, const real_t *d_coef, const real_t *xmin,
+                                       const real_t *xmax, const int *nodes, real_t *d_out,
+                                       void *stream, int *ierror) {
+    GridParams gp;
+    int soft = 0;
+    int rc = make_grid(ndim, xmin, xmax, nodes, nderiv, gp, &soft);
+    if (rc == SPLPAK_OK) {
+        DeviceInfo di;
+        rc = get_device(di);
+        if (rc == SPLPAK_OK)
+            rc = eval_device_impl(gp, di, nderiv, d_x, l1x, nq, d_coef, d_out, (cudaStream_t)stream);
+    }
+    if (rc == SPLPAK_OK && soft) rc = SPLPAK_ERR_NDERIV;
+    if (ierror) *ierror = rc;
+    return rc;
+}
+
+extern "C" int splpak_b200_eval(int ndim, const real_t *x, int l1x, int64_t nq, const int *nderiv,
+                                const real_t *coef, const real_t *xmin, const real_t *xmax,
+                                const int *nodes, real_t *out, int *ierror) {
+    GridParams gp;
+    int soft = 0;
+    int rc = make_grid(ndim, xmin, xmax, nodes, nderiv, gp, &soft);
+    if (rc != SPLPAK_OK || nq <= 0) {
+        if (ierror) *ierror = rc;
+        return rc;
+    }
+    DeviceInfo di;
+    rc = get_device(di);
+    if (rc != SPLPAK_OK) {
+        if (ierror) *ierror = rc;
+        return rc;
+    }
+    cudaStream_t st = nullptr, st2 = nullptr;
+    real_t *d_coef = nullptr, *d_x[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        for (int k = 0; k < 2; ++k) {
+            if (d_x[k]) cudaFree(d_x[k]);
+            if (d_out[k]) cudaFree(d_out[k]);
+            if (ev_in[k]) cudaEventDestroy(ev_in[k]);
+            if (ev_done[k]) cudaEventDestroy(ev_done[k]);
+        }
+        if (d_coef) cudaFree(d_coef);
+        if (st) cudaStreamDestroy(st);
+        if (st2) cudaStreamDestroy(st2);
+    };
+#define EV_TRY(expr)                                        \
+    do {                                                    \
+        if ((expr) != cudaSuccess) {                        \
+            cudaGetLastError();                             \
+            cleanup();                                      \
+            if (ierror) *ierror = SPLPAK_ERR_CUDA;          \
+            return SPLPAK_ERR_CUDA;                         \
+        }                                                   \
+    } while (0)
+    EV_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    EV_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    // chunked, double-buffered: H2D of chunk k+1 (st2) overlaps the kernel + D2H of chunk k (st)
+    const long long chunk = nq < (1LL << 22) ? nq : (1LL << 22);
+    const int nbuf = nq > chunk ? 2 : 1;
+    EV_TRY(cudaMalloc((void **)&d_coef, sizeof(real_t) * (size_t)(gp.ncol + 2)));
+    for (int k = 0; k < nbuf; ++k) {
+        EV_TRY(cudaMalloc((void **)&d_x[k], sizeof(real_t) * (size_t)chunk * l1x));
+        EV_TRY(cudaMalloc((void **)&d_out[k], sizeof(real_t) * (size_t)chunk));
+        EV_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        EV_TRY(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+    }
+    EV_TRY(cudaMemcpyAsync(d_coef, coef, sizeof(real_t) * (size_t)gp.ncol, cudaMemcpyHostToDevice, st));
+    int k = 0;
+    for (long long q0 = 0; q0 < nq; q0 += chunk, k ^= 1) {
+        const long long nc = (nq - q0 < chunk) ? nq - q0 : chunk;
+        EV_TRY(cudaStreamWaitEvent(st2, ev_done[k], 0));      // buffer k free again
+        EV_TRY(cudaMemcpyAsync(d_x[k], x + q0 * (long long)l1x, sizeof(real_t) * (size_t)nc * l1x,
+                               cudaMemcpyHostToDevice, st2));
+        EV_TRY(cudaEventRecord(ev_in[k], st2));
+        EV_TRY(cudaStreamWaitEvent(st, ev_in[k], 0));
+        rc = eval_device_impl(gp, di, nderiv, d_x[k], l1x, nc, d_coef, d_out[k], st);
+        if (rc != SPLPAK_OK) break;
+        EV_TRY(cudaMemcpyAsync(out + q0, d_out[k], sizeof(real_t) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+        EV_TRY(cudaEventRecord(ev_done[k], st));
+    }
+    EV_TRY(cudaStreamSynchronize(st));
+    EV_TRY(cudaStreamSynchronize(st2));
+#undef EV_TRY
+    cleanup();
+    if (rc == SPLPAK_OK && soft) rc = SPLPAK_ERR_NDERIV;
+    if (ierror) *ierror = rc;
+    return rc;
+}
+
+extern "C" real_t splpak_b200_splde(int ndim, const real_t *x, const int *nderiv, const real_t *coef,
+                                    const real_t *xmin, const real_t *xmax, const int *nodes,
+                                    int *ierror) {
+    real_t out = (real_t)0;
+    int nd0[SPL_MAXDIM] = {0, 0, 0, 0};
+    splpak_b200_eval(ndim, x, ndim > 0 ? ndim : 1, 1, nderiv ? nderiv : nd0, coef, xmin, xmax, nodes,
+                     &out, ierror);
+    return out;
+}
+
+extern "C" real_t splpak_b200_splfe(int ndim, const real_t *x, const real_t *coef, const real_t *xmin,
+                                    const real_t *xmax, const int *nodes, int *ierror) {
+    real_t out = (real_t)0;
+    splpak_b200_eval(ndim, x, ndim > 0 ? ndim : 1, 1, nullptr, coef, xmin, xmax, nodes, &out, ierror);
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
+// streaming fit handle
+// ------------------------------------------------------------------------------------------
+#define FIT_MAGIC 0x53504c42u
+#define NTIMER 7
+
+struct splpak_b200_fit_s {
+    unsigned magic;
+    GridParams gp;
+    DeviceInfo di;
+    double xtrap;
+    cudaStream_t st, st_copy;
+    // partial sums, one contiguous buffer: [S | g | cnt | totals(2)]
+    double *d_part;
+    long long n_part;
+    double *d_S, *d_g, *d_cnt, *d_totals;
+    // chunk scratch
+    AssembleScratch sc;
+    long long chunk_cap;          // points the scratch can take
+    real_t *d_stage[2][3];        // host-path staging: x, y, w double-buffered
+    long long stage_cap;
+    cudaEvent_t ev_stage_in[2], ev_stage_free[2];
+    // solve
+    double *d_AB;
+    long long ab_elems;
+    int *d_fail;
+    // timing: accumulated event pairs
+    double ms[NTIMER];
+    cudaEvent_t ev[8];
+    unsigned long long launches0;
+    int finalized;
+    int timers_pending;           // ev[0..3] hold an unharvested assembly measurement
+    long long total_points;
+};
+
+static bool valid(splpak_b200_fit_t h) { return h && h->magic == FIT_MAGIC; }
+
+static void free_handle(splpak_b200_fit_t h) {
+    if (!h) return;
+    if (h->d_part) cudaFree(h->d_part);
+    unsigned *u[] = {h->sc.wincount, h->sc.winstart, h->sc.wincursor, h->sc.itemstart,
+                     h->sc.item_win, h->sc.item_seg, h->sc.meta};
+    for (unsigned *p : u)
+        if (p) cudaFree(p);
+    if (h->sc.records) cudaFree(h->sc.records);
+    for (int k = 0; k < 2; ++k) {
+        for (int a = 0; a < 3; ++a)
+            if (h->d_stage[k][a]) cudaFree(h->d_stage[k][a]);
+        if (h->ev_stage_in[k]) cudaEventDestroy(h->ev_stage_in[k]);
+        if (h->ev_stage_free[k]) cudaEventDestroy(h->ev_stage_free[k]);
+    }
+    if (h->d_AB) cudaFree(h->d_AB);
+    if (h->d_fail) cudaFree(h->d_fail);
+    for (int k = 0; k < 8; ++k)
+        if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+    if (h->st) cudaStreamDestroy(h->st);
+    if (h->st_copy) cudaStreamDestroy(h->st_copy);
+    h->magic = 0;
+    delete h;
+}
+
+extern "C" int splpak_b200_fit_create(int ndim, const real_t *xmin, const real_t *xmax,
+                                      const int *nodes, real_t xtrap, splpak_b200_fit_t *handle,
+                                      int *ierror) {
+    if (handle) *handle = nullptr;
+    GridParams gp;
+    int rc = make_grid(ndim, xmin, xmax, nodes, nullptr, gp, nullptr);
+    if (rc != SPLPAK_OK || !handle) {
+        if (rc == SPLPAK_OK) rc = SPLPAK_ERR_HANDLE;
+        if (ierror) *ierror = rc;
+        return rc;
+    }
+    DeviceInfo di;
+    rc = get_device(di);
+    if (rc != SPLPAK_OK) {
+        if (ierror) *ierror = rc;
+        return rc;
+    }
+    splpak_b200_fit_t h = new (std::nothrow) splpak_b200_fit_s();
+    if (!h) {
+        if (ierror) *ierror = SPLPAK_ERR_ALLOC;
+        return SPLPAK_ERR_ALLOC;
+    }
+    memset(h, 0, sizeof(*h));
+    h->magic = FIT_MAGIC;
+    h->gp = gp;
+    h->di = di;
+    h->xtrap = (double)xtrap;
+    h->launches0 = g_spl_launches;
+    bool ok = true;
+    ok = ok && cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) == cudaSuccess;
+    h->n_part = gp.ncol * gp.nsten + gp.ncol + gp.ncol + 2;
+    ok = ok && cudaMalloc((void **)&h->d_part, sizeof(double) * (size_t)h->n_part) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&h->d_fail, sizeof(int)) == cudaSuccess;
+    for (int k = 0; k < 8 && ok; ++k) ok = cudaEventCreate(&h->ev[k]) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; ++k) {
+        ok = ok && cudaEventCreateWithFlags(&h->ev_stage_in[k], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_stage_free[k], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (ok) {
+        h->d_S = h->d_part;
+        h->d_g = h->d_S + gp.ncol * gp.nsten;
+        h->d_cnt = h->d_g + gp.ncol;
+        h->d_totals = h->d_cnt + gp.ncol;
+        ok = cudaMemsetAsync(h->d_part, 0, sizeof(double) * (size_t)h->n_part, h->st) == cudaSuccess;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        free_handle(h);
+        if (ierror) *ierror = SPLPAK_ERR_ALLOC;
+        return SPLPAK_ERR_ALLOC;
+    }
+    *handle = h;
+    if (ierror) *ierror = SPLPAK_OK;
+    return SPLPAK_OK;
+}
+
+extern "C" int splpak_b200_fit_reset(splpak_b200_fit_t h) {
+    if (!valid(h)) return SPLPAK_ERR_HANDLE;
+    SPL_CUDA_TRY(cudaMemsetAsync(h->d_part, 0, sizeof(double) * (size_t)h->n_part, h->st));
+    for (int k = 0; k < NTIMER; ++k) h->ms[k] = 0.0;
+    h->launches0 = g_spl_launches;
+    h->finalized = 0;
+    h->timers_pending = 0;
+    h->total_points = 0;
+    return SPLPAK_OK;
+}
+
+static int ensure_scratch(splpak_b200_fit_t h, long long n) {
+    if (n <= h->chunk_cap) return SPLPAK_OK;
+    const GridParams &gp = h->gp;
+    AssembleScratch &sc = h->sc;
+    if (sc.records) cudaFree(sc.records);
+    if (sc.item_win) cudaFree(sc.item_win);
+    if (sc.item_seg) cudaFree(sc.item_seg);
+    sc.records = nullptr;
+    sc.item_win = sc.item_seg = nullptr;
+    h->chunk_cap = 0;
+    if (!sc.wincount) {
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.wincount, sizeof(unsigned) * (size_t)gp.nwindows));
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.winstart, sizeof(unsigned) * (size_t)gp.nwindows));
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.wincursor, sizeof(unsigned) * (size_t)gp.nwindows));
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.itemstart, sizeof(unsigned) * (size_t)gp.nwindows));
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.meta, sizeof(unsigned) * 4));
+    }
+    const int ch = spl_acc_chunk_points(gp.ndim);
+    sc.max_items = gp.nwindows + n / ch + 2;
+    SPL_CUDA_TRY(cudaMalloc((void **)&sc.records, sizeof(double) * (size_t)n * (gp.ndim + 2)));
+    SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_win, sizeof(unsigned) * (size_t)sc.max_items));
+    SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_seg, sizeof(unsigned) * (size_t)sc.max_items));
+    h->chunk_cap = n;
+    return SPLPAK_OK;
+}
+
+static void collect_assemble_timers(splpak_b200_fit_t h);
+static void add_ms(splpak_b200_fit_t h, int slot, cudaEvent_t a, cudaEvent_t b) {
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, a, b) == cudaSuccess) h->ms[slot] += f;
+    else cudaGetLastError();
+}
+
+#define DEVICE_CHUNK (1LL << 25)   // points per device-resident chunk (bounds the sort scratch)
+#define HOST_CHUNK (1LL << 22)     // points per host->device staging chunk
+
+static int add_device_chunk(splpak_b200_fit_t h, const real_t *d_x, int l1x, const real_t *d_y,
+                            const real_t *d_w, int weighted, long long n) {
+    collect_assemble_timers(h);   // the events are re-recorded below
+    int rc = ensure_scratch(h, n);
+    if (rc != SPLPAK_OK) return rc;
+    h->timers_pending = 1;
+    rc = spl_assemble_chunk(h->gp, d_x, l1x, d_y, d_w, weighted, n, h->xtrap != 0.0, h->sc, h->d_S,
+                            h->d_g, h->d_cnt, h->d_totals, h->st, h->di.nsm, h->ev);
+    return rc;
+}
+
+static void collect_assemble_timers(splpak_b200_fit_t h) {
+    if (!h->timers_pending) return;
+    h->timers_pending = 0;
+    if (cudaEventSynchronize(h->ev[3]) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    add_ms(h, 0, h->ev[0], h->ev[1]);
+    add_ms(h, 1, h->ev[1], h->ev[2]);
+    add_ms(h, 2, h->ev[2], h->ev[3]);
+}
+
+extern "C" int splpak_b200_fit_add_points_device(splpak_b200_fit_t h, const real_t *d_x, int l1x,
+                                                 const real_t *d_y, const real_t *d_w, int weighted,
+                                                 int64_t n) {
+    if (!valid(h) || h->finalized) return SPLPAK_ERR_HANDLE;
+    if (n <= 0) return SPLPAK_OK;
+    if (l1x < h->gp.ndim) return SPLPAK_ERR_HANDLE;
+    if (!d_w) weighted = 0;
+    for (long long i0 = 0; i0 < n; i0 += DEVICE_CHUNK) {
+        const long long nc = (n - i0 < DEVICE_CHUNK) ? n - i0 : DEVICE_CHUNK;
+        int rc = add_device_chunk(h, d_x + i0 * (long long)l1x, l1x, d_y + i0, d_w ? d_w + i0 : nullptr,
+                                  weighted, nc);
+        if (rc != SPLPAK_OK) return rc;
+    }
+    h->total_points += n;
+    return SPLPAK_OK;   // asynchronous: timers are harvested by the next chunk / compute / fit_timings
+}
+
+extern "C" int splpak_b200_fit_add_points(splpak_b200_fit_t h, const real_t *x, int l1x,
+                                          const real_t *y, const real_t *w, int weighted, int64_t n) {
+    if (!valid(h) || h->finalized) return SPLPAK_ERR_HANDLE;
+    if (n <= 0) return SPLPAK_OK;
+    if (l1x < h->gp.ndim) return SPLPAK_ERR_HANDLE;
+    if (!w) weighted = 0;
+    const long long chunk = n < HOST_CHUNK ? n : HOST_CHUNK;
+    if (chunk > h->stage_cap) {
+        for (int k = 0; k < 2; ++k)
+            for (int a = 0; a < 3; ++a) {
+                if (h->d_stage[k][a]) cudaFree(h->d_stage[k][a]);
+                h->d_stage[k][a] = nullptr;
+            }
+        h->stage_cap = 0;
+        for (int k = 0; k < 2; ++k) {
+            SPL_CUDA_TRY(cudaMalloc((void **)&h->d_stage[k][0], sizeof(real_t) * (size_t)chunk * l1x));
+            SPL_CUDA_TRY(cudaMalloc((void **)&h->d_stage[k][1], sizeof(real_t) * (size_t)chunk));
+            SPL_CUDA_TRY(cudaMalloc((void **)&h->d_stage[k][2], sizeof(real_t) * (size_t)chunk));
+        }
+        h->stage_cap = chunk;
+    }
+    int k = 0;
+    for (long long i0 = 0; i0 < n; i0 += chunk, k ^= 1) {
+        const long long nc = (n - i0 < chunk) ? n - i0 : chunk;
+        // copy stream: wait until the kernels that read staging buffer k have finished
+        SPL_CUDA_TRY(cudaStreamWaitEvent(h->st_copy, h->ev_stage_free[k], 0));
+        SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][0], x + i0 * (long long)l1x,
+                                     sizeof(real_t) * (size_t)nc * l1x, cudaMemcpyHostToDevice, h->st_copy));
+        SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][1], y + i0, sizeof(real_t) * (size_t)nc,
+                                     cudaMemcpyHostToDevice, h->st_copy));
+        if (weighted)
+            SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][2], w + i0, sizeof(real_t) * (size_t)nc,
+                                         cudaMemcpyHostToDevice, h->st_copy));
+        SPL_CUDA_TRY(cudaEventRecord(h->ev_stage_in[k], h->st_copy));
+        SPL_CUDA_TRY(cudaStreamWaitEvent(h->st, h->ev_stage_in[k], 0));
+        int rc = add_device_chunk(h, h->d_stage[k][0], l1x, h->d_stage[k][1],
+                                  weighted ? h->d_stage[k][2] : nullptr, weighted, nc);
+        if (rc != SPLPAK_OK) return rc;
+        SPL_CUDA_TRY(cudaEventRecord(h->ev_stage_free[k], h->st));
+    }
+    collect_assemble_timers(h);
+    h->total_points += n;
+    return SPLPAK_OK;
+}
+
+extern "C" int splpak_b200_fit_partial_buffer(splpak_b200_fit_t h, void **d_ptr, int64_t *count) {
+    if (!valid(h)) return SPLPAK_ERR_HANDLE;
+    if (d_ptr) *d_ptr = h->d_part;
+    if (count) *count = h->n_part;
+    return SPLPAK_OK;
+}
+
+// ---- lazily bound NCCL (libnccl.so.2), so the library has no link-time NCCL dependency ----
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+extern "C" int splpak_b200_fit_allreduce(splpak_b200_fit_t h, void *nccl_comm) {
+    if (!valid(h) || !nccl_comm) return SPLPAK_ERR_HANDLE;
+    static nccl_allreduce_fn fn = nullptr;
+    if (!fn) {
+        void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return SPLPAK_ERR_NCCL;
+        fn = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
+        if (!fn) return SPLPAK_ERR_NCCL;
+    }
+    // ncclFloat64 = 8, ncclSum = 0 (nccl.h)
+    const int rc = fn(h->d_part, h->d_part, (size_t)h->n_part, 8, 0, nccl_comm, h->st);
+    return rc == 0 ? SPLPAK_OK : SPLPAK_ERR_NCCL;
+}
+
+static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_device, int64_t ncf,
+                            int64_t nwrk, int *ierror) {
+    int rc = SPLPAK_OK;
+    if (!valid(h)) {
+        if (ierror) *ierror = SPLPAK_ERR_HANDLE;
+        return SPLPAK_ERR_HANDLE;
+    }
+    const GridParams &gp = h->gp;
+    if (gp.ncol > ncf) rc = SPLPAK_ERR_NCF;                                    // :751
+    if (rc == SPLPAK_OK && nwrk >= 0) {
+        // :757-781 and suprls :1443-1454
+        const long long nwrk1 = (h->xtrap != 0.0) ? gp.ncol + 1 : 1;
+        const long long nwlft = (long long)nwrk - nwrk1 + 1;
+        const long long nreq = ((gp.ncol + 5) * gp.ncol + 2) / 2;
+        if (nwlft < 1) rc = SPLPAK_ERR_NWRK;
+        else if (nwlft < nreq) rc = SPLPAK_ERR_SOLVER;
+    }
+    if (rc != SPLPAK_OK) {
+        if (ierror) *ierror = rc;
+        return rc;
+    }
+    if (h->finalized) {
+        if (ierror) *ierror = SPLPAK_ERR_HANDLE;
+        return SPLPAK_ERR_HANDLE;
+    }
+    cudaStream_t st = h->st;
+    const int bw = spl_half_bandwidth(gp);
+    const long long lda = spl_band_lda(bw);
+    const long long need = gp.ncol * lda + lda;
+    if (need > h->ab_elems) {
+        if (h->d_AB) cudaFree(h->d_AB);
+        h->d_AB = nullptr;
+        h->ab_elems = 0;
+        if (cudaMalloc((void **)&h->d_AB, sizeof(double) * (size_t)need) != cudaSuccess) {
+            cudaGetLastError();
+            if (ierror) *ierror = SPLPAK_ERR_ALLOC;
+            return SPLPAK_ERR_ALLOC;
+        }
+        h->ab_elems = need;
+    }
+    SPL_CUDA_TRY(cudaEventRecord(h->ev[4], st));
+    if (h->xtrap != 0.0) {
+        rc = spl_constraints_launch(gp, h->xtrap, h->d_cnt, h->d_totals, h->d_S, h->d_totals, st, h->di.nsm);
+        if (rc != SPLPAK_OK) {
+            if (ierror) *ierror = rc;
+            return rc;
+        }
+    }
+    SPL_CUDA_TRY(cudaEventRecord(h->ev[5], st));
+    SPL_CUDA_TRY(cudaMemsetAsync(h->d_AB, 0, sizeof(double) * (size_t)need, st));
+    SPL_CUDA_TRY(cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
+    cudaEvent_t sev[4];
+    for (int k = 0; k < 4; ++k) SPL_CUDA_TRY(cudaEventCreate(&sev[k]));
+    // the solve overwrites g with the solution
+    rc = spl_solve_launch(gp, h->d_S, h->d_AB, h->d_g, h->d_fail, st, h->di.nsm, sev);
+    int fail = 0;
+    double totals[2] = {0.0, 0.0};
+    if (rc == SPLPAK_OK) {
+        if (coef_on_device) {
+            spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(h->d_g, coef, gp.ncol);
+            ++g_spl_launches;
+        }
+        SPL_CUDA_TRY(cudaMemcpyAsync(&fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SPL_CUDA_TRY(cudaMemcpyAsync(totals, h->d_totals, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+        if (!coef_on_device) {
+            if (sizeof(real_t) == sizeof(double)) {
+                SPL_CUDA_TRY(cudaMemcpyAsync(coef, h->d_g, sizeof(double) * (size_t)gp.ncol,
+                                             cudaMemcpyDeviceToHost, st));
+            } else {
+                real_t *tmp = reinterpret_cast<real_t *>(h->d_AB);   // band storage is dead now
+                spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(h->d_g, tmp, gp.ncol);
+                ++g_spl_launches;
+                SPL_CUDA_TRY(cudaMemcpyAsync(coef, tmp, sizeof(real_t) * (size_t)gp.ncol,
+                                             cudaMemcpyDeviceToHost, st));
+            }
+        }
+        SPL_CUDA_TRY(cudaStreamSynchronize(st));
+        collect_assemble_timers(h);
+        add_ms(h, 3, h->ev[4], h->ev[5]);
+        add_ms(h, 4, sev[0], sev[1]);
+        add_ms(h, 5, sev[1], sev[2]);
+        add_ms(h, 6, sev[2], sev[3]);
+        // fewer rows than columns (suprls error 33, :1650) or a non-positive pivot -> 107
+        if (fail || totals[1] < (double)gp.ncol) rc = SPLPAK_ERR_SOLVER;
+    }
+    for (int k = 0; k < 4; ++k) cudaEventDestroy(sev[k]);
+    h->finalized = 1;
+    if (ierror) *ierror = rc;
+    return rc;
+}
+
+extern "C" int splpak_b200_fit_compute(splpak_b200_fit_t h, real_t *coef, int64_t ncf, int64_t nwrk,
+                                       int *ierror) {
+    return fit_compute_impl(h, coef, 0, ncf, nwrk, ierror);
+}
+extern "C" int splpak_b200_fit_compute_device(splpak_b200_fit_t h, real_t *d_coef, int64_t ncf,
+                                              int64_t nwrk, int *ierror) {
+    return fit_compute_impl(h, d_coef, 1, ncf, nwrk, ierror);
+}
+
+extern "C" void *splpak_b200_fit_stream(splpak_b200_fit_t h) { return valid(h) ? (void *)h->st : nullptr; }
+
+extern "C" int splpak_b200_fit_timings(splpak_b200_fit_t h, double *ms, int n) {
+    if (!valid(h)) return SPLPAK_ERR_HANDLE;
+    SPL_CUDA_TRY(cudaStreamSynchronize(h->st));
+    collect_assemble_timers(h);
+    for (int k = 0; k < n && k < NTIMER; ++k) ms[k] = h->ms[k];
+    return SPLPAK_OK;
+}
+
+extern "C" int64_t splpak_b200_fit_launch_count(splpak_b200_fit_t h) {
+    return valid(h) ? (int64_t)(g_spl_launches - h->launches0) : -1;
+}
+extern "C" int64_t splpak_b200_total_launches(void) { return (int64_t)g_spl_launches; }
+
+extern "C" int splpak_b200_fit_get_normal_equations(splpak_b200_fit_t h, double *S, double *g,
+                                                    double *cnt, double *totals) {
+    if (!valid(h)) return SPLPAK_ERR_HANDLE;
+    const GridParams &gp = h->gp;
+    SPL_CUDA_TRY(cudaStreamSynchronize(h->st));
+    if (S) SPL_CUDA_TRY(cudaMemcpy(S, h->d_S, sizeof(double) * (size_t)(gp.ncol * gp.nsten), cudaMemcpyDeviceToHost));
+    if (g) SPL_CUDA_TRY(cudaMemcpy(g, h->d_g, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToHost));
+    if (cnt) SPL_CUDA_TRY(cudaMemcpy(cnt, h->d_cnt, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToHost));
+    if (totals) SPL_CUDA_TRY(cudaMemcpy(totals, h->d_totals, sizeof(double) * 2, cudaMemcpyDeviceToHost));
+    return SPLPAK_OK;
+}
+
+extern "C" int splpak_b200_fit_destroy(splpak_b200_fit_t h) {
+    if (!valid(h)) return SPLPAK_ERR_HANDLE;
+    cudaStreamSynchronize(h->st);
+    cudaStreamSynchronize(h->st_copy);
+    free_handle(h);
+    return SPLPAK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// one-shot fit (splcw / splcc)
+// ------------------------------------------------------------------------------------------
+extern "C" int splpak_b200_splcw(int ndim, const real_t *xdata, int l1xdat, const real_t *ydata,
+                                 const real_t *wdata, int64_t ndata, const real_t *xmin,
+                                 const real_t *xmax, const int *nodes, real_t xtrap, real_t *coef,
+                                 int64_t ncf, real_t *work, int64_t nwrk, int *ierror) {
+    (void)work;
+    int rc = SPLPAK_OK;
+    // validation in the reference's order: 101, 102, 103 (:718-750), 104 (:751), 105 (:759), 106 (:776)
+    GridParams gp;
+    rc = make_grid(ndim, xmin, xmax, nodes, nullptr, gp, nullptr);
+    if (rc == SPLPAK_OK && gp.ncol > ncf) rc = SPLPAK_ERR_NCF;
+    if (rc == SPLPAK_OK && ndata < 1) rc = SPLPAK_ERR_NDATA;
+    if (rc == SPLPAK_OK) {
+        const long long nwrk1 = (xtrap != (real_t)0) ? gp.ncol + 1 : 1;
+        if ((long long)nwrk - nwrk1 + 1 < 1) rc = SPLPAK_ERR_NWRK;
+    }
+    if (rc != SPLPAK_OK) {
+        if (ierror) *ierror = rc;
+        return rc;
+    }
+    splpak_b200_fit_t h = nullptr;
+    rc = splpak_b200_fit_create(ndim, xmin, xmax, nodes, xtrap, &h, ierror);
+    if (rc != SPLPAK_OK) return rc;
+    const int weighted = (wdata != nullptr) && (wdata[0] >= (real_t)0);        // :796
+    rc = splpak_b200_fit_add_points(h, xdata, l1xdat, ydata, wdata, weighted, ndata);
+    if (rc == SPLPAK_OK) rc = splpak_b200_fit_compute(h, coef, ncf, nwrk, ierror);
+    else if (ierror) *ierror = rc;
+    splpak_b200_fit_destroy(h);
+    return rc;
+}
+
+extern "C" int splpak_b200_splcc(int ndim, const real_t *xdata, int l1xdat, const real_t *ydata,
+                                 int64_t ndata, const real_t *xmin, const real_t *xmax,
+                                 const int *nodes, real_t xtrap, real_t *coef, int64_t ncf,
+                                 real_t *work, int64_t nwrk, int *ierror) {
+    const real_t wdata[1] = {(real_t)-1.0};    // :440
+    return splpak_b200_splcw(ndim, xdata, l1xdat, ydata, wdata, ndata, xmin, xmax, nodes, xtrap, coef,
+                             ncf, work, nwrk, ierror);
+}
+
+extern "C" int splpak_b200_measure_peaks(double *out, int n) { return spl_measure_peaks_impl(out, n); }

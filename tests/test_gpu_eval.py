@@ -1,0 +1,141 @@
+"""GPU parity: batched splfe/splde (CUDA, through the C ABI) against the oracle's scalar loop."""
+import numpy as np
+import pytest
+
+import splpak_b200 as sp
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    (1, [10]), (1, [4]), (1, [50]),
+    (2, [6, 7]), (2, [4, 4]), (2, [64, 64]),
+    (3, [5, 4, 6]), (3, [24, 24, 24]),
+    (4, [4, 5, 4, 6]), (4, [12, 12, 12, 12]),
+]
+
+
+def _queries(rng, ndim, nq, mn, mx):
+    q = rng.random((nq, ndim)) * 1.5 - 0.25          # inside and outside the grid
+    q = mn + q * (mx - mn)
+    # exact node / boundary hits
+    q[0] = mn
+    q[1] = mx
+    q[2] = mn + (mx - mn) * 0.5
+    return q
+
+
+def _tol(coef, ndim):
+    # |delta| <= ~50 eps * sum |c_j Phi_j|; edge basis values reach 6 per dimension
+    return 64 * np.finfo(float).eps * np.abs(coef).max() * 6.0 ** ndim
+
+
+@pytest.mark.parametrize("ndim,nodes", CASES)
+def test_splfe_matches_oracle(oracle, ndim, nodes):
+    rng = np.random.default_rng(11 * ndim + nodes[0])
+    ncol = int(np.prod(nodes))
+    coef = rng.standard_normal(ncol)
+    mn = -rng.random(ndim)
+    mx = 1.0 + rng.random(ndim)
+    q = _queries(rng, ndim, 4000, mn, mx)
+    ref, ie = oracle.evaluate_batch(ndim, q, coef, mn, mx, nodes)
+    got, ierr = sp.eval_batch(ndim, q, coef, mn, mx, nodes)
+    assert ie == 0 and ierr == 0
+    np.testing.assert_allclose(got, ref, rtol=0, atol=_tol(coef, ndim))
+
+
+@pytest.mark.parametrize("ndim,nodes", [(1, [10]), (2, [6, 7]), (3, [5, 4, 6]), (3, [24, 24, 24]), (4, [4, 5, 4, 6])])
+def test_splde_all_derivative_orders(oracle, ndim, nodes):
+    rng = np.random.default_rng(5 + ndim)
+    ncol = int(np.prod(nodes))
+    coef = rng.standard_normal(ncol)
+    mn = np.zeros(ndim)
+    mx = np.full(ndim, 2.0)
+    q = _queries(rng, ndim, 1500, mn, mx)
+    dxin = (np.array(nodes) - 1) / (mx - mn)
+    for code in range(3 ** ndim):
+        nd = [(code // 3 ** d) % 3 for d in range(ndim)]
+        ref, _ = oracle.evaluate_batch(ndim, q, coef, mn, mx, nodes, nderiv=nd)
+        got, ierr = sp.eval_batch(ndim, q, coef, mn, mx, nodes, nderiv=nd)
+        assert ierr == 0
+        scale = np.prod(dxin ** np.array(nd))
+        np.testing.assert_allclose(got, ref, rtol=0, atol=_tol(coef, ndim) * scale, err_msg=str(nd))
+
+
+def test_scalar_entry_points_and_generic(oracle):
+    """splfe / splde one point per call, and the splpak_type generic resolution."""
+    rng = np.random.default_rng(2)
+    nodes = [7, 5]
+    coef = rng.standard_normal(35)
+    s = sp.SplpakType(quiet=True)
+    for _ in range(5):
+        x = rng.random(2) * 1.4 - 0.2
+        ref, _ = oracle.evaluate(2, x, coef, [0, 0], [1, 1], nodes)
+        got, ierr = s.evaluate(2, x, coef, [0, 0], [1, 1], nodes)
+        assert ierr == 0 and abs(got - ref) <= _tol(coef, 2)
+        ref, _ = oracle.evaluate(2, x, coef, [0, 0], [1, 1], nodes, nderiv=[1, 2])
+        got, ierr = s.evaluate(2, x, [1, 2], coef, [0, 0], [1, 1], nodes)
+        assert ierr == 0 and abs(got - ref) <= _tol(coef, 2) * 6 * 16
+
+
+def test_nderiv_out_of_range_sets_104_but_still_evaluates(oracle):
+    """:1190-1194 sets 104 and does NOT return; the value is whatever bascmp's select-case gives."""
+    rng = np.random.default_rng(8)
+    coef = rng.standard_normal(12)
+    q = rng.random((64, 1)) * 1.2 - 0.1
+    for nd in ([3], [-1], [4]):
+        ref, ie = oracle.evaluate_batch(1, q, coef, [0.0], [1.0], [12], nderiv=nd)
+        got, ierr = sp.eval_batch(1, q, coef, [0.0], [1.0], [12], nderiv=nd)
+        assert ie == 104 and ierr == 104
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9 * max(1.0, np.abs(ref).max()))
+
+
+def test_large_table_goes_through_global_path(oracle):
+    """A coefficient table larger than shared memory (2-D 200x200 = 320 KB) uses the L2 gather path."""
+    rng = np.random.default_rng(4)
+    nodes = [200, 200]
+    coef = rng.standard_normal(40000)
+    q = rng.random((3000, 2)) * 1.2 - 0.1
+    ref, _ = oracle.evaluate_batch(2, q, coef, [0, 0], [1, 1], nodes)
+    got, ierr = sp.eval_batch(2, q, coef, [0, 0], [1, 1], nodes)
+    assert ierr == 0
+    np.testing.assert_allclose(got, ref, rtol=0, atol=_tol(coef, 2))
+
+
+def test_odd_ncol_and_strided_x(oracle):
+    """ncol odd (bulk copy needs padding) and l1x > ndim."""
+    rng = np.random.default_rng(6)
+    nodes = [5, 7]
+    coef = rng.standard_normal(35)
+    q = np.zeros((500, 4))
+    q[:, :2] = rng.random((500, 2))
+    q[:, 2:] = 99.0
+    ref, _ = oracle.evaluate_batch(2, q, coef, [0, 0], [1, 1], nodes)
+    got, ierr = sp.eval_batch(2, q, coef, [0, 0], [1, 1], nodes)
+    assert ierr == 0
+    np.testing.assert_allclose(got, ref, rtol=0, atol=_tol(coef, 2))
+
+
+def test_chunked_host_path_many_queries(oracle):
+    """More queries than one staging chunk (2^22): exercises the double-buffered H2D/D2H pipeline."""
+    rng = np.random.default_rng(9)
+    nodes = [24, 24, 24]
+    coef = rng.standard_normal(24 ** 3)
+    nq = (1 << 22) * 2 + 12345
+    q = rng.random((nq, 3))
+    got, ierr = sp.eval_batch(3, q, coef, [0, 0, 0], [1, 1, 1], nodes)
+    assert ierr == 0
+    pick = rng.integers(0, nq, 3000)
+    pick[:3] = [0, (1 << 22), nq - 1]
+    ref, _ = oracle.evaluate_batch(3, q[pick], coef, [0, 0, 0], [1, 1, 1], nodes)
+    np.testing.assert_allclose(got[pick], ref, rtol=0, atol=_tol(coef, 3))
+
+
+def test_real32_library(oracle32):
+    rng = np.random.default_rng(10)
+    nodes = [8, 9]
+    coef = rng.standard_normal(72).astype(np.float32)
+    q = (rng.random((2000, 2)) * 1.2 - 0.1).astype(np.float32)
+    ref, _ = oracle32.evaluate_batch(2, q, coef, [0, 0], [1, 1], nodes)
+    got, ierr = sp.eval_batch(2, q, coef, [0, 0], [1, 1], nodes, real32=True)
+    assert ierr == 0 and got.dtype == np.float32
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-4 * np.abs(coef).max())

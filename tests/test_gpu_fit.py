@@ -1,0 +1,227 @@
+"""GPU parity: splcc/splcw (CUDA assembly + Cholesky, through the C ABI) against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import splpak_b200 as sp
+from util import coef_tolerance, dense_from_stencil, make_problem
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _gram_from_oracle(oracle, ndim, x, y, w, mn, mx, nodes, xtrap):
+    A, r = oracle.rows(ndim, x, y, w, mn, mx, nodes, xtrap)
+    return A.T @ A, A.T @ r, A, r
+
+
+FIT_CASES = [
+    # ndim, nodes, ndata, xtrap, weighted, hole, outside
+    (1, [10], 200, 1.0, True, False, 0.0),
+    (1, [50], 10000, 1.0, True, False, 0.0),        # config 1 scale
+    (1, [4], 50, 0.0, False, False, 0.0),
+    (2, [6, 7], 2000, 1.0, True, False, 0.0),
+    (2, [9, 8], 3000, 1.0, False, True, 0.0),       # splcc with a data hole: constraint rows fire
+    (2, [8, 8], 3000, 1.0, True, False, 0.2),       # points outside the grid (extrapolation, :899 quirk)
+    (3, [5, 4, 6], 4000, 1.0, True, False, 0.0),
+    (3, [6, 6, 6], 5000, 1.0, True, True, 0.1),
+    (4, [4, 5, 4, 4], 6000, 1.0, True, False, 0.0),
+    (4, [5, 5, 5, 5], 8000, 0.5, False, True, 0.0),
+]
+
+
+@pytest.mark.parametrize("ndim,nodes,ndata,xtrap,weighted,hole,outside", FIT_CASES)
+def test_normal_equations_match_oracle_rows(oracle, ndim, nodes, ndata, xtrap, weighted, hole, outside):
+    """G, g (data rows only) and the nearest-node histogram against B^T W^2 B from the oracle's rows."""
+    x, y, w, mn, mx = make_problem(ndim, nodes, ndata, seed=ndim * 7 + nodes[0], weighted=weighted, hole=hole,
+                                   outside=outside)
+    h = sp.FitHandle(ndim, mn, mx, nodes, xtrap)
+    assert h.ierror == 0
+    assert h.add_points(x, y, w) == 0
+    S, g, cnt, totlwt, nrows = h.normal_equations()
+    G = dense_from_stencil(S, nodes)
+    Gref, gref, A, r = _gram_from_oracle(oracle, ndim, x, y, w, mn, mx, nodes, 0.0)   # data rows only
+    scale = np.abs(np.diag(Gref)).max()
+    np.testing.assert_allclose(G, Gref, rtol=0, atol=1e-12 * scale)
+    np.testing.assert_allclose(g, gref, rtol=0, atol=1e-12 * max(np.abs(gref).max(), 1e-300))
+    assert nrows == A.shape[0]
+    wsum = float(len(x)) if w is None else float(np.sum(w))
+    assert abs(totlwt - wsum) <= 1e-10 * wsum
+    assert abs(cnt.sum() - wsum) <= 1e-10 * wsum
+    h.destroy()
+
+
+@pytest.mark.parametrize("ndim,nodes,ndata,xtrap,weighted,hole,outside", FIT_CASES)
+def test_coefficients_match_oracle(oracle, ndim, nodes, ndata, xtrap, weighted, hole, outside):
+    x, y, w, mn, mx = make_problem(ndim, nodes, ndata, seed=ndim * 7 + nodes[0], weighted=weighted, hole=hole,
+                                   outside=outside)
+    ref, ie = oracle.initialize(ndim, x, y, w, mn, mx, nodes, xtrap)
+    s = sp.SplpakType(quiet=True)
+    if weighted:
+        got, ierr = s.initialize(ndim, x, x.shape[1], y, w, len(x), mn, mx, nodes, xtrap)
+    else:
+        got, ierr = s.initialize(ndim, x, x.shape[1], y, len(x), mn, mx, nodes, xtrap)
+    assert ie == 0 and ierr == 0
+    Gref, _, A, r = _gram_from_oracle(oracle, ndim, x, y, w, mn, mx, nodes, xtrap)
+    if xtrap != 0 and hole:
+        assert A.shape[0] > len(x), "constraint rows were expected to fire in this case"
+    tol, cond = coef_tolerance(Gref)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err <= tol, f"coef rel err {err:.3e} > {tol:.3e} (cond(G) {cond:.3e})"
+    # fitted values at the data points are far better conditioned than the coefficients
+    fit_ref = A[: len(x)] @ ref
+    fit_got = A[: len(x)] @ got
+    np.testing.assert_allclose(fit_got, fit_ref, rtol=0, atol=1e-10 * max(1.0, np.abs(fit_ref).max()))
+
+
+def test_reference_linear_test_on_gpu():
+    """/root/reference/test/splpak_test_linear.f90 end to end through the splpak_type mirror."""
+    g = json.load(open(os.path.join(GOLD, "splpak_test_linear.json")))
+    x = np.array(g["xdata"]).reshape(-1, 1)
+    solver = sp.SplpakType(quiet=True)
+    coef, ierror = solver.initialize(1, x, 1, g["ydata"], g["wdata"], len(x), g["xmin"], g["xmax"], g["nodes"],
+                                     g["xtrap"], 10, g["nwrk"])
+    assert ierror == 0
+    errmax = 0.0
+    for xe in g["x_est"][::7]:
+        f, ierror = solver.evaluate(1, [xe], coef, g["xmin"], g["xmax"], g["nodes"])
+        assert ierror == 0
+        errmax = max(errmax, abs(f - 2.0 * xe))
+    assert errmax <= g["errmax_tol"]
+    fleft, ierror = solver.evaluate(1, [0.0], [1], coef, g["xmin"], g["xmax"], g["nodes"])
+    assert ierror == 0 and abs(fleft - 2.0) <= g["slope_tol"]
+    fright, ierror = solver.evaluate(1, [1.0], [1], coef, g["xmin"], g["xmax"], g["nodes"])
+    assert ierror == 0 and abs(fright - 2.0) <= g["slope_tol"]
+    np.testing.assert_allclose(27.0 * coef, g["coef_times_27"], atol=1e-11)
+
+
+def test_reference_noisy_test_on_gpu():
+    """/root/reference/test/splpak_test.f90: weighted noisy fit, errmax <= 1e-1 (:84)."""
+    rng = np.random.default_rng(42)
+    n = 20
+    r = (rng.random(n) - 0.5) / 10.0
+    x = (np.arange(n) / (n - 1)).reshape(-1, 1)
+    f1 = lambda t: 0.5 * (t * np.exp(-t) + np.sin(t))
+    solver = sp.SplpakType(quiet=True)
+    coef, ierror = solver.initialize(1, x, 1, f1(x[:, 0]) + r, 1.0 - np.abs(r), n, [0.0], [1.0], [10], 1.0, 10, 111)
+    assert ierror == 0
+    xe = (np.arange(100) / 100).reshape(-1, 1)
+    v, ierror = sp.eval_batch(1, xe, coef, [0.0], [1.0], [10])
+    assert ierror == 0 and np.abs(v - f1(xe[:, 0])).max() <= 1e-1
+
+
+def test_multilinear_reproduction_K1():
+    """Analytic known answer independent of any implementation."""
+    rng = np.random.default_rng(3)
+    for ndim, nodes in ((2, [9, 7]), (3, [8, 6, 7]), (4, [5, 6, 5, 4])):
+        x = rng.random((20000, ndim))
+        a = rng.random(ndim) + 0.5
+        b = rng.random(ndim) - 0.5
+        f = lambda p: np.prod(a + b * p, axis=-1)
+        coef, ierr = sp.splcc(ndim, x, ndim, f(x), len(x), [0] * ndim, [1] * ndim, nodes, 0.0, quiet=True)
+        assert ierr == 0
+        q = rng.random((500, ndim)) * 1.6 - 0.3
+        v, _ = sp.eval_batch(ndim, q, coef, [0] * ndim, [1] * ndim, nodes)
+        np.testing.assert_allclose(v, f(q), rtol=0, atol=2e-11)
+        v, _ = sp.eval_batch(ndim, q, coef, [0] * ndim, [1] * ndim, nodes, nderiv=[1] * ndim)
+        np.testing.assert_allclose(v, np.prod(b), rtol=0, atol=1e-8)
+
+
+def test_zero_weights_are_skipped(oracle):
+    x, y, w, mn, mx = make_problem(2, [6, 6], 1500, seed=21)
+    w[::3] = 0.0
+    ref, ie = oracle.initialize(2, x, y, w, mn, mx, [6, 6], 1.0)
+    got, ierr = sp.splcw(2, x, 2, y, w, len(x), mn, mx, [6, 6], 1.0, quiet=True)
+    assert ie == 0 and ierr == 0
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-10 * np.abs(ref).max())
+    keep = w != 0
+    got2, _ = sp.splcw(2, x[keep], 2, y[keep], w[keep], keep.sum(), mn, mx, [6, 6], 1.0, quiet=True)
+    np.testing.assert_allclose(got2, got, rtol=0, atol=1e-11 * np.abs(ref).max())
+
+
+def test_negative_first_weight_means_unweighted(oracle):
+    x, y, w, mn, mx = make_problem(1, [9], 300, seed=22)
+    w[0] = -1.0
+    ref, _ = oracle.initialize(1, x, y, w, mn, mx, [9], 1.0)
+    ref_cc, _ = oracle.initialize(1, x, y, None, mn, mx, [9], 1.0)
+    got, ierr = sp.splcw(1, x, 1, y, w, len(x), mn, mx, [9], 1.0, quiet=True)
+    assert ierr == 0
+    np.testing.assert_allclose(ref, ref_cc, atol=1e-14)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-10 * np.abs(ref).max())
+
+
+def test_solver_failures_map_to_107(oracle):
+    x, y, w, mn, mx = make_problem(1, [10], 30, seed=1)
+    a = dict(quiet=True)
+    assert oracle.initialize(1, x[:5], y[:5], w[:5], mn, mx, [10], 0.0)[1] == 107
+    assert sp.splcw(1, x[:5], 1, y[:5], w[:5], 5, mn, mx, [10], 0.0, **a)[1] == 107           # too few rows
+    assert sp.splcw(1, x, 1, y, np.zeros(30), 30, mn, mx, [10], 0.0, **a)[1] == 107          # all weights zero
+    assert sp.splcw(1, x, 1, y, w, 30, mn, mx, [10], 1.0, nwrk=50, **a)[1] == 107            # suprls scratch (32)
+    # a data hole with xtrap = 0: rank deficient -> non-positive pivot
+    xh = np.concatenate([np.linspace(0, 0.2, 40), np.linspace(0.8, 1, 40)]).reshape(-1, 1)
+    assert sp.splcc(1, xh, 1, xh[:, 0], 80, [0.0], [1.0], [20], 0.0, **a)[1] == 107
+
+
+def test_streaming_add_points_equals_one_shot(oracle):
+    """add_points in several calls (host chunks) == one splcw call; compute() twice is refused."""
+    x, y, w, mn, mx = make_problem(3, [6, 5, 6], 9000, seed=33)
+    one, ierr = sp.splcw(3, x, 3, y, w, len(x), mn, mx, [6, 5, 6], 1.0, quiet=True)
+    assert ierr == 0
+    h = sp.FitHandle(3, mn, mx, [6, 5, 6], 1.0)
+    for lo in range(0, len(x), 2500):
+        assert h.add_points(x[lo:lo + 2500], y[lo:lo + 2500], w[lo:lo + 2500]) == 0
+    got, ierr = h.compute()
+    assert ierr == 0
+    np.testing.assert_allclose(got, one, rtol=0, atol=1e-11 * np.abs(one).max())
+    assert h.compute()[1] == 203
+    t = h.timings()
+    assert t["accumulate"] > 0 and t["factor"] > 0
+    assert h.launch_count() > 0
+    h.reset()
+    assert h.add_points(x, y, w) == 0
+    again, ierr = h.compute()
+    np.testing.assert_allclose(again, one, rtol=0, atol=1e-11 * np.abs(one).max())
+    h.destroy()
+
+
+def test_emulated_ranks_sum_to_single_rank(oracle):
+    """Multi-GPU contract on one device: R partial buffers summed == single-rank buffer."""
+    import torch
+
+    x, y, w, mn, mx = make_problem(2, [8, 8], 6000, seed=44, hole=True)
+    nodes = [8, 8]
+    full = sp.FitHandle(2, mn, mx, nodes, 1.0)
+    full.add_points(x, y, w)
+    tfull = full.partial_tensor().clone()
+    parts = []
+    R = 4
+    total = None
+    for r in range(R):
+        lo, hi = r * len(x) // R, (r + 1) * len(x) // R
+        hr = sp.FitHandle(2, mn, mx, nodes, 1.0)
+        hr.add_points(x[lo:hi], y[lo:hi], w[lo:hi], weighted=True)
+        hr.synchronize()
+        t = hr.partial_tensor().clone()
+        total = t if total is None else total + t
+        parts.append(hr)
+    torch.testing.assert_close(total, tfull, rtol=0, atol=1e-10 * float(tfull.abs().max()))
+    # write the reduced buffer back into rank 0's handle and solve there
+    parts[0].partial_tensor().copy_(total)
+    c_multi, ierr = parts[0].compute()
+    c_single, ierr2 = full.compute()
+    assert ierr == 0 and ierr2 == 0
+    np.testing.assert_allclose(c_multi, c_single, rtol=0, atol=1e-10 * np.abs(c_single).max())
+    for p in parts:
+        p.destroy()
+    full.destroy()
+
+
+def test_real32_fit(oracle32):
+    x, y, w, mn, mx = make_problem(2, [6, 6], 1500, seed=55)
+    ref, ie = oracle32.initialize(2, x, y, w, mn, mx, [6, 6], 1.0)
+    got, ierr = sp.splcw(2, x.astype(np.float32), 2, y.astype(np.float32), w.astype(np.float32), len(x),
+                         mn, mx, [6, 6], 1.0, quiet=True, real32=True)
+    assert ie == 0 and ierr == 0 and got.dtype == np.float32
+    np.testing.assert_allclose(got, ref, rtol=0, atol=5e-3 * np.abs(ref).max())

@@ -1,0 +1,59 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import numpy as np
+
+
+def make_problem(ndim, nodes, ndata, seed=0, weighted=True, hole=False, outside=0.0, xmin=None, xmax=None):
+    """Seeded scattered data on [xmin, xmax]^ndim (optionally with a data hole so constraint rows fire,
+    and a fraction `outside` of points beyond the grid to exercise extrapolation / the :899 quirk)."""
+    rng = np.random.default_rng(seed)
+    xmin = np.zeros(ndim) if xmin is None else np.asarray(xmin, float)
+    xmax = np.ones(ndim) if xmax is None else np.asarray(xmax, float)
+    u = rng.random((ndata, ndim))
+    if outside > 0:
+        nout = int(ndata * outside)
+        u[:nout] = u[:nout] * 1.6 - 0.3
+    if hole:
+        c = 0.5
+        r = np.sqrt(((u - c) ** 2).sum(axis=1))
+        keep = r > 0.3
+        u = u[keep]
+    x = xmin + u * (xmax - xmin)
+    f = np.ones(len(x))
+    for d in range(ndim):
+        f = f * np.sin(2.0 * u[:, d] + 0.3 * d) + 0.1 * u[:, d]
+    y = f + 0.01 * rng.standard_normal(len(x))
+    w = rng.random(len(x)) + 0.5 if weighted else None
+    return x, y, w, xmin, xmax
+
+
+def dense_from_stencil(S, nodes):
+    """Expand the orthant-stencil storage S[node, 4^ndim] into the dense symmetric Gram matrix."""
+    nodes = [int(n) for n in nodes]
+    ndim = len(nodes)
+    ncol = int(np.prod(nodes))
+    idx = np.arange(ncol)
+    multi = []
+    k = idx.copy()
+    for d in range(ndim):
+        multi.append(k % nodes[d])
+        k = k // nodes[d]
+    multi = np.stack(multi, axis=1)            # (ncol, ndim), dimension 1 fastest
+    G = np.zeros((ncol, ncol))
+    strides = np.cumprod([1] + nodes[:-1])
+    for i in range(ncol):
+        delta = np.abs(multi - multi[i])        # (ncol, ndim)
+        ok = (delta <= 3).all(axis=1)
+        mn = np.minimum(multi, multi[i])
+        node = (mn * strides).sum(axis=1)
+        sten = (delta * (4 ** np.arange(ndim))).sum(axis=1)
+        G[i, ok] = S[node[ok], sten[ok]]
+    return G
+
+
+def coef_tolerance(G, base=1e-10):
+    """max(1e-10, 0.1 * eps * cond(G))."""
+    try:
+        cond = np.linalg.cond(G)
+    except Exception:
+        cond = 1e16
+    return max(base, 0.1 * np.finfo(float).eps * cond), cond
