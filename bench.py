@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the splpak fit-and-evaluate hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU restatement of the reference
+
+Workload (BASELINE.json configs[2], the config the metric is quoted on; it fits one GPU):
+  3-D splcw weighted fit of 1e8 scattered points on 24^3 nodes (xtrap = 1) + splfe at 1e9 points,
+  real64, PER GPU ("weak" scaling: every rank holds its own 1e8-point / 1e9-query shard of one global
+  problem; the partial normal equations are summed with ONE NCCL all-reduce before the replicated solve).
+A step = one fit (assembly + all-reduce + constraints + Cholesky solve) followed by one evaluation
+pass, inputs resident in HBM.  Inputs (4 GB + 24 GB per GPU) are far larger than the 126 MB L2, so no
+L2 flush is needed between steps.
+
+One JSON line on stdout (rank 0).  `value` = data points fitted per second (whole job), `evals_per_s`
+= spline evaluations per second; `e2e` = the same metric through the host-array C-ABI entry points
+(pinned host buffers, H2D/D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NDIM = 3
+NODES = [24, 24, 24]
+XMIN = [0.0, 0.0, 0.0]
+XMAX = [1.0, 1.0, 1.0]
+XTRAP = 1.0
+NCOL = 24 ** 3
+WORKLOAD = "cfg3: 3-D splcw weighted fit, 1e8 points/GPU on 24^3 nodes (xtrap=1) + splfe at 1e9 points/GPU, real64"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (C restatement of the reference), steady-state sample
+# -------------------------------------------------------------------------------------------------
+def cpu_fit_sample(m_rows, seed=42):
+    """Seconds for m_rows real cfg3 data rows entering a FULL 13,824-column triangle through the
+    restated splcw row loop + suprls Householder update (the reference's steady state: ~2*ncol^2 flops
+    per point).  The fill phase (first ncol rows, ~1.8e12 flops) is excluded -- it would take tens of
+    minutes on one core -- so this is an optimistic per-point cost for the reference."""
+    from oracle import Oracle
+    from splpak_b200 import synth
+
+    o = Oracle()
+    x, y, w = synth.points_numpy(NDIM, m_rows, start=0, seed=seed)
+    return o.suprls_steady_sample(NDIM, x, y, w, m_rows, XMIN, XMAX, NODES)
+
+
+def cpu_eval_sample(nq, seed=43):
+    from oracle import Oracle
+    from splpak_b200 import synth
+
+    o = Oracle()
+    q = synth.queries_numpy(NDIM, nq, seed=seed)
+    coef = np.random.default_rng(0).standard_normal(NCOL)
+    t0 = time.perf_counter()
+    o.evaluate_batch(NDIM, q, coef, XMIN, XMAX, NODES)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import build_oracle
+
+    build_oracle()
+    m = args.cpu_rows
+    for _ in range(args.warmup):
+        cpu_fit_sample(m)
+    ts = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ts.append(cpu_fit_sample(m))
+    t_wall = time.perf_counter() - t_wall0
+    sec = sum(ts) / len(ts)
+    value = m / sec
+    te = cpu_eval_sample(200_000)
+    sample = (f"{m} cfg3 data rows per step entering a full {NCOL}-column triangle (steady-state suprls "
+              f"Householder update, fill phase excluded); 1 thread, the reference is serial")
+    line = {
+        "impl": "reference", "metric": "data points fitted/s (3-D splcw, 24^3 nodes)", "value": value,
+        "unit": "points/s", "evals_per_s": 200_000 / te, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_arm": "C restatement of src/splpak.F90 (oracle/); no Fortran "
+                   "compiler exists in the image so the reference itself cannot be built"},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": t_wall,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# -------------------------------------------------------------------------------------------------
+# this repo's CUDA path
+# -------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import splpak_b200 as sp
+    from splpak_b200 import synth
+
+    sp.build()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def reduce_max(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    npts, nq = args.npoints, args.nqueries
+    hbm_peak, peak_src = load_peaks()
+
+    # ---- synthetic shard of this rank (counter-based: global point index = rank*npts + i) ----
+    x, y, w = synth.points_torch(NDIM, npts, start=rank * npts, seed=42, device=dev)
+    q = synth.queries_torch(NDIM, nq, start=rank * nq, seed=43, device=dev)
+    out = torch.empty(nq, dtype=torch.float64, device=dev)
+    dcoef = torch.zeros(NCOL, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    h = sp.FitHandle(NDIM, XMIN, XMAX, NODES, XTRAP)
+    if h.ierror != 0:
+        raise SystemExit(f"fit_create failed: {h.ierror}")
+    stream = torch.cuda.ExternalStream(h.stream(), device=dev)
+    part = h.partial_tensor()
+
+    def fit_step():
+        h.reset()
+        rc = h.add_points_device(x, NDIM, y, w, npts, True)
+        if rc != 0:
+            raise SystemExit(f"add_points_device failed: {rc}")
+        if world > 1:
+            dist.all_reduce(part)            # one NCCL all-reduce (sum) of [G | g | histogram | totals]
+        ierr = h.compute_device(dcoef)
+        if ierr != 0:
+            raise SystemExit(f"compute failed: ierror {ierr}")
+
+    def eval_step():
+        ierr = sp.eval_batch_device(NDIM, q, NDIM, nq, dcoef, XMIN, XMAX, NODES, out, stream=stream)
+        if ierr != 0:
+            raise SystemExit(f"eval failed: ierror {ierr}")
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            fit_step()
+            eval_step()
+        torch.cuda.synchronize()
+        barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = sp.total_launches()
+        evs = []
+        stage_ms = {}
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+            fit_step()
+            e1.record(stream)
+            eval_step()
+            e2.record(stream)
+            evs.append((e0, e1, e2))
+            for k, v in h.timings().items():
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+        torch.cuda.synchronize()
+        barrier()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        launches = sp.total_launches() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+
+    fit_ms = sum(a.elapsed_time(b) for a, b, _ in evs) / args.steps
+    eval_ms = sum(b.elapsed_time(c) for _, b, c in evs) / args.steps
+    fit_ms, eval_ms = reduce_max(fit_ms), reduce_max(eval_ms)
+    stage_ms = {k: reduce_max(v / args.steps) for k, v in stage_ms.items()}
+    launches_total = reduce_sum(float(launches))
+    checksum = float(out[:: max(1, nq // 1000)].sum().item())
+
+    # ---- end to end through the host-array C ABI (pinned host buffers, copies inside the timed region) ----
+    nq_e2e = min(nq, args.e2e_queries)
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty((npts, NDIM), dtype=torch.float64, pin_memory=True)
+        hy = torch.empty(npts, dtype=torch.float64, pin_memory=True)
+        hw = torch.empty(npts, dtype=torch.float64, pin_memory=True)
+        hq = torch.empty((nq_e2e, NDIM), dtype=torch.float64, pin_memory=True)
+        hx.copy_(x); hy.copy_(y); hw.copy_(w); hq.copy_(q[:nq_e2e])
+        torch.cuda.synchronize()
+        xa, ya, wa, qa = hx.numpy(), hy.numpy(), hw.numpy(), hq.numpy()
+        hout = torch.empty(nq_e2e, dtype=torch.float64, pin_memory=True)
+        import ctypes as C
+        lib = sp.load()
+
+        def e2e_step():
+            h.reset()
+            rc = h.add_points(xa, ya, wa, weighted=True)              # chunked H2D overlapped with the kernels
+            if rc != 0:
+                raise SystemExit(f"add_points failed: {rc}")
+            if world > 1:
+                h.synchronize()
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(part)
+                torch.cuda.synchronize()
+            coef, ierr = h.compute()                                   # D2H of the coefficients
+            if ierr != 0:
+                raise SystemExit(f"compute failed: {ierr}")
+            t_mid = time.perf_counter()
+            ie = C.c_int(0)
+            mn = (C.c_double * 3)(*XMIN); mx = (C.c_double * 3)(*XMAX); no = (C.c_int * 3)(*NODES)
+            lib.splpak_b200_eval(NDIM, C.c_void_p(qa.ctypes.data), NDIM, nq_e2e, None,
+                                 C.c_void_p(coef.ctypes.data), mn, mx, no, C.c_void_p(hout.data_ptr()), C.byref(ie))
+            if ie.value != 0:
+                raise SystemExit(f"eval failed: {ie.value}")
+            return t_mid
+
+        e2e_step()                                                     # warm-up
+        barrier()
+        fit_s, eval_s = [], []
+        for _ in range(args.e2e_steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            t_mid = e2e_step()
+            t1 = time.perf_counter()
+            fit_s.append(t_mid - t0)
+            eval_s.append(t1 - t_mid)
+        e2e_fit = reduce_max(sum(fit_s) / len(fit_s))
+        e2e_eval = reduce_max(sum(eval_s) / len(eval_s))
+        e2e = {
+            "value": world * npts / e2e_fit, "unit": "points/s",
+            "evals_per_s": world * nq_e2e / e2e_eval,
+            "h2d_bytes_per_step": int(npts * (NDIM + 2) * 8 + nq_e2e * NDIM * 8 + NCOL * 8),
+            "d2h_bytes_per_step": int(NCOL * 8 + nq_e2e * 8),
+            "fit_ms": 1e3 * e2e_fit, "eval_ms": 1e3 * e2e_eval, "steps": args.e2e_steps,
+            "note": f"host API: FitHandle.add_points+compute on {npts} pinned host points, splpak_b200_eval on "
+                    f"{nq_e2e} pinned host queries (bounded sample of the {nq} device-resident queries)",
+        }
+        del hx, hy, hw, hq, hout
+
+    h.destroy()
+
+    if rank == 0:
+        # ---- rooflines ----
+        try:
+            dfma_tf, dmma_tf, copy_gbs = sp.measure_peaks()
+        except Exception:
+            dfma_tf = dmma_tf = copy_gbs = None
+        acc_ms = stage_ms.get("accumulate", 0.0)
+        eval_bytes = nq * (NDIM + 1) * 8
+        asm_bytes = npts * (NDIM + 2) * 8
+        eval_roof = {"kernel": "spl_eval_kernel<3,smem>", "bound": "hbm", "achieved": eval_bytes / (eval_ms * 1e-3) / 1e9,
+                     "peak": hbm_peak, "unit": "GB/s", "traffic": None}
+        eval_roof["frac"] = eval_roof["achieved"] / hbm_peak
+        # accumulate: 1000 G + 64 rhs FMAs per point actually needed (Kronecker-symmetric form), flops = 2*FMA
+        acc_flops = npts * 2.0 * (1000 + 64)
+        acc_roof = {"kernel": "spl_accumulate_kernel<3>", "bound": "fp64", "unit": "TFLOP/s",
+                    "achieved": acc_flops / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None,
+                    "peak": dfma_tf, "peak_source": "DFMA micro-benchmark in this run (splpak_b200_measure_peaks)",
+                    "hbm_achieved_gbs": asm_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
+                    "hbm_frac": (asm_bytes / (acc_ms * 1e-3) / 1e9) / hbm_peak if acc_ms > 0 else None}
+        if acc_roof["achieved"] and dfma_tf:
+            acc_roof["frac"] = acc_roof["achieved"] / dfma_tf
+        dominant = eval_roof if eval_ms >= acc_ms else {
+            "kernel": acc_roof["kernel"], "bound": "hbm", "achieved": acc_roof["hbm_achieved_gbs"], "peak": hbm_peak,
+            "unit": "GB/s", "frac": acc_roof["hbm_frac"], "traffic": None,
+            "note": "FP64-pipe-bound kernel; see roofline_fp64 for the binding roof"}
+        dominant = dict(dominant)
+        dominant["peak_source"] = peak_src
+
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            sec = cpu_fit_sample(args.cpu_rows)
+            te = cpu_eval_sample(1_000_000)
+            cpu = {"value": args.cpu_rows / sec, "unit": "points/s", "cores": 1, "kind": "port",
+                   "evals_per_s": 1_000_000 / te,
+                   "sample": f"{args.cpu_rows} cfg3 data rows entering a full {NCOL}-column triangle through the "
+                             f"restated splcw row loop + suprls Householder update ({sec:.2f} s; steady state, fill "
+                             f"phase excluded); eval: 1e6 scalar splfe calls ({te:.2f} s)"}
+
+        line = {
+            "metric": "data points fitted/s (3-D splcw, 24^3 nodes); spline evals/s in evals_per_s",
+            "value": world * npts / (fit_ms * 1e-3), "unit": "points/s",
+            "evals_per_s": world * nq / (eval_ms * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": fit_ms + eval_ms, "fit_ms": fit_ms, "eval_ms": eval_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "ndim": NDIM, "nodes": NODES, "points_per_gpu": npts,
+                       "queries_per_gpu": nq, "xtrap": XTRAP, "query_order": "uniform random",
+                       "l2": "inputs (4 GB points + 24 GB queries per GPU) exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"point-sharded x{world}, one all-reduce, replicated solve"},
+            "stages_ms": stage_ms,
+            "roofline": dominant, "roofline_eval": eval_roof, "roofline_fp64": acc_roof,
+            "fp64_peaks": {"dfma_tflops": dfma_tf, "dmma_tflops": dmma_tf, "copy_gbs": copy_gbs},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_total),
+            "clocks": clocks, "checksum": checksum, "wall_s": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--npoints", type=int, default=100_000_000, help="data points per GPU (cfg3: 1e8)")
+    ap.add_argument("--nqueries", type=int, default=1_000_000_000, help="evaluation points per GPU (cfg3: 1e9)")
+    ap.add_argument("--e2e-queries", type=int, default=100_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-rows", type=int, default=8)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                       # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
