@@ -24,9 +24,16 @@ def _queries(rng, ndim, nq, mn, mx):
     return q
 
 
-def _tol(coef, ndim):
-    # |delta| <= ~50 eps * sum |c_j Phi_j|; edge basis values reach 6 per dimension
-    return 64 * np.finfo(float).eps * np.abs(coef).max() * 6.0 ** ndim
+def _tol(coef, ndim, oracle=None, q=None, mn=None, mx=None, nodes=None):
+    """Pure reordering roundoff: |delta| <= ~50 eps * sum_j |c_j Phi_j(x)|.  The sum is
+    evaluated per query with the oracle on |coef| (value basis functions are non-negative, and they
+    grow linearly outside the grid, so the bound must be per point, not global)."""
+    eps = np.finfo(float).eps
+    floor = 64 * eps * np.abs(coef).max() * 6.0 ** ndim
+    if oracle is None:
+        return floor
+    bound, _ = oracle.evaluate_batch(ndim, q, np.abs(coef), mn, mx, nodes)
+    return np.maximum(floor, 128 * eps * np.abs(bound))
 
 
 @pytest.mark.parametrize("ndim,nodes", CASES)
@@ -40,7 +47,7 @@ def test_splfe_matches_oracle(oracle, ndim, nodes):
     ref, ie = oracle.evaluate_batch(ndim, q, coef, mn, mx, nodes)
     got, ierr = sp.eval_batch(ndim, q, coef, mn, mx, nodes)
     assert ie == 0 and ierr == 0
-    np.testing.assert_allclose(got, ref, rtol=0, atol=_tol(coef, ndim))
+    assert (np.abs(got - ref) <= _tol(coef, ndim, oracle, q, mn, mx, nodes)).all(), np.abs(got - ref).max()
 
 
 @pytest.mark.parametrize("ndim,nodes", [(1, [10]), (2, [6, 7]), (3, [5, 4, 6]), (3, [24, 24, 24]), (4, [4, 5, 4, 6])])
@@ -57,8 +64,9 @@ def test_splde_all_derivative_orders(oracle, ndim, nodes):
         ref, _ = oracle.evaluate_batch(ndim, q, coef, mn, mx, nodes, nderiv=nd)
         got, ierr = sp.eval_batch(ndim, q, coef, mn, mx, nodes, nderiv=nd)
         assert ierr == 0
-        scale = np.prod(dxin ** np.array(nd))
-        np.testing.assert_allclose(got, ref, rtol=0, atol=_tol(coef, ndim) * scale, err_msg=str(nd))
+        scale = np.prod((3.0 * dxin) ** np.array(nd))     # |d^k Phi| <= (3 dxin)^k * O(value bound)
+        tol = _tol(coef, ndim, oracle, q, mn, mx, nodes) * scale
+        assert (np.abs(got - ref) <= tol).all(), (nd, np.abs(got - ref).max())
 
 
 def test_scalar_entry_points_and_generic(oracle):
@@ -98,7 +106,7 @@ def test_large_table_goes_through_global_path(oracle):
     ref, _ = oracle.evaluate_batch(2, q, coef, [0, 0], [1, 1], nodes)
     got, ierr = sp.eval_batch(2, q, coef, [0, 0], [1, 1], nodes)
     assert ierr == 0
-    np.testing.assert_allclose(got, ref, rtol=0, atol=_tol(coef, 2))
+    assert (np.abs(got - ref) <= _tol(coef, 2, oracle, q, [0, 0], [1, 1], nodes)).all()
 
 
 def test_odd_ncol_and_strided_x(oracle):
