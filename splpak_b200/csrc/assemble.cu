@@ -10,10 +10,13 @@
 //   1. spl_classify_kernel   one pass over the raw AoS points: window id -> per-window counts,
 //                            nearest-node histogram (with the :899 quirk), totlwt, row count
 //   2. spl_scan_kernel       exclusive scan of the counts -> window segment starts + work items
-//   3. spl_scatter_kernel    second pass: counting-sort scatter of (x.., y, w) records by window
+//   3. spl_perm_kernel       second pass: counting sort of the point INDICES by window (4 bytes per
+//                            point; scattering 40-byte records instead was LSU-bound)
 //   4. spl_items_kernel      work-item table (window, segment of <= CH points)
-//   5. spl_accumulate_kernel persistent CTAs; per work item the window-local block of G is
-//                            accumulated in REGISTERS and flushed once with red.global.add.f64
+//   5. spl_accumulate_kernel persistent CTAs; per work item the points are gathered through the
+//                            permutation (prefetched two batches ahead, hidden under the FP64 work),
+//                            the window-local block of G is accumulated in REGISTERS and flushed once
+//                            with red.global.add.f64
 //
 // The per-point outer product of a tensor-product basis has only 10^ndim distinct entries
 // (10 symmetric pairs per dimension), not 4^ndim(4^ndim+1)/2: G is symmetric under swapping the row
@@ -166,20 +169,18 @@ spl_scan_kernel(const unsigned *__restrict__ wincount, long long nwindows, unsig
 
 template <int NDIM>
 __global__ void __launch_bounds__(256)
-spl_scatter_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
-                   const real_t *__restrict__ y, const real_t *__restrict__ w, int weighted,
-                   long long n, const unsigned *__restrict__ winstart,
-                   unsigned *__restrict__ wincursor, double *__restrict__ records) {
+spl_perm_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
+                const real_t *__restrict__ w, int weighted, long long n,
+                const unsigned *__restrict__ winstart, unsigned *__restrict__ wincursor,
+                unsigned *__restrict__ perm) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long nround = ((n + stride - 1) / stride) * stride;
     const unsigned lane = threadIdx.x & 31;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         unsigned key = 0xffffffffu;
-        double wv = 0.0;
-        const real_t *xp = x + i * (long long)l1x;
         if (i < n) {
-            wv = weighted ? (double)w[i] : 1.0;
-            if (wv != 0.0) key = spl_window_key<NDIM>(gp, xp);
+            const double wv = weighted ? (double)w[i] : 1.0;
+            if (wv != 0.0) key = spl_window_key<NDIM>(gp, x + i * (long long)l1x);
         }
         const unsigned peers = __match_any_sync(0xffffffffu, key);
         const int leader = __ffs(peers) - 1;
@@ -189,12 +190,7 @@ spl_scatter_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
         base = __shfl_sync(0xffffffffu, base, leader);
         if (key != 0xffffffffu) {
             const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-            const long long pos = (long long)winstart[key] + base + rank;
-            double *r = records + pos * (NDIM + 2);
-#pragma unroll
-            for (int d = 0; d < NDIM; ++d) r[d] = (double)xp[d];
-            r[NDIM] = (double)y[i];
-            r[NDIM + 1] = wv;
+            perm[(long long)winstart[key] + base + rank] = (unsigned)i;
         }
     }
 }
@@ -220,9 +216,11 @@ spl_items_kernel(const unsigned *__restrict__ wincount, const unsigned *__restri
 
 template <int NDIM> struct AccTraits;
 template <> struct AccTraits<1> { static constexpr int R = 1, LPG = 2,   NT = 256, PB = 256, CH = 16384, RS = 22;  };
-template <> struct AccTraits<2> { static constexpr int R = 4, LPG = 4,   NT = 256, PB = 128, CH = 4096,  RS = 38;  };
-template <> struct AccTraits<3> { static constexpr int R = 4, LPG = 32,  NT = 256, PB = 64,  CH = 8192,  RS = 48;  };
-template <> struct AccTraits<4> { static constexpr int R = 4, LPG = 288, NT = 288, PB = 32,  CH = 4096,  RS = 178; };
+template <> struct AccTraits<2> { static constexpr int R = 4, LPG = 4,   NT = 256, PB = 256, CH = 8192,  RS = 38;  };
+// RS (doubles per staged point) is even (16-byte aligned LDS.128 of the inner vector) with RS/2 odd,
+// so consecutive points start 4 banks apart: staging stores of neighbouring points do not collide.
+template <> struct AccTraits<3> { static constexpr int R = 4, LPG = 32,  NT = 256, PB = 256, CH = 8192,  RS = 50;  };
+template <> struct AccTraits<4> { static constexpr int R = 4, LPG = 288, NT = 288, PB = 72,  CH = 4096,  RS = 178; };
 
 template <int NDIM> struct AccDerived {
     using T = AccTraits<NDIM>;
@@ -239,6 +237,7 @@ template <int NDIM> struct AccDerived {
     static constexpr int NH = (NDIM <= 2) ? 2 : (NDIM == 3 ? 14 : 116);
     static constexpr int OFF_TMP = OFF_H + NH;                   // 4-D only: T4'[14], T3[14]
     static constexpr int HRHS = (NDIM <= 2) ? 1 : NOUT / 10;     // first rhs entry of H
+    static constexpr int TPT = (T::PB * NDIM + T::NT - 1) / T::NT;   // staging tasks per thread
     static_assert(NGT + NRT <= T::LPG, "group too small");
     static_assert(OFF_TMP + (NDIM == 4 ? 28 : 0) <= T::RS, "record stride too small");
 };
@@ -286,13 +285,15 @@ __device__ __forceinline__ void spl_flush_entry(const GridParams &gp, const int 
 
 template <int NDIM>
 __global__ void __launch_bounds__(AccTraits<NDIM>::NT)
-spl_accumulate_kernel(const __grid_constant__ GridParams gp, const double *__restrict__ records,
-                      const unsigned *__restrict__ wincount, const unsigned *__restrict__ winstart,
-                      const unsigned *__restrict__ item_win, const unsigned *__restrict__ item_seg,
-                      unsigned *__restrict__ meta, double *__restrict__ S, double *__restrict__ g) {
+spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
+                      const real_t *__restrict__ y, const real_t *__restrict__ w, int weighted,
+                      const unsigned *__restrict__ perm, const unsigned *__restrict__ wincount,
+                      const unsigned *__restrict__ winstart, const unsigned *__restrict__ item_win,
+                      const unsigned *__restrict__ item_seg, unsigned *__restrict__ meta,
+                      double *__restrict__ S, double *__restrict__ g) {
     using T = AccTraits<NDIM>;
     using D = AccDerived<NDIM>;
-    constexpr int R = T::R, RS = T::RS, PB = T::PB, NT = T::NT;
+    constexpr int R = T::R, RS = T::RS, PB = T::PB, NT = T::NT, TPT = D::TPT;
     extern __shared__ __align__(16) double smem[];
     double *s_pts = smem;                       // PB * RS
     double *s_red = smem + PB * RS;             // LPGW * R * 10 (unused for 4-D)
@@ -322,6 +323,15 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const double *__res
     const int ibase = D::OFF_I + (is_rhs ? 10 : 0);
     const unsigned nitems = meta[0];
 
+    // staging task j of this thread: point tp[j] of the batch, dimension td[j]
+    int tp[TPT], td[TPT];
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) {
+        const int idx = tid + j * NT;
+        tp[j] = idx / NDIM;
+        td[j] = idx - tp[j] * NDIM;
+    }
+
     for (;;) {
         __syncthreads();                        // protects s_item, s_pts and s_red reuse
         if (tid == 0) s_item = atomicAdd(meta + 2, 1u);
@@ -349,66 +359,99 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const double *__res
 #pragma unroll
             for (int a = 0; a < 10; ++a) acc[r][a] = 0.0;
 
+        // ---- software pipeline: permutation entries two batches ahead, point data one batch ahead ----
+        unsigned pi[TPT];
+        double dx_[TPT], dy_[TPT], dw_[TPT];
+        auto load_perm = [&](int b0) {
+#pragma unroll
+            for (int j = 0; j < TPT; ++j) {
+                const int p = b0 + tp[j];
+                pi[j] = (tp[j] < PB && p < npts) ? perm[first + p] : 0xffffffffu;
+            }
+        };
+        auto load_data = [&]() {
+#pragma unroll
+            for (int j = 0; j < TPT; ++j) {
+                dx_[j] = 0.0;
+                dy_[j] = 0.0;
+                dw_[j] = 0.0;
+                if (pi[j] != 0xffffffffu) {
+                    const long long i = pi[j];
+                    dx_[j] = (double)x[i * (long long)l1x + td[j]];
+                    if (td[j] == NDIM - 1) {
+                        dy_[j] = (double)y[i];
+                        dw_[j] = weighted ? (double)w[i] : 1.0;
+                    }
+                }
+            }
+        };
+        load_perm(0);
+        load_data();
+        load_perm(PB);
+
         for (int b0 = 0; b0 < npts; b0 += PB) {
             const int nb = min(PB, npts - b0);
             if (b0 > 0) __syncthreads();        // previous batch fully consumed
-            // ---- stage: 1-D bases, pair products and outer tables of nb points ----
-            for (int idx = tid; idx < nb * NDIM; idx += NT) {
-                const int p = idx / NDIM;
-                const int d = idx - p * NDIM;
-                const double *rec = records + (first + b0 + p) * (NDIM + 2);
-                double b[4], s[10];
-                int wsd;
-                spl_window_weights(rec[d], gp.xmin[d], gp.dx[d], gp.dxin[d], gp.nodes[d], 0, wsd, b);
-                {
-                    int a = 0;
+            // ---- stage: 1-D bases, pair products and outer tables of the nb points ----
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < TPT; ++j) {
+                const int p = tp[j], d = td[j];
+                if (p < nb) {
+                    double b[4], s[10];
+                    int wsd;
+                    spl_window_weights_value(dx_[j], gp.xmin[d], gp.dx[d], gp.dxin[d], gp.nodes[d], wsd, b);
+                    {
+                        int a = 0;
 #pragma unroll
-                        for (int j = i; j < 4; ++j) s[a++] = b[i] * b[j];
-                }
-                double *out = s_pts + p * RS;
-                if (d == 0) {
+                        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int a = 0; a < 10; ++a) out[D::OFF_I + a] = s[a];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) out[D::OFF_I + 10 + i] = b[i];
-#pragma unroll
-                    for (int i = 14; i < 20; ++i) out[D::OFF_I + i] = 0.0;
-                }
-                if (NDIM >= 2 && d == 1) {
-#pragma unroll
-                    for (int a = 0; a < 10; ++a) out[D::OFF_T2 + a] = s[a];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) out[D::OFF_T2 + 10 + i] = b[i];
-                }
-                if (d == NDIM - 1) {
-                    const double yv = rec[NDIM], wv = rec[NDIM + 1];
-                    const double w2 = wv * wv;             // row = w*phi, rhs = w*y (:806, :837)
-                    const double w2y = w2 * yv;
-                    if (NDIM <= 2) {
-                        out[D::OFF_H + 0] = w2;
-                        out[D::OFF_H + 1] = w2y;
-                    } else if (NDIM == 3) {
-#pragma unroll
-                        for (int a = 0; a < 10; ++a) out[D::OFF_H + a] = w2 * s[a];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) out[D::OFF_H + 10 + i] = w2y * b[i];
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < 10; ++a) out[D::OFF_TMP + a] = w2 * s[a];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) out[D::OFF_TMP + 10 + i] = w2y * b[i];
+                            for (int jj = i; jj < 4; ++jj) s[a++] = b[i] * b[jj];
                     }
-                }
-                if (NDIM == 4 && d == 2) {
+                    double *out = s_pts + p * RS;
+                    if (d == 0) {
 #pragma unroll
-                    for (int a = 0; a < 10; ++a) out[D::OFF_TMP + 14 + a] = s[a];
+                        for (int a = 0; a < 10; ++a) out[D::OFF_I + a] = s[a];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) out[D::OFF_TMP + 24 + i] = b[i];
+                        for (int i = 0; i < 4; ++i) out[D::OFF_I + 10 + i] = b[i];
+                        // out[OFF_I+14..19] only feed accumulators the flush ignores: left unwritten
+                    }
+                    if (NDIM >= 2 && d == 1) {
+#pragma unroll
+                        for (int a = 0; a < 10; ++a) out[D::OFF_T2 + a] = s[a];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) out[D::OFF_T2 + 10 + i] = b[i];
+                    }
+                    if (d == NDIM - 1) {
+                        const double w2 = dw_[j] * dw_[j];      // row = w*phi, rhs = w*y (:806, :837)
+                        const double w2y = w2 * dy_[j];
+                        if (NDIM <= 2) {
+                            out[D::OFF_H + 0] = w2;
+                            out[D::OFF_H + 1] = w2y;
+                        } else if (NDIM == 3) {
+#pragma unroll
+                            for (int a = 0; a < 10; ++a) out[D::OFF_H + a] = w2 * s[a];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) out[D::OFF_H + 10 + i] = w2y * b[i];
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < 10; ++a) out[D::OFF_TMP + a] = w2 * s[a];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) out[D::OFF_TMP + 10 + i] = w2y * b[i];
+                        }
+                    }
+                    if (NDIM == 4 && d == 2) {
+#pragma unroll
+                        for (int a = 0; a < 10; ++a) out[D::OFF_TMP + 14 + a] = s[a];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) out[D::OFF_TMP + 24 + i] = b[i];
+                    }
                 }
             }
             __syncthreads();
+            // issue the gathers of the next batch and the permutation loads of the one after: they
+            // complete underneath the FP64 work below
+            if (b0 + PB < npts) load_data();
+            if (b0 + 2 * PB < npts) load_perm(b0 + 2 * PB);
             if (NDIM == 4) {
                 // H[a4*10+a3] = T4'[a4]*T3[a3];  H[100 + i4*4+i3] = T4'[10+i4]*T3[10+i3]
                 for (int idx = tid; idx < nb * 116; idx += NT) {
@@ -423,6 +466,7 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const double *__res
                 __syncthreads();
             }
             // ---- accumulate: group grp takes points grp, grp+NG, ... of the batch ----
+#pragma unroll 2
             for (int p = grp; p < nb; p += D::NG) {
                 const double *rec = s_pts + p * RS;
                 double in[10];
@@ -453,15 +497,16 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const double *__res
                         acc[r][a] += __shfl_xor_sync(0xffffffffu, acc[r][a], off);
         }
         if (D::NG > 1) {
-            for (int w = 0; w < D::NW; ++w) {
-                if (warp == w && lane < D::LPGW) {
+            __syncthreads();                    // every group finished its last batch (s_red is separate, but keep order simple)
+            for (int w2_ = 0; w2_ < D::NW; ++w2_) {
+                if (warp == w2_ && lane < D::LPGW) {
                     const int ul = lane;   // == u for the first group of the warp
 #pragma unroll
                     for (int r = 0; r < R; ++r)
 #pragma unroll
                         for (int a = 0; a < 10; ++a) {
                             double *dst = s_red + (ul * R + r) * 10 + a;
-                            *dst = (w == 0 ? 0.0 : *dst) + acc[r][a];
+                            *dst = (w2_ == 0 ? 0.0 : *dst) + acc[r][a];
                         }
                 }
                 __syncthreads();
@@ -485,7 +530,7 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const double *__res
 // ------------------------------------------------------------------------------------------
 struct AssembleScratch {
     unsigned *wincount, *winstart, *wincursor, *itemstart, *item_win, *item_seg, *meta;
-    double *records;
+    unsigned *perm;
     long long max_items;
 };
 
@@ -517,8 +562,8 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
     if (ev) cudaEventRecord(ev[1], st);
     spl_scan_kernel<<<1, 1024, 0, st>>>(sc.wincount, gp.nwindows, (unsigned)T::CH, sc.winstart,
                                         sc.itemstart, sc.meta);
-    spl_scatter_kernel<NDIM><<<grid, 256, 0, st>>>(gp, d_x, l1x, d_y, d_w, weighted, n, sc.winstart,
-                                                   sc.wincursor, sc.records);
+    spl_perm_kernel<NDIM><<<grid, 256, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.winstart, sc.wincursor,
+                                                sc.perm);
     spl_items_kernel<<<spl_div_up(gp.nwindows, 256), 256, 0, st>>>(sc.wincount, sc.itemstart, gp.nwindows,
                                                                    (unsigned)T::CH, sc.item_win, sc.item_seg);
     if (ev) cudaEventRecord(ev[2], st);
@@ -531,8 +576,8 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
     long long agrid = (long long)nsm * per_sm;
     const long long max_items = gp.nwindows + n / T::CH + 1;
     if (agrid > max_items) agrid = max_items;
-    kern<<<(unsigned)agrid, T::NT, smem, st>>>(gp, sc.records, sc.wincount, sc.winstart, sc.item_win,
-                                               sc.item_seg, sc.meta, d_S, d_g);
+    kern<<<(unsigned)agrid, T::NT, smem, st>>>(gp, d_x, l1x, d_y, d_w, weighted, sc.perm, sc.wincount,
+                                               sc.winstart, sc.item_win, sc.item_seg, sc.meta, d_S, d_g);
     if (ev) cudaEventRecord(ev[3], st);
     g_spl_launches += 5;
     SPL_CUDA_TRY(cudaGetLastError());

@@ -101,6 +101,29 @@ __device__ __forceinline__ double spl_bas1(int ib, int nod, int nder, double x, 
     return bas1;
 }
 
+// Value-only (nder = 0) 1-D basis, branch-free.  With s = 2-|u| (chapeau), 2-u (left edge) or 2+u
+// (right edge), u = dxin*(x-xb), all three value formulas of bascmp (:253-270, :342-379) read
+//   v = alpha*max(s,0)^3 - max(s-1,0)^3,  alpha = 1/4 (chapeau) or 1/2 (edge);  edge and s >= 2: 3s-3.
+// Every intermediate equals the reference's up to an exact sign flip (z = -s) or an exact
+// power-of-two scaling, so the result is bit-identical to spl_bas1(.., nder = 0, ..) without the
+// divergent select-case.  Used by the hot kernels (evaluation with nderiv = 0, assembly).
+__device__ __forceinline__ double spl_bas1_value(int ib, int nod, double x, double xmin, double dx,
+                                                 double dxin) {
+    const double xb = spl_add(xmin, spl_mul((double)ib, dx));       // :246
+    const double u = spl_mul(dxin, spl_sub(x, xb));
+    const bool is_l = ib <= 1;
+    const bool edge = is_l || ib >= nod - 2;
+    const double w = edge ? (is_l ? -u : u) : -fabs(u);
+    const double s = spl_add(2.0, w);
+    const double sp = fmax(s, 0.0);
+    const double s3 = spl_mul(spl_mul(sp, sp), sp);
+    const double m = fmax(spl_sub(s, 1.0), 0.0);
+    const double m3 = spl_mul(spl_mul(m, m), m);
+    double v = spl_sub(spl_mul(edge ? 0.5 : 0.25, s3), m3);
+    if (edge && s >= 2.0) v = spl_sub(spl_mul(3.0, s), 3.0);
+    return v;
+}
+
 // Index box of one dimension (:821-827 and :1201-1207):
 //   it = trunc(dxin*(x-xmin)); ibmn = min(max(it-1,0),nod-2); ibmx = max(min(it+2,nod-1),1).
 // The fixed 4-wide window ws = clamp(it-1, 0, nod-4) always covers [ibmn, ibmx]; the callers
@@ -116,6 +139,19 @@ __device__ __forceinline__ void spl_box(double x, double xmin, double dxin, int 
     ibmn = min(max(it - 1, 0), nod - 2);
     ibmx = max(min(it + 2, nod - 1), 1);
     ws = min(max(it - 1, 0), nod - 4);
+}
+
+// Same as spl_window_weights below for nder = 0, through the branch-free value formula.
+__device__ __forceinline__ void spl_window_weights_value(double x, double xmin, double dx, double dxin,
+                                                         int nod, int &ws, double b[4]) {
+    int ibmn, ibmx;
+    spl_box(x, xmin, dxin, nod, ws, ibmn, ibmx);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ib = ws + k;
+        const double v = spl_bas1_value(ib, nod, x, xmin, dx, dxin);
+        b[k] = (ib >= ibmn && ib <= ibmx) ? v : 0.0;
+    }
 }
 
 // The four window weights of one dimension: b[k] = basis of node ws+k at x (0 outside the box).

@@ -13,12 +13,12 @@ unsigned long long g_spl_launches = 0;
 // ---- kernels' host launchers (other translation units) ----
 struct AssembleScratch {
     unsigned *wincount, *winstart, *wincursor, *itemstart, *item_win, *item_seg, *meta;
-    double *records;
+    unsigned *perm;
     long long max_items;
 };
 int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, int l1x, long long nq,
                     const double *d_coef, long long ncol_padded, real_t *d_out, cudaStream_t stream,
-                    int nsm, size_t smem_optin);
+                    int nsm, size_t smem_optin, unsigned long long *d_counter);
 int spl_acc_chunk_points(int ndim);
 int spl_assemble_chunk(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y,
                        const real_t *d_w, int weighted, long long n, int do_hist,
@@ -29,8 +29,9 @@ int spl_constraints_launch(const GridParams &gp, double xtrap, const double *d_c
                            cudaStream_t st, int nsm);
 long long spl_band_lda(int bw);
 int spl_half_bandwidth(const GridParams &gp);
-int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, double *d_y, int *d_fail,
-                     cudaStream_t st, int nsm, cudaEvent_t *ev);
+long long spl_solve_workspace(const GridParams &gp);
+int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, double *d_g, double *d_work,
+                     double **d_coef_out, int *d_fail, cudaStream_t st, int nsm, cudaEvent_t *ev);
 int spl_measure_peaks_impl(double *out, int n);
 
 // ------------------------------------------------------------------------------------------
@@ -160,7 +161,10 @@ static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const in
         ++g_spl_launches;
         coef64 = tmp;
     }
-    int rc = spl_eval_launch(gp, nderiv, d_x, l1x, nq, coef64, npad, d_out, st, di.nsm, di.smem_optin);
+    unsigned long long *counter = nullptr;   // tile counter of the dynamic scheduler (stream-ordered scratch)
+    SPL_CUDA_TRY(cudaMallocAsync((void **)&counter, sizeof(unsigned long long), st));
+    int rc = spl_eval_launch(gp, nderiv, d_x, l1x, nq, coef64, npad, d_out, st, di.nsm, di.smem_optin, counter);
+    cudaFreeAsync(counter, st);
     if (tmp) cudaFreeAsync(tmp, st);
     return rc;
 }
@@ -318,7 +322,7 @@ static void free_handle(splpak_b200_fit_t h) {
                      h->sc.item_win, h->sc.item_seg, h->sc.meta};
     for (unsigned *p : u)
         if (p) cudaFree(p);
-    if (h->sc.records) cudaFree(h->sc.records);
+    if (h->sc.perm) cudaFree(h->sc.perm);
     for (int k = 0; k < 2; ++k) {
         for (int a = 0; a < 3; ++a)
             if (h->d_stage[k][a]) cudaFree(h->d_stage[k][a]);
@@ -407,10 +411,10 @@ static int ensure_scratch(splpak_b200_fit_t h, long long n) {
     if (n <= h->chunk_cap) return SPLPAK_OK;
     const GridParams &gp = h->gp;
     AssembleScratch &sc = h->sc;
-    if (sc.records) cudaFree(sc.records);
+    if (sc.perm) cudaFree(sc.perm);
     if (sc.item_win) cudaFree(sc.item_win);
     if (sc.item_seg) cudaFree(sc.item_seg);
-    sc.records = nullptr;
+    sc.perm = nullptr;
     sc.item_win = sc.item_seg = nullptr;
     h->chunk_cap = 0;
     if (!sc.wincount) {
@@ -422,7 +426,7 @@ static int ensure_scratch(splpak_b200_fit_t h, long long n) {
     }
     const int ch = spl_acc_chunk_points(gp.ndim);
     sc.max_items = gp.nwindows + n / ch + 2;
-    SPL_CUDA_TRY(cudaMalloc((void **)&sc.records, sizeof(double) * (size_t)n * (gp.ndim + 2)));
+    SPL_CUDA_TRY(cudaMalloc((void **)&sc.perm, sizeof(unsigned) * (size_t)n));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_win, sizeof(unsigned) * (size_t)sc.max_items));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_seg, sizeof(unsigned) * (size_t)sc.max_items));
     h->chunk_cap = n;
@@ -436,7 +440,7 @@ static void add_ms(splpak_b200_fit_t h, int slot, cudaEvent_t a, cudaEvent_t b) 
     else cudaGetLastError();
 }
 
-#define DEVICE_CHUNK (1LL << 25)   // points per device-resident chunk (bounds the sort scratch)
+#define DEVICE_CHUNK (1LL << 27)   // points per device-resident chunk (bounds the 4-byte/point permutation scratch)
 #define HOST_CHUNK (1LL << 22)     // points per host->device staging chunk
 
 static int add_device_chunk(splpak_b200_fit_t h, const real_t *d_x, int l1x, const real_t *d_y,
@@ -576,7 +580,9 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
     cudaStream_t st = h->st;
     const int bw = spl_half_bandwidth(gp);
     const long long lda = spl_band_lda(bw);
-    const long long need = gp.ncol * lda + lda;
+    // element (i, j) lives at i + j*lda, so the last one, (n-1, n-1), is at (n-1)*(lda+1)
+    const long long band_elems = gp.ncol * (lda + 1) + 64;
+    const long long need = band_elems + spl_solve_workspace(gp);
     if (need > h->ab_elems) {
         if (h->d_AB) cudaFree(h->d_AB);
         h->d_AB = nullptr;
@@ -601,24 +607,25 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
     SPL_CUDA_TRY(cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
     cudaEvent_t sev[4];
     for (int k = 0; k < 4; ++k) SPL_CUDA_TRY(cudaEventCreate(&sev[k]));
-    // the solve overwrites g with the solution
-    rc = spl_solve_launch(gp, h->d_S, h->d_AB, h->d_g, h->d_fail, st, h->di.nsm, sev);
+    // the solve destroys g; the solution comes back in the workspace behind the band matrix
+    double *d_sol = nullptr;
+    rc = spl_solve_launch(gp, h->d_S, h->d_AB, h->d_g, h->d_AB + band_elems, &d_sol, h->d_fail, st, h->di.nsm, sev);
     int fail = 0;
     double totals[2] = {0.0, 0.0};
     if (rc == SPLPAK_OK) {
         if (coef_on_device) {
-            spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(h->d_g, coef, gp.ncol);
+            spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(d_sol, coef, gp.ncol);
             ++g_spl_launches;
         }
         SPL_CUDA_TRY(cudaMemcpyAsync(&fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
         SPL_CUDA_TRY(cudaMemcpyAsync(totals, h->d_totals, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
         if (!coef_on_device) {
             if (sizeof(real_t) == sizeof(double)) {
-                SPL_CUDA_TRY(cudaMemcpyAsync(coef, h->d_g, sizeof(double) * (size_t)gp.ncol,
+                SPL_CUDA_TRY(cudaMemcpyAsync(coef, d_sol, sizeof(double) * (size_t)gp.ncol,
                                              cudaMemcpyDeviceToHost, st));
             } else {
                 real_t *tmp = reinterpret_cast<real_t *>(h->d_AB);   // band storage is dead now
-                spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(h->d_g, tmp, gp.ncol);
+                spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(d_sol, tmp, gp.ncol);
                 ++g_spl_launches;
                 SPL_CUDA_TRY(cudaMemcpyAsync(coef, tmp, sizeof(real_t) * (size_t)gp.ncol,
                                              cudaMemcpyDeviceToHost, st));

@@ -8,22 +8,26 @@
 //     factored directly, G = L L^T, in LOWER BAND storage (half bandwidth
 //     b = 3 * sum_d prod_{d'<d} nodes(d')), which is the dense algorithm when b = n-1.
 //
-// Band storage: element (i, j), 0 <= i-j <= lda, lives at AB[i + j*lda] -- a dense column-major
-// matrix with leading dimension lda = b + NB, so every block kernel below is an ordinary dense
-// column-major kernel on a sub-block.
+// Band storage: element (i, j), 0 <= i-j < lda, lives at AB[i + j*lda] -- LAPACK band storage with
+// ldab = lda + 1 viewed as a dense column-major matrix with leading dimension lda = b + NB, so every
+// block kernel below is an ordinary dense column-major kernel on a sub-block (ncol*(lda+1) doubles).
 //
 // Right-looking blocked Cholesky, panel width NB = 64, two launches per panel:
-//   spl_panel_kernel   every CTA factors the NB x NB diagonal block in shared memory (redundantly,
-//                      which saves a launch and a dependency per panel), forward-substitutes the
-//                      right-hand side of the block, then solves its 128 rows of the sub-diagonal
-//                      panel L21 = A21 L11^-T and updates the right-hand side below: the forward
+//   spl_panel_kernel   every CTA factors the NB x NB diagonal block AND inverts the factor in
+//                      registers (redundantly: it is a latency chain, and this saves a launch and a
+//                      dependency per panel), forward-solves the right-hand side of the block, then
+//                      forms its 64 rows of the sub-diagonal panel L21 = A21 L11^-T as a tensor-core
+//                      GEMM against the inverse and updates the right-hand side below: the forward
 //                      solve L y = g rides along with the factorization.
 //   spl_syrk_kernel    trailing update A22 -= L21 L21^T on the lower-triangular 64 x 64 tiles of
 //                      the (<= b) x (<= b) window, with FP64 tensor-core MMA
 //                      (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), operands staged k-major in
 //                      shared memory.
 // Back-substitution L^T c = y runs block by block from the end (spl_backsolve_kernel): every CTA
-// solves the diagonal block for c_k, then eliminates c_k from its slice of the b preceding entries.
+// forms c_k = L11^-T y_k from the stored block inverse, then eliminates c_k from its slice of the b
+// preceding entries.
+#include <stdlib.h>
+
 #include "basis.cuh"
 
 #define SOLVE_NB 64
@@ -183,104 +187,191 @@ spl_expand_band_kernel(const __grid_constant__ GridParams gp, const double *__re
 }
 
 // ------------------------------------------------------------------------------------------
-// panel: diagonal-block Cholesky + forward substitution + TRSM of the sub-diagonal panel
+// panel: diagonal-block Cholesky + inverse (registers), rhs forward solve, TRSM as a DMMA GEMM
 // ------------------------------------------------------------------------------------------
-#define PANEL_THREADS 128
-#define PANEL_LD (SOLVE_NB + 1)
+#define PANEL_THREADS 256
+#define TILE_LD 68      // 64 + 4: (t4*68 + g) hits 16 distinct 8-byte banks per half-warp (conflict-free LDS.64)
 
-// Factor the nb x nb lower block held in s_L (row-major, leading dim PANEL_LD) in place.
-// Left-looking by columns; all PANEL_THREADS threads cooperate.  Returns false on a bad pivot.
-__device__ __forceinline__ bool spl_block_cholesky(double *s_L, int nb, int *s_flag) {
-    const int t = threadIdx.x;
-    for (int k = 0; k < nb; ++k) {
-        // column k: rows i >= k get  A[i][k] - sum_{c<k} L[i][c] L[k][c]
-        if (t >= k && t < nb) {
-            double s0 = 0.0, s1 = 0.0;
-            int c = 0;
-            for (; c + 1 < k; c += 2) {
-                s0 = fma(s_L[t * PANEL_LD + c], s_L[k * PANEL_LD + c], s0);
-                s1 = fma(s_L[t * PANEL_LD + c + 1], s_L[k * PANEL_LD + c + 1], s1);
-            }
-            if (c < k) s0 = fma(s_L[t * PANEL_LD + c], s_L[k * PANEL_LD + c], s0);
-            s_L[t * PANEL_LD + k] -= (s0 + s1);
-        }
-        __syncthreads();
-        const double d = s_L[k * PANEL_LD + k];
-        if (!(d > 0.0)) {          // non-positive (or NaN) pivot -> solver failure (107)
-            if (t == 0) *s_flag = 1;
-            __syncthreads();
-            return false;
-        }
-        const double piv = sqrt(d);
-        __syncthreads();
-        if (t == k) s_L[k * PANEL_LD + k] = piv;
-        else if (t > k && t < nb) s_L[t * PANEL_LD + k] = s_L[t * PANEL_LD + k] / piv;
-        __syncthreads();
-    }
-    return true;
+__device__ __forceinline__ void spl_dmma_8x8x4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void spl_cp_async8(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void spl_cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+// Every CTA factors the nb x nb diagonal block A11 = L11 L11^T and inverts L11 in registers (thread
+// (ti, tj) of a 16 x 16 grid owns a 4 x 4 sub-block of A and of X = L11^-1; one barrier per pivot,
+// pivot column / row broadcast through double-buffered shared memory).  Doing this redundantly in
+// every CTA costs no time (it is a latency chain) and saves a launch + dependency per panel.
+// Then  y1 = L11^-1 g1,  L21 = A21 L11^-T  for this CTA's 64 rows (FP64 tensor-core MMA against the
+// inverse, so no per-row substitution chain) and  g2 -= L21 y1.
+// CTA 0 stores L11^-1 (for the back-substitution) and y1.
 __global__ void __launch_bounds__(PANEL_THREADS)
-spl_panel_kernel(double *__restrict__ AB, long long lda, long long n, long long j0, int nb, int m,
-                 double *__restrict__ y, int *__restrict__ fail) {
-    __shared__ double s_L[SOLVE_NB * PANEL_LD];
-    __shared__ double s_y[SOLVE_NB];
-    __shared__ double s_rd[SOLVE_NB];
-    __shared__ int s_flag;
-    const int t = threadIdx.x;
-    if (t == 0) s_flag = 0;
-    if (*fail) return;   // an earlier panel already failed (uniform across the grid)
-    // load the diagonal block (lower triangle; upper part zeroed)
-    for (int e = t; e < nb * nb; e += PANEL_THREADS) {
-        const int c = e / nb, r = e - c * nb;     // column-major walk: coalesced over r
-        s_L[r * PANEL_LD + c] = (r >= c) ? AB[(j0 + r) + (j0 + c) * lda] : 0.0;
+spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, int m,
+                 double *__restrict__ g, double *__restrict__ ysol, double *__restrict__ linv_blk,
+                 int *__restrict__ fail) {
+    extern __shared__ __align__(16) double s_pan[];
+    double *sA = s_pan;                          // [k][row]  A21 tile, 64 x TILE_LD
+    double *sB = s_pan + 64 * TILE_LD;           // [k][n]    L11^-1 [n][k]
+    double *s_col = sB + 64 * TILE_LD;           // 2 x 64   pivot column (double buffered)
+    double *s_row = s_col + 128;                 // 2 x 64   pivot row of X
+    double *s_g = s_row + 128;                   // 64       g1, then y1
+    const int tid = threadIdx.x;
+    if (*fail) return;                           // an earlier panel failed (uniform across the grid)
+    const int R0 = blockIdx.x * 64;              // first row of this CTA's tile, relative to j0 + nb
+    const long long r0 = j0 + nb;
+
+    // ---- start streaming this CTA's A21 tile into shared memory; it lands under the factorization ----
+    for (int e = tid; e < 64 * 64; e += PANEL_THREADS) {
+        const int k = e >> 6, r = e & 63;
+        double *dst = sA + k * TILE_LD + r;
+        if (k < nb && R0 + r < m) spl_cp_async8(dst, AB + (r0 + R0 + r) + (j0 + k) * lda);
+        else *dst = 0.0;
     }
-    if (t < nb) s_y[t] = y[j0 + t];
-    __syncthreads();
-    if (!spl_block_cholesky(s_L, nb, &s_flag)) {
-        if (blockIdx.x == 0 && t == 0) *fail = 1;
-        return;
-    }
-    // forward substitution on the block: y1 = L11^-1 g1 (warp 0, sequential over columns)
-    if (t < 32) {
-        for (int k = 0; k < nb; ++k) {
-            const double yk = s_y[k] / s_L[k * PANEL_LD + k];
-            __syncwarp();
-            if (t == 0) s_y[k] = yk;
-            for (int i = k + 1 + t; i < nb; i += 32) s_y[i] = fma(-s_L[i * PANEL_LD + k], yk, s_y[i]);
-            __syncwarp();
-        }
-    }
-    if (t < nb) s_rd[t] = 1.0 / s_L[t * PANEL_LD + t];
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        for (int e = t; e < nb * nb; e += PANEL_THREADS) {
-            const int c = e / nb, r = e - c * nb;
-            if (r >= c) AB[(j0 + r) + (j0 + c) * lda] = s_L[r * PANEL_LD + c];
-        }
-        if (t < nb) y[j0 + t] = s_y[t];
-    }
-    // TRSM: row r of A21 (global row j0+nb+r):  x L11^T = a, forward over the nb columns
-    const int r = blockIdx.x * PANEL_THREADS + t;
-    if (r < m) {
-        const long long gi = j0 + nb + r;
-        double xr[SOLVE_NB];
-        double dot = 0.0;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // ---- load A11 (4 x 4 per thread) ----
+    const int ti = tid >> 4, tj = tid & 15;
+    double A[4][4], X[4][4];
 #pragma unroll
-        for (int c = 0; c < SOLVE_NB; ++c) {
-            if (c < nb) {
-                double s = AB[gi + (j0 + c) * lda];
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int cp = 0; cp < c; ++cp) s = fma(-xr[cp], s_L[c * PANEL_LD + cp], s);
-                s *= s_rd[c];
-                xr[c] = s;
-                AB[gi + (j0 + c) * lda] = s;
-                dot = fma(s, s_y[c], dot);
-            } else {
-                xr[c] = 0.0;
+        for (int b = 0; b < 4; ++b) {
+            const int i = 4 * ti + a, j = 4 * tj + b;
+            double v = (i == j) ? 1.0 : 0.0;                 // identity padding when nb < 64
+            if (i < nb && j < nb && i >= j) v = AB[(j0 + i) + (j0 + j) * lda];
+            A[a][b] = v;
+            X[a][b] = (i == j) ? 1.0 : 0.0;
+        }
+    if (tid < 64) s_g[tid] = (tid < nb) ? g[j0 + tid] : 0.0;
+
+    bool bad = false;
+#pragma unroll 1
+    for (int kb = 0; kb < 16; ++kb) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = 4 * kb + kk;
+            double *col = s_col + (k & 1) * 64;
+            double *row = s_row + (k & 1) * 64;
+            if (tj == kb) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) col[4 * ti + a] = A[a][kk];
+            }
+            if (ti == kb) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) row[4 * tj + b] = X[kk][b];
+            }
+            __syncthreads();
+            const double d = col[k];
+            if (!(d > 0.0)) bad = true;                       // non-positive (or NaN) pivot -> 107
+            const double rinv = bad ? 0.0 : rsqrt(d);
+            double li[4], lj[4], xr[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) li[a] = col[4 * ti + a] * rinv;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                lj[b] = col[4 * tj + b] * rinv;
+                xr[b] = row[4 * tj + b] * rinv;
+            }
+            if (tj == kb) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) A[a][kk] = li[a];          // column k of L11 (rows >= k valid)
+            }
+            if (ti == kb) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) X[kk][b] = xr[b];          // row k of L11^-1
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const bool row_gt = (ti > kb) || (ti == kb && a > kk);      // global row > k
+                if (row_gt) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const bool col_gt = (tj > kb) || (tj == kb && b > kk);
+                        if (col_gt) A[a][b] = fma(-li[a], lj[b], A[a][b]);
+                        X[a][b] = fma(-li[a], xr[b], X[a][b]);
+                    }
+                }
             }
         }
-        y[gi] -= dot;     // right-hand side below the block: g2 -= L21 y1
+    }
+    if (bad) {
+        if (blockIdx.x == 0 && tid == 0) *fail = 1;
+        spl_cp_async_wait_all();
+        return;
+    }
+
+    // ---- stage L11^-1 as the B operand: sB[k][n] = Linv[n][k];  CTA 0 also stores it for the backsolve ----
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int n = 4 * ti + a, k = 4 * tj + b;
+            const double v = (n >= k) ? X[a][b] : 0.0;
+            sB[k * TILE_LD + n] = v;
+            if (blockIdx.x == 0) linv_blk[n * 64 + k] = v;
+        }
+    spl_cp_async_wait_all();
+    __syncthreads();
+    // y1[c] = sum_k Linv[c][k] g1[k]
+    double y1c = 0.0;
+    if (tid < 64) {
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) y1c = fma(sB[k * TILE_LD + tid], s_g[k], y1c);
+    }
+    __syncthreads();
+    if (tid < 64) {
+        s_g[tid] = y1c;
+        if (blockIdx.x == 0 && tid < nb) ysol[j0 + tid] = y1c;
+    }
+    __syncthreads();
+    if (m <= 0) return;
+
+    // ---- L21 tile = A21 tile * Linv^T: out[r][c] = sum_k A21[r][k] Linv[c][k] ----
+    const int warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, t4 = lane & 3;
+    const int wy = (warp >> 1) * 16, wx = (warp & 1) * 32;
+    double acc[2][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll 4
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+        double af[2], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) af[mi] = sA[(k0 + t4) * TILE_LD + wy + mi * 8 + gq];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = sB[(k0 + t4) * TILE_LD + wx + ni * 8 + gq];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+    // store L21 and update the right-hand side below the block: g2 -= L21 y1
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+        const int r = R0 + wy + mi * 8 + gq;
+        double part = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = wx + ni * 8 + 2 * t4 + h;
+                const double v = acc[mi][ni][h];
+                if (r < m && c < nb) AB[(r0 + r) + (j0 + c) * lda] = v;
+                part = fma(v, s_g[c], part);
+            }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if (t4 == 0 && r < m && part != 0.0) atomicAdd(g + r0 + r, -part);
     }
 }
 
@@ -288,25 +379,19 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long n, long long 
 // trailing update with FP64 tensor-core MMA
 // ------------------------------------------------------------------------------------------
 #define SYRK_TILE 64
-#define SYRK_LD 68      // 64 + 4: t4*68 + g hits 16 distinct 8-byte banks per half-warp (conflict-free LDS.64)
 #define SYRK_THREADS 128
 
-__device__ __forceinline__ void spl_dmma_8x8x4(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
 // C[I,J] -= P[I,:] P[J,:]^T over the lower-triangular tiles of the m x m window whose first
-// row/column is global index r0; P = panel rows r0.., columns j0..j0+nb-1.
+// row/column is global index r0; P = panel rows r0.., columns j0..j0+nb-1.  Operand tiles are
+// streamed with cp.async (k-major, conflict-free fragment reads); the C tile is prefetched into the
+// accumulators while the operands are in flight, so the kernel is one global round trip long.
 __global__ void __launch_bounds__(SYRK_THREADS)
 spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long j0, int nb, int m,
                 const int *__restrict__ fail) {
     extern __shared__ __align__(16) double s_ab[];
-    double *sA = s_ab;                          // [k][row], SOLVE_NB x SYRK_LD
-    double *sB = s_ab + SOLVE_NB * SYRK_LD;
+    double *sA = s_ab;                          // [k][row]
+    double *sB = s_ab + 64 * TILE_LD;
     if (*fail) return;
-    // linear tile id -> (ti >= tj)
     const int tile = blockIdx.x;
     int ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
     while ((long long)(ti + 1) * (ti + 2) / 2 <= tile) ++ti;
@@ -314,42 +399,26 @@ spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long 
     const int tj = tile - ti * (ti + 1) / 2;
     const int I0 = ti * SYRK_TILE, J0 = tj * SYRK_TILE;
     const int t = threadIdx.x;
+    const bool diag = (ti == tj);
 
-    for (int e = t; e < SOLVE_NB * SYRK_TILE; e += SYRK_THREADS) {
-        const int k = e / SYRK_TILE, r = e - k * SYRK_TILE;   // coalesced over r
-        double va = 0.0, vb = 0.0;
-        if (k < nb) {
-            if (I0 + r < m) va = AB[(r0 + I0 + r) + (j0 + k) * lda];
-            if (J0 + r < m) vb = AB[(r0 + J0 + r) + (j0 + k) * lda];
+    for (int e = t; e < 64 * 64; e += SYRK_THREADS) {
+        const int k = e >> 6, r = e & 63;
+        double *da = sA + k * TILE_LD + r;
+        if (k < nb && I0 + r < m) spl_cp_async8(da, AB + (r0 + I0 + r) + (j0 + k) * lda);
+        else *da = 0.0;
+        if (!diag) {
+            double *db = sB + k * TILE_LD + r;
+            if (k < nb && J0 + r < m) spl_cp_async8(db, AB + (r0 + J0 + r) + (j0 + k) * lda);
+            else *db = 0.0;
         }
-        sA[k * SYRK_LD + r] = va;
-        sB[k * SYRK_LD + r] = vb;
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
     const int warp = t >> 5, lane = t & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const int wy = (warp >> 1) * 32, wx = (warp & 1) * 32;
+    // prefetch the C tile into the accumulators (lower triangle, inside the window)
     double acc[4][4][2];
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-#pragma unroll 4
-    for (int k0 = 0; k0 < SOLVE_NB; k0 += 4) {
-        double a[4], b[4];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) a[mi] = sA[(k0 + t4) * SYRK_LD + wy + mi * 8 + g];
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = sB[(k0 + t4) * SYRK_LD + wx + ni * 8 + g];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-    }
-
-    // epilogue: C -= acc on the lower triangle, inside the window
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -358,51 +427,71 @@ spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long 
             for (int h = 0; h < 2; ++h) {
                 const int li = I0 + wy + mi * 8 + g;
                 const int lj = J0 + wx + ni * 8 + 2 * t4 + h;
-                if (li < m && lj < m && li >= lj) {
-                    double *p = AB + (r0 + li) + (r0 + lj) * lda;
-                    *p -= acc[mi][ni][h];
-                }
+                acc[mi][ni][h] = (li < m && lj < m && li >= lj) ? AB[(r0 + li) + (r0 + lj) * lda] : 0.0;
+            }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const double *pB = diag ? sA : sB;
+
+#pragma unroll 4
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[mi] = -sA[(k0 + t4) * TILE_LD + wy + mi * 8 + g];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = pB[(k0 + t4) * TILE_LD + wx + ni * 8 + g];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int li = I0 + wy + mi * 8 + g;
+                const int lj = J0 + wx + ni * 8 + 2 * t4 + h;
+                if (li < m && lj < m && li >= lj) AB[(r0 + li) + (r0 + lj) * lda] = acc[mi][ni][h];
             }
 }
 
 // ------------------------------------------------------------------------------------------
-// back-substitution L^T c = y, block by block from the end
+// back-substitution L^T c = y, block by block from the end, using the stored block inverses
 // ------------------------------------------------------------------------------------------
 #define BACK_THREADS 128
 __global__ void __launch_bounds__(BACK_THREADS)
 spl_backsolve_kernel(const double *__restrict__ AB, long long lda, long long j0, int nb, int bw,
-                     double *__restrict__ y, const int *__restrict__ fail) {
-    __shared__ double s_L[SOLVE_NB * PANEL_LD];
-    __shared__ double s_c[SOLVE_NB];
+                     const double *__restrict__ linv_blk, double *__restrict__ ysol,
+                     double *__restrict__ csol, const int *__restrict__ fail) {
+    __shared__ double s_y[64];
+    __shared__ double s_c[64];
     const int t = threadIdx.x;
     if (*fail) return;
-    for (int e = t; e < nb * nb; e += BACK_THREADS) {
-        const int c = e / nb, r = e - c * nb;
-        s_L[r * PANEL_LD + c] = (r >= c) ? AB[(j0 + r) + (j0 + c) * lda] : 0.0;
-    }
-    if (t < nb) s_c[t] = y[j0 + t];
+    if (t < 64) s_y[t] = (t < nb) ? ysol[j0 + t] : 0.0;
     __syncthreads();
-    // solve L11^T c = y_k (warp 0): from the last row up
-    if (t < 32) {
-        for (int k = nb - 1; k >= 0; --k) {
-            const double ck = s_c[k] / s_L[k * PANEL_LD + k];
-            __syncwarp();
-            if (t == 0) s_c[k] = ck;
-            for (int i = t; i < k; i += 32) s_c[i] = fma(-s_L[k * PANEL_LD + i], ck, s_c[i]);
-            __syncwarp();
-        }
+    // c_k = L11^-T y_k:  c[i] = sum_{r >= i} Linv[r][i] y[r]   (coalesced over i)
+    if (t < 64) {
+        double c = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) c = fma(linv_blk[r * 64 + t], s_y[r], c);
+        s_c[t] = c;
+        if (blockIdx.x == 0 && t < nb) csol[j0 + t] = c;
     }
     __syncthreads();
-    if (blockIdx.x == 0 && t < nb) y[j0 + t] = s_c[t];
     // eliminate c_k from the bw preceding unknowns: y[j] -= sum_i L[i][j] c[i], i in the block
     const long long jlo = (j0 - bw > 0) ? j0 - bw : 0;
     const long long j = jlo + (long long)blockIdx.x * BACK_THREADS + t;
     if (j < j0) {
         const double *col = AB + j0 + j * lda;     // rows j0.. of column j, contiguous
-        double s = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < nb; ++i) s = fma(col[i], s_c[i], s);
-        y[j] -= s;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 16
+        for (int i = 0; i < 64; i += 2) {
+            if (i < nb) s0 = fma(col[i], s_c[i], s0);
+            if (i + 1 < nb) s1 = fma(col[i + 1], s_c[i + 1], s1);
+        }
+        ysol[j] -= (s0 + s1);
     }
 }
 
@@ -421,12 +510,24 @@ int spl_half_bandwidth(const GridParams &gp) {
     return (int)b;
 }
 
-// AB must hold ncol*lda + lda doubles and be zero-filled on entry.  y enters as g, leaves as coef.
-int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, double *d_y, int *d_fail,
-                     cudaStream_t st, int nsm, cudaEvent_t *ev) {
+// Workspace (doubles) next to the band matrix: block inverses (64*64 per panel) + ysol (n) + csol (n).
+long long spl_solve_workspace(const GridParams &gp) {
+    const long long nblk = (gp.ncol + SOLVE_NB - 1) / SOLVE_NB;
+    return nblk * 64 * 64 + 2 * (gp.ncol + 64);
+}
+
+// AB must hold ncol*(lda+1) doubles and be zero-filled on entry.  g enters as the right-hand side
+// (destroyed); the solution is left in d_work + nblk*4096 + (ncol+64)  (returned through *d_coef_out).
+int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, double *d_g, double *d_work,
+                     double **d_coef_out, int *d_fail, cudaStream_t st, int nsm, cudaEvent_t *ev) {
     const long long n = gp.ncol;
     const int bw = spl_half_bandwidth(gp);
     const long long lda = spl_band_lda(bw);
+    const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    double *d_linv = d_work;
+    double *d_ysol = d_work + nblk * 4096;
+    double *d_csol = d_ysol + (n + 64);
+    *d_coef_out = d_csol;
     (void)nsm;
     if (ev) cudaEventRecord(ev[0], st);
     {
@@ -437,18 +538,21 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         ++g_spl_launches;
     }
     if (ev) cudaEventRecord(ev[1], st);
-    const size_t syrk_smem = sizeof(double) * 2 * SOLVE_NB * SYRK_LD;
-    SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)syrk_smem));
-    for (long long j0 = 0; j0 < n; j0 += SOLVE_NB) {
+    const size_t syrk_smem = sizeof(double) * 2 * 64 * TILE_LD;
+    const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 128 + 64);
+    SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
+    SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
+    for (long long kb = 0; kb < nblk; ++kb) {
+        const long long j0 = kb * SOLVE_NB;
         const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
         const long long r0 = j0 + nb;
         long long mm = n - r0;
         if (mm > bw) mm = bw;
         const int m = (int)mm;
-        int pblocks = (m + PANEL_THREADS - 1) / PANEL_THREADS;
+        int pblocks = (m + 63) / 64;
         if (pblocks < 1) pblocks = 1;
-        spl_panel_kernel<<<pblocks, PANEL_THREADS, 0, st>>>(d_AB, lda, n, j0, nb, m, d_y, d_fail);
+        spl_panel_kernel<<<pblocks, PANEL_THREADS, panel_smem, st>>>(d_AB, lda, j0, nb, m, d_g, d_ysol,
+                                                                     d_linv + kb * 4096, d_fail);
         ++g_spl_launches;
         if (m > 0) {
             const int T = (m + SYRK_TILE - 1) / SYRK_TILE;
@@ -456,16 +560,55 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
             spl_syrk_kernel<<<tiles, SYRK_THREADS, syrk_smem, st>>>(d_AB, lda, r0, j0, nb, m, d_fail);
             ++g_spl_launches;
         }
+        if (getenv("SPLPAK_B200_DEBUG")) {
+            int f = 0;
+            cudaError_t e = cudaStreamSynchronize(st);
+            cudaMemcpy(&f, d_fail, sizeof(int), cudaMemcpyDeviceToHost);
+            double dg[4] = {0, 0, 0, 0};
+            const long long jn = (j0 + nb < n) ? j0 + nb : j0;
+            cudaMemcpy(dg, d_AB + jn + jn * lda, sizeof(double), cudaMemcpyDeviceToHost);
+            cudaMemcpy(dg + 1, d_AB + (j0 + nb - 1) + (j0) * lda, sizeof(double), cudaMemcpyDeviceToHost);
+            // host Cholesky of the NEXT diagonal block (as the next panel will see it)
+            double minpiv = 0.0;
+            int badk = -1;
+            if (j0 + nb < n) {
+                const long long jj = j0 + nb;
+                const int nn2 = (int)((n - jj < 64) ? n - jj : 64);
+                static double blk[64 * 64];
+                for (int c = 0; c < nn2; ++c)
+                    cudaMemcpy(blk + c * 64, d_AB + (jj) + (jj + c) * lda, sizeof(double) * nn2, cudaMemcpyDeviceToHost);
+                // blk[c*64 + r] = A[jj + r][jj + c] for r >= c (column c starts at row jj, so shift)
+                double Lh[64][64];
+                for (int r = 0; r < nn2; ++r) for (int c = 0; c <= r; ++c) Lh[r][c] = blk[c * 64 + r];
+                minpiv = 1e300;
+                for (int k2 = 0; k2 < nn2 && badk < 0; ++k2) {
+                    double d2 = Lh[k2][k2];
+                    for (int c = 0; c < k2; ++c) d2 -= Lh[k2][c] * Lh[k2][c];
+                    if (d2 < minpiv) minpiv = d2;
+                    if (!(d2 > 0)) { badk = k2; break; }
+                    double pv = sqrt(d2);
+                    Lh[k2][k2] = pv;
+                    for (int r = k2 + 1; r < nn2; ++r) {
+                        double v = Lh[r][k2];
+                        for (int c = 0; c < k2; ++c) v -= Lh[r][c] * Lh[k2][c];
+                        Lh[r][k2] = v / pv;
+                    }
+                }
+            }
+            fprintf(stderr, "panel kb=%lld j0=%lld nb=%d m=%d fail=%d err=%s nextdiag=%g lastrow0=%g next-block host chol: minpiv=%g badk=%d\n",
+                    kb, j0, nb, m, f, cudaGetErrorString(e), dg[0], dg[1], minpiv, badk);
+            if (f) break;
+        }
     }
     if (ev) cudaEventRecord(ev[2], st);
-    const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
     for (long long kb = nblk - 1; kb >= 0; --kb) {
         const long long j0 = kb * SOLVE_NB;
         const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
         const long long span = (j0 < bw) ? j0 : bw;
         int blocks = (int)((span + BACK_THREADS - 1) / BACK_THREADS);
         if (blocks < 1) blocks = 1;
-        spl_backsolve_kernel<<<blocks, BACK_THREADS, 0, st>>>(d_AB, lda, j0, nb, bw, d_y, d_fail);
+        spl_backsolve_kernel<<<blocks, BACK_THREADS, 0, st>>>(d_AB, lda, j0, nb, bw, d_linv + kb * 4096, d_ysol,
+                                                              d_csol, d_fail);
         ++g_spl_launches;
     }
     if (ev) cudaEventRecord(ev[3], st);

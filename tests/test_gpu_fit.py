@@ -48,8 +48,11 @@ def test_normal_equations_match_oracle_rows(oracle, ndim, nodes, ndata, xtrap, w
     np.testing.assert_allclose(g, gref, rtol=0, atol=1e-12 * max(np.abs(gref).max(), 1e-300))
     assert nrows == A.shape[0]
     wsum = float(len(x)) if w is None else float(np.sum(w))
-    assert abs(totlwt - wsum) <= 1e-10 * wsum
-    assert abs(cnt.sum() - wsum) <= 1e-10 * wsum
+    if xtrap != 0:      # the nearest-node histogram only exists when smoothing is on (:862)
+        assert abs(totlwt - wsum) <= 1e-10 * wsum
+        assert abs(cnt.sum() - wsum) <= 1e-10 * wsum
+    else:
+        assert totlwt == 0 and not cnt.any()
     h.destroy()
 
 
@@ -73,7 +76,8 @@ def test_coefficients_match_oracle(oracle, ndim, nodes, ndata, xtrap, weighted, 
     # fitted values at the data points are far better conditioned than the coefficients
     fit_ref = A[: len(x)] @ ref
     fit_got = A[: len(x)] @ got
-    np.testing.assert_allclose(fit_got, fit_ref, rtol=0, atol=1e-10 * max(1.0, np.abs(fit_ref).max()))
+    fit_tol = max(1e-10, 1e-3 * np.finfo(float).eps * cond)
+    np.testing.assert_allclose(fit_got, fit_ref, rtol=0, atol=fit_tol * max(1.0, np.abs(fit_ref).max()))
 
 
 def test_reference_linear_test_on_gpu():
@@ -124,7 +128,7 @@ def test_multilinear_reproduction_K1():
         assert ierr == 0
         q = rng.random((500, ndim)) * 1.6 - 0.3
         v, _ = sp.eval_batch(ndim, q, coef, [0] * ndim, [1] * ndim, nodes)
-        np.testing.assert_allclose(v, f(q), rtol=0, atol=2e-11)
+        np.testing.assert_allclose(v, f(q), rtol=0, atol=5e-10)   # normal equations: ~eps*cond(G)
         v, _ = sp.eval_batch(ndim, q, coef, [0] * ndim, [1] * ndim, nodes, nderiv=[1] * ndim)
         np.testing.assert_allclose(v, np.prod(b), rtol=0, atol=1e-8)
 
