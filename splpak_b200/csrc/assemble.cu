@@ -215,72 +215,78 @@ spl_items_kernel(const unsigned *__restrict__ wincount, const unsigned *__restri
 // ------------------------------------------------------------------------------------------
 
 template <int NDIM> struct AccTraits;
-template <> struct AccTraits<1> { static constexpr int R = 1, LPG = 2,   NT = 256, PB = 256, CH = 16384, RS = 22;  };
-template <> struct AccTraits<2> { static constexpr int R = 4, LPG = 4,   NT = 256, PB = 256, CH = 8192,  RS = 38;  };
-// RS (doubles per staged point) is even (16-byte aligned LDS.128 of the inner vector) with RS/2 odd,
-// so consecutive points start 4 banks apart: staging stores of neighbouring points do not collide.
-template <> struct AccTraits<3> { static constexpr int R = 4, LPG = 32,  NT = 256, PB = 256, CH = 8192,  RS = 50;  };
-template <> struct AccTraits<4> { static constexpr int R = 4, LPG = 288, NT = 288, PB = 72,  CH = 4096,  RS = 178; };
+// R   outer tuples per lane (x 10 inner = accumulators per lane)
+// LPG lanes per group (a group owns one point at a time); NT threads per CTA
+// PB  points staged per batch; CH max points per work item
+// RS  doubles per staged point: even (16-byte aligned 128-bit loads) with RS/2 odd, so consecutive
+//     points start 4 banks apart and the staging stores of neighbouring points do not collide.
+template <> struct AccTraits<1> { static constexpr int R = 1, LPG = 1,   NT = 256, PB = 256, CH = 16384, RS = 18;  };
+template <> struct AccTraits<2> { static constexpr int R = 4, LPG = 4,   NT = 256, PB = 256, CH = 8192,  RS = 34;  };
+template <> struct AccTraits<3> { static constexpr int R = 4, LPG = 32,  NT = 256, PB = 256, CH = 8192,  RS = 46;  };
+template <> struct AccTraits<4> { static constexpr int R = 4, LPG = 256, NT = 256, PB = 72,  CH = 4096,  RS = 178; };
 
 template <int NDIM> struct AccDerived {
     using T = AccTraits<NDIM>;
-    static constexpr int NOUT = spl_ipow(10, NDIM - 1);          // G outer tuples
-    static constexpr int NRO = spl_ipow(4, NDIM - 1);            // rhs outer tuples
-    static constexpr int NGT = (NOUT + T::R - 1) / T::R;         // lanes holding G tuples
-    static constexpr int NRT = (NRO + T::R - 1) / T::R;          // lanes holding rhs tuples
+    static constexpr int NOUT = spl_ipow(10, NDIM - 1);          // G outer tuples (a_N..a_2)
+    static constexpr int NGT = (NOUT + T::R - 1) / T::R;         // lanes of a group holding G tuples
     static constexpr int NG = T::NT / T::LPG;                    // groups per CTA
     static constexpr int NW = T::NT / 32;                        // warps per CTA
     static constexpr int LPGW = T::LPG < 32 ? T::LPG : 32;       // lanes of a group inside one warp
-    static constexpr int OFF_I = 0;                              // s_1[10], b_1[4], 6 zeros
-    static constexpr int OFF_T2 = 20;                            // s_2[10], b_2[4]
-    static constexpr int OFF_H = (NDIM >= 2) ? 34 : 20;          // outer table
+    static constexpr int NRACC = spl_ipow(4, NDIM);              // rhs accumulators of a window
+    static constexpr int APL = NRACC / T::LPG;                   // rhs accumulators per lane (4,4,2,1)
+    // staged record of one point (doubles):
+    static constexpr int OFF_I = 0;                              // s_1[10], b_1[4], 2 pad
+    static constexpr int OFF_T2 = 16;                            // s_2[10], s_2[0], s_2[1] (cyclic), b_2[4]
+    static constexpr int OFF_H = (NDIM >= 2) ? 32 : 16;          // outer table
     static constexpr int NH = (NDIM <= 2) ? 2 : (NDIM == 3 ? 14 : 116);
     static constexpr int OFF_TMP = OFF_H + NH;                   // 4-D only: T4'[14], T3[14]
     static constexpr int HRHS = (NDIM <= 2) ? 1 : NOUT / 10;     // first rhs entry of H
     static constexpr int TPT = (T::PB * NDIM + T::NT - 1) / T::NT;   // staging tasks per thread
-    static_assert(NGT + NRT <= T::LPG, "group too small");
+    static_assert(NGT <= T::LPG, "group too small");
+    static_assert(APL * T::LPG == NRACC && APL >= 1 && APL <= 4, "rhs split");
     static_assert(OFF_TMP + (NDIM == 4 ? 28 : 0) <= T::RS, "record stride too small");
+    static_assert(T::RS % 2 == 0 && (T::RS / 2) % 2 == 1, "record stride must be 2*odd");
 };
 
+// G accumulator (outer tuple o = u*R + r, inner pair a) -> S
 template <int NDIM>
-__device__ __forceinline__ void spl_flush_entry(const GridParams &gp, const int *ws, int u, int r,
-                                                int a, double v, double *__restrict__ S,
-                                                double *__restrict__ g) {
+__device__ __forceinline__ void spl_flush_g(const GridParams &gp, const int *ws, int u, int r, int a,
+                                            double v, double *__restrict__ S) {
     using D = AccDerived<NDIM>;
     using T = AccTraits<NDIM>;
-    if (v == 0.0) return;
-    if (u < D::NGT) {
-        int o = u * T::R + r;
-        if (o >= D::NOUT) return;
-        long long node = 0, nstride = 1;
-        int sten = 0, sstride = 1;
-        int ad = a;
+    if (v == 0.0 || u >= D::NGT) return;
+    int o = u * T::R + r;
+    if (o >= D::NOUT) return;
+    long long node = 0, nstride = 1;
+    int sten = 0, sstride = 1;
+    int ad = a;
 #pragma unroll
-        for (int d = 0; d < NDIM; ++d) {
-            int i, j;
-            spl_pair(ad, i, j);
-            node += (long long)(ws[d] + i) * nstride;
-            sten += (j - i) * sstride;
-            nstride *= gp.nodes[d];
-            sstride *= 4;
-            ad = o % 10;
-            o /= 10;
-        }
-        atomicAdd(S + node * gp.nsten + sten, v);
-    } else if (u < D::NGT + D::NRT) {
-        int o = (u - D::NGT) * T::R + r;
-        if (o >= D::NRO || a >= 4) return;
-        long long node = 0, nstride = 1;
-        int id = a;
-#pragma unroll
-        for (int d = 0; d < NDIM; ++d) {
-            node += (long long)(ws[d] + id) * nstride;
-            nstride *= gp.nodes[d];
-            id = o % 4;
-            o /= 4;
-        }
-        atomicAdd(g + node, v);
+    for (int d = 0; d < NDIM; ++d) {
+        int i, j;
+        spl_pair(ad, i, j);
+        node += (long long)(ws[d] + i) * nstride;
+        sten += (j - i) * sstride;
+        nstride *= gp.nodes[d];
+        sstride *= 4;
+        ad = o % 10;
+        o /= 10;
     }
+    atomicAdd(S + node * gp.nsten + sten, v);
+}
+
+// rhs accumulator e = (i_N..i_1) in base 4, i_1 fastest -> g
+template <int NDIM>
+__device__ __forceinline__ void spl_flush_rhs(const GridParams &gp, const int *ws, int e, double v,
+                                              double *__restrict__ g) {
+    if (v == 0.0) return;
+    long long node = 0, nstride = 1;
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) {
+        node += (long long)(ws[d] + (e & 3)) * nstride;
+        nstride *= gp.nodes[d];
+        e >>= 2;
+    }
+    atomicAdd(g + node, v);
 }
 
 template <int NDIM>
@@ -293,10 +299,10 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
                       double *__restrict__ S, double *__restrict__ g) {
     using T = AccTraits<NDIM>;
     using D = AccDerived<NDIM>;
-    constexpr int R = T::R, RS = T::RS, PB = T::PB, NT = T::NT, TPT = D::TPT;
+    constexpr int R = T::R, RS = T::RS, PB = T::PB, NT = T::NT, TPT = D::TPT, APL = D::APL;
     extern __shared__ __align__(16) double smem[];
     double *s_pts = smem;                       // PB * RS
-    double *s_red = smem + PB * RS;             // LPGW * R * 10 (unused for 4-D)
+    double *s_red = smem + PB * RS;             // LPGW * (R * 10 + APL)   (unused for 4-D)
     __shared__ unsigned s_item;
 
     const int tid = threadIdx.x;
@@ -304,23 +310,19 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
     const int warp = tid >> 5;
     const int grp = tid / T::LPG;
     const int u = tid % T::LPG;
-    const bool is_rhs = (u >= D::NGT);
 
-    // per-thread constant table indices
-    int hidx[R], lidx[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (!is_rhs) {
-            const int o = min(u * R + r, D::NOUT - 1);
-            hidx[r] = o / 10;
-            lidx[r] = o % 10;
-        } else {
-            const int o = min((u - D::NGT) * R + r, D::NRO - 1);
-            hidx[r] = D::HRHS + o / 4;
-            lidx[r] = 10 + o % 4;
-        }
-    }
-    const int ibase = D::OFF_I + (is_rhs ? 10 : 0);
+    // per-lane constant offsets into a staged record.  The lane's R = 4 outer tuples o = 4u + r use
+    // T2[(4u) % 10 .. +1], T2[(4u+2) % 10 .. +1] (two aligned 128-bit loads thanks to the cyclic copy)
+    // and H[(4u)/10], H[(4u+2)/10] (a multiple of 10 can only fall between r = 1 and r = 2).
+    const int uo = min(u, D::NGT - 1) * R;
+    const int offT = D::OFF_T2 + (uo % 10);
+    const int offHa = D::OFF_H + (NDIM == 1 ? 0 : uo / 10);
+    const int offHb = D::OFF_H + (NDIM == 1 ? 0 : (uo + 2) / 10);
+    // rhs: accumulators e = u*APL + j share (i_N..i_2); i_1 = (u*APL) % 4 + j
+    const int e0 = u * APL;
+    const int offRI = D::OFF_I + 10 + (e0 & 3);
+    const int offRT = D::OFF_T2 + 12 + ((e0 >> 2) & 3);
+    const int offRH = D::OFF_H + D::HRHS + (NDIM >= 3 ? (e0 >> 4) : 0);
     const unsigned nitems = meta[0];
 
     // staging task j of this thread: point tp[j] of the batch, dimension td[j]
@@ -354,10 +356,13 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
         }
 
         double acc[R][10];
+        double racc[APL];
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int a = 0; a < 10; ++a) acc[r][a] = 0.0;
+#pragma unroll
+        for (int j = 0; j < APL; ++j) racc[j] = 0.0;
 
         // ---- software pipeline: permutation entries two batches ahead, point data one batch ahead ----
         unsigned pi[TPT];
@@ -413,13 +418,14 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
                         for (int a = 0; a < 10; ++a) out[D::OFF_I + a] = s[a];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) out[D::OFF_I + 10 + i] = b[i];
-                        // out[OFF_I+14..19] only feed accumulators the flush ignores: left unwritten
                     }
                     if (NDIM >= 2 && d == 1) {
 #pragma unroll
                         for (int a = 0; a < 10; ++a) out[D::OFF_T2 + a] = s[a];
+                        out[D::OFF_T2 + 10] = s[0];
+                        out[D::OFF_T2 + 11] = s[1];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) out[D::OFF_T2 + 10 + i] = b[i];
+                        for (int i = 0; i < 4; ++i) out[D::OFF_T2 + 12 + i] = b[i];
                     }
                     if (d == NDIM - 1) {
                         const double w2 = dw_[j] * dw_[j];      // row = w*phi, rhs = w*y (:806, :837)
@@ -465,62 +471,89 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
                 }
                 __syncthreads();
             }
-            // ---- accumulate: group grp takes points grp, grp+NG, ... of the batch ----
+            // ---- G: group grp takes points grp, grp+NG, ... of the batch ----
 #pragma unroll 2
             for (int p = grp; p < nb; p += D::NG) {
                 const double *rec = s_pts + p * RS;
                 double in[10];
 #pragma unroll
                 for (int a = 0; a < 10; a += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(rec + ibase + a);
+                    const double2 v = *reinterpret_cast<const double2 *>(rec + D::OFF_I + a);
                     in[a] = v.x;
                     in[a + 1] = v.y;
                 }
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    double P = rec[D::OFF_H + hidx[r]];
-                    if (NDIM >= 2) P *= rec[D::OFF_T2 + lidx[r]];
-#pragma unroll
-                    for (int a = 0; a < 10; ++a) acc[r][a] = fma(P, in[a], acc[r][a]);
+                double P[R];
+                if constexpr (NDIM == 1) {
+                    P[0] = rec[D::OFF_H];
+                } else {
+                    const double2 ta = *reinterpret_cast<const double2 *>(rec + offT);
+                    const double2 tb = *reinterpret_cast<const double2 *>(rec + offT + 2);
+                    const double ha = rec[offHa], hb = rec[offHb];
+                    P[0] = ha * ta.x;
+                    P[1] = ha * ta.y;
+                    P[2] = hb * tb.x;
+                    P[3] = hb * tb.y;
                 }
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int a = 0; a < 10; ++a) acc[r][a] = fma(P[r], in[a], acc[r][a]);
+            }
+            // ---- right-hand side of the same points: APL accumulators per lane ----
+#pragma unroll 2
+            for (int p = grp; p < nb; p += D::NG) {
+                const double *rec = s_pts + p * RS;
+                double t = rec[offRH];
+                if (NDIM >= 2) t *= rec[offRT];
+#pragma unroll
+                for (int j = 0; j < APL; ++j) racc[j] = fma(t, rec[offRI + j], racc[j]);
             }
         }
 
         // ---- reduce the K-split groups and flush once per work item ----
         if (T::LPG < 32) {
 #pragma unroll
-            for (int off = T::LPG; off < 32; off <<= 1)
+            for (int off = T::LPG; off < 32; off <<= 1) {
 #pragma unroll
                 for (int r = 0; r < R; ++r)
 #pragma unroll
                     for (int a = 0; a < 10; ++a)
                         acc[r][a] += __shfl_xor_sync(0xffffffffu, acc[r][a], off);
+#pragma unroll
+                for (int j = 0; j < APL; ++j) racc[j] += __shfl_xor_sync(0xffffffffu, racc[j], off);
+            }
         }
         if (D::NG > 1) {
-            __syncthreads();                    // every group finished its last batch (s_red is separate, but keep order simple)
+            constexpr int PER = R * 10 + APL;   // values per lane
+            __syncthreads();
             for (int w2_ = 0; w2_ < D::NW; ++w2_) {
                 if (warp == w2_ && lane < D::LPGW) {
-                    const int ul = lane;   // == u for the first group of the warp
+                    double *dst = s_red + lane * PER;       // lane == u for the first group of the warp
 #pragma unroll
                     for (int r = 0; r < R; ++r)
 #pragma unroll
-                        for (int a = 0; a < 10; ++a) {
-                            double *dst = s_red + (ul * R + r) * 10 + a;
-                            *dst = (w2_ == 0 ? 0.0 : *dst) + acc[r][a];
-                        }
+                        for (int a = 0; a < 10; ++a)
+                            dst[r * 10 + a] = (w2_ == 0 ? 0.0 : dst[r * 10 + a]) + acc[r][a];
+#pragma unroll
+                    for (int j = 0; j < APL; ++j)
+                        dst[R * 10 + j] = (w2_ == 0 ? 0.0 : dst[R * 10 + j]) + racc[j];
                 }
                 __syncthreads();
             }
-            for (int idx = tid; idx < (D::NGT + D::NRT) * R * 10; idx += NT) {
-                const int slot = idx / 10;
-                const int a = idx - slot * 10;
-                spl_flush_entry<NDIM>(gp, ws, slot / R, slot % R, a, s_red[idx], S, g);
+            for (int idx = tid; idx < D::LPGW * PER; idx += NT) {
+                const int ul = idx / PER;
+                const int k = idx - ul * PER;
+                const double v = s_red[idx];
+                if (k < R * 10) spl_flush_g<NDIM>(gp, ws, ul, k / 10, k % 10, v, S);
+                else spl_flush_rhs<NDIM>(gp, ws, ul * APL + (k - R * 10), v, g);
             }
         } else {
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
-                for (int a = 0; a < 10; ++a) spl_flush_entry<NDIM>(gp, ws, u, r, a, acc[r][a], S, g);
+                for (int a = 0; a < 10; ++a) spl_flush_g<NDIM>(gp, ws, u, r, a, acc[r][a], S);
+#pragma unroll
+            for (int j = 0; j < APL; ++j) spl_flush_rhs<NDIM>(gp, ws, u * APL + j, racc[j], g);
         }
     }
 }
@@ -567,7 +600,7 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
     spl_items_kernel<<<spl_div_up(gp.nwindows, 256), 256, 0, st>>>(sc.wincount, sc.itemstart, gp.nwindows,
                                                                    (unsigned)T::CH, sc.item_win, sc.item_seg);
     if (ev) cudaEventRecord(ev[2], st);
-    const size_t smem = sizeof(double) * ((size_t)T::PB * T::RS + (size_t)D::LPGW * T::R * 10);
+    const size_t smem = sizeof(double) * ((size_t)T::PB * T::RS + (size_t)D::LPGW * (T::R * 10 + D::APL));
     auto kern = spl_accumulate_kernel<NDIM>;
     SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;

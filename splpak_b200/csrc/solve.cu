@@ -255,48 +255,73 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     bool bad = false;
 #pragma unroll 1
     for (int kb = 0; kb < 16; ++kb) {
+        const bool rows_live = (ti >= kb);      // this thread still owns rows >= the pivot block
+        const bool cols_live = (tj >= kb);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const int k = 4 * kb + kk;
             double *col = s_col + (k & 1) * 64;
             double *row = s_row + (k & 1) * 64;
             if (tj == kb) {
-#pragma unroll
-                for (int a = 0; a < 4; ++a) col[4 * ti + a] = A[a][kk];
+                *reinterpret_cast<double2 *>(col + 4 * ti) = make_double2(A[0][kk], A[1][kk]);
+                *reinterpret_cast<double2 *>(col + 4 * ti + 2) = make_double2(A[2][kk], A[3][kk]);
             }
             if (ti == kb) {
-#pragma unroll
-                for (int b = 0; b < 4; ++b) row[4 * tj + b] = X[kk][b];
+                *reinterpret_cast<double2 *>(row + 4 * tj) = make_double2(X[kk][0], X[kk][1]);
+                *reinterpret_cast<double2 *>(row + 4 * tj + 2) = make_double2(X[kk][2], X[kk][3]);
             }
             __syncthreads();
             const double d = col[k];
             if (!(d > 0.0)) bad = true;                       // non-positive (or NaN) pivot -> 107
-            const double rinv = bad ? 0.0 : rsqrt(d);
-            double li[4], lj[4], xr[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) li[a] = col[4 * ti + a] * rinv;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                lj[b] = col[4 * tj + b] * rinv;
-                xr[b] = row[4 * tj + b] * rinv;
+            // 1/sqrt(d): single-precision seed + two Newton steps in double (full precision, and a
+            // much shorter dependent chain than the library rsqrt on this latency-bound path)
+            double rinv;
+            {
+                const float df = (float)d;
+                if (df > 1e-30f && df < 1e30f) {
+                    double r = (double)rsqrtf(df);
+                    const double hd = 0.5 * d;
+                    r = r * fma(-hd * r, r, 1.5);
+                    r = r * fma(-hd * r, r, 1.5);
+                    rinv = r;
+                } else {
+                    rinv = bad ? 0.0 : rsqrt(d);
+                }
             }
-            if (tj == kb) {
+            if (rows_live) {
+                const double2 c01 = *reinterpret_cast<const double2 *>(col + 4 * ti);
+                const double2 c23 = *reinterpret_cast<const double2 *>(col + 4 * ti + 2);
+                const double2 r01 = *reinterpret_cast<const double2 *>(row + 4 * tj);
+                const double2 r23 = *reinterpret_cast<const double2 *>(row + 4 * tj + 2);
+                const double li[4] = {c01.x * rinv, c01.y * rinv, c23.x * rinv, c23.y * rinv};
+                const double xr[4] = {r01.x * rinv, r01.y * rinv, r23.x * rinv, r23.y * rinv};
+                if (tj == kb) {
 #pragma unroll
-                for (int a = 0; a < 4; ++a) A[a][kk] = li[a];          // column k of L11 (rows >= k valid)
-            }
-            if (ti == kb) {
+                    for (int a = 0; a < 4; ++a) A[a][kk] = li[a];          // column k of L11 (rows >= k valid)
+                }
+                if (ti == kb) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) X[kk][b] = xr[b];          // row k of L11^-1
-            }
+                    for (int b = 0; b < 4; ++b) X[kk][b] = xr[b];          // row k of L11^-1
+                }
+                double lj[4] = {0.0, 0.0, 0.0, 0.0};
+                if (cols_live) {
+                    const double2 d01 = *reinterpret_cast<const double2 *>(col + 4 * tj);
+                    const double2 d23 = *reinterpret_cast<const double2 *>(col + 4 * tj + 2);
+                    lj[0] = d01.x * rinv;
+                    lj[1] = d01.y * rinv;
+                    lj[2] = d23.x * rinv;
+                    lj[3] = d23.y * rinv;
+                }
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const bool row_gt = (ti > kb) || (ti == kb && a > kk);      // global row > k
-                if (row_gt) {
+                for (int a = 0; a < 4; ++a) {
+                    const bool row_gt = (ti > kb) || (a > kk);             // global row > k (ti >= kb here)
+                    if (row_gt) {
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const bool col_gt = (tj > kb) || (tj == kb && b > kk);
-                        if (col_gt) A[a][b] = fma(-li[a], lj[b], A[a][b]);
-                        X[a][b] = fma(-li[a], xr[b], X[a][b]);
+                        for (int b = 0; b < 4; ++b) {
+                            const bool col_gt = (tj > kb) || (tj == kb && b > kk);
+                            if (col_gt) A[a][b] = fma(-li[a], lj[b], A[a][b]);
+                            X[a][b] = fma(-li[a], xr[b], X[a][b]);
+                        }
                     }
                 }
             }
@@ -465,31 +490,48 @@ __global__ void __launch_bounds__(BACK_THREADS)
 spl_backsolve_kernel(const double *__restrict__ AB, long long lda, long long j0, int nb, int bw,
                      const double *__restrict__ linv_blk, double *__restrict__ ysol,
                      double *__restrict__ csol, const int *__restrict__ fail) {
+    __shared__ double s_li[64 * 65];
     __shared__ double s_y[64];
     __shared__ double s_c[64];
     const int t = threadIdx.x;
     if (*fail) return;
+    // the column this thread eliminates from, prefetched while the block solve runs
+    const long long jlo = (j0 - bw > 0) ? j0 - bw : 0;
+    const long long j = jlo + (long long)blockIdx.x * BACK_THREADS + t;
+    double colv[64];
+    if (j < j0) {
+        const double *col = AB + j0 + j * lda;     // rows j0.. of column j, contiguous
+#pragma unroll
+        for (int i = 0; i < 64; ++i) colv[i] = (i < nb) ? col[i] : 0.0;
+    }
+    // stage L11^-1 (row-major [r][c]) and y_k
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        const int idx = t + e * BACK_THREADS;
+        s_li[(idx >> 6) * 65 + (idx & 63)] = linv_blk[idx];
+    }
     if (t < 64) s_y[t] = (t < nb) ? ysol[j0 + t] : 0.0;
     __syncthreads();
-    // c_k = L11^-T y_k:  c[i] = sum_{r >= i} Linv[r][i] y[r]   (coalesced over i)
+    // c_k = L11^-T y_k:  c[i] = sum_{r >= i} Linv[r][i] y[r]
     if (t < 64) {
-        double c = 0.0;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) c = fma(linv_blk[r * 64 + t], s_y[r], c);
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 64; r += 2) {
+            c0 = fma(s_li[r * 65 + t], s_y[r], c0);
+            c1 = fma(s_li[(r + 1) * 65 + t], s_y[r + 1], c1);
+        }
+        const double c = c0 + c1;
         s_c[t] = c;
         if (blockIdx.x == 0 && t < nb) csol[j0 + t] = c;
     }
     __syncthreads();
     // eliminate c_k from the bw preceding unknowns: y[j] -= sum_i L[i][j] c[i], i in the block
-    const long long jlo = (j0 - bw > 0) ? j0 - bw : 0;
-    const long long j = jlo + (long long)blockIdx.x * BACK_THREADS + t;
     if (j < j0) {
-        const double *col = AB + j0 + j * lda;     // rows j0.. of column j, contiguous
         double s0 = 0.0, s1 = 0.0;
-#pragma unroll 16
+#pragma unroll
         for (int i = 0; i < 64; i += 2) {
-            if (i < nb) s0 = fma(col[i], s_c[i], s0);
-            if (i + 1 < nb) s1 = fma(col[i + 1], s_c[i + 1], s1);
+            s0 = fma(colv[i], s_c[i], s0);
+            s1 = fma(colv[i + 1], s_c[i + 1], s1);
         }
         ysol[j] -= (s0 + s1);
     }
