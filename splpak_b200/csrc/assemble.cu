@@ -217,13 +217,13 @@ spl_items_kernel(const unsigned *__restrict__ wincount, const unsigned *__restri
 template <int NDIM> struct AccTraits;
 // R   outer tuples per lane (x 10 inner = accumulators per lane)
 // LPG lanes per group (a group owns one point at a time); NT threads per CTA
-// PB  points staged per batch; CH max points per work item
+// PB  points staged per batch (double buffered); CH max points per work item
 // RS  doubles per staged point: even (16-byte aligned 128-bit loads) with RS/2 odd, so consecutive
 //     points start 4 banks apart and the staging stores of neighbouring points do not collide.
 template <> struct AccTraits<1> { static constexpr int R = 1, LPG = 1,   NT = 256, PB = 256, CH = 16384, RS = 18;  };
 template <> struct AccTraits<2> { static constexpr int R = 4, LPG = 4,   NT = 256, PB = 256, CH = 8192,  RS = 34;  };
 template <> struct AccTraits<3> { static constexpr int R = 4, LPG = 32,  NT = 256, PB = 256, CH = 8192,  RS = 46;  };
-template <> struct AccTraits<4> { static constexpr int R = 4, LPG = 256, NT = 256, PB = 72,  CH = 4096,  RS = 178; };
+template <> struct AccTraits<4> { static constexpr int R = 4, LPG = 256, NT = 256, PB = 72,  CH = 4096,  RS = 150; };
 
 template <int NDIM> struct AccDerived {
     using T = AccTraits<NDIM>;
@@ -239,13 +239,16 @@ template <int NDIM> struct AccDerived {
     static constexpr int OFF_T2 = 16;                            // s_2[10], s_2[0], s_2[1] (cyclic), b_2[4]
     static constexpr int OFF_H = (NDIM >= 2) ? 32 : 16;          // outer table
     static constexpr int NH = (NDIM <= 2) ? 2 : (NDIM == 3 ? 14 : 116);
-    static constexpr int OFF_TMP = OFF_H + NH;                   // 4-D only: T4'[14], T3[14]
     static constexpr int HRHS = (NDIM <= 2) ? 1 : NOUT / 10;     // first rhs entry of H
-    static constexpr int TPT = (T::PB * NDIM + T::NT - 1) / T::NT;   // staging tasks per thread
+    // staging tasks per point: one per dimension; in 4-D dimensions 3 and 4 share a task (it also
+    // forms their 116 products, so no second staging phase is needed)
+    static constexpr int NTASK = (NDIM == 4) ? 3 : NDIM;
+    static constexpr int TPT = (T::PB * NTASK + T::NT - 1) / T::NT;   // staging tasks per thread
     static_assert(NGT <= T::LPG, "group too small");
     static_assert(APL * T::LPG == NRACC && APL >= 1 && APL <= 4, "rhs split");
-    static_assert(OFF_TMP + (NDIM == 4 ? 28 : 0) <= T::RS, "record stride too small");
+    static_assert(OFF_H + NH <= T::RS, "record stride too small");
     static_assert(T::RS % 2 == 0 && (T::RS / 2) % 2 == 1, "record stride must be 2*odd");
+    static_assert(NW == 8, "warp de-phasing assumes 8 warps (two per scheduler)");
 };
 
 // G accumulator (outer tuple o = u*R + r, inner pair a) -> S
@@ -300,9 +303,10 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
     using T = AccTraits<NDIM>;
     using D = AccDerived<NDIM>;
     constexpr int R = T::R, RS = T::RS, PB = T::PB, NT = T::NT, TPT = D::TPT, APL = D::APL;
+    constexpr int NTASK = D::NTASK;
     extern __shared__ __align__(16) double smem[];
-    double *s_pts = smem;                       // PB * RS
-    double *s_red = smem + PB * RS;             // LPGW * (R * 10 + APL)   (unused for 4-D)
+    double *s_pts = smem;                       // 2 x PB x RS (double buffered)
+    double *s_red = smem + 2 * PB * RS;         // LPGW * (R * 10 + APL)   (unused for 4-D)
     __shared__ unsigned s_item;
 
     const int tid = threadIdx.x;
@@ -310,6 +314,10 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
     const int warp = tid >> 5;
     const int grp = tid / T::LPG;
     const int u = tid % T::LPG;
+    // Two warps share a scheduler (warp % 4).  One of them stages the next batch BEFORE accumulating
+    // the current one, the other AFTER, so the latency-bound staging of one overlaps the FP64-bound
+    // accumulation of the other instead of every warp stalling in the same phase.
+    const bool stage_first = ((warp >> 2) & 1) == 0;
 
     // per-lane constant offsets into a staged record.  The lane's R = 4 outer tuples o = 4u + r use
     // T2[(4u) % 10 .. +1], T2[(4u+2) % 10 .. +1] (two aligned 128-bit loads thanks to the cyclic copy)
@@ -325,13 +333,13 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
     const int offRH = D::OFF_H + D::HRHS + (NDIM >= 3 ? (e0 >> 4) : 0);
     const unsigned nitems = meta[0];
 
-    // staging task j of this thread: point tp[j] of the batch, dimension td[j]
-    int tp[TPT], td[TPT];
+    // staging task j of this thread: point tp[j] of the batch, task type tt[j]
+    int tp[TPT], tt[TPT];
 #pragma unroll
     for (int j = 0; j < TPT; ++j) {
         const int idx = tid + j * NT;
-        tp[j] = idx / NDIM;
-        td[j] = idx - tp[j] * NDIM;
+        tp[j] = idx / NTASK;
+        tt[j] = idx - tp[j] * NTASK;
     }
 
     for (;;) {
@@ -345,6 +353,7 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
         const unsigned wc = wincount[win];
         const long long first = (long long)winstart[win] + (long long)seg * T::CH;
         const int npts = (int)min((unsigned)T::CH, wc - seg * (unsigned)T::CH);
+        const int nbatch = (npts + PB - 1) / PB;
         int ws[NDIM];
         {
             unsigned k = win;
@@ -364,70 +373,70 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
 #pragma unroll
         for (int j = 0; j < APL; ++j) racc[j] = 0.0;
 
-        // ---- software pipeline: permutation entries two batches ahead, point data one batch ahead ----
+        // ---- software pipeline registers: permutation entries and gathered point data ----
         unsigned pi[TPT];
-        double dx_[TPT], dy_[TPT], dw_[TPT];
-        auto load_perm = [&](int b0) {
+        double dx_[TPT], dx2_[NDIM == 4 ? TPT : 1], dy_[TPT], dw_[TPT];
+        auto load_perm = [&](int b) {           // permutation entries of batch b
 #pragma unroll
             for (int j = 0; j < TPT; ++j) {
-                const int p = b0 + tp[j];
+                const int p = b * PB + tp[j];
                 pi[j] = (tp[j] < PB && p < npts) ? perm[first + p] : 0xffffffffu;
             }
         };
-        auto load_data = [&]() {
+        auto load_data = [&]() {                // gather the points named by pi[]
 #pragma unroll
             for (int j = 0; j < TPT; ++j) {
                 dx_[j] = 0.0;
                 dy_[j] = 0.0;
                 dw_[j] = 0.0;
+                if (NDIM == 4) dx2_[j] = 0.0;
                 if (pi[j] != 0xffffffffu) {
                     const long long i = pi[j];
-                    dx_[j] = (double)x[i * (long long)l1x + td[j]];
-                    if (td[j] == NDIM - 1) {
+                    const int d = (NDIM == 4 && tt[j] == 2) ? 2 : tt[j];
+                    dx_[j] = (double)x[i * (long long)l1x + d];
+                    if (NDIM == 4 && tt[j] == 2) dx2_[j] = (double)x[i * (long long)l1x + 3];
+                    if (tt[j] == NTASK - 1) {
                         dy_[j] = (double)y[i];
                         dw_[j] = weighted ? (double)w[i] : 1.0;
                     }
                 }
             }
         };
-        load_perm(0);
-        load_data();
-        load_perm(PB);
-
-        for (int b0 = 0; b0 < npts; b0 += PB) {
-            const int nb = min(PB, npts - b0);
-            if (b0 > 0) __syncthreads();        // previous batch fully consumed
-            // ---- stage: 1-D bases, pair products and outer tables of the nb points ----
+        // ---- stage batch b (held in dx_/dy_/dw_) into its shared-memory buffer ----
+        auto stage = [&](int b) {
+            const int nb = min(PB, npts - b * PB);
+            double *buf = s_pts + (b & 1) * (PB * RS);
 #pragma unroll
             for (int j = 0; j < TPT; ++j) {
-                const int p = tp[j], d = td[j];
+                const int p = tp[j], t = tt[j];
                 if (p < nb) {
-                    double b[4], s[10];
+                    const int d = (NDIM == 4 && t == 2) ? 2 : t;
+                    double bb[4], s[10];
                     int wsd;
-                    spl_window_weights_value(dx_[j], gp.xmin[d], gp.dx[d], gp.dxin[d], gp.nodes[d], wsd, b);
+                    spl_window_weights_value(dx_[j], gp.xmin[d], gp.dx[d], gp.dxin[d], gp.nodes[d], wsd, bb);
                     {
                         int a = 0;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int jj = i; jj < 4; ++jj) s[a++] = b[i] * b[jj];
+                            for (int jj = i; jj < 4; ++jj) s[a++] = bb[i] * bb[jj];
                     }
-                    double *out = s_pts + p * RS;
-                    if (d == 0) {
+                    double *out = buf + p * RS;
+                    if (t == 0) {
 #pragma unroll
                         for (int a = 0; a < 10; ++a) out[D::OFF_I + a] = s[a];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) out[D::OFF_I + 10 + i] = b[i];
+                        for (int i = 0; i < 4; ++i) out[D::OFF_I + 10 + i] = bb[i];
                     }
-                    if (NDIM >= 2 && d == 1) {
+                    if (NDIM >= 2 && t == 1) {
 #pragma unroll
                         for (int a = 0; a < 10; ++a) out[D::OFF_T2 + a] = s[a];
                         out[D::OFF_T2 + 10] = s[0];
                         out[D::OFF_T2 + 11] = s[1];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) out[D::OFF_T2 + 12 + i] = b[i];
+                        for (int i = 0; i < 4; ++i) out[D::OFF_T2 + 12 + i] = bb[i];
                     }
-                    if (d == NDIM - 1) {
+                    if (t == NTASK - 1) {
                         const double w2 = dw_[j] * dw_[j];      // row = w*phi, rhs = w*y (:806, :837)
                         const double w2y = w2 * dy_[j];
                         if (NDIM <= 2) {
@@ -437,44 +446,41 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
 #pragma unroll
                             for (int a = 0; a < 10; ++a) out[D::OFF_H + a] = w2 * s[a];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) out[D::OFF_H + 10 + i] = w2y * b[i];
+                            for (int i = 0; i < 4; ++i) out[D::OFF_H + 10 + i] = w2y * bb[i];
                         } else {
+                            // 4-D: this task owns dimensions 3 (in bb/s) and 4:
+                            // H[a4*10+a3] = w2 s4[a4] s3[a3];  H[100 + i4*4+i3] = w2y b4[i4] b3[i3]
+                            double b4[4];
+                            int ws4;
+                            spl_window_weights_value(dx2_[j], gp.xmin[3], gp.dx[3], gp.dxin[3], gp.nodes[3], ws4, b4);
+                            int a4 = 0;
 #pragma unroll
-                            for (int a = 0; a < 10; ++a) out[D::OFF_TMP + a] = w2 * s[a];
+                            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) out[D::OFF_TMP + 10 + i] = w2y * b[i];
+                                for (int jj = i; jj < 4; ++jj) {
+                                    const double s4 = w2 * (b4[i] * b4[jj]);
+#pragma unroll
+                                    for (int a3 = 0; a3 < 10; ++a3) out[D::OFF_H + a4 * 10 + a3] = s4 * s[a3];
+                                    ++a4;
+                                }
+#pragma unroll
+                            for (int i4 = 0; i4 < 4; ++i4) {
+                                const double t4 = w2y * b4[i4];
+#pragma unroll
+                                for (int i3 = 0; i3 < 4; ++i3) out[D::OFF_H + 100 + i4 * 4 + i3] = t4 * bb[i3];
+                            }
                         }
                     }
-                    if (NDIM == 4 && d == 2) {
-#pragma unroll
-                        for (int a = 0; a < 10; ++a) out[D::OFF_TMP + 14 + a] = s[a];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) out[D::OFF_TMP + 24 + i] = b[i];
-                    }
                 }
             }
-            __syncthreads();
-            // issue the gathers of the next batch and the permutation loads of the one after: they
-            // complete underneath the FP64 work below
-            if (b0 + PB < npts) load_data();
-            if (b0 + 2 * PB < npts) load_perm(b0 + 2 * PB);
-            if (NDIM == 4) {
-                // H[a4*10+a3] = T4'[a4]*T3[a3];  H[100 + i4*4+i3] = T4'[10+i4]*T3[10+i3]
-                for (int idx = tid; idx < nb * 116; idx += NT) {
-                    const int p = idx / 116;
-                    const int e = idx - p * 116;
-                    double *rec = s_pts + p * RS;
-                    double v;
-                    if (e < 100) v = rec[D::OFF_TMP + e / 10] * rec[D::OFF_TMP + 14 + e % 10];
-                    else v = rec[D::OFF_TMP + 10 + (e - 100) / 4] * rec[D::OFF_TMP + 24 + (e - 100) % 4];
-                    rec[D::OFF_H + e] = v;
-                }
-                __syncthreads();
-            }
-            // ---- G: group grp takes points grp, grp+NG, ... of the batch ----
+        };
+        // ---- accumulate batch b: group grp takes points grp, grp+NG, ... ----
+        auto accumulate = [&](int b) {
+            const int nb = min(PB, npts - b * PB);
+            const double *buf = s_pts + (b & 1) * (PB * RS);
 #pragma unroll 2
             for (int p = grp; p < nb; p += D::NG) {
-                const double *rec = s_pts + p * RS;
+                const double *rec = buf + p * RS;
                 double in[10];
 #pragma unroll
                 for (int a = 0; a < 10; a += 2) {
@@ -494,20 +500,42 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
                     P[2] = hb * tb.x;
                     P[3] = hb * tb.y;
                 }
+                // right-hand side of the same point: APL accumulators per lane
+                double t = rec[offRH];
+                if (NDIM >= 2) t *= rec[offRT];
+#pragma unroll
+                for (int j = 0; j < APL; ++j) racc[j] = fma(t, rec[offRI + j], racc[j]);
 #pragma unroll
                 for (int r = 0; r < R; ++r)
 #pragma unroll
                     for (int a = 0; a < 10; ++a) acc[r][a] = fma(P[r], in[a], acc[r][a]);
             }
-            // ---- right-hand side of the same points: APL accumulators per lane ----
-#pragma unroll 2
-            for (int p = grp; p < nb; p += D::NG) {
-                const double *rec = s_pts + p * RS;
-                double t = rec[offRH];
-                if (NDIM >= 2) t *= rec[offRT];
-#pragma unroll
-                for (int j = 0; j < APL; ++j) racc[j] = fma(t, rec[offRI + j], racc[j]);
+        };
+        // stage batch b+1 and keep the gathers (one batch ahead) / permutation loads (two ahead) going
+        auto advance = [&](int b) {
+            if (b + 1 < nbatch) {
+                stage(b + 1);
+                if (b + 2 < nbatch) load_data();
+                if (b + 3 < nbatch) load_perm(b + 3);
             }
+        };
+
+        load_perm(0);
+        load_data();
+        load_perm(1);
+        stage(0);
+        if (1 < nbatch) load_data();
+        if (2 < nbatch) load_perm(2);
+        __syncthreads();
+        for (int b = 0; b < nbatch; ++b) {
+            if (stage_first) {
+                advance(b);
+                accumulate(b);
+            } else {
+                accumulate(b);
+                advance(b);
+            }
+            __syncthreads();
         }
 
         // ---- reduce the K-split groups and flush once per work item ----
@@ -525,7 +553,6 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
         }
         if (D::NG > 1) {
             constexpr int PER = R * 10 + APL;   // values per lane
-            __syncthreads();
             for (int w2_ = 0; w2_ < D::NW; ++w2_) {
                 if (warp == w2_ && lane < D::LPGW) {
                     double *dst = s_red + lane * PER;       // lane == u for the first group of the warp
@@ -600,7 +627,7 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
     spl_items_kernel<<<spl_div_up(gp.nwindows, 256), 256, 0, st>>>(sc.wincount, sc.itemstart, gp.nwindows,
                                                                    (unsigned)T::CH, sc.item_win, sc.item_seg);
     if (ev) cudaEventRecord(ev[2], st);
-    const size_t smem = sizeof(double) * ((size_t)T::PB * T::RS + (size_t)D::LPGW * (T::R * 10 + D::APL));
+    const size_t smem = sizeof(double) * (2 * (size_t)T::PB * T::RS + (size_t)D::LPGW * (T::R * 10 + D::APL));
     auto kern = spl_accumulate_kernel<NDIM>;
     SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
