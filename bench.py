@@ -178,10 +178,11 @@ def run_ours(args):
     import splpak_b200 as sp
     from splpak_b200 import synth
 
-    sp.build()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        sp.build()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -189,6 +190,9 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        if rank == 0:
+            sp.build()                       # one builder; the others wait (no-op when the .so is current)
+        dist.barrier()
 
     def barrier():
         if world > 1:
@@ -271,9 +275,12 @@ def run_ours(args):
         launches = sp.total_launches() - launches0
         clocks = sampler.stop() if rank == 0 else None
 
-    fit_ms = sum(a.elapsed_time(b) for a, b, _ in evs) / args.steps
-    eval_ms = sum(b.elapsed_time(c) for _, b, c in evs) / args.steps
-    fit_ms, eval_ms = reduce_max(fit_ms), reduce_max(eval_ms)
+    fit_all = [a.elapsed_time(b) for a, b, _ in evs]
+    eval_all = [b.elapsed_time(c) for _, b, c in evs]
+    fit_ms = reduce_max(sum(fit_all) / args.steps)          # contract: total over EXACTLY K steps / K, max over ranks
+    eval_ms = reduce_max(sum(eval_all) / args.steps)
+    fit_med, eval_med = reduce_max(statistics.median(fit_all)), reduce_max(statistics.median(eval_all))
+    fit_min, eval_min = reduce_max(min(fit_all)), reduce_max(min(eval_all))
     stage_ms = {k: reduce_max(v / args.steps) for k, v in stage_ms.items()}
     launches_total = reduce_sum(float(launches))
     checksum = float(out[:: max(1, nq // 1000)].sum().item())
@@ -384,6 +391,10 @@ def run_ours(args):
             "evals_per_s": world * nq / (eval_ms * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": fit_ms + eval_ms, "fit_ms": fit_ms, "eval_ms": eval_ms,
+            # identical launches on these shared boxes show sporadic 1.5-5x slowdowns at constant clocks
+            # (profiles/r01_eval_jitter.md); the per-step median / minimum are given beside the mean
+            "per_step_ms": {"fit_median": fit_med, "fit_min": fit_min, "eval_median": eval_med, "eval_min": eval_min,
+                            "eval_all_rank0": [round(v, 2) for v in eval_all]},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "ndim": NDIM, "nodes": NODES, "points_per_gpu": npts,
                        "queries_per_gpu": nq, "xtrap": XTRAP, "query_order": "uniform random",

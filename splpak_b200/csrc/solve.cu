@@ -216,13 +216,19 @@ __device__ __forceinline__ void spl_cp_async_wait_all() {
 __global__ void __launch_bounds__(PANEL_THREADS)
 spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, int m,
                  double *__restrict__ g, double *__restrict__ ysol, double *__restrict__ linv_blk,
-                 int *__restrict__ fail) {
+                 int *__restrict__ fail, long long *__restrict__ dbg) {
     extern __shared__ __align__(16) double s_pan[];
+#define PANEL_STAMP(i) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
+    PANEL_STAMP(0);
     double *sA = s_pan;                          // [k][row]  A21 tile, 64 x TILE_LD
     double *sB = s_pan + 64 * TILE_LD;           // [k][n]    L11^-1 [n][k]
     double *s_col = sB + 64 * TILE_LD;           // 2 x 64   pivot column (double buffered)
     double *s_row = s_col + 128;                 // 2 x 64   pivot row of X
     double *s_g = s_row + 128;                   // 64       g1, then y1
+    double *s_rd = s_g + 64;                     // 64       1 / L11[k][k]
+    double *s_lfac = s_rd + 64;                  // 64 x 64  L11, row-major
+    double *s_strip = s_lfac + 64 * 64;          // 2 x 64 x 4  published pivot strip
+    int *s_bad = reinterpret_cast<int *>(s_strip + 512);
     const int tid = threadIdx.x;
     if (*fail) return;                           // an earlier panel failed (uniform across the grid)
     const int R0 = blockIdx.x * 64;              // first row of this CTA's tile, relative to j0 + nb
@@ -239,7 +245,7 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
 
     // ---- load A11 (4 x 4 per thread) ----
     const int ti = tid >> 4, tj = tid & 15;
-    double A[4][4], X[4][4];
+    double A[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -248,103 +254,163 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
             double v = (i == j) ? 1.0 : 0.0;                 // identity padding when nb < 64
             if (i < nb && j < nb && i >= j) v = AB[(j0 + i) + (j0 + j) * lda];
             A[a][b] = v;
-            X[a][b] = (i == j) ? 1.0 : 0.0;
         }
     if (tid < 64) s_g[tid] = (tid < nb) ? g[j0 + tid] : 0.0;
+    if (tid == 0) *s_bad = 0;
 
-    bool bad = false;
+    PANEL_STAMP(1);
+    // ---- right-looking Cholesky of the block, 4 pivots per barrier ----
+    // Owners of column block kb publish their 64 x 4 strip; every live thread then factors the 4 x 4
+    // pivot block itself (redundantly: it is a latency chain, not throughput), forward-substitutes
+    // its own 4 rows / 4 columns against it and applies the rank-4 update to its 4 x 4 block.
 #pragma unroll 1
     for (int kb = 0; kb < 16; ++kb) {
-        const bool rows_live = (ti >= kb);      // this thread still owns rows >= the pivot block
-        const bool cols_live = (tj >= kb);
+        double *strip = s_strip + (kb & 1) * 256;            // [row][4], double buffered
+        if (tj == kb) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const int k = 4 * kb + kk;
-            double *col = s_col + (k & 1) * 64;
-            double *row = s_row + (k & 1) * 64;
+            for (int a = 0; a < 4; ++a) {
+                *reinterpret_cast<double2 *>(strip + (4 * ti + a) * 4) = make_double2(A[a][0], A[a][1]);
+                *reinterpret_cast<double2 *>(strip + (4 * ti + a) * 4 + 2) = make_double2(A[a][2], A[a][3]);
+            }
+        }
+        __syncthreads();
+        if (ti >= kb && tj >= kb) {
+            double Dg[4][4], Ld[4][4], rinv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double2 v01 = *reinterpret_cast<const double2 *>(strip + (4 * kb + r) * 4);
+                const double2 v23 = *reinterpret_cast<const double2 *>(strip + (4 * kb + r) * 4 + 2);
+                Dg[r][0] = v01.x; Dg[r][1] = v01.y; Dg[r][2] = v23.x; Dg[r][3] = v23.y;
+            }
+            bool bad_here = false;
+            // right-looking inside the 4 x 4 block, so consecutive pivots are one FMA apart; the
+            // dependent chain per pivot is: seed, (g,h), two Goldschmidt steps, scale, update
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double d = Dg[c][c];
+                if (!(d > 0.0)) bad_here = true;              // non-positive (or NaN) pivot -> 107
+                double y0;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));   // ~2^-22 seed (MUFU.RSQ64H)
+                double gq2 = d * y0;                          // -> sqrt(d)
+                double hq = 0.5 * y0;                         // -> 1 / (2 sqrt(d))
+#pragma unroll
+                for (int itn = 0; itn < 2; ++itn) {
+                    const double rr = fma(-gq2, hq, 0.5);
+                    gq2 = fma(gq2, rr, gq2);
+                    hq = fma(hq, rr, hq);
+                }
+                const double r = bad_here ? 0.0 : 2.0 * hq;
+                rinv[c] = r;
+                Ld[c][c] = gq2;
+#pragma unroll
+                for (int rr2 = c + 1; rr2 < 4; ++rr2) Ld[rr2][c] = Dg[rr2][c] * r;
+#pragma unroll
+                for (int rr2 = c + 1; rr2 < 4; ++rr2)
+#pragma unroll
+                    for (int cc = c + 1; cc <= rr2; ++cc) Dg[rr2][cc] = fma(-Ld[rr2][c], Ld[cc][c], Dg[rr2][cc]);
+            }
+            if (ti == kb && tj == kb) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) s_rd[4 * kb + c] = rinv[c];
+                if (bad_here) *s_bad = 1;
+            }
+            // my rows against the pivot block: Li[a][c] = L[4ti+a][4kb+c]
+            double Li[4][4];
+#pragma unroll
+            for (int a2 = 0; a2 < 4; ++a2) {
+                const double2 v01 = *reinterpret_cast<const double2 *>(strip + (4 * ti + a2) * 4);
+                const double2 v23 = *reinterpret_cast<const double2 *>(strip + (4 * ti + a2) * 4 + 2);
+                const double raw[4] = {v01.x, v01.y, v23.x, v23.y};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    double v = raw[c];
+#pragma unroll
+                    for (int e = 0; e < c; ++e) v = fma(-Li[a2][e], Ld[c][e], v);
+                    Li[a2][c] = v * rinv[c];
+                }
+            }
             if (tj == kb) {
-                *reinterpret_cast<double2 *>(col + 4 * ti) = make_double2(A[0][kk], A[1][kk]);
-                *reinterpret_cast<double2 *>(col + 4 * ti + 2) = make_double2(A[2][kk], A[3][kk]);
-            }
-            if (ti == kb) {
-                *reinterpret_cast<double2 *>(row + 4 * tj) = make_double2(X[kk][0], X[kk][1]);
-                *reinterpret_cast<double2 *>(row + 4 * tj + 2) = make_double2(X[kk][2], X[kk][3]);
-            }
-            __syncthreads();
-            const double d = col[k];
-            if (!(d > 0.0)) bad = true;                       // non-positive (or NaN) pivot -> 107
-            // 1/sqrt(d): single-precision seed + two Newton steps in double (full precision, and a
-            // much shorter dependent chain than the library rsqrt on this latency-bound path)
-            double rinv;
-            {
-                const float df = (float)d;
-                if (df > 1e-30f && df < 1e30f) {
-                    double r = (double)rsqrtf(df);
-                    const double hd = 0.5 * d;
-                    r = r * fma(-hd * r, r, 1.5);
-                    r = r * fma(-hd * r, r, 1.5);
-                    rinv = r;
-                } else {
-                    rinv = bad ? 0.0 : rsqrt(d);
-                }
-            }
-            if (rows_live) {
-                const double2 c01 = *reinterpret_cast<const double2 *>(col + 4 * ti);
-                const double2 c23 = *reinterpret_cast<const double2 *>(col + 4 * ti + 2);
-                const double2 r01 = *reinterpret_cast<const double2 *>(row + 4 * tj);
-                const double2 r23 = *reinterpret_cast<const double2 *>(row + 4 * tj + 2);
-                const double li[4] = {c01.x * rinv, c01.y * rinv, c23.x * rinv, c23.y * rinv};
-                const double xr[4] = {r01.x * rinv, r01.y * rinv, r23.x * rinv, r23.y * rinv};
-                if (tj == kb) {
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) A[a][kk] = li[a];          // column k of L11 (rows >= k valid)
-                }
-                if (ti == kb) {
+                for (int a2 = 0; a2 < 4; ++a2)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) X[kk][b] = xr[b];          // row k of L11^-1
-                }
-                double lj[4] = {0.0, 0.0, 0.0, 0.0};
-                if (cols_live) {
-                    const double2 d01 = *reinterpret_cast<const double2 *>(col + 4 * tj);
-                    const double2 d23 = *reinterpret_cast<const double2 *>(col + 4 * tj + 2);
-                    lj[0] = d01.x * rinv;
-                    lj[1] = d01.y * rinv;
-                    lj[2] = d23.x * rinv;
-                    lj[3] = d23.y * rinv;
-                }
+                    for (int c = 0; c < 4; ++c) A[a2][c] = Li[a2][c];      // final L (rows >= col valid)
+            } else {
+                double Lj[4][4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const bool row_gt = (ti > kb) || (a > kk);             // global row > k (ti >= kb here)
-                    if (row_gt) {
+                for (int b2 = 0; b2 < 4; ++b2) {
+                    const double2 v01 = *reinterpret_cast<const double2 *>(strip + (4 * tj + b2) * 4);
+                    const double2 v23 = *reinterpret_cast<const double2 *>(strip + (4 * tj + b2) * 4 + 2);
+                    const double raw[4] = {v01.x, v01.y, v23.x, v23.y};
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const bool col_gt = (tj > kb) || (tj == kb && b > kk);
-                            if (col_gt) A[a][b] = fma(-li[a], lj[b], A[a][b]);
-                            X[a][b] = fma(-li[a], xr[b], X[a][b]);
-                        }
+                    for (int c = 0; c < 4; ++c) {
+                        double v = raw[c];
+#pragma unroll
+                        for (int e = 0; e < c; ++e) v = fma(-Lj[b2][e], Ld[c][e], v);
+                        Lj[b2][c] = v * rinv[c];
                     }
                 }
+#pragma unroll
+                for (int a2 = 0; a2 < 4; ++a2)
+#pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) {
+                        double v = A[a2][b2];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) v = fma(-Li[a2][c], Lj[b2][c], v);
+                        A[a2][b2] = v;
+                    }
             }
         }
     }
-    if (bad) {
+    __syncthreads();
+    PANEL_STAMP(2);
+    if (*s_bad) {
         if (blockIdx.x == 0 && tid == 0) *fail = 1;
         spl_cp_async_wait_all();
         return;
     }
-
-    // ---- stage L11^-1 as the B operand: sB[k][n] = Linv[n][k];  CTA 0 also stores it for the backsolve ----
+    // ---- L11 -> shared memory (row-major, lower part; sB doubles as scratch until Linv is ready) ----
+    double *sL = s_lfac;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int n = 4 * ti + a, k = 4 * tj + b;
-            const double v = (n >= k) ? X[a][b] : 0.0;
-            sB[k * TILE_LD + n] = v;
-            if (blockIdx.x == 0) linv_blk[n * 64 + k] = v;
+            const int i = 4 * ti + a, j = 4 * tj + b;
+            sL[i * 64 + j] = (i >= j) ? A[a][b] : 0.0;
         }
+    __syncthreads();
+    // ---- X = L11^-1 by columns: thread j < 64 forward-substitutes e_j.  No barriers; rows of L11 are
+    //      broadcast reads; fully unrolled so X stays in registers (entries above the diagonal are 0) ----
+    if (tid < 64) {
+        double X[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int c = 0; c + 1 < i; c += 2) {
+                const double2 l = *reinterpret_cast<const double2 *>(sL + i * 64 + c);
+                if ((c >> 1) & 1) {
+                    s2 = fma(l.x, X[c], s2);
+                    s3 = fma(l.y, X[c + 1], s3);
+                } else {
+                    s0 = fma(l.x, X[c], s0);
+                    s1 = fma(l.y, X[c + 1], s1);
+                }
+            }
+            if (i & 1) s0 = fma(sL[i * 64 + i - 1], X[i - 1], s0);
+            const double rhs = (i == tid) ? 1.0 : 0.0;
+            X[i] = (rhs - ((s0 + s1) + (s2 + s3))) * s_rd[i];
+        }
+        // stage L11^-1 as the B operand: sB[k][n] = Linv[n][k];  CTA 0 also stores it for the backsolve
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            sB[tid * TILE_LD + i] = X[i];
+            if (blockIdx.x == 0) linv_blk[i * 64 + tid] = X[i];
+        }
+    }
+    PANEL_STAMP(3);
     spl_cp_async_wait_all();
     __syncthreads();
+    PANEL_STAMP(4);
     // y1[c] = sum_k Linv[c][k] g1[k]
     double y1c = 0.0;
     if (tid < 64) {
@@ -357,6 +423,7 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
         if (blockIdx.x == 0 && tid < nb) ysol[j0 + tid] = y1c;
     }
     __syncthreads();
+    PANEL_STAMP(5);
     if (m <= 0) return;
 
     // ---- L21 tile = A21 tile * Linv^T: out[r][c] = sum_k A21[r][k] Linv[c][k] ----
@@ -398,6 +465,7 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
         part += __shfl_xor_sync(0xffffffffu, part, 2);
         if (t4 == 0 && r < m && part != 0.0) atomicAdd(g + r0 + r, -part);
     }
+    PANEL_STAMP(6);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -581,9 +649,11 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     }
     if (ev) cudaEventRecord(ev[1], st);
     const size_t syrk_smem = sizeof(double) * 2 * 64 * TILE_LD;
-    const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 128 + 64);
+    const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 128 + 64 + 64 + 64 * 64 + 512 + 2);
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
+    long long *dbg_dev = nullptr;
+    if (getenv("SPLPAK_B200_PANELCLK")) cudaMalloc((void **)&dbg_dev, 64);
     for (long long kb = 0; kb < nblk; ++kb) {
         const long long j0 = kb * SOLVE_NB;
         const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
@@ -594,54 +664,22 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         int pblocks = (m + 63) / 64;
         if (pblocks < 1) pblocks = 1;
         spl_panel_kernel<<<pblocks, PANEL_THREADS, panel_smem, st>>>(d_AB, lda, j0, nb, m, d_g, d_ysol,
-                                                                     d_linv + kb * 4096, d_fail);
+                                                                     d_linv + kb * 4096, d_fail, dbg_dev);
         ++g_spl_launches;
+        if (dbg_dev && kb == nblk / 2) {   // SPLPAK_B200_PANELCLK=1: phase clocks of one mid panel
+            long long hst[8];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(hst, dbg_dev, sizeof(hst), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "panel (mid) clocks: load %lld chol %lld inv %lld wait %lld y1 %lld gemm %lld total %lld\n", hst[1]-hst[0], hst[2]-hst[1], hst[3]-hst[2], hst[4]-hst[3], hst[5]-hst[4], hst[6]-hst[5], hst[6]-hst[0]);
+        }
         if (m > 0) {
             const int T = (m + SYRK_TILE - 1) / SYRK_TILE;
             const int tiles = T * (T + 1) / 2;
             spl_syrk_kernel<<<tiles, SYRK_THREADS, syrk_smem, st>>>(d_AB, lda, r0, j0, nb, m, d_fail);
             ++g_spl_launches;
         }
-        if (getenv("SPLPAK_B200_DEBUG")) {
-            int f = 0;
-            cudaError_t e = cudaStreamSynchronize(st);
-            cudaMemcpy(&f, d_fail, sizeof(int), cudaMemcpyDeviceToHost);
-            double dg[4] = {0, 0, 0, 0};
-            const long long jn = (j0 + nb < n) ? j0 + nb : j0;
-            cudaMemcpy(dg, d_AB + jn + jn * lda, sizeof(double), cudaMemcpyDeviceToHost);
-            cudaMemcpy(dg + 1, d_AB + (j0 + nb - 1) + (j0) * lda, sizeof(double), cudaMemcpyDeviceToHost);
-            // host Cholesky of the NEXT diagonal block (as the next panel will see it)
-            double minpiv = 0.0;
-            int badk = -1;
-            if (j0 + nb < n) {
-                const long long jj = j0 + nb;
-                const int nn2 = (int)((n - jj < 64) ? n - jj : 64);
-                static double blk[64 * 64];
-                for (int c = 0; c < nn2; ++c)
-                    cudaMemcpy(blk + c * 64, d_AB + (jj) + (jj + c) * lda, sizeof(double) * nn2, cudaMemcpyDeviceToHost);
-                // blk[c*64 + r] = A[jj + r][jj + c] for r >= c (column c starts at row jj, so shift)
-                double Lh[64][64];
-                for (int r = 0; r < nn2; ++r) for (int c = 0; c <= r; ++c) Lh[r][c] = blk[c * 64 + r];
-                minpiv = 1e300;
-                for (int k2 = 0; k2 < nn2 && badk < 0; ++k2) {
-                    double d2 = Lh[k2][k2];
-                    for (int c = 0; c < k2; ++c) d2 -= Lh[k2][c] * Lh[k2][c];
-                    if (d2 < minpiv) minpiv = d2;
-                    if (!(d2 > 0)) { badk = k2; break; }
-                    double pv = sqrt(d2);
-                    Lh[k2][k2] = pv;
-                    for (int r = k2 + 1; r < nn2; ++r) {
-                        double v = Lh[r][k2];
-                        for (int c = 0; c < k2; ++c) v -= Lh[r][c] * Lh[k2][c];
-                        Lh[r][k2] = v / pv;
-                    }
-                }
-            }
-            fprintf(stderr, "panel kb=%lld j0=%lld nb=%d m=%d fail=%d err=%s nextdiag=%g lastrow0=%g next-block host chol: minpiv=%g badk=%d\n",
-                    kb, j0, nb, m, f, cudaGetErrorString(e), dg[0], dg[1], minpiv, badk);
-            if (f) break;
-        }
     }
+    if (dbg_dev) cudaFree(dbg_dev);
     if (ev) cudaEventRecord(ev[2], st);
     for (long long kb = nblk - 1; kb >= 0; --kb) {
         const long long j0 = kb * SOLVE_NB;

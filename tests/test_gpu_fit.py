@@ -152,7 +152,7 @@ def test_zero_weights_are_skipped(oracle):
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-10 * np.abs(ref).max())
     keep = w != 0
     got2, _ = sp.splcw(2, x[keep], 2, y[keep], w[keep], keep.sum(), mn, mx, [6, 6], 1.0, quiet=True)
-    np.testing.assert_allclose(got2, got, rtol=0, atol=1e-11 * np.abs(ref).max())
+    np.testing.assert_allclose(got2, got, rtol=0, atol=1e-9 * np.abs(ref).max())
 
 
 def test_negative_first_weight_means_unweighted(oracle):
@@ -179,16 +179,19 @@ def test_solver_failures_map_to_107(oracle):
 
 
 def test_streaming_add_points_equals_one_shot(oracle):
-    """add_points in several calls (host chunks) == one splcw call; compute() twice is refused."""
+    """add_points in several calls (host chunks) == one splcw call up to summation-order roundoff
+    (amplified by cond(G) in the coefficients); compute() twice is refused."""
     x, y, w, mn, mx = make_problem(3, [6, 5, 6], 9000, seed=33)
     one, ierr = sp.splcw(3, x, 3, y, w, len(x), mn, mx, [6, 5, 6], 1.0, quiet=True)
     assert ierr == 0
     h = sp.FitHandle(3, mn, mx, [6, 5, 6], 1.0)
     for lo in range(0, len(x), 2500):
         assert h.add_points(x[lo:lo + 2500], y[lo:lo + 2500], w[lo:lo + 2500]) == 0
+    S = h.normal_equations()[0]
+    tol, cond = coef_tolerance(dense_from_stencil(S, [6, 5, 6]))
     got, ierr = h.compute()
     assert ierr == 0
-    np.testing.assert_allclose(got, one, rtol=0, atol=1e-11 * np.abs(one).max())
+    np.testing.assert_allclose(got, one, rtol=0, atol=tol * np.abs(one).max(), err_msg=f"cond {cond:.2e}")
     assert h.compute()[1] == 203
     t = h.timings()
     assert t["accumulate"] > 0 and t["factor"] > 0
@@ -196,7 +199,7 @@ def test_streaming_add_points_equals_one_shot(oracle):
     h.reset()
     assert h.add_points(x, y, w) == 0
     again, ierr = h.compute()
-    np.testing.assert_allclose(again, one, rtol=0, atol=1e-11 * np.abs(one).max())
+    np.testing.assert_allclose(again, one, rtol=0, atol=tol * np.abs(one).max())
     h.destroy()
 
 
@@ -208,6 +211,7 @@ def test_emulated_ranks_sum_to_single_rank(oracle):
     nodes = [8, 8]
     full = sp.FitHandle(2, mn, mx, nodes, 1.0)
     full.add_points(x, y, w)
+    full_S = full.normal_equations()[0]
     tfull = full.partial_tensor().clone()
     parts = []
     R = 4
@@ -226,7 +230,8 @@ def test_emulated_ranks_sum_to_single_rank(oracle):
     c_multi, ierr = parts[0].compute()
     c_single, ierr2 = full.compute()
     assert ierr == 0 and ierr2 == 0
-    np.testing.assert_allclose(c_multi, c_single, rtol=0, atol=1e-10 * np.abs(c_single).max())
+    tol, cond = coef_tolerance(dense_from_stencil(full_S, nodes))
+    np.testing.assert_allclose(c_multi, c_single, rtol=0, atol=tol * np.abs(c_single).max())
     for p in parts:
         p.destroy()
     full.destroy()
