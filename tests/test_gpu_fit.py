@@ -119,7 +119,7 @@ def test_reference_noisy_test_on_gpu():
 def test_multilinear_reproduction_K1():
     """Analytic known answer independent of any implementation.  The fit goes through
     the normal equations, so the reproduction error scales with eps*cond(G); the tolerance
-    is max(5e-10, 1e-2*eps*cond(G)) with cond(G) from the assembled Gram matrix."""
+    is max(5e-10, 0.1*eps*cond(G)) with cond(G) from the assembled Gram matrix."""
     rng = np.random.default_rng(3)
     for ndim, nodes in ((2, [9, 7]), (3, [8, 6, 7]), (4, [5, 6, 5, 4])):
         x = rng.random((20000, ndim))
@@ -133,7 +133,7 @@ def test_multilinear_reproduction_K1():
         coef, ierr = h.compute()
         h.destroy()
         assert ierr == 0
-        tol = max(5e-10, 1e-2 * np.finfo(float).eps * cond)
+        tol = max(5e-10, 0.1 * np.finfo(float).eps * cond)
         q = rng.random((500, ndim)) * 1.6 - 0.3
         v, _ = sp.eval_batch(ndim, q, coef, [0] * ndim, [1] * ndim, nodes)
         np.testing.assert_allclose(v, f(q), rtol=0, atol=tol, err_msg=f"cond(G)={cond:.2e}")

@@ -51,11 +51,13 @@ def dense_from_stencil(S, nodes):
 
 
 def coef_tolerance(G, base=1e-10):
-    """max(1e-10, eps * cond(G)): the north star's "~1e-10 relative, scaled by the system's condition
+    """max(1e-10, 10 * eps * cond(G)): the north star's "~1e-10 relative, scaled by the system's condition
     estimate".  (SURVEY 8c guessed 0.1*eps*cond from a QR-vs-Cholesky comparison; two runs of THIS
-    solver that differ only in summation order already differ by ~eps*cond, measured.)"""
+    solver that differ only in the order of the atomic flushes -- a few eps relative in G -- were
+    measured to differ by up to 3.2*eps*cond in the coefficients, so the constant is 10.  Fitted VALUES
+    are compared separately at a far tighter tolerance: they are well conditioned.)"""
     try:
         cond = np.linalg.cond(G)
     except Exception:
         cond = 1e16
-    return max(base, np.finfo(float).eps * cond), cond
+    return max(base, 10.0 * np.finfo(float).eps * cond), cond
