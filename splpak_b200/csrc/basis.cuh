@@ -131,26 +131,60 @@ __device__ __forceinline__ double spl_bas1_value(int ib, int nod, double x, doub
 // terms is exactly the reference's.
 __device__ __forceinline__ void spl_box(double x, double xmin, double dxin, int nod, int &ws,
                                         int &ibmn, int &ibmx) {
-    double t = spl_mul(dxin, spl_sub(x, xmin));
-    // Fortran real->integer assignment truncates toward zero; far-away points are clamped first
-    // (any it <= -2 or >= nod+2 gives the same box), which also defines the NaN case (it = 0).
-    t = fmin(fmax(t, -4.0), (double)nod + 4.0);
-    const int it = __double2int_rz(t);
+    const double t = spl_mul(dxin, spl_sub(x, xmin));
+    // Fortran real->integer assignment truncates toward zero.  The conversion saturates (and maps NaN
+    // to 0); far-away points are then clamped (any it <= -2 or >= nod+2 gives the same box).
+    const int it = min(max(__double2int_rz(t), -4), nod + 4);
     ibmn = min(max(it - 1, 0), nod - 2);
     ibmx = max(min(it + 2, nod - 1), 1);
     ws = min(max(it - 1, 0), nod - 4);
 }
 
-// Same as spl_window_weights below for nder = 0, through the branch-free value formula.
+// s < 0 ? 0 : s through the sign bit (three integer-pipe instructions instead of the DSETP/SEL/FSEL/LOP3
+// sequence fmax() compiles to; -0 and NaN pass through, both harmless below).
+__device__ __forceinline__ double spl_clamp0(double s) {
+    const int hi = __double2hiint(s);
+    const int keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, __double2loint(s) & keep);
+}
+
+// The four window weights of one dimension for nder = 0 -- the hot-path form used by evaluation
+// (splfe) and assembly.  Arithmetic per node is EXACTLY that of spl_bas1_value (same operations, same
+// order, no FMA), so the values are bit-identical to the reference's bascmp; what is different is the
+// plumbing around it, which the instruction mix of the evaluation kernel showed to dominate:
+//   * it = trunc(t) through the saturating F2I (NaN -> 0) instead of a floating clamp;
+//   * sign manipulation (-u, -|u|), max(.,0), the alpha select and the s >= 2 test on the high word
+//     with integer-pipe instructions instead of FP64-pipe DADD/DSETP + paired FSELs;
+//   * no box mask: a window node outside the reference's box [ibmn, ibmx] is >= 2 cells away from x,
+//     so s <= 0 (up to one ulp of u, i.e. a term <= 1e-47 instead of an exact 0) and the value formula
+//     returns 0 for it anyway.
 __device__ __forceinline__ void spl_window_weights_value(double x, double xmin, double dx, double dxin,
                                                          int nod, int &ws, double b[4]) {
-    int ibmn, ibmx;
-    spl_box(x, xmin, dxin, nod, ws, ibmn, ibmx);
+    const double t = spl_mul(dxin, spl_sub(x, xmin));
+    const int it = max(__double2int_rz(t), -4);              // Fortran int(): truncation toward zero
+    ws = min(max(it - 1, 0), nod - 4);
+    const double wsf = (double)ws;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int ib = ws + k;
-        const double v = spl_bas1_value(ib, nod, x, xmin, dx, dxin);
-        b[k] = (ib >= ibmn && ib <= ibmx) ? v : 0.0;
+        const double xb = spl_add(xmin, spl_mul(wsf + (double)k, dx));     // :246 (wsf + k is exact)
+        const double u = spl_mul(dxin, spl_sub(x, xb));
+        const bool is_l = ib <= 1;
+        const bool edge = is_l || ib >= nod - 2;
+        // w = -u (left edge), u (right edge), -|u| (chapeau): flip / keep / set the sign bit
+        const unsigned flip = is_l ? 0x80000000u : 0u;
+        const unsigned set = edge ? 0u : 0x80000000u;
+        const double w = __hiloint2double((int)(((unsigned)__double2hiint(u) ^ flip) | set), __double2loint(u));
+        const double s = spl_add(2.0, w);
+        const double sp = spl_clamp0(s);
+        const double s3 = spl_mul(spl_mul(sp, sp), sp);
+        const double m = spl_clamp0(spl_sub(s, 1.0));
+        const double m3 = spl_mul(spl_mul(m, m), m);
+        const double alpha = __hiloint2double(edge ? 0x3fe00000 : 0x3fd00000, 0);   // 1/2 : 1/4
+        double v = spl_sub(spl_mul(alpha, s3), m3);
+        const double lin = spl_sub(spl_mul(3.0, s), 3.0);
+        if (edge && __double2hiint(s) >= 0x40000000) v = lin;                      // s >= 2 (s < 0 has the sign bit set)
+        b[k] = v;
     }
 }
 

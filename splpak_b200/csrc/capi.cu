@@ -3,6 +3,7 @@
 // eval.cu / assemble.cu / solve.cu.  There is no CPU fallback anywhere in this file: without a
 // usable CUDA device every compute entry point returns SPLPAK_ERR_CUDA.
 #include <dlfcn.h>
+#include <mutex>
 #include <new>
 #include <string.h>
 
@@ -64,10 +65,26 @@ static int get_device(DeviceInfo &di) {
         return SPLPAK_ERR_CUDA;
     }
     SPL_CUDA_TRY(cudaGetDevice(&di.dev));
-    cudaDeviceProp p;
-    SPL_CUDA_TRY(cudaGetDeviceProperties(&p, di.dev));
-    di.nsm = p.multiProcessorCount;
-    di.smem_optin = p.sharedMemPerBlockOptin;
+    // the two attributes are cached per device (cudaGetDeviceProperties costs milliseconds per call)
+    static std::mutex mu;
+    static int c_nsm[64] = {0};
+    static size_t c_smem[64] = {0};
+    std::lock_guard<std::mutex> lk(mu);
+    const int slot = (di.dev >= 0 && di.dev < 64) ? di.dev : -1;
+    if (slot < 0 || c_nsm[slot] == 0) {
+        int nsm = 0, smem = 0;
+        SPL_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, di.dev));
+        SPL_CUDA_TRY(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, di.dev));
+        di.nsm = nsm;
+        di.smem_optin = (size_t)smem;
+        if (slot >= 0) {
+            c_nsm[slot] = nsm;
+            c_smem[slot] = (size_t)smem;
+        }
+    } else {
+        di.nsm = c_nsm[slot];
+        di.smem_optin = c_smem[slot];
+    }
     di.ok = 1;
     return SPLPAK_OK;
 }
@@ -145,6 +162,22 @@ extern "C" const char *splpak_b200_strerror(int code, int evaluation) {
 // ------------------------------------------------------------------------------------------
 // evaluation
 // ------------------------------------------------------------------------------------------
+#define EVAL_COUNTERS 1024
+static unsigned long long *eval_counter_slot(int device) {
+    static std::mutex mu;
+    static unsigned long long *pool[64] = {nullptr};
+    static unsigned next[64] = {0};
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pool[device]) {
+        if (cudaMalloc((void **)&pool[device], sizeof(unsigned long long) * EVAL_COUNTERS) != cudaSuccess) {
+            pool[device] = nullptr;
+            return nullptr;
+        }
+    }
+    return pool[device] + (next[device]++ % EVAL_COUNTERS);
+}
+
 static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const int *nderiv,
                             const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
                             real_t *d_out, cudaStream_t st) {
@@ -161,10 +194,12 @@ static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const in
         ++g_spl_launches;
         coef64 = tmp;
     }
-    unsigned long long *counter = nullptr;   // tile counter of the dynamic scheduler (stream-ordered scratch)
-    SPL_CUDA_TRY(cudaMallocAsync((void **)&counter, sizeof(unsigned long long), st));
+    // tile counter of the dynamic scheduler: one slot of a persistent per-device pool, handed out round
+    // robin (a slot is reused only after EVAL_COUNTERS further launches; each launch zeroes its slot
+    // on its own stream)
+    unsigned long long *counter = eval_counter_slot(di.dev);
+    if (!counter) return SPLPAK_ERR_ALLOC;
     int rc = spl_eval_launch(gp, nderiv, d_x, l1x, nq, coef64, npad, d_out, st, di.nsm, di.smem_optin, counter);
-    cudaFreeAsync(counter, st);
     if (tmp) cudaFreeAsync(tmp, st);
     return rc;
 }
