@@ -129,7 +129,9 @@ int splpak_b200_fit_create(int ndim, const splpak_real *xmin, const splpak_real 
  * as in :796-800.  HOST arrays; the copy is chunked and overlapped with the kernels. */
 int splpak_b200_fit_add_points(splpak_b200_fit_t h, const splpak_real *x, int l1x,
                                const splpak_real *y, const splpak_real *w, int weighted, int64_t n);
-/* Same with DEVICE arrays; asynchronous on the handle's stream. */
+/* Same with DEVICE arrays; asynchronous on the handle's stream (splpak_b200_fit_stream), which does NOT
+ * synchronise with other streams: the arrays must be complete before the call (synchronise the producing
+ * stream or make the handle's stream wait on its event). */
 int splpak_b200_fit_add_points_device(splpak_b200_fit_t h, const splpak_real *d_x, int l1x,
                                       const splpak_real *d_y, const splpak_real *d_w, int weighted,
                                       int64_t n);

@@ -66,6 +66,12 @@ __device__ __forceinline__ long long spl_nearest_node(const GridParams &gp, cons
     return iin;
 }
 
+// Both binning passes are latency-bound (one dependent global round trip per point), so every thread
+// handles BIN_U points per iteration with all their loads -- and, in the second pass, all their
+// returning atomics -- in flight together.  Counts use fire-and-forget RED (no warp aggregation:
+// MATCH.ANY costs more than the reds it saves on scattered data).
+#define BIN_U 4
+
 template <int NDIM>
 __global__ void __launch_bounds__(256)
 spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
@@ -75,27 +81,33 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
     double tot = 0.0;
     double rows = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nround = ((n + stride - 1) / stride) * stride;   // uniform trip count per warp
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        unsigned key = 0xffffffffu;
-        double wv = 0.0;
-        if (i < n) {
-            wv = weighted ? (double)w[i] : 1.0;
-            if (wv != 0.0) {
-                const real_t *xp = x + i * (long long)l1x;
-                key = spl_window_key<NDIM>(gp, xp);
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * BIN_U) {
+        double wv[BIN_U];
+        real_t xp[BIN_U][NDIM];
+#pragma unroll
+        for (int u = 0; u < BIN_U; ++u) {
+            const long long i = i0 + u * stride;
+            wv[u] = 0.0;
+            if (i < n) {
+                wv[u] = weighted ? (double)w[i] : 1.0;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) xp[u][d] = x[i * (long long)l1x + d];
+            } else {
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) xp[u][d] = (real_t)0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BIN_U; ++u) {
+            if (wv[u] != 0.0) {                                  // zero-weight points are skipped (:796-800)
+                atomicAdd(wincount + spl_window_key<NDIM>(gp, xp[u]), 1u);
                 rows += 1.0;
                 if (do_hist) {
-                    const long long iin = spl_nearest_node<NDIM>(gp, xp);
-                    atomicAdd(cnt + iin, wv);
-                    tot += wv;
+                    atomicAdd(cnt + spl_nearest_node<NDIM>(gp, xp[u]), wv[u]);
+                    tot += wv[u];
                 }
             }
         }
-        // warp-aggregated count: one atomic per distinct window in the warp
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        if (key != 0xffffffffu && (threadIdx.x & 31) == (__ffs(peers) - 1))
-            atomicAdd(wincount + key, (unsigned)__popc(peers));
     }
     // block reduction of totlwt and the row count
     __shared__ double s_tot[8], s_rows[8];
@@ -174,24 +186,37 @@ spl_perm_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict_
                 const unsigned *__restrict__ winstart, unsigned *__restrict__ wincursor,
                 unsigned *__restrict__ perm) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nround = ((n + stride - 1) / stride) * stride;
-    const unsigned lane = threadIdx.x & 31;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        unsigned key = 0xffffffffu;
-        if (i < n) {
-            const double wv = weighted ? (double)w[i] : 1.0;
-            if (wv != 0.0) key = spl_window_key<NDIM>(gp, x + i * (long long)l1x);
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * BIN_U) {
+        double wv[BIN_U];
+        real_t xp[BIN_U][NDIM];
+#pragma unroll
+        for (int u = 0; u < BIN_U; ++u) {
+            const long long i = i0 + u * stride;
+            wv[u] = 0.0;
+            if (i < n) {
+                wv[u] = weighted ? (double)w[i] : 1.0;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) xp[u][d] = x[i * (long long)l1x + d];
+            } else {
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) xp[u][d] = (real_t)0;
+            }
         }
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        const int leader = __ffs(peers) - 1;
-        unsigned base = 0;
-        if (key != 0xffffffffu && (int)lane == leader)
-            base = atomicAdd(wincursor + key, (unsigned)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (key != 0xffffffffu) {
-            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-            perm[(long long)winstart[key] + base + rank] = (unsigned)i;
+        unsigned key[BIN_U], pos[BIN_U], ws0[BIN_U];
+#pragma unroll
+        for (int u = 0; u < BIN_U; ++u) {
+            key[u] = 0xffffffffu;
+            pos[u] = 0;
+            ws0[u] = 0;
+            if (wv[u] != 0.0) {
+                key[u] = spl_window_key<NDIM>(gp, xp[u]);
+                ws0[u] = winstart[key[u]];
+                pos[u] = atomicAdd(wincursor + key[u], 1u);
+            }
         }
+#pragma unroll
+        for (int u = 0; u < BIN_U; ++u)
+            if (key[u] != 0xffffffffu) perm[(long long)ws0[u] + pos[u]] = (unsigned)(i0 + u * stride);
     }
 }
 
