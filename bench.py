@@ -332,6 +332,8 @@ def run_ours(args):
             t1 = time.perf_counter()
             fit_s.append(t_mid - t0)
             eval_s.append(t1 - t_mid)
+        print(f"[bench rank {rank}] e2e per-step fit {[round(1e3 * v, 1) for v in fit_s]} ms, "
+              f"eval {[round(1e3 * v, 1) for v in eval_s]} ms", file=sys.stderr, flush=True)
         e2e_fit = reduce_max(sum(fit_s) / len(fit_s))
         e2e_eval = reduce_max(sum(eval_s) / len(eval_s))
         e2e = {

@@ -72,12 +72,20 @@ __device__ __forceinline__ long long spl_nearest_node(const GridParams &gp, cons
 // MATCH.ANY costs more than the reds it saves on scattered data).
 #define BIN_U 4
 
-template <int NDIM>
-__global__ void __launch_bounds__(256)
+// SMEMH: the per-window counts are first accumulated in a shared-memory histogram (native 32-bit
+// ATOMS) and flushed once per CTA -- the L2 atomic units, not HBM, bound this pass when every point
+// issues two global reductions.  Used when the window table fits (launcher decides).
+template <int NDIM, bool SMEMH>
+__global__ void __launch_bounds__(512, 2)
 spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
                     const real_t *__restrict__ w, int weighted, long long n,
                     unsigned *__restrict__ wincount, int do_hist, double *__restrict__ cnt,
                     double *__restrict__ totals) {
+    extern __shared__ unsigned s_hist[];
+    if (SMEMH) {
+        for (int e = threadIdx.x; e < (int)gp.nwindows; e += blockDim.x) s_hist[e] = 0u;
+        __syncthreads();
+    }
     double tot = 0.0;
     double rows = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -100,7 +108,9 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
 #pragma unroll
         for (int u = 0; u < BIN_U; ++u) {
             if (wv[u] != 0.0) {                                  // zero-weight points are skipped (:796-800)
-                atomicAdd(wincount + spl_window_key<NDIM>(gp, xp[u]), 1u);
+                const unsigned key = spl_window_key<NDIM>(gp, xp[u]);
+                if (SMEMH) atomicAdd(s_hist + key, 1u);
+                else atomicAdd(wincount + key, 1u);
                 rows += 1.0;
                 if (do_hist) {
                     atomicAdd(cnt + spl_nearest_node<NDIM>(gp, xp[u]), wv[u]);
@@ -109,8 +119,15 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
             }
         }
     }
+    if (SMEMH) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < (int)gp.nwindows; e += blockDim.x) {
+            const unsigned c = s_hist[e];
+            if (c) atomicAdd(wincount + e, c);
+        }
+    }
     // block reduction of totlwt and the row count
-    __shared__ double s_tot[8], s_rows[8];
+    __shared__ double s_tot[16], s_rows[16];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         tot += __shfl_xor_sync(0xffffffffu, tot, o);
@@ -642,8 +659,22 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
     const int grid = (int)(nb < cap ? nb : cap);
 
     if (ev) cudaEventRecord(ev[0], st);
-    spl_classify_kernel<NDIM><<<grid, 256, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.wincount, do_hist,
-                                                    d_cnt, d_totals);
+    {
+        // two 512-thread CTAs per SM when the histogram is in shared memory (<= 2 x 96 KB), else 4
+        const size_t hist_bytes = sizeof(unsigned) * (size_t)gp.nwindows;
+        const bool smemh = hist_bytes <= 96 * 1024 && n >= 8 * gp.nwindows;
+        long long cb = (n + 512LL * BIN_U - 1) / (512LL * BIN_U);
+        const long long ccap = (long long)nsm * (smemh ? 2 : 4);
+        const int cgrid = (int)(cb < ccap ? (cb < 1 ? 1 : cb) : ccap);
+        if (smemh) {
+            auto kern = spl_classify_kernel<NDIM, true>;
+            SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+            kern<<<cgrid, 512, hist_bytes, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.wincount, do_hist, d_cnt, d_totals);
+        } else {
+            spl_classify_kernel<NDIM, false><<<cgrid, 512, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.wincount,
+                                                                    do_hist, d_cnt, d_totals);
+        }
+    }
     if (ev) cudaEventRecord(ev[1], st);
     spl_scan_kernel<<<1, 1024, 0, st>>>(sc.wincount, gp.nwindows, (unsigned)T::CH, sc.winstart,
                                         sc.itemstart, sc.meta);

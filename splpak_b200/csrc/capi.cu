@@ -32,7 +32,9 @@ long long spl_band_lda(int bw);
 int spl_half_bandwidth(const GridParams &gp);
 long long spl_solve_workspace(const GridParams &gp);
 int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, double *d_g, double *d_work,
-                     double **d_coef_out, int *d_fail, cudaStream_t st, int nsm, cudaEvent_t *ev);
+                     double **d_coef_out, int *d_fail, cudaStream_t st, cudaStream_t st_aux, int nsm, cudaEvent_t *ev,
+                     void **cache);
+void spl_solve_cache_free(void *cache);
 int spl_measure_peaks_impl(double *out, int n);
 
 // ------------------------------------------------------------------------------------------
@@ -324,7 +326,7 @@ struct splpak_b200_fit_s {
     GridParams gp;
     DeviceInfo di;
     double xtrap;
-    cudaStream_t st, st_copy;
+    cudaStream_t st, st_copy, st_aux;   // st_aux: look-ahead stream of the solve
     // partial sums, one contiguous buffer: [S | g | cnt | totals(2)]
     double *d_part;
     long long n_part;
@@ -339,6 +341,7 @@ struct splpak_b200_fit_s {
     double *d_AB;
     long long ab_elems;
     int *d_fail;
+    void *solve_cache;            // CUDA graphs of the factor / back-substitution loops (solve.cu)
     // timing: accumulated event pairs
     double ms[NTIMER];
     cudaEvent_t ev[8];
@@ -369,7 +372,9 @@ static void free_handle(splpak_b200_fit_t h) {
     for (int k = 0; k < 8; ++k)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     if (h->st) cudaStreamDestroy(h->st);
+    if (h->solve_cache) spl_solve_cache_free(h->solve_cache);
     if (h->st_copy) cudaStreamDestroy(h->st_copy);
+    if (h->st_aux) cudaStreamDestroy(h->st_aux);
     h->magic = 0;
     delete h;
 }
@@ -405,6 +410,7 @@ extern "C" int splpak_b200_fit_create(int ndim, const real_t *xmin, const real_t
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->st_aux, cudaStreamNonBlocking) == cudaSuccess;
     h->n_part = gp.ncol * gp.nsten + gp.ncol + gp.ncol + 2;
     ok = ok && cudaMalloc((void **)&h->d_part, sizeof(double) * (size_t)h->n_part) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&h->d_fail, sizeof(int)) == cudaSuccess;
@@ -644,7 +650,8 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
     for (int k = 0; k < 4; ++k) SPL_CUDA_TRY(cudaEventCreate(&sev[k]));
     // the solve destroys g; the solution comes back in the workspace behind the band matrix
     double *d_sol = nullptr;
-    rc = spl_solve_launch(gp, h->d_S, h->d_AB, h->d_g, h->d_AB + band_elems, &d_sol, h->d_fail, st, h->di.nsm, sev);
+    rc = spl_solve_launch(gp, h->d_S, h->d_AB, h->d_g, h->d_AB + band_elems, &d_sol, h->d_fail, st, h->st_aux, h->di.nsm, sev,
+                          &h->solve_cache);
     int fail = 0;
     double totals[2] = {0.0, 0.0};
     if (rc == SPLPAK_OK) {

@@ -27,6 +27,7 @@
 // forms c_k = L11^-T y_k from the stored block inverse, then eliminates c_k from its slice of the b
 // preceding entries.
 #include <stdlib.h>
+#include <new>
 
 #include "basis.cuh"
 
@@ -478,18 +479,28 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
 // row/column is global index r0; P = panel rows r0.., columns j0..j0+nb-1.  Operand tiles are
 // streamed with cp.async (k-major, conflict-free fragment reads); the C tile is prefetched into the
 // accumulators while the operands are in flight, so the kernel is one global round trip long.
+// part 0: the first tile column (tj = 0, one CTA per tile row) -- all the next panel depends on;
+// part 1: every other lower-triangular tile (ti >= tj >= 1), launched on the auxiliary stream so that it
+// overlaps the next panel's latency chain (look-ahead).
 __global__ void __launch_bounds__(SYRK_THREADS)
 spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long j0, int nb, int m,
-                const int *__restrict__ fail) {
+                const int *__restrict__ fail, int part) {
     extern __shared__ __align__(16) double s_ab[];
     double *sA = s_ab;                          // [k][row]
     double *sB = s_ab + 64 * TILE_LD;
     if (*fail) return;
-    const int tile = blockIdx.x;
-    int ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
-    while ((long long)(ti + 1) * (ti + 2) / 2 <= tile) ++ti;
-    while ((long long)ti * (ti + 1) / 2 > tile) --ti;
-    const int tj = tile - ti * (ti + 1) / 2;
+    int ti, tj;
+    if (part == 0) {
+        ti = blockIdx.x;
+        tj = 0;
+    } else {
+        const int tile = blockIdx.x;
+        ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
+        while ((long long)(ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+        while ((long long)ti * (ti + 1) / 2 > tile) --ti;
+        tj = tile - ti * (ti + 1) / 2 + 1;
+        ti += 1;
+    }
     const int I0 = ti * SYRK_TILE, J0 = tj * SYRK_TILE;
     const int t = threadIdx.x;
     const bool diag = (ti == tj);
@@ -628,33 +639,43 @@ long long spl_solve_workspace(const GridParams &gp) {
 
 // AB must hold ncol*(lda+1) doubles and be zero-filled on entry.  g enters as the right-hand side
 // (destroyed); the solution is left in d_work + nblk*4096 + (ncol+64)  (returned through *d_coef_out).
-int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, double *d_g, double *d_work,
-                     double **d_coef_out, int *d_fail, cudaStream_t st, int nsm, cudaEvent_t *ev) {
-    const long long n = gp.ncol;
-    const int bw = spl_half_bandwidth(gp);
-    const long long lda = spl_band_lda(bw);
+// The factorisation is ~650 small dependent launches with cross-stream events: issued from the host it
+// is bound by the CPU's launch rate (45 us per panel), so both loops are captured once per handle into
+// CUDA graphs and replayed.
+struct SolveGraphs {
+    cudaGraphExec_t factor = nullptr, back = nullptr;
+    const double *key_AB = nullptr, *key_g = nullptr;
+    long long n = 0;
+    int bw = 0;
+    long long nfactor = 0, nback = 0;     // kernel nodes
+};
+
+void spl_solve_cache_free(void *cache) {
+    SolveGraphs *sg = static_cast<SolveGraphs *>(cache);
+    if (!sg) return;
+    if (sg->factor) cudaGraphExecDestroy(sg->factor);
+    if (sg->back) cudaGraphExecDestroy(sg->back);
+    delete sg;
+}
+
+// Right-looking factor loop with look-ahead over two streams.  Panel k+1 depends only on the first tile
+// column of trailing update k, so
+//   st     : panel(k) -> [wait rest(k-1)] -> syrk column 0 (k) -> panel(k+1) ...
+//   st_aux : [wait panel(k)] -> syrk rest (k)
+// and the rest of update k runs under panel k+1's diagonal-block latency chain.  Ordering on shared tiles:
+// rest(k)'s tiles with tj >= 1 are columns 0.. of window k+1, hence the wait before syrk column 0 (k+1);
+// rest(k) and rest(k+1) are ordered by st_aux itself.
+static cudaError_t enqueue_factor(long long n, int bw, long long lda, double *d_AB, double *d_g, double *d_ysol,
+                                  double *d_linv, int *d_fail, cudaStream_t st, cudaStream_t st_aux,
+                                  size_t panel_smem, size_t syrk_smem, long long *nlaunch) {
     const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
-    double *d_linv = d_work;
-    double *d_ysol = d_work + nblk * 4096;
-    double *d_csol = d_ysol + (n + 64);
-    *d_coef_out = d_csol;
-    (void)nsm;
-    if (ev) cudaEventRecord(ev[0], st);
-    {
-        const long long total = n * (long long)(bw + 1);
-        long long blocks = (total + 255) / 256;
-        if (blocks > 148LL * 32) blocks = 148LL * 32;
-        spl_expand_band_kernel<<<(unsigned)blocks, 256, 0, st>>>(gp, d_S, d_AB, lda, bw);
-        ++g_spl_launches;
-    }
-    if (ev) cudaEventRecord(ev[1], st);
-    const size_t syrk_smem = sizeof(double) * 2 * 64 * TILE_LD;
-    const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 128 + 64 + 64 + 64 * 64 + 512 + 2);
-    SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
-    SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
-    long long *dbg_dev = nullptr;
-    if (getenv("SPLPAK_B200_PANELCLK")) cudaMalloc((void **)&dbg_dev, 64);
-    for (long long kb = 0; kb < nblk; ++kb) {
+    cudaEvent_t ev_panel = nullptr, ev_rest = nullptr;
+    cudaError_t e;
+    if ((e = cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ev_rest, cudaEventDisableTiming)) != cudaSuccess) return e;
+    bool rest_pending = false;
+    long long count = 0;
+    for (long long kb = 0; kb < nblk && e == cudaSuccess; ++kb) {
         const long long j0 = kb * SOLVE_NB;
         const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
         const long long r0 = j0 + nb;
@@ -664,23 +685,39 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         int pblocks = (m + 63) / 64;
         if (pblocks < 1) pblocks = 1;
         spl_panel_kernel<<<pblocks, PANEL_THREADS, panel_smem, st>>>(d_AB, lda, j0, nb, m, d_g, d_ysol,
-                                                                     d_linv + kb * 4096, d_fail, dbg_dev);
-        ++g_spl_launches;
-        if (dbg_dev && kb == nblk / 2) {   // SPLPAK_B200_PANELCLK=1: phase clocks of one mid panel
-            long long hst[8];
-            cudaStreamSynchronize(st);
-            cudaMemcpy(hst, dbg_dev, sizeof(hst), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "panel (mid) clocks: load %lld chol %lld inv %lld wait %lld y1 %lld gemm %lld total %lld\n", hst[1]-hst[0], hst[2]-hst[1], hst[3]-hst[2], hst[4]-hst[3], hst[5]-hst[4], hst[6]-hst[5], hst[6]-hst[0]);
-        }
+                                                                     d_linv + kb * 4096, d_fail, nullptr);
+        ++count;
         if (m > 0) {
             const int T = (m + SYRK_TILE - 1) / SYRK_TILE;
-            const int tiles = T * (T + 1) / 2;
-            spl_syrk_kernel<<<tiles, SYRK_THREADS, syrk_smem, st>>>(d_AB, lda, r0, j0, nb, m, d_fail);
-            ++g_spl_launches;
+            if (T > 1) {
+                if ((e = cudaEventRecord(ev_panel, st)) != cudaSuccess) break;
+                if ((e = cudaStreamWaitEvent(st_aux, ev_panel, 0)) != cudaSuccess) break;
+                spl_syrk_kernel<<<(T - 1) * T / 2, SYRK_THREADS, syrk_smem, st_aux>>>(d_AB, lda, r0, j0, nb, m, d_fail, 1);
+                ++count;
+            }
+            if (rest_pending && (e = cudaStreamWaitEvent(st, ev_rest, 0)) != cudaSuccess) break;   // rest(k-1) done
+            rest_pending = false;
+            spl_syrk_kernel<<<T, SYRK_THREADS, syrk_smem, st>>>(d_AB, lda, r0, j0, nb, m, d_fail, 0);
+            ++count;
+            if (T > 1) {
+                if ((e = cudaEventRecord(ev_rest, st_aux)) != cudaSuccess) break;
+                rest_pending = true;
+            }
         }
     }
-    if (dbg_dev) cudaFree(dbg_dev);
-    if (ev) cudaEventRecord(ev[2], st);
+    if (e == cudaSuccess && rest_pending) e = cudaStreamWaitEvent(st, ev_rest, 0);   // join st_aux
+    cudaEventDestroy(ev_panel);
+    cudaEventDestroy(ev_rest);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    *nlaunch = count;
+    return e;
+}
+
+static cudaError_t enqueue_back(long long n, int bw, long long lda, const double *d_AB, const double *d_linv,
+                                double *d_ysol, double *d_csol, const int *d_fail, cudaStream_t st,
+                                long long *nlaunch) {
+    const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    long long count = 0;
     for (long long kb = nblk - 1; kb >= 0; --kb) {
         const long long j0 = kb * SOLVE_NB;
         const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
@@ -689,8 +726,96 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         if (blocks < 1) blocks = 1;
         spl_backsolve_kernel<<<blocks, BACK_THREADS, 0, st>>>(d_AB, lda, j0, nb, bw, d_linv + kb * 4096, d_ysol,
                                                               d_csol, d_fail);
+        ++count;
+    }
+    *nlaunch = count;
+    return cudaGetLastError();
+}
+
+int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, double *d_g, double *d_work,
+                     double **d_coef_out, int *d_fail, cudaStream_t st, cudaStream_t st_aux, int nsm,
+                     cudaEvent_t *ev, void **cache) {
+    const long long n = gp.ncol;
+    const int bw = spl_half_bandwidth(gp);
+    const long long lda = spl_band_lda(bw);
+    const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    double *d_linv = d_work;
+    double *d_ysol = d_work + nblk * 4096;
+    double *d_csol = d_ysol + (n + 64);
+    *d_coef_out = d_csol;
+    (void)nsm;
+    const size_t syrk_smem = sizeof(double) * 2 * 64 * TILE_LD;
+    const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 128 + 64 + 64 + 64 * 64 + 512 + 2);
+    SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
+    SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
+
+    // (re)build the graphs when the buffers or the problem changed
+    SolveGraphs *sg = cache ? static_cast<SolveGraphs *>(*cache) : nullptr;
+    if (cache && (!sg || sg->key_AB != d_AB || sg->key_g != d_g || sg->n != n || sg->bw != bw)) {
+        spl_solve_cache_free(sg);
+        sg = new (std::nothrow) SolveGraphs();
+        *cache = sg;
+        if (sg) {
+            cudaGraph_t gr = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                const cudaError_t eq = enqueue_factor(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux,
+                                                      panel_smem, syrk_smem, &sg->nfactor);
+                e = cudaStreamEndCapture(st, &gr);
+                if (eq != cudaSuccess) e = eq;
+            }
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&sg->factor, gr, 0);
+            if (gr) cudaGraphDestroy(gr);
+            gr = nullptr;
+            if (e == cudaSuccess) e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                const cudaError_t eq = enqueue_back(n, bw, lda, d_AB, d_linv, d_ysol, d_csol, d_fail, st, &sg->nback);
+                e = cudaStreamEndCapture(st, &gr);
+                if (eq != cudaSuccess) e = eq;
+            }
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&sg->back, gr, 0);
+            if (gr) cudaGraphDestroy(gr);
+            if (e != cudaSuccess) {
+                fprintf(stderr, "splpak_b200: CUDA graph capture of the solve failed (%s); launching directly\n",
+                        cudaGetErrorString(e));
+                cudaGetLastError();
+                spl_solve_cache_free(sg);
+                sg = nullptr;
+                *cache = nullptr;
+            } else {
+                sg->key_AB = d_AB;
+                sg->key_g = d_g;
+                sg->n = n;
+                sg->bw = bw;
+            }
+        }
+    }
+
+    if (ev) cudaEventRecord(ev[0], st);
+    {
+        const long long total = n * (long long)(bw + 1);
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148LL * 32) blocks = 148LL * 32;
+        spl_expand_band_kernel<<<(unsigned)blocks, 256, 0, st>>>(gp, d_S, d_AB, lda, bw);
         ++g_spl_launches;
     }
+    if (ev) cudaEventRecord(ev[1], st);
+    long long nl = 0;
+    if (sg && sg->factor) {
+        SPL_CUDA_TRY(cudaGraphLaunch(sg->factor, st));
+        nl = sg->nfactor;
+    } else {
+        SPL_CUDA_TRY(enqueue_factor(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux, panel_smem, syrk_smem, &nl));
+    }
+    g_spl_launches += nl;
+    if (ev) cudaEventRecord(ev[2], st);
+    if (sg && sg->back) {
+        SPL_CUDA_TRY(cudaGraphLaunch(sg->back, st));
+        nl = sg->nback;
+    } else {
+        SPL_CUDA_TRY(enqueue_back(n, bw, lda, d_AB, d_linv, d_ysol, d_csol, d_fail, st, &nl));
+    }
+    g_spl_launches += nl;
     if (ev) cudaEventRecord(ev[3], st);
     SPL_CUDA_TRY(cudaGetLastError());
     return SPLPAK_OK;
