@@ -285,12 +285,12 @@ template <int NDIM> struct AccDerived {
     // staging tasks per point: one per dimension; in 4-D dimensions 3 and 4 share a task (it also
     // forms their 116 products, so no second staging phase is needed)
     static constexpr int NTASK = (NDIM == 4) ? 3 : NDIM;
-    static constexpr int TPT = (T::PB * NTASK + T::NT - 1) / T::NT;   // staging tasks per thread
+    static constexpr int NP = 192;                               // producer (gather + staging) threads
+    static constexpr int TPT = (T::PB * NTASK + NP - 1) / NP;    // staging tasks per producer thread
     static_assert(NGT <= T::LPG, "group too small");
     static_assert(APL * T::LPG == NRACC && APL >= 1 && APL <= 4, "rhs split");
     static_assert(OFF_H + NH <= T::RS, "record stride too small");
     static_assert(T::RS % 2 == 0 && (T::RS / 2) % 2 == 1, "record stride must be 2*odd");
-    static_assert(NW == 8, "warp de-phasing assumes 8 warps (two per scheduler)");
 };
 
 // G accumulator (outer tuple o = u*R + r, inner pair a) -> S
@@ -334,8 +334,24 @@ __device__ __forceinline__ void spl_flush_rhs(const GridParams &gp, const int *w
     atomicAdd(g + node, v);
 }
 
+// named barriers (id 0 is __syncthreads): FULL/EMPTY per staging buffer, one for the consumer warps
+#define ACC_BAR_FULL 1
+#define ACC_BAR_EMPTY 3
+#define ACC_BAR_CONS 5
+__device__ __forceinline__ void spl_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void spl_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Warp-specialised: threads [0, NT) are CONSUMERS (pure register-tiled DFMA stream over staged
+// points), threads [NT, NT + NP) are PRODUCERS (gather through the permutation, 1-D bases, per-point
+// factor tables into the double-buffered staging area).  The two meet only at named barriers
+// (producer: bar.arrive FULL / bar.sync EMPTY; consumer: bar.sync FULL / bar.arrive EMPTY), so the
+// latency-bound staging never stalls the FP64 stream.
 template <int NDIM>
-__global__ void __launch_bounds__(AccTraits<NDIM>::NT)
+__global__ void __launch_bounds__(AccTraits<NDIM>::NT + AccDerived<NDIM>::NP, 1)
 spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
                       const real_t *__restrict__ y, const real_t *__restrict__ w, int weighted,
                       const unsigned *__restrict__ perm, const unsigned *__restrict__ wincount,
@@ -344,7 +360,8 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
                       double *__restrict__ S, double *__restrict__ g) {
     using T = AccTraits<NDIM>;
     using D = AccDerived<NDIM>;
-    constexpr int R = T::R, RS = T::RS, PB = T::PB, NT = T::NT, TPT = D::TPT, APL = D::APL;
+    constexpr int R = T::R, RS = T::RS, PB = T::PB, NT = T::NT, NP = D::NP, TPT = D::TPT, APL = D::APL;
+    constexpr int NALL = NT + NP;
     constexpr int NTASK = D::NTASK;
     extern __shared__ __align__(16) double smem[];
     double *s_pts = smem;                       // 2 x PB x RS (double buffered)
@@ -356,10 +373,8 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
     const int warp = tid >> 5;
     const int grp = tid / T::LPG;
     const int u = tid % T::LPG;
-    // Two warps share a scheduler (warp % 4).  One of them stages the next batch BEFORE accumulating
-    // the current one, the other AFTER, so the latency-bound staging of one overlaps the FP64-bound
-    // accumulation of the other instead of every warp stalling in the same phase.
-    const bool stage_first = ((warp >> 2) & 1) == 0;
+    const bool is_prod = tid >= NT;
+    const int ptid = tid - NT;                  // producer thread index
 
     // per-lane constant offsets into a staged record.  The lane's R = 4 outer tuples o = 4u + r use
     // T2[(4u) % 10 .. +1], T2[(4u+2) % 10 .. +1] (two aligned 128-bit loads thanks to the cyclic copy)
@@ -379,7 +394,7 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
     int tp[TPT], tt[TPT];
 #pragma unroll
     for (int j = 0; j < TPT; ++j) {
-        const int idx = tid + j * NT;
+        const int idx = (is_prod ? ptid : 0) + j * NP;
         tp[j] = idx / NTASK;
         tt[j] = idx - tp[j] * NTASK;
     }
@@ -405,15 +420,6 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
                 k /= (unsigned)gp.nwin[d];
             }
         }
-
-        double acc[R][10];
-        double racc[APL];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int a = 0; a < 10; ++a) acc[r][a] = 0.0;
-#pragma unroll
-        for (int j = 0; j < APL; ++j) racc[j] = 0.0;
 
         // ---- software pipeline registers: permutation entries and gathered point data ----
         unsigned pi[TPT];
@@ -516,113 +522,112 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
                 }
             }
         };
-        // ---- accumulate batch b: group grp takes points grp, grp+NG, ... ----
-        auto accumulate = [&](int b) {
-            const int nb = min(PB, npts - b * PB);
-            const double *buf = s_pts + (b & 1) * (PB * RS);
+        if (is_prod) {
+            // ================= producers =================
+            load_perm(0);
+            load_data();
+            load_perm(1);
+            for (int b = 0; b < nbatch; ++b) {
+                if (b >= 2) spl_bar_sync(ACC_BAR_EMPTY + (b & 1), NALL);     // consumers are done with this buffer
+                stage(b);
+                spl_bar_arrive(ACC_BAR_FULL + (b & 1), NALL);
+                if (b + 1 < nbatch) load_data();                            // gathers one batch ahead
+                if (b + 2 < nbatch) load_perm(b + 2);                       // permutation two ahead
+            }
+        } else {
+            // ================= consumers =================
+            double acc[R][10];
+            double racc[APL];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int a = 0; a < 10; ++a) acc[r][a] = 0.0;
+#pragma unroll
+            for (int j = 0; j < APL; ++j) racc[j] = 0.0;
+            // group grp takes points grp, grp+NG, ... of the batch
+            for (int b = 0; b < nbatch; ++b) {
+                spl_bar_sync(ACC_BAR_FULL + (b & 1), NALL);
+                const int nb = min(PB, npts - b * PB);
+                const double *buf = s_pts + (b & 1) * (PB * RS);
 #pragma unroll 2
-            for (int p = grp; p < nb; p += D::NG) {
-                const double *rec = buf + p * RS;
-                double in[10];
+                for (int p = grp; p < nb; p += D::NG) {
+                    const double *rec = buf + p * RS;
+                    double in[10];
 #pragma unroll
-                for (int a = 0; a < 10; a += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(rec + D::OFF_I + a);
-                    in[a] = v.x;
-                    in[a + 1] = v.y;
+                    for (int a = 0; a < 10; a += 2) {
+                        const double2 v = *reinterpret_cast<const double2 *>(rec + D::OFF_I + a);
+                        in[a] = v.x;
+                        in[a + 1] = v.y;
+                    }
+                    double P[R];
+                    if constexpr (NDIM == 1) {
+                        P[0] = rec[D::OFF_H];
+                    } else {
+                        const double2 ta = *reinterpret_cast<const double2 *>(rec + offT);
+                        const double2 tb = *reinterpret_cast<const double2 *>(rec + offT + 2);
+                        const double ha = rec[offHa], hb = rec[offHb];
+                        P[0] = ha * ta.x;
+                        P[1] = ha * ta.y;
+                        P[2] = hb * tb.x;
+                        P[3] = hb * tb.y;
+                    }
+                    // right-hand side of the same point: APL accumulators per lane
+                    double t = rec[offRH];
+                    if (NDIM >= 2) t *= rec[offRT];
+#pragma unroll
+                    for (int j = 0; j < APL; ++j) racc[j] = fma(t, rec[offRI + j], racc[j]);
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int a = 0; a < 10; ++a) acc[r][a] = fma(P[r], in[a], acc[r][a]);
                 }
-                double P[R];
-                if constexpr (NDIM == 1) {
-                    P[0] = rec[D::OFF_H];
-                } else {
-                    const double2 ta = *reinterpret_cast<const double2 *>(rec + offT);
-                    const double2 tb = *reinterpret_cast<const double2 *>(rec + offT + 2);
-                    const double ha = rec[offHa], hb = rec[offHb];
-                    P[0] = ha * ta.x;
-                    P[1] = ha * ta.y;
-                    P[2] = hb * tb.x;
-                    P[3] = hb * tb.y;
-                }
-                // right-hand side of the same point: APL accumulators per lane
-                double t = rec[offRH];
-                if (NDIM >= 2) t *= rec[offRT];
-#pragma unroll
-                for (int j = 0; j < APL; ++j) racc[j] = fma(t, rec[offRI + j], racc[j]);
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int a = 0; a < 10; ++a) acc[r][a] = fma(P[r], in[a], acc[r][a]);
+                if (b + 2 < nbatch) spl_bar_arrive(ACC_BAR_EMPTY + (b & 1), NALL);
             }
-        };
-        // stage batch b+1 and keep the gathers (one batch ahead) / permutation loads (two ahead) going
-        auto advance = [&](int b) {
-            if (b + 1 < nbatch) {
-                stage(b + 1);
-                if (b + 2 < nbatch) load_data();
-                if (b + 3 < nbatch) load_perm(b + 3);
-            }
-        };
 
-        load_perm(0);
-        load_data();
-        load_perm(1);
-        stage(0);
-        if (1 < nbatch) load_data();
-        if (2 < nbatch) load_perm(2);
-        __syncthreads();
-        for (int b = 0; b < nbatch; ++b) {
-            if (stage_first) {
-                advance(b);
-                accumulate(b);
-            } else {
-                accumulate(b);
-                advance(b);
-            }
-            __syncthreads();
-        }
-
-        // ---- reduce the K-split groups and flush once per work item ----
-        if (T::LPG < 32) {
+            // ---- reduce the K-split groups and flush once per work item ----
+            if (T::LPG < 32) {
 #pragma unroll
-            for (int off = T::LPG; off < 32; off <<= 1) {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int a = 0; a < 10; ++a)
-                        acc[r][a] += __shfl_xor_sync(0xffffffffu, acc[r][a], off);
-#pragma unroll
-                for (int j = 0; j < APL; ++j) racc[j] += __shfl_xor_sync(0xffffffffu, racc[j], off);
-            }
-        }
-        if (D::NG > 1) {
-            constexpr int PER = R * 10 + APL;   // values per lane
-            for (int w2_ = 0; w2_ < D::NW; ++w2_) {
-                if (warp == w2_ && lane < D::LPGW) {
-                    double *dst = s_red + lane * PER;       // lane == u for the first group of the warp
+                for (int off = T::LPG; off < 32; off <<= 1) {
 #pragma unroll
                     for (int r = 0; r < R; ++r)
 #pragma unroll
                         for (int a = 0; a < 10; ++a)
-                            dst[r * 10 + a] = (w2_ == 0 ? 0.0 : dst[r * 10 + a]) + acc[r][a];
+                            acc[r][a] += __shfl_xor_sync(0xffffffffu, acc[r][a], off);
 #pragma unroll
-                    for (int j = 0; j < APL; ++j)
-                        dst[R * 10 + j] = (w2_ == 0 ? 0.0 : dst[R * 10 + j]) + racc[j];
+                    for (int j = 0; j < APL; ++j) racc[j] += __shfl_xor_sync(0xffffffffu, racc[j], off);
                 }
-                __syncthreads();
             }
-            for (int idx = tid; idx < D::LPGW * PER; idx += NT) {
-                const int ul = idx / PER;
-                const int k = idx - ul * PER;
-                const double v = s_red[idx];
-                if (k < R * 10) spl_flush_g<NDIM>(gp, ws, ul, k / 10, k % 10, v, S);
-                else spl_flush_rhs<NDIM>(gp, ws, ul * APL + (k - R * 10), v, g);
+            if (D::NG > 1) {
+                constexpr int PER = R * 10 + APL;   // values per lane
+                for (int w2_ = 0; w2_ < D::NW; ++w2_) {
+                    if (warp == w2_ && lane < D::LPGW) {
+                        double *dst = s_red + lane * PER;       // lane == u for the first group of the warp
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+#pragma unroll
+                            for (int a = 0; a < 10; ++a)
+                                dst[r * 10 + a] = (w2_ == 0 ? 0.0 : dst[r * 10 + a]) + acc[r][a];
+#pragma unroll
+                        for (int j = 0; j < APL; ++j)
+                            dst[R * 10 + j] = (w2_ == 0 ? 0.0 : dst[R * 10 + j]) + racc[j];
+                    }
+                    spl_bar_sync(ACC_BAR_CONS, NT);
+                }
+                for (int idx = tid; idx < D::LPGW * PER; idx += NT) {
+                    const int ul = idx / PER;
+                    const int k = idx - ul * PER;
+                    const double v = s_red[idx];
+                    if (k < R * 10) spl_flush_g<NDIM>(gp, ws, ul, k / 10, k % 10, v, S);
+                    else spl_flush_rhs<NDIM>(gp, ws, ul * APL + (k - R * 10), v, g);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int a = 0; a < 10; ++a) spl_flush_g<NDIM>(gp, ws, u, r, a, acc[r][a], S);
+#pragma unroll
+                for (int j = 0; j < APL; ++j) spl_flush_rhs<NDIM>(gp, ws, u * APL + j, racc[j], g);
             }
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int a = 0; a < 10; ++a) spl_flush_g<NDIM>(gp, ws, u, r, a, acc[r][a], S);
-#pragma unroll
-            for (int j = 0; j < APL; ++j) spl_flush_rhs<NDIM>(gp, ws, u * APL + j, racc[j], g);
         }
     }
 }
@@ -687,12 +692,12 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
     auto kern = spl_accumulate_kernel<NDIM>;
     SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    SPL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T::NT, smem));
+    SPL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T::NT + D::NP, smem));
     if (per_sm < 1) per_sm = 1;
     long long agrid = (long long)nsm * per_sm;
     const long long max_items = gp.nwindows + n / T::CH + 1;
     if (agrid > max_items) agrid = max_items;
-    kern<<<(unsigned)agrid, T::NT, smem, st>>>(gp, d_x, l1x, d_y, d_w, weighted, sc.perm, sc.wincount,
+    kern<<<(unsigned)agrid, T::NT + D::NP, smem, st>>>(gp, d_x, l1x, d_y, d_w, weighted, sc.perm, sc.wincount,
                                                sc.winstart, sc.item_win, sc.item_seg, sc.meta, d_S, d_g);
     if (ev) cudaEventRecord(ev[3], st);
     g_spl_launches += 5;
