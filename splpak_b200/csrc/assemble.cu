@@ -264,7 +264,7 @@ template <int NDIM> struct AccTraits;
 //     points start 4 banks apart and the staging stores of neighbouring points do not collide.
 template <> struct AccTraits<1> { static constexpr int R = 1, LPG = 1,   NT = 256, PB = 256, CH = 16384, RS = 18;  };
 template <> struct AccTraits<2> { static constexpr int R = 4, LPG = 4,   NT = 256, PB = 256, CH = 8192,  RS = 34;  };
-template <> struct AccTraits<3> { static constexpr int R = 4, LPG = 32,  NT = 256, PB = 256, CH = 8192,  RS = 46;  };
+template <> struct AccTraits<3> { static constexpr int R = 4, LPG = 32,  NT = 256, PB = 256, CH = 16384, RS = 46;  };
 template <> struct AccTraits<4> { static constexpr int R = 4, LPG = 256, NT = 256, PB = 72,  CH = 4096,  RS = 150; };
 
 template <int NDIM> struct AccDerived {
@@ -285,7 +285,7 @@ template <int NDIM> struct AccDerived {
     // staging tasks per point: one per dimension; in 4-D dimensions 3 and 4 share a task (it also
     // forms their 116 products, so no second staging phase is needed)
     static constexpr int NTASK = (NDIM == 4) ? 3 : NDIM;
-    static constexpr int NP = 192;                               // producer (gather + staging) threads
+    static constexpr int NP = 128;                               // producer (gather + staging) threads
     static constexpr int TPT = (T::PB * NTASK + NP - 1) / NP;    // staging tasks per producer thread
     static_assert(NGT <= T::LPG, "group too small");
     static_assert(APL * T::LPG == NRACC && APL >= 1 && APL <= 4, "rhs split");
