@@ -41,6 +41,16 @@ NCOL = 24 ** 3
 WORKLOAD = "cfg3: 3-D splcw weighted fit, 1e8 points/GPU on 24^3 nodes (xtrap=1) + splfe at 1e9 points/GPU, real64"
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the two dominant kernels, from the committed
+    `ncu --set full` capture of this same command (profiles/r01_traffic.json, written by scripts/gpu_profile.sh)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -67,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i",
                  str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -358,21 +368,32 @@ def run_ours(args):
         acc_ms = stage_ms.get("accumulate", 0.0)
         eval_bytes = nq * (NDIM + 1) * 8
         asm_bytes = npts * (NDIM + 2) * 8
+        traffic = load_traffic()
+
+        def traffic_for(kernel, units):
+            t = traffic.get(kernel)
+            # the capture is per launch at t["units"] units (points or queries); DRAM traffic is linear in them
+            return None if not t else t["dram_bytes"] * (units / t["units"])
+
         eval_roof = {"kernel": "spl_eval_kernel<3,smem>", "bound": "hbm", "achieved": eval_bytes / (eval_ms * 1e-3) / 1e9,
-                     "peak": hbm_peak, "unit": "GB/s", "traffic": None}
+                     "peak": hbm_peak, "unit": "GB/s", "traffic": traffic_for("spl_eval_kernel<3>", nq),
+                     "algorithmic_bytes": eval_bytes,
+                     "note": "uniform-random 3-D real64 queries are bound by the shared-memory gather (64 x 8 B per "
+                             "query, ~3-way bank conflicts) and the FP64 pipe, not by HBM: DESIGN.md 4.5"}
         eval_roof["frac"] = eval_roof["achieved"] / hbm_peak
         # accumulate: 1000 G + 64 rhs FMAs per point actually needed (Kronecker-symmetric form), flops = 2*FMA
         acc_flops = npts * 2.0 * (1000 + 64)
         acc_roof = {"kernel": "spl_accumulate_kernel<3>", "bound": "fp64", "unit": "TFLOP/s",
                     "achieved": acc_flops / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None,
                     "peak": dfma_tf, "peak_source": "DFMA micro-benchmark in this run (splpak_b200_measure_peaks)",
+                    "traffic": traffic_for("spl_accumulate_kernel<3>", npts), "algorithmic_bytes": asm_bytes,
                     "hbm_achieved_gbs": asm_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
                     "hbm_frac": (asm_bytes / (acc_ms * 1e-3) / 1e9) / hbm_peak if acc_ms > 0 else None}
         if acc_roof["achieved"] and dfma_tf:
             acc_roof["frac"] = acc_roof["achieved"] / dfma_tf
         dominant = eval_roof if eval_ms >= acc_ms else {
             "kernel": acc_roof["kernel"], "bound": "hbm", "achieved": acc_roof["hbm_achieved_gbs"], "peak": hbm_peak,
-            "unit": "GB/s", "frac": acc_roof["hbm_frac"], "traffic": None,
+            "unit": "GB/s", "frac": acc_roof["hbm_frac"], "traffic": acc_roof["traffic"],
             "note": "FP64-pipe-bound kernel; see roofline_fp64 for the binding roof"}
         dominant = dict(dominant)
         dominant["peak_source"] = peak_src

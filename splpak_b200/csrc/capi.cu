@@ -164,6 +164,32 @@ extern "C" const char *splpak_b200_strerror(int code, int evaluation) {
 // ------------------------------------------------------------------------------------------
 // evaluation
 // ------------------------------------------------------------------------------------------
+static cudaMemPool_t eval_scratch_pool(int device) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {nullptr};
+    static bool tried[64] = {false};
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!tried[device]) {
+        tried[device] = true;
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t p = nullptr;
+        if (cudaMemPoolCreate(&p, &props) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
+            pools[device] = p;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    return pools[device];
+}
+
 #define EVAL_COUNTERS 1024
 static unsigned long long *eval_counter_slot(int device) {
     static std::mutex mu;
@@ -191,7 +217,11 @@ static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const in
     if (direct) {
         coef64 = reinterpret_cast<const double *>(d_coef);
     } else {
-        SPL_CUDA_TRY(cudaMallocAsync((void **)&tmp, sizeof(double) * npad, st));
+        // stream-ordered scratch from a private pool that keeps its memory across synchronisations (the
+        // default pool hands everything back to the driver at every sync: ~1 ms per call to get it again)
+        cudaMemPool_t pool = eval_scratch_pool(di.dev);
+        if (pool) SPL_CUDA_TRY(cudaMallocFromPoolAsync((void **)&tmp, sizeof(double) * npad, pool, st));
+        else SPL_CUDA_TRY(cudaMallocAsync((void **)&tmp, sizeof(double) * npad, st));
         spl_to_double_kernel<<<spl_div_up(npad, 256), 256, 0, st>>>(d_coef, tmp, gp.ncol, npad);
         ++g_spl_launches;
         coef64 = tmp;
