@@ -153,6 +153,27 @@ int splpak_b200_fit_compute(splpak_b200_fit_t h, splpak_real *coef, int64_t ncf,
 int splpak_b200_fit_compute_device(splpak_b200_fit_t h, splpak_real *d_coef, int64_t ncf,
                                    int64_t nwrk, int *ierror);
 
+/* Refinement by corrected semi-normal equations -- (new) no counterpart in the reference, whose orthogonal
+ * solver (suprls, src/splpak.F90:1375-1695) does not need it.  The Cholesky solve works at cond(G) =
+ * cond(A)^2; when derivative-constraint rows fire (xtrap != 0 and data holes) that is what separates its
+ * coefficients from suprls's.  One step = a second pass over THE SAME points (any chunking), residuals formed row by
+ * row, one more solve with the same G:
+ *     fit_compute -> [fit_refine_begin -> fit_refine_add_points* -> (all-reduce fit_rhs_buffer across ranks)
+ *                     -> fit_refine_compute] x k
+ * splpak_b200_splcw / splcc run two steps automatically when constraint rows fired.  A no-op in the REAL32 library. */
+int splpak_b200_fit_refine_begin(splpak_b200_fit_t h);
+int splpak_b200_fit_refine_add_points(splpak_b200_fit_t h, const splpak_real *x, int l1x,
+                                      const splpak_real *y, const splpak_real *w, int weighted, int64_t n);
+int splpak_b200_fit_refine_add_points_device(splpak_b200_fit_t h, const splpak_real *d_x, int l1x,
+                                             const splpak_real *d_y, const splpak_real *d_w, int weighted,
+                                             int64_t n);
+int splpak_b200_fit_refine_compute(splpak_b200_fit_t h, splpak_real *coef, int64_t ncf, int *ierror);
+int splpak_b200_fit_refine_compute_device(splpak_b200_fit_t h, splpak_real *d_coef, int64_t ncf, int *ierror);
+/* 1 if the last fit_compute added derivative-constraint rows (the regime where refinement pays). */
+int splpak_b200_fit_constraints_fired(splpak_b200_fit_t h);
+/* The right-hand-side slice (ncol float64) of the partial buffer: what a multi-GPU refinement step sums. */
+int splpak_b200_fit_rhs_buffer(splpak_b200_fit_t h, void **d_ptr, int64_t *count);
+
 /* Start a new fit on the same grid (zeroes the partial sums). */
 int splpak_b200_fit_reset(splpak_b200_fit_t h);
 /* cudaStream_t (as void*) the handle launches on. */

@@ -32,6 +32,13 @@ SYMBOLS = [
     "splpak_b200_fit_allreduce",
     "splpak_b200_fit_compute",
     "splpak_b200_fit_compute_device",
+    "splpak_b200_fit_refine_begin",
+    "splpak_b200_fit_refine_add_points",
+    "splpak_b200_fit_refine_add_points_device",
+    "splpak_b200_fit_refine_compute",
+    "splpak_b200_fit_refine_compute_device",
+    "splpak_b200_fit_constraints_fired",
+    "splpak_b200_fit_rhs_buffer",
     "splpak_b200_fit_reset",
     "splpak_b200_fit_stream",
     "splpak_b200_fit_timings",
@@ -103,6 +110,13 @@ def load(real32: bool = False) -> C.CDLL:
         "splpak_b200_fit_allreduce": (C.c_int, [vp, vp]),
         "splpak_b200_fit_compute": (C.c_int, [vp, vp, i64, i64, ip]),
         "splpak_b200_fit_compute_device": (C.c_int, [vp, vp, i64, i64, ip]),
+        "splpak_b200_fit_refine_begin": (C.c_int, [vp]),
+        "splpak_b200_fit_refine_add_points": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, i64]),
+        "splpak_b200_fit_refine_add_points_device": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, i64]),
+        "splpak_b200_fit_refine_compute": (C.c_int, [vp, vp, i64, ip]),
+        "splpak_b200_fit_refine_compute_device": (C.c_int, [vp, vp, i64, ip]),
+        "splpak_b200_fit_constraints_fired": (C.c_int, [vp]),
+        "splpak_b200_fit_rhs_buffer": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "splpak_b200_fit_reset": (C.c_int, [vp]),
         "splpak_b200_fit_stream": (vp, [vp]),
         "splpak_b200_fit_timings": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),

@@ -295,6 +295,67 @@ class FitHandle:
         self.lib.splpak_b200_fit_compute_device(self.h, _dev_ptr(d_coef), ncf, int(nwrk), C.byref(ierr))
         return ierr.value
 
+    def refine(self, x, y, w=None, weighted=None, steps=1):
+        """Corrected-semi-normal-equations refinement with the same HOST points (after compute).
+        Returns (coef, ierror)."""
+        self._check()
+        xa = np.ascontiguousarray(x, dtype=self.dt)
+        if xa.ndim == 1:
+            xa = xa.reshape(-1, 1)
+        ya = _vec(y, self.dt)
+        wa = _vec(w, self.dt) if w is not None else None
+        if weighted is None:
+            weighted = wa is not None and wa.size > 0 and wa[0] >= 0
+        coef = np.zeros(self.ncol, dtype=self.dt)
+        ierr = C.c_int(0)
+        for _ in range(steps):
+            rc = self.lib.splpak_b200_fit_refine_begin(self.h)
+            if rc == 0:
+                rc = self.lib.splpak_b200_fit_refine_add_points(self.h, _ptr(xa), xa.shape[1], _ptr(ya),
+                                                                _ptr(wa) if wa is not None else None,
+                                                                int(bool(weighted)), xa.shape[0])
+            if rc != 0:
+                return coef, rc
+            self.lib.splpak_b200_fit_refine_compute(self.h, _ptr(coef), self.ncol, C.byref(ierr))
+            if ierr.value != 0:
+                break
+        return coef, ierr.value
+
+    def refine_device(self, d_x, l1x, d_y, d_w, n, d_coef, weighted=True, allreduce=None):
+        """One refinement step with DEVICE points; `allreduce` (optional callable) is applied to the right-hand
+        side tensor between the residual pass and the solve (multi-GPU)."""
+        self._check()
+        rc = self.lib.splpak_b200_fit_refine_begin(self.h)
+        if rc != 0:
+            return rc
+        rc = self.lib.splpak_b200_fit_refine_add_points_device(self.h, _dev_ptr(d_x), int(l1x), _dev_ptr(d_y),
+                                                               _dev_ptr(d_w), int(bool(weighted and d_w is not None)),
+                                                               int(n))
+        if rc != 0:
+            return rc
+        if allreduce is not None:
+            allreduce(self.rhs_tensor())
+        ierr = C.c_int(0)
+        self.lib.splpak_b200_fit_refine_compute_device(self.h, _dev_ptr(d_coef), self.ncol, C.byref(ierr))
+        return ierr.value
+
+    def rhs_tensor(self):
+        import torch
+
+        p = C.c_void_p()
+        n = C.c_int64(0)
+        self.lib.splpak_b200_fit_rhs_buffer(self.h, C.byref(p), C.byref(n))
+        ptr, cnt = p.value, n.value
+
+        class _Wrap:
+            __cuda_array_interface__ = {"shape": (cnt,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+        return torch.as_tensor(_Wrap(), device=torch.device("cuda", torch.cuda.current_device()))
+
+    def constraints_fired(self):
+        self._check()
+        return bool(self.lib.splpak_b200_fit_constraints_fired(self.h))
+
     def reset(self):
         self._check()
         return self.lib.splpak_b200_fit_reset(self.h)

@@ -350,7 +350,9 @@ __device__ __forceinline__ void spl_bar_arrive(int id, int nthreads) {
 // factor tables into the double-buffered staging area).  The two meet only at named barriers
 // (producer: bar.arrive FULL / bar.sync EMPTY; consumer: bar.sync FULL / bar.arrive EMPTY), so the
 // latency-bound staging never stalls the FP64 stream.
-template <int NDIM>
+// RHS_ONLY: only g = sum (w phi)(w y) is accumulated (the refinement pass of capi.cu re-assembles the
+// right-hand side from residuals; G is already there).
+template <int NDIM, bool RHS_ONLY>
 __global__ void __launch_bounds__(AccTraits<NDIM>::NT + AccDerived<NDIM>::NP, 1)
 spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
                       const real_t *__restrict__ y, const real_t *__restrict__ w, int weighted,
@@ -576,10 +578,12 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
                     if (NDIM >= 2) t *= rec[offRT];
 #pragma unroll
                     for (int j = 0; j < APL; ++j) racc[j] = fma(t, rec[offRI + j], racc[j]);
+                    if (!RHS_ONLY) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
+                        for (int r = 0; r < R; ++r)
 #pragma unroll
-                        for (int a = 0; a < 10; ++a) acc[r][a] = fma(P[r], in[a], acc[r][a]);
+                            for (int a = 0; a < 10; ++a) acc[r][a] = fma(P[r], in[a], acc[r][a]);
+                    }
                 }
                 if (b + 2 < nbatch) spl_bar_arrive(ACC_BAR_EMPTY + (b & 1), NALL);
             }
@@ -617,14 +621,17 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
                     const int ul = idx / PER;
                     const int k = idx - ul * PER;
                     const double v = s_red[idx];
-                    if (k < R * 10) spl_flush_g<NDIM>(gp, ws, ul, k / 10, k % 10, v, S);
-                    else spl_flush_rhs<NDIM>(gp, ws, ul * APL + (k - R * 10), v, g);
+                    if (k < R * 10) {
+                        if (!RHS_ONLY) spl_flush_g<NDIM>(gp, ws, ul, k / 10, k % 10, v, S);
+                    } else spl_flush_rhs<NDIM>(gp, ws, ul * APL + (k - R * 10), v, g);
                 }
             } else {
+                if (!RHS_ONLY) {
 #pragma unroll
-                for (int r = 0; r < R; ++r)
+                    for (int r = 0; r < R; ++r)
 #pragma unroll
-                    for (int a = 0; a < 10; ++a) spl_flush_g<NDIM>(gp, ws, u, r, a, acc[r][a], S);
+                        for (int a = 0; a < 10; ++a) spl_flush_g<NDIM>(gp, ws, u, r, a, acc[r][a], S);
+                }
 #pragma unroll
                 for (int j = 0; j < APL; ++j) spl_flush_rhs<NDIM>(gp, ws, u * APL + j, racc[j], g);
             }
@@ -652,7 +659,7 @@ int spl_acc_chunk_points(int ndim) {
 
 template <int NDIM>
 static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y,
-                            const real_t *d_w, int weighted, long long n, int do_hist,
+                            const real_t *d_w, int weighted, long long n, int do_hist, int rhs_only,
                             const AssembleScratch &sc, double *d_S, double *d_g, double *d_cnt,
                             double *d_totals, cudaStream_t st, int nsm, cudaEvent_t *ev) {
     using T = AccTraits<NDIM>;
@@ -689,7 +696,7 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
                                                                    (unsigned)T::CH, sc.item_win, sc.item_seg);
     if (ev) cudaEventRecord(ev[2], st);
     const size_t smem = sizeof(double) * (2 * (size_t)T::PB * T::RS + (size_t)D::LPGW * (T::R * 10 + D::APL));
-    auto kern = spl_accumulate_kernel<NDIM>;
+    auto kern = rhs_only ? spl_accumulate_kernel<NDIM, true> : spl_accumulate_kernel<NDIM, false>;
     SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     SPL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T::NT + D::NP, smem));
@@ -706,14 +713,14 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
 }
 
 int spl_assemble_chunk(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y,
-                       const real_t *d_w, int weighted, long long n, int do_hist,
+                       const real_t *d_w, int weighted, long long n, int do_hist, int rhs_only,
                        const AssembleScratch &sc, double *d_S, double *d_g, double *d_cnt,
                        double *d_totals, cudaStream_t st, int nsm, cudaEvent_t *ev) {
     switch (gp.ndim) {
-    case 1: return assemble_chunk_t<1>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
-    case 2: return assemble_chunk_t<2>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
-    case 3: return assemble_chunk_t<3>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
-    case 4: return assemble_chunk_t<4>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 1: return assemble_chunk_t<1>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 2: return assemble_chunk_t<2>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 3: return assemble_chunk_t<3>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 4: return assemble_chunk_t<4>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
     }
     return SPLPAK_ERR_NDIM;
 }

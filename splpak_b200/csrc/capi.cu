@@ -22,7 +22,7 @@ int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, 
                     int nsm, size_t smem_optin, unsigned long long *d_counter);
 int spl_acc_chunk_points(int ndim);
 int spl_assemble_chunk(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y,
-                       const real_t *d_w, int weighted, long long n, int do_hist,
+                       const real_t *d_w, int weighted, long long n, int do_hist, int rhs_only,
                        const AssembleScratch &sc, double *d_S, double *d_g, double *d_cnt,
                        double *d_totals, cudaStream_t st, int nsm, cudaEvent_t *ev);
 int spl_constraints_launch(const GridParams &gp, double xtrap, const double *d_cnt,
@@ -35,6 +35,9 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
                      double **d_coef_out, int *d_fail, cudaStream_t st, cudaStream_t st_aux, int nsm, cudaEvent_t *ev,
                      void **cache);
 void spl_solve_cache_free(void *cache);
+int spl_constraints_residual_launch(const GridParams &gp, double xtrap, const double *d_cnt,
+                                    const double *d_totals_in, const double *d_coef, double *d_g,
+                                    cudaStream_t st, int nsm);
 int spl_measure_peaks_impl(double *out, int n);
 
 // ------------------------------------------------------------------------------------------
@@ -46,6 +49,16 @@ __global__ void spl_to_double_kernel(const real_t *__restrict__ in, double *__re
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += stride)
         out[i] = (i < n) ? (double)in[i] : 0.0;
 }
+// residual of a chunk, in place: r[i] = y[i] - r[i]   (r holds the spline values on entry)
+__global__ void spl_residual_kernel(const real_t *__restrict__ y, real_t *__restrict__ r, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) r[i] = (real_t)((double)y[i] - (double)r[i]);
+}
+__global__ void spl_axpy_kernel(double *__restrict__ c, const double *__restrict__ d, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) c[i] += d[i];
+}
+
 __global__ void spl_from_double_kernel(const double *__restrict__ in, real_t *__restrict__ out,
                                        long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -349,6 +362,7 @@ extern "C" real_t splpak_b200_splfe(int ndim, const real_t *x, const real_t *coe
 // streaming fit handle
 // ------------------------------------------------------------------------------------------
 #define FIT_MAGIC 0x53504c42u
+#define SPLPAK_REFINE_STEPS 2
 #define NTIMER 7
 
 struct splpak_b200_fit_s {
@@ -372,6 +386,14 @@ struct splpak_b200_fit_s {
     long long ab_elems;
     int *d_fail;
     void *solve_cache;            // CUDA graphs of the factor / back-substitution loops (solve.cu)
+    // refinement (corrected semi-normal equations): current solution, residual scratch
+    double *d_coef64;             // ncol: solution of the last compute / refine step
+    real_t *d_res;                // residuals y - s(x) of the chunk being re-assembled
+    long long res_cap;
+    double *d_dummy_tot;          // classify's row/weight totals of refinement passes (discarded)
+    int solved;                   // compute succeeded: d_coef64 is valid
+    int refining;
+    int constraints_fired;        // derivative-constraint rows were added by compute
     // timing: accumulated event pairs
     double ms[NTIMER];
     cudaEvent_t ev[8];
@@ -403,6 +425,9 @@ static void free_handle(splpak_b200_fit_t h) {
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     if (h->st) cudaStreamDestroy(h->st);
     if (h->solve_cache) spl_solve_cache_free(h->solve_cache);
+    if (h->d_coef64) cudaFree(h->d_coef64);
+    if (h->d_res) cudaFree(h->d_res);
+    if (h->d_dummy_tot) cudaFree(h->d_dummy_tot);
     if (h->st_copy) cudaStreamDestroy(h->st_copy);
     if (h->st_aux) cudaStreamDestroy(h->st_aux);
     h->magic = 0;
@@ -444,6 +469,8 @@ extern "C" int splpak_b200_fit_create(int ndim, const real_t *xmin, const real_t
     h->n_part = gp.ncol * gp.nsten + gp.ncol + gp.ncol + 2;
     ok = ok && cudaMalloc((void **)&h->d_part, sizeof(double) * (size_t)h->n_part) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&h->d_fail, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&h->d_coef64, sizeof(double) * (size_t)(gp.ncol + 2)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&h->d_dummy_tot, sizeof(double) * 2) == cudaSuccess;
     for (int k = 0; k < 8 && ok; ++k) ok = cudaEventCreate(&h->ev[k]) == cudaSuccess;
     for (int k = 0; k < 2 && ok; ++k) {
         ok = ok && cudaEventCreateWithFlags(&h->ev_stage_in[k], cudaEventDisableTiming) == cudaSuccess;
@@ -475,6 +502,7 @@ extern "C" int splpak_b200_fit_reset(splpak_b200_fit_t h) {
     h->finalized = 0;
     h->timers_pending = 0;
     h->total_points = 0;
+    h->solved = h->refining = h->constraints_fired = 0;
     return SPLPAK_OK;
 }
 
@@ -520,7 +548,7 @@ static int add_device_chunk(splpak_b200_fit_t h, const real_t *d_x, int l1x, con
     int rc = ensure_scratch(h, n);
     if (rc != SPLPAK_OK) return rc;
     h->timers_pending = 1;
-    rc = spl_assemble_chunk(h->gp, d_x, l1x, d_y, d_w, weighted, n, h->xtrap != 0.0, h->sc, h->d_S,
+    rc = spl_assemble_chunk(h->gp, d_x, l1x, d_y, d_w, weighted, n, h->xtrap != 0.0, 0, h->sc, h->d_S,
                             h->d_g, h->d_cnt, h->d_totals, h->st, h->di.nsm, h->ev);
     return rc;
 }
@@ -665,6 +693,11 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
         }
         h->ab_elems = need;
     }
+    double rows_before = 0.0;
+    if (h->xtrap != 0.0) {
+        SPL_CUDA_TRY(cudaMemcpyAsync(&rows_before, h->d_totals + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+        SPL_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     SPL_CUDA_TRY(cudaEventRecord(h->ev[4], st));
     if (h->xtrap != 0.0) {
         rc = spl_constraints_launch(gp, h->xtrap, h->d_cnt, h->d_totals, h->d_S, h->d_totals, st, h->di.nsm);
@@ -685,6 +718,7 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
     int fail = 0;
     double totals[2] = {0.0, 0.0};
     if (rc == SPLPAK_OK) {
+        SPL_CUDA_TRY(cudaMemcpyAsync(h->d_coef64, d_sol, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToDevice, st));
         if (coef_on_device) {
             spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(d_sol, coef, gp.ncol);
             ++g_spl_launches;
@@ -711,6 +745,8 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
         add_ms(h, 6, sev[2], sev[3]);
         // fewer rows than columns (suprls error 33, :1650) or a non-positive pivot -> 107
         if (fail || totals[1] < (double)gp.ncol) rc = SPLPAK_ERR_SOLVER;
+        h->solved = (rc == SPLPAK_OK);
+        h->constraints_fired = (h->xtrap != 0.0) && (totals[1] > rows_before);
     }
     for (int k = 0; k < 4; ++k) cudaEventDestroy(sev[k]);
     h->finalized = 1;
@@ -725,6 +761,161 @@ extern "C" int splpak_b200_fit_compute(splpak_b200_fit_t h, real_t *coef, int64_
 extern "C" int splpak_b200_fit_compute_device(splpak_b200_fit_t h, real_t *d_coef, int64_t ncf,
                                               int64_t nwrk, int *ierror) {
     return fit_compute_impl(h, d_coef, 1, ncf, nwrk, ierror);
+}
+
+// ------------------------------------------------------------------------------------------
+// refinement: corrected semi-normal equations (Bjorck 1987).  The Cholesky solve of G c = g loses
+// eps*cond(G) = eps*cond(A)^2, which is what separates it from the reference's QR (suprls) when
+// derivative-constraint rows with weights ~dxin^2 sit next to O(1) data rows.  One step
+//     r = b - A c  (row by row: data rows through a second pass over the points, constraint rows from the
+//                   node histogram),   G dc = A^T r  (same factorisation),   c += dc
+// recovers the accuracy of the orthogonal method as long as eps*cond(G) < 1.
+// ------------------------------------------------------------------------------------------
+extern "C" int splpak_b200_fit_refine_begin(splpak_b200_fit_t h) {
+    if (!valid(h) || !h->finalized || !h->solved) return SPLPAK_ERR_HANDLE;
+    if (sizeof(real_t) != sizeof(double)) return SPLPAK_OK;            // fp32 I/O: nothing to gain
+    SPL_CUDA_TRY(cudaMemsetAsync(h->d_g, 0, sizeof(double) * (size_t)h->gp.ncol, h->st));
+    h->refining = 1;
+    return SPLPAK_OK;
+}
+
+static int refine_device_chunk(splpak_b200_fit_t h, const real_t *d_x, int l1x, const real_t *d_y,
+                               const real_t *d_w, int weighted, long long n) {
+    int rc = ensure_scratch(h, n);
+    if (rc != SPLPAK_OK) return rc;
+    if (n > h->res_cap) {
+        if (h->d_res) cudaFree(h->d_res);
+        h->d_res = nullptr;
+        h->res_cap = 0;
+        SPL_CUDA_TRY(cudaMalloc((void **)&h->d_res, sizeof(real_t) * (size_t)n));
+        h->res_cap = n;
+    }
+    // s(x_i) with the current coefficients, then r_i = y_i - s(x_i), then g += sum (w phi)(w r)
+    rc = eval_device_impl(h->gp, h->di, nullptr, d_x, l1x, n, reinterpret_cast<const real_t *>(h->d_coef64), h->d_res,
+                          h->st);
+    if (rc != SPLPAK_OK) return rc;
+    spl_residual_kernel<<<spl_div_up(n, 256), 256, 0, h->st>>>(d_y, h->d_res, n);
+    ++g_spl_launches;
+    return spl_assemble_chunk(h->gp, d_x, l1x, h->d_res, d_w, weighted, n, 0, 1, h->sc, h->d_S, h->d_g, h->d_cnt,
+                              h->d_dummy_tot, h->st, h->di.nsm, nullptr);
+}
+
+extern "C" int splpak_b200_fit_refine_add_points_device(splpak_b200_fit_t h, const real_t *d_x, int l1x,
+                                                        const real_t *d_y, const real_t *d_w, int weighted,
+                                                        int64_t n) {
+    if (!valid(h) || !h->refining) return SPLPAK_ERR_HANDLE;
+    if (sizeof(real_t) != sizeof(double) || n <= 0) return SPLPAK_OK;
+    if (l1x < h->gp.ndim) return SPLPAK_ERR_HANDLE;
+    if (!d_w) weighted = 0;
+    for (long long i0 = 0; i0 < n; i0 += DEVICE_CHUNK) {
+        const long long nc = (n - i0 < DEVICE_CHUNK) ? n - i0 : DEVICE_CHUNK;
+        int rc = refine_device_chunk(h, d_x + i0 * (long long)l1x, l1x, d_y + i0, weighted ? d_w + i0 : nullptr,
+                                     weighted, nc);
+        if (rc != SPLPAK_OK) return rc;
+    }
+    return SPLPAK_OK;
+}
+
+extern "C" int splpak_b200_fit_refine_add_points(splpak_b200_fit_t h, const real_t *x, int l1x,
+                                                 const real_t *y, const real_t *w, int weighted, int64_t n) {
+    if (!valid(h) || !h->refining) return SPLPAK_ERR_HANDLE;
+    if (sizeof(real_t) != sizeof(double) || n <= 0) return SPLPAK_OK;
+    if (l1x < h->gp.ndim) return SPLPAK_ERR_HANDLE;
+    if (!w) weighted = 0;
+    const long long chunk = n < HOST_CHUNK ? n : HOST_CHUNK;
+    if (chunk > h->stage_cap) return SPLPAK_ERR_HANDLE;                // the staging buffers of add_points are reused
+    int k = 0;
+    for (long long i0 = 0; i0 < n; i0 += chunk, k ^= 1) {
+        const long long nc = (n - i0 < chunk) ? n - i0 : chunk;
+        SPL_CUDA_TRY(cudaStreamWaitEvent(h->st_copy, h->ev_stage_free[k], 0));
+        SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][0], x + i0 * (long long)l1x, sizeof(real_t) * (size_t)nc * l1x,
+                                     cudaMemcpyHostToDevice, h->st_copy));
+        SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][1], y + i0, sizeof(real_t) * (size_t)nc, cudaMemcpyHostToDevice,
+                                     h->st_copy));
+        if (weighted)
+            SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][2], w + i0, sizeof(real_t) * (size_t)nc, cudaMemcpyHostToDevice,
+                                         h->st_copy));
+        SPL_CUDA_TRY(cudaEventRecord(h->ev_stage_in[k], h->st_copy));
+        SPL_CUDA_TRY(cudaStreamWaitEvent(h->st, h->ev_stage_in[k], 0));
+        int rc = refine_device_chunk(h, h->d_stage[k][0], l1x, h->d_stage[k][1], weighted ? h->d_stage[k][2] : nullptr,
+                                     weighted, nc);
+        if (rc != SPLPAK_OK) return rc;
+        SPL_CUDA_TRY(cudaEventRecord(h->ev_stage_free[k], h->st));
+    }
+    return SPLPAK_OK;
+}
+
+static int fit_refine_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_device, int64_t ncf, int *ierror) {
+    int rc = SPLPAK_OK;
+    if (!valid(h) || !h->refining) rc = SPLPAK_ERR_HANDLE;
+    else if (h->gp.ncol > ncf) rc = SPLPAK_ERR_NCF;
+    if (rc != SPLPAK_OK) {
+        if (ierror) *ierror = rc;
+        return rc;
+    }
+    const GridParams &gp = h->gp;
+    cudaStream_t st = h->st;
+    h->refining = 0;
+    if (sizeof(real_t) == sizeof(double)) {
+        if (h->xtrap != 0.0) {
+            rc = spl_constraints_residual_launch(gp, h->xtrap, h->d_cnt, h->d_totals, h->d_coef64, h->d_g, st, h->di.nsm);
+            if (rc != SPLPAK_OK) {
+                if (ierror) *ierror = rc;
+                return rc;
+            }
+        }
+        const int bw = spl_half_bandwidth(gp);
+        const long long lda = spl_band_lda(bw);
+        const long long band_elems = gp.ncol * (lda + 1) + 64;
+        const long long need = band_elems + spl_solve_workspace(gp);
+        if (need > h->ab_elems) rc = SPLPAK_ERR_HANDLE;               // compute allocated it
+        if (rc == SPLPAK_OK) {
+            SPL_CUDA_TRY(cudaMemsetAsync(h->d_AB, 0, sizeof(double) * (size_t)need, st));
+            SPL_CUDA_TRY(cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
+            double *d_sol = nullptr;
+            rc = spl_solve_launch(gp, h->d_S, h->d_AB, h->d_g, h->d_AB + band_elems, &d_sol, h->d_fail, st, h->st_aux,
+                                  h->di.nsm, nullptr, &h->solve_cache);
+            if (rc == SPLPAK_OK) {
+                spl_axpy_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(h->d_coef64, d_sol, gp.ncol);
+                ++g_spl_launches;
+            }
+        }
+    }
+    if (rc == SPLPAK_OK) {
+        int fail = 0;
+        SPL_CUDA_TRY(cudaMemcpyAsync(&fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (coef_on_device) {
+            spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(h->d_coef64, coef, gp.ncol);
+            ++g_spl_launches;
+        } else if (sizeof(real_t) == sizeof(double)) {
+            SPL_CUDA_TRY(cudaMemcpyAsync(coef, h->d_coef64, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
+        } else {
+            real_t *tmp = reinterpret_cast<real_t *>(h->d_AB);
+            spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(h->d_coef64, tmp, gp.ncol);
+            ++g_spl_launches;
+            SPL_CUDA_TRY(cudaMemcpyAsync(coef, tmp, sizeof(real_t) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
+        }
+        SPL_CUDA_TRY(cudaStreamSynchronize(st));
+        if (fail) rc = SPLPAK_ERR_SOLVER;
+    }
+    if (ierror) *ierror = rc;
+    return rc;
+}
+
+extern "C" int splpak_b200_fit_refine_compute(splpak_b200_fit_t h, real_t *coef, int64_t ncf, int *ierror) {
+    return fit_refine_compute_impl(h, coef, 0, ncf, ierror);
+}
+extern "C" int splpak_b200_fit_refine_compute_device(splpak_b200_fit_t h, real_t *d_coef, int64_t ncf, int *ierror) {
+    return fit_refine_compute_impl(h, d_coef, 1, ncf, ierror);
+}
+extern "C" int splpak_b200_fit_constraints_fired(splpak_b200_fit_t h) {
+    return valid(h) ? h->constraints_fired : 0;
+}
+extern "C" int splpak_b200_fit_rhs_buffer(splpak_b200_fit_t h, void **d_ptr, int64_t *count) {
+    if (!valid(h)) return SPLPAK_ERR_HANDLE;
+    if (d_ptr) *d_ptr = h->d_g;
+    if (count) *count = h->gp.ncol;
+    return SPLPAK_OK;
 }
 
 extern "C" void *splpak_b200_fit_stream(splpak_b200_fit_t h) { return valid(h) ? (void *)h->st : nullptr; }
@@ -791,6 +982,17 @@ extern "C" int splpak_b200_splcw(int ndim, const real_t *xdata, int l1xdat, cons
     rc = splpak_b200_fit_add_points(h, xdata, l1xdat, ydata, wdata, weighted, ndata);
     if (rc == SPLPAK_OK) rc = splpak_b200_fit_compute(h, coef, ncf, nwrk, ierror);
     else if (ierror) *ierror = rc;
+    // Data-sparse constraint rows fired: their weights make cond(G) = cond(A)^2 explode, so two refinement
+    // steps over the same (still valid) host arrays bring the coefficients back to the accuracy of the
+    // reference's orthogonal solver (see the refinement section above).
+    if (rc == SPLPAK_OK && sizeof(real_t) == sizeof(double) && splpak_b200_fit_constraints_fired(h)) {
+        for (int step = 0; step < SPLPAK_REFINE_STEPS && rc == SPLPAK_OK; ++step) {
+            rc = splpak_b200_fit_refine_begin(h);
+            if (rc == SPLPAK_OK) rc = splpak_b200_fit_refine_add_points(h, xdata, l1xdat, ydata, wdata, weighted, ndata);
+            if (rc == SPLPAK_OK) rc = splpak_b200_fit_refine_compute(h, coef, ncf, ierror);
+            else if (ierror) *ierror = rc;
+        }
+    }
     splpak_b200_fit_destroy(h);
     return rc;
 }

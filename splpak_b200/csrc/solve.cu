@@ -137,6 +137,136 @@ spl_constraints_kernel(const __grid_constant__ GridParams gp, double xtrap,
     }
 }
 
+// Refinement (capi.cu): the constraint rows' share of A^T (b - A c), i.e. -C^T (C c), computed ROW BY ROW
+// (v = row . c first, then g -= rowwt^2 * row * v) instead of through the formed C^T C, whose entries are
+// ~dxin^4 times larger than v and would cancel catastrophically.  Same node selection and row weights as
+// spl_constraints_kernel.
+template <int NDIM>
+__global__ void __launch_bounds__(128)
+spl_constraints_residual_kernel(const __grid_constant__ GridParams gp, double xtrap,
+                                const double *__restrict__ cnt, const double *__restrict__ totals_in,
+                                const double *__restrict__ coef, double *__restrict__ g) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const double spcrit = 0.75;
+    long long nrect = 1;
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) nrect *= (gp.nodes[d] - 1);
+    const double wtprrc = __ddiv_rn(totals_in[0], (double)nrect);
+    constexpr int NBOX = spl_ipow(3, NDIM);
+    constexpr int PER = (NBOX + 31) / 32;
+
+    for (long long node = warp_global; node < gp.ncol; node += nwarps) {
+        int in[NDIM];
+        {
+            long long k = node;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                in[d] = (int)(k % gp.nodes[d]);
+                k /= gp.nodes[d];
+            }
+        }
+        double expect = wtprrc;
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d)
+            if (in[d] == 0 || in[d] == gp.nodes[d] - 1) expect = spl_mul(0.5, expect);
+        const double have = cnt[node];
+        if (!(have < spl_mul(spcrit, expect))) continue;
+        const double dcwght = spl_mul(xtrap, spl_sub(expect, have));
+        int ibmn[NDIM], nbox[NDIM];
+        double xn[NDIM];
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) {
+            xn[d] = spl_add(gp.xmin[d], spl_mul((double)in[d], gp.dx[d]));
+            int lo = in[d] - 1, hi = in[d] + 1;
+            if (in[d] == 0) lo = 0;
+            if (in[d] == gp.nodes[d] - 1) hi = gp.nodes[d] - 1;
+            ibmn[d] = lo;
+            nbox[d] = hi - lo + 1;
+        }
+        for (int idm = 0; idm < NDIM; ++idm) {
+            for (int jdm = idm; jdm < NDIM; ++jdm) {
+                int nder[NDIM];
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) nder[d] = 0;
+                bool boundary = true;
+                double rowwt = spl_mul(2.0, dcwght);
+                if (jdm == idm) {
+                    rowwt = dcwght;
+                    nder[jdm] = 2;
+                    if (in[idm] != 0 && in[idm] != gp.nodes[idm] - 1) boundary = false;
+                }
+                if (boundary) {
+                    nder[idm] = 1;
+                    nder[jdm] = 1;
+                }
+                double phi[NDIM][3];
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        phi[d][k] = (k < nbox[d]) ? spl_bas1(ibmn[d] + k, gp.nodes[d], nder[d], xn[d],
+                                                             gp.xmin[d], gp.dx[d], gp.dxin[d])
+                                                  : 0.0;
+                // row entries owned by this lane: b[e], column nd[e]
+                double b[PER];
+                long long col[PER];
+                double v = 0.0;
+#pragma unroll
+                for (int e = 0; e < PER; ++e) {
+                    const int c = lane + 32 * e;
+                    b[e] = 0.0;
+                    col[e] = 0;
+                    if (c < NBOX) {
+                        int cc = c;
+                        double bv = 1.0;
+                        long long nd = 0, nstride = 1;
+                        bool ok = true;
+#pragma unroll
+                        for (int d = 0; d < NDIM; ++d) {
+                            const int k = cc % 3;
+                            cc /= 3;
+                            if (k >= nbox[d]) ok = false;
+                            bv *= phi[d][k];
+                            nd += (long long)(ibmn[d] + k) * nstride;
+                            nstride *= gp.nodes[d];
+                        }
+                        if (ok) {
+                            b[e] = bv;
+                            col[e] = nd;
+                            v = fma(bv, coef[nd], v);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                const double scale = -(rowwt * rowwt) * v;
+#pragma unroll
+                for (int e = 0; e < PER; ++e)
+                    if (b[e] != 0.0) atomicAdd(g + col[e], scale * b[e]);
+            }
+        }
+    }
+}
+
+int spl_constraints_residual_launch(const GridParams &gp, double xtrap, const double *d_cnt,
+                                    const double *d_totals_in, const double *d_coef, double *d_g,
+                                    cudaStream_t st, int nsm) {
+    long long blocks = (gp.ncol + 3) / 4;
+    if (blocks > (long long)nsm * 16) blocks = (long long)nsm * 16;
+    switch (gp.ndim) {
+    case 1: spl_constraints_residual_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_coef, d_g); break;
+    case 2: spl_constraints_residual_kernel<2><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_coef, d_g); break;
+    case 3: spl_constraints_residual_kernel<3><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_coef, d_g); break;
+    case 4: spl_constraints_residual_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_coef, d_g); break;
+    default: return SPLPAK_ERR_NDIM;
+    }
+    ++g_spl_launches;
+    SPL_CUDA_TRY(cudaGetLastError());
+    return SPLPAK_OK;
+}
+
 int spl_constraints_launch(const GridParams &gp, double xtrap, const double *d_cnt,
                            const double *d_totals_in, double *d_S, double *d_totals_out,
                            cudaStream_t st, int nsm) {
