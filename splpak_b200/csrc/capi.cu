@@ -267,6 +267,18 @@ extern "C" int splpak_b200_eval_device(int ndim, const real_t *d_x, int l1x, int
     return rc;
 }
 
+struct EvalHostCtx {
+    std::mutex mu;
+    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    real_t *d_coef = nullptr, *d_x[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
+    size_t coef_cap = 0, x_cap[2] = {0, 0}, out_cap[2] = {0, 0};
+};
+static EvalHostCtx &eval_host_ctx(int device) {
+    static EvalHostCtx ctx[64];
+    return ctx[(device >= 0 && device < 64) ? device : 0];
+}
+
 extern "C" int splpak_b200_eval(int ndim, const real_t *x, int l1x, int64_t nq, const int *nderiv,
                                 const real_t *coef, const real_t *xmin, const real_t *xmax,
                                 const int *nodes, real_t *out, int *ierror) {
@@ -283,59 +295,73 @@ extern "C" int splpak_b200_eval(int ndim, const real_t *x, int l1x, int64_t nq, 
         if (ierror) *ierror = rc;
         return rc;
     }
-    cudaStream_t st = nullptr, st2 = nullptr;
-    real_t *d_coef = nullptr, *d_x[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    auto cleanup = [&]() {
-        for (int k = 0; k < 2; ++k) {
-            if (d_x[k]) cudaFree(d_x[k]);
-            if (d_out[k]) cudaFree(d_out[k]);
-            if (ev_in[k]) cudaEventDestroy(ev_in[k]);
-            if (ev_done[k]) cudaEventDestroy(ev_done[k]);
-        }
-        if (d_coef) cudaFree(d_coef);
-        if (st) cudaStreamDestroy(st);
-        if (st2) cudaStreamDestroy(st2);
-    };
+    // Streams, events and device staging buffers of the host path are cached per device (grow-only) and
+    // the call holds the device's lock: creating and freeing ~270 MB of device memory per call made
+    // identical calls take anywhere between 52 and 900 ms.
+    EvalHostCtx &cx = eval_host_ctx(di.dev);
+    std::lock_guard<std::mutex> lk(cx.mu);
+    const long long chunk = nq < (1LL << 22) ? nq : (1LL << 22);
+    const int nbuf = nq > chunk ? 2 : 1;
 #define EV_TRY(expr)                                        \
     do {                                                    \
         if ((expr) != cudaSuccess) {                        \
             cudaGetLastError();                             \
-            cleanup();                                      \
             if (ierror) *ierror = SPLPAK_ERR_CUDA;          \
             return SPLPAK_ERR_CUDA;                         \
         }                                                   \
     } while (0)
-    EV_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    EV_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
-    // chunked, double-buffered: H2D of chunk k+1 (st2) overlaps the kernel + D2H of chunk k (st)
-    const long long chunk = nq < (1LL << 22) ? nq : (1LL << 22);
-    const int nbuf = nq > chunk ? 2 : 1;
-    EV_TRY(cudaMalloc((void **)&d_coef, sizeof(real_t) * (size_t)(gp.ncol + 2)));
-    for (int k = 0; k < nbuf; ++k) {
-        EV_TRY(cudaMalloc((void **)&d_x[k], sizeof(real_t) * (size_t)chunk * l1x));
-        EV_TRY(cudaMalloc((void **)&d_out[k], sizeof(real_t) * (size_t)chunk));
-        EV_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-        EV_TRY(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+    if (!cx.st) {
+        EV_TRY(cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking));
+        EV_TRY(cudaStreamCreateWithFlags(&cx.st2, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            EV_TRY(cudaEventCreateWithFlags(&cx.ev_in[k], cudaEventDisableTiming));
+            EV_TRY(cudaEventCreateWithFlags(&cx.ev_done[k], cudaEventDisableTiming));
+        }
     }
+    if ((size_t)(gp.ncol + 2) > cx.coef_cap) {
+        if (cx.d_coef) cudaFree(cx.d_coef);
+        cx.d_coef = nullptr;
+        cx.coef_cap = 0;
+        EV_TRY(cudaMalloc((void **)&cx.d_coef, sizeof(real_t) * (size_t)(gp.ncol + 2)));
+        cx.coef_cap = (size_t)(gp.ncol + 2);
+    }
+    const size_t xneed = (size_t)chunk * l1x, oneed = (size_t)chunk;
+    for (int k = 0; k < nbuf; ++k) {
+        if (xneed > cx.x_cap[k]) {
+            if (cx.d_x[k]) cudaFree(cx.d_x[k]);
+            cx.d_x[k] = nullptr;
+            cx.x_cap[k] = 0;
+            EV_TRY(cudaMalloc((void **)&cx.d_x[k], sizeof(real_t) * xneed));
+            cx.x_cap[k] = xneed;
+        }
+        if (oneed > cx.out_cap[k]) {
+            if (cx.d_out[k]) cudaFree(cx.d_out[k]);
+            cx.d_out[k] = nullptr;
+            cx.out_cap[k] = 0;
+            EV_TRY(cudaMalloc((void **)&cx.d_out[k], sizeof(real_t) * oneed));
+            cx.out_cap[k] = oneed;
+        }
+    }
+    cudaStream_t st = cx.st, st2 = cx.st2;
+    real_t *d_coef = cx.d_coef;
+    // chunked, double-buffered: H2D of chunk k+1 (st2) overlaps the kernel + D2H of chunk k (st)
     EV_TRY(cudaMemcpyAsync(d_coef, coef, sizeof(real_t) * (size_t)gp.ncol, cudaMemcpyHostToDevice, st));
     int k = 0;
     for (long long q0 = 0; q0 < nq; q0 += chunk, k ^= 1) {
         const long long nc = (nq - q0 < chunk) ? nq - q0 : chunk;
-        EV_TRY(cudaStreamWaitEvent(st2, ev_done[k], 0));      // buffer k free again
-        EV_TRY(cudaMemcpyAsync(d_x[k], x + q0 * (long long)l1x, sizeof(real_t) * (size_t)nc * l1x,
+        EV_TRY(cudaStreamWaitEvent(st2, cx.ev_done[k], 0));      // buffer k free again
+        EV_TRY(cudaMemcpyAsync(cx.d_x[k], x + q0 * (long long)l1x, sizeof(real_t) * (size_t)nc * l1x,
                                cudaMemcpyHostToDevice, st2));
-        EV_TRY(cudaEventRecord(ev_in[k], st2));
-        EV_TRY(cudaStreamWaitEvent(st, ev_in[k], 0));
-        rc = eval_device_impl(gp, di, nderiv, d_x[k], l1x, nc, d_coef, d_out[k], st);
+        EV_TRY(cudaEventRecord(cx.ev_in[k], st2));
+        EV_TRY(cudaStreamWaitEvent(st, cx.ev_in[k], 0));
+        rc = eval_device_impl(gp, di, nderiv, cx.d_x[k], l1x, nc, d_coef, cx.d_out[k], st);
         if (rc != SPLPAK_OK) break;
-        EV_TRY(cudaMemcpyAsync(out + q0, d_out[k], sizeof(real_t) * (size_t)nc, cudaMemcpyDeviceToHost, st));
-        EV_TRY(cudaEventRecord(ev_done[k], st));
+        EV_TRY(cudaMemcpyAsync(out + q0, cx.d_out[k], sizeof(real_t) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+        EV_TRY(cudaEventRecord(cx.ev_done[k], st));
     }
     EV_TRY(cudaStreamSynchronize(st));
     EV_TRY(cudaStreamSynchronize(st2));
 #undef EV_TRY
-    cleanup();
     if (rc == SPLPAK_OK && soft) rc = SPLPAK_ERR_NDERIV;
     if (ierror) *ierror = rc;
     return rc;
