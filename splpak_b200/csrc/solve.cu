@@ -337,10 +337,10 @@ __device__ __forceinline__ void spl_cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// Every CTA factors the nb x nb diagonal block A11 = L11 L11^T and inverts L11 in registers (thread
-// (ti, tj) of a 16 x 16 grid owns a 4 x 4 sub-block of A and of X = L11^-1; one barrier per pivot,
-// pivot column / row broadcast through double-buffered shared memory).  Doing this redundantly in
-// every CTA costs no time (it is a latency chain) and saves a launch + dependency per panel.
+// Every CTA factors the nb x nb diagonal block A11 = L11 L11^T (four threads per row, 16 entries each in
+// registers, one barrier per pivot, pivot column broadcast through double-buffered shared memory) and
+// inverts L11.  Doing this redundantly in every CTA costs no time (it is a latency chain) and saves a
+// launch + dependency per panel.
 // Then  y1 = L11^-1 g1,  L21 = A21 L11^-T  for this CTA's 64 rows (FP64 tensor-core MMA against the
 // inverse, so no per-row substitution chain) and  g2 -= L21 y1.
 // CTA 0 stores L11^-1 (for the back-substitution) and y1.
@@ -374,122 +374,53 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 
-    // ---- load A11 (4 x 4 per thread) ----
-    const int ti = tid >> 4, tj = tid & 15;
-    double A[4][4];
+    // ---- load A11: thread (i, c) = (tid / 4, tid % 4) owns u[kk] = A[i][4 kk + c], kk = 0..15 ----
+    const int ri = tid >> 2, rc = tid & 3;
+    double u[16];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int i = 4 * ti + a, j = 4 * tj + b;
-            double v = (i == j) ? 1.0 : 0.0;                 // identity padding when nb < 64
-            if (i < nb && j < nb && i >= j) v = AB[(j0 + i) + (j0 + j) * lda];
-            A[a][b] = v;
-        }
+    for (int kk = 0; kk < 16; ++kk) {
+        const int k = 4 * kk + rc;
+        double v = (ri == k) ? 1.0 : 0.0;                     // identity padding when nb < 64
+        if (ri < nb && k < nb && k <= ri) v = AB[(j0 + ri) + (j0 + k) * lda];
+        u[kk] = v;
+    }
     if (tid < 64) s_g[tid] = (tid < nb) ? g[j0 + tid] : 0.0;
     if (tid == 0) *s_bad = 0;
 
     PANEL_STAMP(1);
-    // ---- right-looking Cholesky of the block, 4 pivots per barrier ----
-    // Owners of column block kb publish their 64 x 4 strip; every live thread then factors the 4 x 4
-    // pivot block itself (redundantly: it is a latency chain, not throughput), forward-substitutes
-    // its own 4 rows / 4 columns against it and applies the rank-4 update to its 4 x 4 block.
-#pragma unroll 1
-    for (int kb = 0; kb < 16; ++kb) {
-        double *strip = s_strip + (kb & 1) * 256;            // [row][4], double buffered
-        if (tj == kb) {
+    // ---- right-looking Cholesky in the square-root-free form, one barrier per column.
+    // Column j of the Schur complement is published unscaled (u_ij); every thread forms 1/d_j itself
+    // (d_j = u_jj) and applies  u_ik -= (u_ij / d_j) u_kj  to its 16 entries.  The dependent chain per pivot is
+    // publish -> barrier -> reciprocal -> one multiply -> one FMA (the entry of column j+1), instead of a 4 x 4
+    // block factorisation + two triangular solves per four pivots; L = U diag(d)^-1/2 is formed at the end. ----
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                *reinterpret_cast<double2 *>(strip + (4 * ti + a) * 4) = make_double2(A[a][0], A[a][1]);
-                *reinterpret_cast<double2 *>(strip + (4 * ti + a) * 4 + 2) = make_double2(A[a][2], A[a][3]);
-            }
-        }
+    for (int j = 0; j < 64; ++j) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int kj = j >> 2, cj = j & 3;
+        double *col = s_col + (j & 1) * 64;
+        if (rc == cj) col[ri] = u[kj];
         __syncthreads();
-        if (ti >= kb && tj >= kb) {
-            double Dg[4][4], Ld[4][4], rinv[4];
+        const double d = col[j];
+        // 1/d: hardware seed + two Newton steps (d > 0 and finite for a valid pivot)
+        double rinv;
+        {
+            double y0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+            double e = fma(-d, y0, 1.0);
+            y0 = fma(y0, e, y0);
+            e = fma(-d, y0, 1.0);
+            rinv = fma(y0, e, y0);
+        }
+        if (tid == 0) {
+            s_rd[j] = d;                                     // d_j for now; 1/L_jj after the loop
+            if (!(d > 0.0)) *s_bad = 1;                      // non-positive (or NaN) pivot -> 107
+        }
+        const double ci = col[ri] * rinv;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const double2 v01 = *reinterpret_cast<const double2 *>(strip + (4 * kb + r) * 4);
-                const double2 v23 = *reinterpret_cast<const double2 *>(strip + (4 * kb + r) * 4 + 2);
-                Dg[r][0] = v01.x; Dg[r][1] = v01.y; Dg[r][2] = v23.x; Dg[r][3] = v23.y;
-            }
-            bool bad_here = false;
-            // right-looking inside the 4 x 4 block, so consecutive pivots are one FMA apart; the
-            // dependent chain per pivot is: seed, (g,h), two Goldschmidt steps, scale, update
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double d = Dg[c][c];
-                if (!(d > 0.0)) bad_here = true;              // non-positive (or NaN) pivot -> 107
-                double y0;
-                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));   // ~2^-22 seed (MUFU.RSQ64H)
-                double gq2 = d * y0;                          // -> sqrt(d)
-                double hq = 0.5 * y0;                         // -> 1 / (2 sqrt(d))
-#pragma unroll
-                for (int itn = 0; itn < 2; ++itn) {
-                    const double rr = fma(-gq2, hq, 0.5);
-                    gq2 = fma(gq2, rr, gq2);
-                    hq = fma(hq, rr, hq);
-                }
-                const double r = bad_here ? 0.0 : 2.0 * hq;
-                rinv[c] = r;
-                Ld[c][c] = gq2;
-#pragma unroll
-                for (int rr2 = c + 1; rr2 < 4; ++rr2) Ld[rr2][c] = Dg[rr2][c] * r;
-#pragma unroll
-                for (int rr2 = c + 1; rr2 < 4; ++rr2)
-#pragma unroll
-                    for (int cc = c + 1; cc <= rr2; ++cc) Dg[rr2][cc] = fma(-Ld[rr2][c], Ld[cc][c], Dg[rr2][cc]);
-            }
-            if (ti == kb && tj == kb) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) s_rd[4 * kb + c] = rinv[c];
-                if (bad_here) *s_bad = 1;
-            }
-            // my rows against the pivot block: Li[a][c] = L[4ti+a][4kb+c]
-            double Li[4][4];
-#pragma unroll
-            for (int a2 = 0; a2 < 4; ++a2) {
-                const double2 v01 = *reinterpret_cast<const double2 *>(strip + (4 * ti + a2) * 4);
-                const double2 v23 = *reinterpret_cast<const double2 *>(strip + (4 * ti + a2) * 4 + 2);
-                const double raw[4] = {v01.x, v01.y, v23.x, v23.y};
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    double v = raw[c];
-#pragma unroll
-                    for (int e = 0; e < c; ++e) v = fma(-Li[a2][e], Ld[c][e], v);
-                    Li[a2][c] = v * rinv[c];
-                }
-            }
-            if (tj == kb) {
-#pragma unroll
-                for (int a2 = 0; a2 < 4; ++a2)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) A[a2][c] = Li[a2][c];      // final L (rows >= col valid)
-            } else {
-                double Lj[4][4];
-#pragma unroll
-                for (int b2 = 0; b2 < 4; ++b2) {
-                    const double2 v01 = *reinterpret_cast<const double2 *>(strip + (4 * tj + b2) * 4);
-                    const double2 v23 = *reinterpret_cast<const double2 *>(strip + (4 * tj + b2) * 4 + 2);
-                    const double raw[4] = {v01.x, v01.y, v23.x, v23.y};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        double v = raw[c];
-#pragma unroll
-                        for (int e = 0; e < c; ++e) v = fma(-Lj[b2][e], Ld[c][e], v);
-                        Lj[b2][c] = v * rinv[c];
-                    }
-                }
-#pragma unroll
-                for (int a2 = 0; a2 < 4; ++a2)
-#pragma unroll
-                    for (int b2 = 0; b2 < 4; ++b2) {
-                        double v = A[a2][b2];
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) v = fma(-Li[a2][c], Lj[b2][c], v);
-                        A[a2][b2] = v;
-                    }
-            }
+        for (int kk = kj; kk < 16; ++kk) {
+            const int k = 4 * kk + rc;
+            if (k > j) u[kk] = fma(-ci, col[k], u[kk]);
         }
     }
     __syncthreads();
@@ -499,15 +430,28 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
         spl_cp_async_wait_all();
         return;
     }
-    // ---- L11 -> shared memory (row-major, lower part; sB doubles as scratch until Linv is ready) ----
+    // ---- 1 / L_jj = d_j^-1/2 (seed + two Goldschmidt steps), then L11 = U diag(d)^-1/2 -> shared memory ----
+    if (tid < 64) {
+        const double d = s_rd[tid];
+        double y0;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+        double gq2 = d * y0;
+        double hq = 0.5 * y0;
+#pragma unroll
+        for (int itn = 0; itn < 2; ++itn) {
+            const double rr = fma(-gq2, hq, 0.5);
+            gq2 = fma(gq2, rr, gq2);
+            hq = fma(hq, rr, hq);
+        }
+        s_rd[tid] = 2.0 * hq;
+    }
+    __syncthreads();
     double *sL = s_lfac;
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int i = 4 * ti + a, j = 4 * tj + b;
-            sL[i * 64 + j] = (i >= j) ? A[a][b] : 0.0;
-        }
+    for (int kk = 0; kk < 16; ++kk) {
+        const int k = 4 * kk + rc;
+        sL[ri * 64 + k] = (k <= ri) ? u[kk] * s_rd[k] : 0.0;
+    }
     __syncthreads();
     // ---- X = L11^-1 by columns: thread j < 64 forward-substitutes e_j.  No barriers; rows of L11 are
     //      broadcast reads; fully unrolled so X stays in registers (entries above the diagonal are 0) ----
