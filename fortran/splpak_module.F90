@@ -56,6 +56,7 @@
         procedure,public :: create                       !! (new) streaming fit: create
         procedure,public :: add_points                   !! (new) streaming fit: accumulate points
         procedure,public :: compute                      !! (new) streaming fit: constraints + solve
+        procedure,public :: refine                       !! (new) streaming fit: one refinement pass over the same points
         procedure,private :: splcc
         procedure,private :: splcw
         procedure,private :: splfe
@@ -140,6 +141,27 @@
             integer(c_int),intent(out) :: ierror
             integer(c_int) :: rc
         end function c_fit_compute
+        function c_fit_refine_begin(h) bind(C,name='splpak_b200_fit_refine_begin') result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr),value :: h
+            integer(c_int) :: rc
+        end function c_fit_refine_begin
+        function c_fit_refine_add_points(h,x,l1x,y,w,weighted,n) bind(C,name='splpak_b200_fit_refine_add_points') result(rc)
+            import :: c_int, c_int64_t, c_ptr, cwp
+            type(c_ptr),value :: h
+            real(cwp),intent(in) :: x(*), y(*), w(*)
+            integer(c_int),value :: l1x, weighted
+            integer(c_int64_t),value :: n
+            integer(c_int) :: rc
+        end function c_fit_refine_add_points
+        function c_fit_refine_compute(h,coef,ncf,ierror) bind(C,name='splpak_b200_fit_refine_compute') result(rc)
+            import :: c_int, c_int64_t, c_ptr, cwp
+            type(c_ptr),value :: h
+            real(cwp) :: coef(*)
+            integer(c_int64_t),value :: ncf
+            integer(c_int),intent(out) :: ierror
+            integer(c_int) :: rc
+        end function c_fit_refine_compute
         function c_fit_destroy(h) bind(C,name='splpak_b200_fit_destroy') result(rc)
             import :: c_int, c_ptr
             type(c_ptr),value :: h
@@ -315,5 +337,37 @@
         ierror = ie
         call cfaerr(ierror,.false.)
     end subroutine compute
+
+    !> (new) one step of corrected-semi-normal-equations refinement after `compute`, with the SAME points
+    !> (initialize => splcc/splcw do this by themselves when derivative-constraint rows fired).
+    subroutine refine(me,xdata,l1xdat,ydata,ndata,coef,ncf,ierror,wdata)
+        class(splpak_type),intent(inout) :: me
+        integer,intent(in) :: l1xdat, ncf
+        integer(int64),intent(in) :: ndata
+        real(wp),intent(in) :: xdata(l1xdat,ndata), ydata(ndata)
+        real(wp),intent(out) :: coef(ncf)
+        integer,intent(out) :: ierror
+        real(wp),intent(in),optional :: wdata(ndata)
+        integer(c_int) :: weighted, rc, ie
+        real(wp) :: dummy(1)
+        ierror = c_fit_refine_begin(me%handle)
+        if (ierror /= 0) then
+            call cfaerr(ierror,.false.)
+            return
+        end if
+        weighted = 0
+        if (present(wdata)) then
+            if (wdata(1) >= 0.0_wp) weighted = 1
+            ierror = c_fit_refine_add_points(me%handle,xdata,int(l1xdat,c_int),ydata,wdata,weighted,int(ndata,c_int64_t))
+        else
+            dummy = -1.0_wp
+            ierror = c_fit_refine_add_points(me%handle,xdata,int(l1xdat,c_int),ydata,dummy,weighted,int(ndata,c_int64_t))
+        end if
+        if (ierror == 0) then
+            rc = c_fit_refine_compute(me%handle,coef,int(ncf,c_int64_t),ie)
+            ierror = ie
+        end if
+        call cfaerr(ierror,.false.)
+    end subroutine refine
 
     end module splpak_module

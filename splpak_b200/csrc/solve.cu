@@ -354,12 +354,10 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     double *sA = s_pan;                          // [k][row]  A21 tile, 64 x TILE_LD
     double *sB = s_pan + 64 * TILE_LD;           // [k][n]    L11^-1 [n][k]
     double *s_col = sB + 64 * TILE_LD;           // 2 x 64   pivot column (double buffered)
-    double *s_row = s_col + 128;                 // 2 x 64   pivot row of X
-    double *s_g = s_row + 128;                   // 64       g1, then y1
-    double *s_rd = s_g + 64;                     // 64       1 / L11[k][k]
+    double *s_g = s_col + 128;                   // 64       g1, then y1
+    double *s_rd = s_g + 64;                     // 64       d_k, then 1 / L11[k][k]
     double *s_lfac = s_rd + 64;                  // 64 x 64  L11, row-major
-    double *s_strip = s_lfac + 64 * 64;          // 2 x 64 x 4  published pivot strip
-    int *s_bad = reinterpret_cast<int *>(s_strip + 512);
+    int *s_bad = reinterpret_cast<int *>(s_lfac + 64 * 64);
     const int tid = threadIdx.x;
     if (*fail) return;                           // an earlier panel failed (uniform across the grid)
     const int R0 = blockIdx.x * 64;              // first row of this CTA's tile, relative to j0 + nb
@@ -819,7 +817,7 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     *d_coef_out = d_csol;
     (void)nsm;
     const size_t syrk_smem = sizeof(double) * 2 * 64 * TILE_LD;
-    const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 128 + 64 + 64 + 64 * 64 + 512 + 2);
+    const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 64 + 64 + 64 * 64 + 2);
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
 

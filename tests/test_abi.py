@@ -105,3 +105,24 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert "oracle" not in txt.lower() or f == "basis.cuh", f"{f} mentions the oracle"
+
+
+def test_fortran_shim_binds_only_exported_symbols():
+    """Every bind(C, name=...) of fortran/splpak_module.F90 (which cannot be compiled here: no Fortran compiler)
+    names a symbol the header declares and the library exports, and the shim keeps the reference's public names."""
+    import re
+
+    from splpak_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "fortran", "splpak_module.F90")).read()
+    names = set(re.findall(r"bind\(C,\s*name='([A-Za-z0-9_]+)'\)", src))
+    assert names, "no bind(C) interfaces found"
+    assert names <= set(_lib.SYMBOLS), names - set(_lib.SYMBOLS)
+    for must in ("splpak_b200_splcw", "splpak_b200_splcc", "splpak_b200_splde", "splpak_b200_splfe"):
+        assert must in names
+    # the reference's public surface (src/splpak.F90:43-45, :117-119)
+    for text in ("module splpak_module", "type,public :: splpak_type", "integer,parameter,public :: splpak_wp",
+                 "generic,public   :: initialize => splcc, splcw", "generic,public   :: evaluate   => splfe, splde",
+                 "procedure,public :: destroy"):
+        assert text in src, text
