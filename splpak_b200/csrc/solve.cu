@@ -405,10 +405,11 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
         {
             double y0;
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-            double e = fma(-d, y0, 1.0);
-            y0 = fma(y0, e, y0);
-            e = fma(-d, y0, 1.0);
-            rinv = fma(y0, e, y0);
+            // one cubically convergent step: y0 (1 + e + e^2), e = 1 - d y0 ~ 2^-23 -> 2^-69 (three dependent
+            // operations; two Newton steps are four, and FP64 latency is what this loop is made of)
+            const double e = fma(-d, y0, 1.0);
+            const double e2 = fma(e, e, e);
+            rinv = fma(y0, e2, y0);
         }
         if (tid == 0) {
             s_rd[j] = d;                                     // d_j for now; 1/L_jj after the loop
@@ -737,6 +738,19 @@ void spl_solve_cache_free(void *cache) {
 // and the rest of update k runs under panel k+1's diagonal-block latency chain.  Ordering on shared tiles:
 // rest(k)'s tiles with tj >= 1 are columns 0.. of window k+1, hence the wait before syrk column 0 (k+1);
 // rest(k) and rest(k+1) are ordered by st_aux itself.
+// SPLPAK_B200_PANELCLK=1: phase clocks of one mid-matrix panel (device buffer handed to that launch only)
+static long long *spl_panel_dbg_buffer() {
+    static long long *buf = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        if (getenv("SPLPAK_B200_PANELCLK")) {
+            if (cudaMalloc((void **)&buf, 64) != cudaSuccess) buf = nullptr;
+        }
+    }
+    return buf;
+}
+
 static cudaError_t enqueue_factor(long long n, int bw, long long lda, double *d_AB, double *d_g, double *d_ysol,
                                   double *d_linv, int *d_fail, cudaStream_t st, cudaStream_t st_aux,
                                   size_t panel_smem, size_t syrk_smem, long long *nlaunch) {
@@ -757,7 +771,8 @@ static cudaError_t enqueue_factor(long long n, int bw, long long lda, double *d_
         int pblocks = (m + 63) / 64;
         if (pblocks < 1) pblocks = 1;
         spl_panel_kernel<<<pblocks, PANEL_THREADS, panel_smem, st>>>(d_AB, lda, j0, nb, m, d_g, d_ysol,
-                                                                     d_linv + kb * 4096, d_fail, nullptr);
+                                                                     d_linv + kb * 4096, d_fail,
+                                                                     kb == nblk / 2 ? spl_panel_dbg_buffer() : nullptr);
         ++count;
         if (m > 0) {
             const int T = (m + SYRK_TILE - 1) / SYRK_TILE;
@@ -821,6 +836,7 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
 
+    (void)spl_panel_dbg_buffer();        // allocate (if asked for) outside stream capture
     // (re)build the graphs when the buffers or the problem changed
     SolveGraphs *sg = cache ? static_cast<SolveGraphs *>(*cache) : nullptr;
     if (cache && (!sg || sg->key_AB != d_AB || sg->key_g != d_g || sg->n != n || sg->bw != bw)) {
@@ -880,6 +896,14 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         SPL_CUDA_TRY(enqueue_factor(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux, panel_smem, syrk_smem, &nl));
     }
     g_spl_launches += nl;
+    if (spl_panel_dbg_buffer()) {
+        long long hst[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hst, spl_panel_dbg_buffer(), sizeof(hst), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "panel (mid) clocks: load %lld chol %lld inverse %lld wait %lld y1 %lld gemm+store %lld total %lld\n",
+                hst[1] - hst[0], hst[2] - hst[1], hst[3] - hst[2], hst[4] - hst[3], hst[5] - hst[4], hst[6] - hst[5],
+                hst[6] - hst[0]);
+    }
     if (ev) cudaEventRecord(ev[2], st);
     if (sg && sg->back) {
         SPL_CUDA_TRY(cudaGraphLaunch(sg->back, st));
