@@ -112,6 +112,19 @@ int splpak_b200_eval_device(int ndim, const splpak_real *d_x, int l1x, int64_t n
                             const splpak_real *xmax, const int *nodes, splpak_real *d_out,
                             void *stream, int *ierror);
 
+/* Evaluation on a REGULAR OUTPUT GRID (new; the upstream fit-then-grid use, README.md:60): the value (nderiv NULL)
+ * or partial derivative of the spline at every point (a1[i1], .., aN[iN]) of the tensor grid spanned by ndim axes.
+ * axes = the axes concatenated (axis d has naxis[d] points, any order, inside or outside [xmin, xmax]);
+ * out(naxis(1), .., naxis(ndim)), dimension 1 fastest.  Same basis values as splfe/splde point by point; the
+ * contraction runs one dimension at a time, so the cost is 4 FMAs and 8 bytes per output point instead of a
+ * 4^ndim gather.  HOST arrays (the output is produced in slabs along the last axis) / DEVICE arrays. */
+int splpak_b200_eval_grid(int ndim, const splpak_real *axes, const int64_t *naxis, const int *nderiv,
+                          const splpak_real *coef, const splpak_real *xmin, const splpak_real *xmax,
+                          const int *nodes, splpak_real *out, int *ierror);
+int splpak_b200_eval_grid_device(int ndim, const splpak_real *d_axes, const int64_t *naxis, const int *nderiv,
+                                 const splpak_real *d_coef, const splpak_real *xmin, const splpak_real *xmax,
+                                 const int *nodes, splpak_real *d_out, void *stream, int *ierror);
+
 /* ------------------------------------------------------------------------------------------
  * Streaming fit handle: create -> add_points (any number of calls, host or device arrays)
  * -> [all-reduce the partial buffer across ranks] -> compute.  This is the assembly / solve

@@ -12,6 +12,8 @@ from .api import (  # noqa: F401
     cfaerr_text,
     eval_batch,
     eval_batch_device,
+    eval_grid,
+    eval_grid_device,
     measure_peaks,
     splcc,
     splcw,
@@ -22,6 +24,6 @@ from .api import (  # noqa: F401
 
 __all__ = [
     "SplpakType", "FitHandle", "SplpakError", "splcc", "splcw", "splfe", "splde", "eval_batch",
-    "eval_batch_device", "measure_peaks", "total_launches", "cfaerr_text", "build", "load",
+    "eval_batch_device", "eval_grid", "eval_grid_device", "measure_peaks", "total_launches", "cfaerr_text", "build", "load",
     "lib_path", "SYMBOLS",
 ]

@@ -177,6 +177,42 @@ def eval_batch_device(ndim, d_x, l1x, nq, d_coef, xmin, xmax, nodes, d_out, nder
     return ierr.value
 
 
+def eval_grid(ndim, axes, coef, xmin, xmax, nodes, nderiv=None, *, quiet=True, real32=False):
+    """Spline (or partial derivative) on the tensor grid spanned by `axes` (a list of ndim 1-D arrays).
+    Returns (values with shape (len(axes[ndim-1]), ..., len(axes[0])), i.e. dimension 1 fastest; ierror)."""
+    lib = _lib.load(real32)
+    dt = _np_dtype(real32)
+    ax = [np.ascontiguousarray(a, dtype=dt).reshape(-1) for a in axes]
+    cat = np.concatenate(ax) if ax else np.zeros(0, dtype=dt)
+    na = (C.c_int64 * max(len(ax), 1))(*[len(a) for a in ax])
+    keep, (mnp, mxp, nop) = _grid_args(lib, ndim, xmin, xmax, nodes, real32)
+    ca = _vec(coef, dt)
+    ndp = None
+    if nderiv is not None:
+        nd = _vec(nderiv, np.int32)
+        ndp = nd.ctypes.data_as(C.POINTER(C.c_int))
+    out = np.zeros(int(np.prod([len(a) for a in ax])) if ax else 0, dtype=dt)
+    ierr = C.c_int(0)
+    lib.splpak_b200_eval_grid(int(ndim), _ptr(cat), na, ndp, _ptr(ca), mnp, mxp, nop, _ptr(out), C.byref(ierr))
+    _report(ierr.value, True, quiet, real32)
+    return out.reshape([len(a) for a in reversed(ax)]), ierr.value
+
+
+def eval_grid_device(ndim, d_axes, naxis, d_coef, xmin, xmax, nodes, d_out, nderiv=None, stream=None, *, real32=False):
+    """Same with device arrays: d_axes = the axes concatenated, naxis = their lengths, d_out = prod(naxis) values."""
+    lib = _lib.load(real32)
+    keep, (mnp, mxp, nop) = _grid_args(lib, ndim, xmin, xmax, nodes, real32)
+    na = (C.c_int64 * len(naxis))(*[int(v) for v in naxis])
+    ndp = None
+    if nderiv is not None:
+        nd = _vec(nderiv, np.int32)
+        ndp = nd.ctypes.data_as(C.POINTER(C.c_int))
+    ierr = C.c_int(0)
+    lib.splpak_b200_eval_grid_device(int(ndim), _dev_ptr(d_axes), na, ndp, _dev_ptr(d_coef), mnp, mxp, nop,
+                                     _dev_ptr(d_out), _stream_ptr(stream), C.byref(ierr))
+    return ierr.value
+
+
 def _dev_ptr(t):
     if t is None:
         return None

@@ -20,6 +20,10 @@ struct AssembleScratch {
 int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, int l1x, long long nq,
                     const double *d_coef, long long ncol_padded, real_t *d_out, cudaStream_t stream,
                     int nsm, size_t smem_optin, unsigned long long *d_counter);
+long long spl_grid_tmp_elems(const GridParams &gp, const long long *naxis);
+int spl_eval_grid_launch(const GridParams &gp, const int *nderiv, const real_t *const *d_axis, const long long *naxis,
+                         const double *d_coef64, real_t *d_out, double *d_tmp, long long tmp_elems, int *d_iws,
+                         double *d_w4, cudaStream_t st, int nsm);
 int spl_acc_chunk_points(int ndim);
 int spl_assemble_chunk(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y,
                        const real_t *d_w, int weighted, long long n, int do_hist, int rhs_only,
@@ -262,6 +266,140 @@ extern "C" int splpak_b200_eval_device(int ndim, const real_t *d_x, int l1x, int
         if (rc == SPLPAK_OK)
             rc = eval_device_impl(gp, di, nderiv, d_x, l1x, nq, d_coef, d_out, (cudaStream_t)stream);
     }
+    if (rc == SPLPAK_OK && soft) rc = SPLPAK_ERR_NDERIV;
+    if (ierror) *ierror = rc;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// evaluation on a regular output grid (grid.cu)
+// ------------------------------------------------------------------------------------------
+static int eval_grid_device_impl(const GridParams &gp, const DeviceInfo &di, const int *nderiv,
+                                 const real_t *const *d_axis, const long long *naxis, const real_t *d_coef,
+                                 real_t *d_out, cudaStream_t st) {
+    long long nsum = 0;
+    for (int d = 0; d < gp.ndim; ++d) {
+        if (naxis[d] <= 0) return SPLPAK_OK;
+        nsum += naxis[d];
+    }
+    const long long tmp_elems = spl_grid_tmp_elems(gp, naxis);
+    const bool direct = sizeof(real_t) == sizeof(double);
+    // one stream-ordered scratch block: [coef64 (if converted) | 2 x tmp | w4 | iws]
+    const size_t coef_d = direct ? 0 : (size_t)gp.ncol;
+    const size_t bytes = sizeof(double) * (coef_d + 2 * (size_t)tmp_elems + 4 * (size_t)nsum) + sizeof(int) * (size_t)nsum + 64;
+    char *blk = nullptr;
+    cudaMemPool_t pool = eval_scratch_pool(di.dev);
+    if (pool) SPL_CUDA_TRY(cudaMallocFromPoolAsync((void **)&blk, bytes, pool, st));
+    else SPL_CUDA_TRY(cudaMallocAsync((void **)&blk, bytes, st));
+    double *c64 = reinterpret_cast<double *>(blk);
+    double *tmp = c64 + coef_d;
+    double *w4 = tmp + 2 * tmp_elems;
+    int *iws = reinterpret_cast<int *>(w4 + 4 * nsum);
+    const double *coef64 = reinterpret_cast<const double *>(d_coef);
+    if (!direct) {
+        spl_to_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(d_coef, c64, gp.ncol, gp.ncol);
+        ++g_spl_launches;
+        coef64 = c64;
+    }
+    const int rc = spl_eval_grid_launch(gp, nderiv, d_axis, naxis, coef64, d_out, tmp, tmp_elems, iws, w4, st, di.nsm);
+    cudaFreeAsync(blk, st);
+    return rc;
+}
+
+// axes: the ndim axes concatenated (axis d has naxis[d] points); out(naxis(1),...,naxis(ndim)), dimension 1 fastest
+extern "C" int splpak_b200_eval_grid_device(int ndim, const real_t *d_axes, const int64_t *naxis, const int *nderiv,
+                                            const real_t *d_coef, const real_t *xmin, const real_t *xmax,
+                                            const int *nodes, real_t *d_out, void *stream, int *ierror) {
+    GridParams gp;
+    int soft = 0;
+    int rc = make_grid(ndim, xmin, xmax, nodes, nderiv, gp, &soft);
+    if (rc == SPLPAK_OK) {
+        DeviceInfo di;
+        rc = get_device(di);
+        if (rc == SPLPAK_OK) {
+            const real_t *ax[SPL_MAXDIM] = {nullptr, nullptr, nullptr, nullptr};
+            long long na[SPL_MAXDIM] = {0, 0, 0, 0}, off = 0;
+            for (int d = 0; d < gp.ndim; ++d) {
+                ax[d] = d_axes + off;
+                na[d] = (long long)naxis[d];
+                off += na[d] > 0 ? na[d] : 0;
+            }
+            rc = eval_grid_device_impl(gp, di, nderiv, ax, na, d_coef, d_out, (cudaStream_t)stream);
+        }
+    }
+    if (rc == SPLPAK_OK && soft) rc = SPLPAK_ERR_NDERIV;
+    if (ierror) *ierror = rc;
+    return rc;
+}
+
+// HOST arrays; the output is produced in slabs along the last axis so that device memory stays bounded
+extern "C" int splpak_b200_eval_grid(int ndim, const real_t *axes, const int64_t *naxis, const int *nderiv,
+                                     const real_t *coef, const real_t *xmin, const real_t *xmax, const int *nodes,
+                                     real_t *out, int *ierror) {
+    GridParams gp;
+    int soft = 0;
+    int rc = make_grid(ndim, xmin, xmax, nodes, nderiv, gp, &soft);
+    DeviceInfo di;
+    if (rc == SPLPAK_OK) rc = get_device(di);
+    if (rc != SPLPAK_OK) {
+        if (ierror) *ierror = rc;
+        return rc;
+    }
+    long long na[SPL_MAXDIM] = {0, 0, 0, 0}, nsum = 0, plane = 1;
+    for (int d = 0; d < gp.ndim; ++d) {
+        na[d] = (long long)naxis[d];
+        if (na[d] <= 0) {
+            if (ierror) *ierror = soft ? SPLPAK_ERR_NDERIV : SPLPAK_OK;
+            return soft ? SPLPAK_ERR_NDERIV : SPLPAK_OK;
+        }
+        nsum += na[d];
+        if (d + 1 < gp.ndim) plane *= na[d];
+    }
+    long long slab = (1LL << 25) / plane;                      // ~32M outputs (256 MB) per slab
+    if (slab < 1) slab = 1;
+    if (slab > na[gp.ndim - 1]) slab = na[gp.ndim - 1];
+    real_t *d_axes = nullptr, *d_coef = nullptr, *d_out = nullptr;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() {
+        if (d_axes) cudaFree(d_axes);
+        if (d_coef) cudaFree(d_coef);
+        if (d_out) cudaFree(d_out);
+        if (st) cudaStreamDestroy(st);
+    };
+#define GR_TRY(expr)                                        \
+    do {                                                    \
+        if ((expr) != cudaSuccess) {                        \
+            cudaGetLastError();                             \
+            cleanup();                                      \
+            if (ierror) *ierror = SPLPAK_ERR_CUDA;          \
+            return SPLPAK_ERR_CUDA;                         \
+        }                                                   \
+    } while (0)
+    GR_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    GR_TRY(cudaMalloc((void **)&d_axes, sizeof(real_t) * (size_t)nsum));
+    GR_TRY(cudaMalloc((void **)&d_coef, sizeof(real_t) * (size_t)(gp.ncol + 2)));
+    GR_TRY(cudaMalloc((void **)&d_out, sizeof(real_t) * (size_t)(plane * slab)));
+    GR_TRY(cudaMemcpyAsync(d_axes, axes, sizeof(real_t) * (size_t)nsum, cudaMemcpyHostToDevice, st));
+    GR_TRY(cudaMemcpyAsync(d_coef, coef, sizeof(real_t) * (size_t)gp.ncol, cudaMemcpyHostToDevice, st));
+    const real_t *ax[SPL_MAXDIM] = {nullptr, nullptr, nullptr, nullptr};
+    long long off = 0;
+    for (int d = 0; d < gp.ndim; ++d) {
+        ax[d] = d_axes + off;
+        off += na[d];
+    }
+    const real_t *last0 = ax[gp.ndim - 1];
+    const long long nlast = na[gp.ndim - 1];
+    for (long long lo = 0; lo < nlast && rc == SPLPAK_OK; lo += slab) {
+        const long long ns = (nlast - lo < slab) ? nlast - lo : slab;
+        ax[gp.ndim - 1] = last0 + lo;
+        na[gp.ndim - 1] = ns;
+        rc = eval_grid_device_impl(gp, di, nderiv, ax, na, d_coef, d_out, st);
+        if (rc != SPLPAK_OK) break;
+        GR_TRY(cudaMemcpyAsync(out + lo * plane, d_out, sizeof(real_t) * (size_t)(plane * ns), cudaMemcpyDeviceToHost, st));
+        GR_TRY(cudaStreamSynchronize(st));
+    }
+#undef GR_TRY
+    cleanup();
     if (rc == SPLPAK_OK && soft) rc = SPLPAK_ERR_NDERIV;
     if (ierror) *ierror = rc;
     return rc;

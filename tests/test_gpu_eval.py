@@ -147,3 +147,63 @@ def test_real32_library(oracle32):
     got, ierr = sp.eval_batch(2, q, coef, [0, 0], [1, 1], nodes, real32=True)
     assert ierr == 0 and got.dtype == np.float32
     np.testing.assert_allclose(got, ref, rtol=0, atol=2e-4 * np.abs(coef).max())
+
+
+@pytest.mark.parametrize("ndim,nodes,naxis,nderiv", [
+    (1, [9], [37], None),
+    (1, [12], [50], [2]),
+    (2, [8, 6], [23, 17], None),
+    (2, [7, 9], [15, 31], [1, 0]),
+    (3, [6, 5, 7], [13, 9, 11], None),
+    (3, [8, 8, 8], [10, 12, 9], [0, 1, 2]),
+    (4, [5, 4, 6, 5], [7, 5, 6, 4], None),
+    (4, [5, 5, 5, 5], [4, 6, 5, 7], [1, 0, 0, 1]),
+])
+def test_eval_grid_matches_pointwise_and_oracle(oracle, ndim, nodes, naxis, nderiv):
+    """splpak_b200_eval_grid (separable mode products) == splfe/splde at every grid point: same 1-D basis values,
+    different summation order only (tolerance 50 eps sum|c Phi| as for the point-wise path)."""
+    rng = np.random.default_rng(100 + ndim)
+    coef = rng.standard_normal(int(np.prod(nodes)))
+    mn = [-0.5 + 0.1 * d for d in range(ndim)]
+    mx = [1.0 + 0.2 * d for d in range(ndim)]
+    axes = [np.sort(rng.random(n) * (mx[d] - mn[d]) * 1.4 + mn[d] - 0.2 * (mx[d] - mn[d])) for d, n in enumerate(naxis)]
+    got, ierr = sp.eval_grid(ndim, axes, coef, mn, mx, nodes, nderiv=nderiv)
+    assert ierr == 0 and got.shape == tuple(reversed(naxis))
+    mesh = np.meshgrid(*axes, indexing="ij")                       # mesh[d][i1, ..., iN]
+    pts = np.stack([m.transpose(*reversed(range(ndim))).ravel() for m in mesh], axis=1)   # dimension 1 fastest
+    want, ierr = sp.eval_batch(ndim, pts, coef, mn, mx, nodes, nderiv=nderiv)
+    assert ierr == 0
+    scale = np.abs(coef).max() * 4 ** ndim * 6 ** ndim
+    if nderiv is not None:
+        for d in range(ndim):
+            scale *= ((nodes[d] - 1) / (mx[d] - mn[d])) ** nderiv[d]
+    tol = 50 * np.finfo(float).eps * scale
+    np.testing.assert_allclose(got.ravel(), want, rtol=0, atol=tol)
+    pick = rng.integers(0, len(pts), 300)
+    ref, _ = oracle.evaluate_batch(ndim, pts[pick], coef, mn, mx, nodes, nderiv=nderiv)
+    np.testing.assert_allclose(got.ravel()[pick], ref, rtol=0, atol=tol)
+
+
+def test_eval_grid_large_device_and_slabs(oracle):
+    """Device variant on a 600 x 500 x 400 grid (1.2e8 points) and the host variant's slab loop (> 32M outputs)."""
+    import torch
+
+    rng = np.random.default_rng(7)
+    nodes = [24, 24, 24]
+    coef = rng.standard_normal(24 ** 3)
+    naxis = [600, 500, 400]
+    axes = [np.linspace(-0.05, 1.05, n) for n in naxis]
+    d_axes = torch.tensor(np.concatenate(axes), device="cuda")
+    d_coef = torch.tensor(coef, device="cuda")
+    d_out = torch.empty(int(np.prod(naxis)), dtype=torch.float64, device="cuda")
+    assert sp.eval_grid_device(3, d_axes, naxis, d_coef, [0, 0, 0], [1, 1, 1], nodes, d_out) == 0
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy().reshape(400, 500, 600)
+    idx = rng.integers(0, [600, 500, 400], size=(2000, 3))
+    pts = np.stack([axes[d][idx[:, d]] for d in range(3)], axis=1)
+    ref, _ = oracle.evaluate_batch(3, pts, coef, [0, 0, 0], [1, 1, 1], nodes)
+    tol = 50 * np.finfo(float).eps * 64 * 216 * np.abs(coef).max()
+    np.testing.assert_allclose(out[idx[:, 2], idx[:, 1], idx[:, 0]], ref, rtol=0, atol=tol)
+    host, ierr = sp.eval_grid(3, axes, coef, [0, 0, 0], [1, 1, 1], nodes)
+    assert ierr == 0
+    np.testing.assert_array_equal(host, out)
