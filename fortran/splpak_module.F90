@@ -53,6 +53,7 @@
         generic,public   :: evaluate   => splfe, splde   !! evaluate the spline
         procedure,public :: destroy    => destroy_splpak
         procedure,public :: evaluate_batch               !! (new) batched splfe/splde
+        procedure,public :: evaluate_grid                !! (new) splfe/splde on a regular output grid
         procedure,public :: create                       !! (new) streaming fit: create
         procedure,public :: add_points                   !! (new) streaming fit: accumulate points
         procedure,public :: compute                      !! (new) streaming fit: constraints + solve
@@ -115,6 +116,18 @@
             integer(c_int),intent(out) :: ierror
             integer(c_int) :: rc
         end function c_eval
+        function c_eval_grid(ndim,axes,naxis,nderiv,coef,xmin,xmax,nodes,out,ierror) &
+                 bind(C,name='splpak_b200_eval_grid') result(rc)
+            import :: c_int, c_int64_t, c_ptr, cwp
+            integer(c_int),value :: ndim
+            real(cwp),intent(in) :: axes(*), coef(*), xmin(*), xmax(*)
+            integer(c_int64_t),intent(in) :: naxis(*)
+            type(c_ptr),value :: nderiv                      !! c_null_ptr => values (splfe)
+            integer(c_int),intent(in) :: nodes(*)
+            real(cwp) :: out(*)
+            integer(c_int),intent(out) :: ierror
+            integer(c_int) :: rc
+        end function c_eval_grid
         function c_fit_create(ndim,xmin,xmax,nodes,xtrap,handle,ierror) bind(C,name='splpak_b200_fit_create') result(rc)
             import :: c_int, c_ptr, cwp
             integer(c_int),value :: ndim
@@ -289,6 +302,26 @@
         ierror = ie
         call cfaerr(ierror,.true.)
     end subroutine evaluate_batch
+
+    !> (new) value or partial derivative on the tensor grid spanned by the ndim axes stored one after the other in
+    !> `axes` (axis d has naxis(d) points); f(naxis(1),...,naxis(ndim)); nderiv absent => splfe.
+    subroutine evaluate_grid(me,ndim,axes,naxis,coef,xmin,xmax,nodes,f,ierror,nderiv)
+        class(splpak_type),intent(inout) :: me
+        integer,intent(in) :: ndim
+        integer(int64),intent(in) :: naxis(ndim)
+        real(wp),intent(in) :: axes(*), coef(*), xmin(ndim), xmax(ndim)
+        integer,intent(in) :: nodes(ndim)
+        real(wp),intent(out) :: f(*)
+        integer,intent(out) :: ierror
+        integer,intent(in),optional,target :: nderiv(ndim)
+        integer(c_int) :: rc, ie
+        type(c_ptr) :: pn
+        pn = c_null_ptr
+        if (present(nderiv)) pn = c_loc(nderiv)
+        rc = c_eval_grid(int(ndim,c_int),axes,naxis,pn,coef,xmin,xmax,nodes,f,ie)
+        ierror = ie
+        call cfaerr(ierror,.true.)
+    end subroutine evaluate_grid
 
     !> (new) streaming fit: validates the grid like splcw (101,102,103) and allocates device buffers.
     subroutine create(me,ndim,xmin,xmax,nodes,xtrap,ierror)
