@@ -307,3 +307,38 @@ def test_cfg4_scale_multilinear():
     assert sp.eval_batch_device(ndim, q, ndim, nq, dcoef, [0] * 4, [1] * 4, nodes, out, nderiv=[1, 1, 1, 1]) == 0
     torch.cuda.synchronize()
     assert float((out - float(np.prod(b))).abs().max()) <= 5e-6 * 11 ** 4 * 0.1
+
+
+def test_more_than_2_31_queries_and_points(oracle):
+    """64-bit indexing end to end (the reference's default integers stop at 2^31 - 1): a 1-D fit of
+    2.2e9 unweighted points (17 chunks of 2^27) of a linear function -> analytic K2 coefficients, then 2.2e9
+    evaluations, checked against the oracle at both ends of the array.  Empty inputs are no-ops."""
+    n = 2_200_000_000
+    nodes, a, b = [50], 0.3, 1.7
+    x = torch.empty((n, 1), dtype=torch.float64, device="cuda")
+    for lo in range(0, n, 1 << 28):
+        hi = min(n, lo + (1 << 28))
+        synth.queries_torch(1, hi - lo, start=lo, out=x[lo:hi])
+    y = a + b * x[:, 0]
+    torch.cuda.synchronize()
+    h = sp.FitHandle(1, [0.0], [1.0], nodes, 0.0)
+    assert h.add_points_device(x, 1, y, None, 0, False) == 0            # empty chunk: nothing happens
+    assert h.add_points_device(x, 1, y, None, n, False) == 0
+    dcoef = torch.zeros(50, dtype=torch.float64, device="cuda")
+    assert h.compute_device(dcoef) == 0
+    S, g, cnt, totlwt, nrows = h.normal_equations()
+    assert nrows == n
+    h.destroy()
+    got = dcoef.cpu().numpy()
+    want = c1d_linear(50, 0.0, 1.0, a, b)
+    assert np.abs(got - want).max() <= 1e-9
+    del y
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    assert sp.eval_batch_device(1, x, 1, 0, dcoef, [0.0], [1.0], nodes, out) == 0   # nq = 0
+    assert sp.eval_batch_device(1, x, 1, n, dcoef, [0.0], [1.0], nodes, out) == 0
+    torch.cuda.synchronize()
+    for sl in (slice(0, 1000), slice(n - 1000, n), slice((1 << 31) - 500, (1 << 31) + 500)):
+        qh = x[sl].cpu().numpy()
+        ref, _ = oracle.evaluate_batch(1, qh, got, [0.0], [1.0], nodes)
+        np.testing.assert_allclose(out[sl].cpu().numpy(), ref, rtol=0, atol=50 * EPS * 4 * np.abs(got).max())
+    assert float((out - (a + b * x[:, 0])).abs().max()) <= 1e-8
