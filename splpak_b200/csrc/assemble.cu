@@ -30,6 +30,9 @@
 // accumulators, and different groups take different points (K-split), reduced at the end of the
 // work item with warp shuffles + one shared-memory pass.  The right-hand side g rides along as
 // 4^(ndim-1) extra outer tuples whose inner vector is b_1[0..3] instead of s_1[0..9].
+#include <stdlib.h>
+#include <string.h>
+
 #include "basis.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -46,6 +49,29 @@ __device__ __forceinline__ unsigned spl_window_key(const GridParams &gp, const r
         key = key * (unsigned)gp.nwin[d] + (unsigned)ws;
     }
     return key;
+}
+
+// Cell id (moment path): every dimension has nodes+1 cells -- the nodes-1 node intervals plus the two
+// exterior half-lines, on which the basis continues linearly (bascmp's s >= 2 branch, :342-379).  Inside
+// one cell every 1-D basis function is a single polynomial of degree <= 3.
+__device__ __forceinline__ int spl_cell_of(double x, double xmin, double dxin, int nod) {
+    const double t = spl_mul(dxin, spl_sub(x, xmin));
+    const int it = min(__double2int_rz(t), nod - 1);         // saturating; NaN -> 0
+    return (t < 0.0) ? 0 : it + 1;
+}
+template <int NDIM>
+__device__ __forceinline__ unsigned spl_cell_key(const GridParams &gp, const real_t *xp) {
+    unsigned key = 0;
+#pragma unroll
+    for (int dd = 0; dd < NDIM; ++dd) {
+        const int d = NDIM - 1 - dd;
+        key = key * (unsigned)(gp.nodes[d] + 1) + (unsigned)spl_cell_of((double)xp[d], gp.xmin[d], gp.dxin[d], gp.nodes[d]);
+    }
+    return key;
+}
+template <int NDIM, bool CELL>
+__device__ __forceinline__ unsigned spl_bin_key(const GridParams &gp, const real_t *xp) {
+    return CELL ? spl_cell_key<NDIM>(gp, xp) : spl_window_key<NDIM>(gp, xp);
 }
 
 // Nearest-node address of :893-902, including the quirk at :899 (a dimension whose index is out of
@@ -75,15 +101,15 @@ __device__ __forceinline__ long long spl_nearest_node(const GridParams &gp, cons
 // SMEMH: the per-window counts are first accumulated in a shared-memory histogram (native 32-bit
 // ATOMS) and flushed once per CTA -- the L2 atomic units, not HBM, bound this pass when every point
 // issues two global reductions.  Used when the window table fits (launcher decides).
-template <int NDIM, bool SMEMH>
+template <int NDIM, bool SMEMH, bool CELL>
 __global__ void __launch_bounds__(512, 2)
 spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
-                    const real_t *__restrict__ w, int weighted, long long n,
+                    const real_t *__restrict__ w, int weighted, long long n, int nbins,
                     unsigned *__restrict__ wincount, int do_hist, double *__restrict__ cnt,
                     double *__restrict__ totals) {
     extern __shared__ unsigned s_hist[];
     if (SMEMH) {
-        for (int e = threadIdx.x; e < (int)gp.nwindows; e += blockDim.x) s_hist[e] = 0u;
+        for (int e = threadIdx.x; e < nbins; e += blockDim.x) s_hist[e] = 0u;
         __syncthreads();
     }
     double tot = 0.0;
@@ -108,7 +134,7 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
 #pragma unroll
         for (int u = 0; u < BIN_U; ++u) {
             if (wv[u] != 0.0) {                                  // zero-weight points are skipped (:796-800)
-                const unsigned key = spl_window_key<NDIM>(gp, xp[u]);
+                const unsigned key = spl_bin_key<NDIM, CELL>(gp, xp[u]);
                 if (SMEMH) atomicAdd(s_hist + key, 1u);
                 else atomicAdd(wincount + key, 1u);
                 rows += 1.0;
@@ -121,7 +147,7 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
     }
     if (SMEMH) {
         __syncthreads();
-        for (int e = threadIdx.x; e < (int)gp.nwindows; e += blockDim.x) {
+        for (int e = threadIdx.x; e < nbins; e += blockDim.x) {
             const unsigned c = s_hist[e];
             if (c) atomicAdd(wincount + e, c);
         }
@@ -196,7 +222,7 @@ spl_scan_kernel(const unsigned *__restrict__ wincount, long long nwindows, unsig
     }
 }
 
-template <int NDIM>
+template <int NDIM, bool CELL>
 __global__ void __launch_bounds__(256)
 spl_perm_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
                 const real_t *__restrict__ w, int weighted, long long n,
@@ -226,7 +252,7 @@ spl_perm_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict_
             pos[u] = 0;
             ws0[u] = 0;
             if (wv[u] != 0.0) {
-                key[u] = spl_window_key<NDIM>(gp, xp[u]);
+                key[u] = spl_bin_key<NDIM, CELL>(gp, xp[u]);
                 ws0[u] = winstart[key[u]];
                 pos[u] = atomicAdd(wincursor + key[u], 1u);
             }
@@ -642,13 +668,10 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
 // ------------------------------------------------------------------------------------------
 // host-side launch of the chunk pipeline
 // ------------------------------------------------------------------------------------------
-struct AssembleScratch {
-    unsigned *wincount, *winstart, *wincursor, *itemstart, *item_win, *item_seg, *meta;
-    unsigned *perm;
-    long long max_items;
-};
+#include "moments.cuh"
 
-int spl_acc_chunk_points(int ndim) {
+int spl_acc_chunk_points(int ndim, int moments) {
+    if (moments) return MOM_CH;
     switch (ndim) {
     case 1: return AccTraits<1>::CH;
     case 2: return AccTraits<2>::CH;
@@ -657,15 +680,55 @@ int spl_acc_chunk_points(int ndim) {
     }
 }
 
-template <int NDIM>
+// Bin tables, work counter and (moment path) the per-cell coefficient tables and moment sums.
+// SPLPAK_B200_ASSEMBLY=direct keeps 3-D on the direct orthant-stencil accumulation (A/B tests).
+int spl_assemble_scratch_init(const GridParams &gp, AssembleScratch &sc, cudaStream_t st) {
+    const char *mode = getenv("SPLPAK_B200_ASSEMBLY");
+    sc.moments = (gp.ndim == 3 && !(mode && strcmp(mode, "direct") == 0)) ? 1 : 0;
+    sc.nbins = gp.nwindows;
+    if (sc.moments) {
+        sc.nbins = 1;
+        long long ntab = 0;
+        for (int d = 0; d < gp.ndim; ++d) {
+            sc.nbins *= gp.nodes[d] + 1;
+            ntab += gp.nodes[d] + 1;
+        }
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.celltab, sizeof(double) * (size_t)ntab * MOM_CW));
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.cellmom, sizeof(double) * (size_t)sc.nbins * MOM_MG));
+        SPL_CUDA_TRY(cudaMemsetAsync(sc.cellmom, 0, sizeof(double) * (size_t)sc.nbins * MOM_MG, st));
+        spl_cell_tables_kernel<<<spl_div_up(ntab, 128), 128, 0, st>>>(gp, sc.celltab);
+        ++g_spl_launches;
+        SPL_CUDA_TRY(cudaGetLastError());
+    }
+    SPL_CUDA_TRY(cudaMalloc((void **)&sc.wincount, sizeof(unsigned) * (size_t)sc.nbins));
+    SPL_CUDA_TRY(cudaMalloc((void **)&sc.winstart, sizeof(unsigned) * (size_t)sc.nbins));
+    SPL_CUDA_TRY(cudaMalloc((void **)&sc.wincursor, sizeof(unsigned) * (size_t)sc.nbins));
+    SPL_CUDA_TRY(cudaMalloc((void **)&sc.itemstart, sizeof(unsigned) * (size_t)sc.nbins));
+    SPL_CUDA_TRY(cudaMalloc((void **)&sc.meta, sizeof(unsigned) * 4));
+    return SPLPAK_OK;
+}
+
+void spl_assemble_scratch_free(AssembleScratch &sc) {
+    unsigned *u[] = {sc.wincount, sc.winstart, sc.wincursor, sc.itemstart, sc.meta};
+    for (unsigned *p : u)
+        if (p) cudaFree(p);
+    if (sc.celltab) cudaFree(sc.celltab);
+    if (sc.cellmom) cudaFree(sc.cellmom);
+    sc.wincount = sc.winstart = sc.wincursor = sc.itemstart = sc.meta = nullptr;
+    sc.celltab = sc.cellmom = nullptr;
+}
+
+template <int NDIM, bool CELL>
 static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y,
                             const real_t *d_w, int weighted, long long n, int do_hist, int rhs_only,
                             const AssembleScratch &sc, double *d_S, double *d_g, double *d_cnt,
                             double *d_totals, cudaStream_t st, int nsm, cudaEvent_t *ev) {
     using T = AccTraits<NDIM>;
     using D = AccDerived<NDIM>;
-    SPL_CUDA_TRY(cudaMemsetAsync(sc.wincount, 0, sizeof(unsigned) * gp.nwindows, st));
-    SPL_CUDA_TRY(cudaMemsetAsync(sc.wincursor, 0, sizeof(unsigned) * gp.nwindows, st));
+    const long long nbins = sc.nbins;
+    const unsigned ch = CELL ? (unsigned)MOM_CH : (unsigned)T::CH;
+    SPL_CUDA_TRY(cudaMemsetAsync(sc.wincount, 0, sizeof(unsigned) * nbins, st));
+    SPL_CUDA_TRY(cudaMemsetAsync(sc.wincursor, 0, sizeof(unsigned) * nbins, st));
     long long nb = (n + 255) / 256;
     const long long cap = (long long)nsm * 8;
     const int grid = (int)(nb < cap ? nb : cap);
@@ -673,41 +736,60 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
     if (ev) cudaEventRecord(ev[0], st);
     {
         // two 512-thread CTAs per SM when the histogram is in shared memory (<= 2 x 96 KB), else 4
-        const size_t hist_bytes = sizeof(unsigned) * (size_t)gp.nwindows;
-        const bool smemh = hist_bytes <= 96 * 1024 && n >= 8 * gp.nwindows;
+        const size_t hist_bytes = sizeof(unsigned) * (size_t)nbins;
+        const bool smemh = hist_bytes <= 96 * 1024 && n >= 8 * nbins;
         long long cb = (n + 512LL * BIN_U - 1) / (512LL * BIN_U);
         const long long ccap = (long long)nsm * (smemh ? 2 : 4);
         const int cgrid = (int)(cb < ccap ? (cb < 1 ? 1 : cb) : ccap);
         if (smemh) {
-            auto kern = spl_classify_kernel<NDIM, true>;
+            auto kern = spl_classify_kernel<NDIM, true, CELL>;
             SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-            kern<<<cgrid, 512, hist_bytes, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.wincount, do_hist, d_cnt, d_totals);
+            kern<<<cgrid, 512, hist_bytes, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins, sc.wincount, do_hist,
+                                                 d_cnt, d_totals);
         } else {
-            spl_classify_kernel<NDIM, false><<<cgrid, 512, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.wincount,
-                                                                    do_hist, d_cnt, d_totals);
+            spl_classify_kernel<NDIM, false, CELL><<<cgrid, 512, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins,
+                                                                          sc.wincount, do_hist, d_cnt, d_totals);
         }
     }
     if (ev) cudaEventRecord(ev[1], st);
-    spl_scan_kernel<<<1, 1024, 0, st>>>(sc.wincount, gp.nwindows, (unsigned)T::CH, sc.winstart,
-                                        sc.itemstart, sc.meta);
-    spl_perm_kernel<NDIM><<<grid, 256, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.winstart, sc.wincursor,
-                                                sc.perm);
-    spl_items_kernel<<<spl_div_up(gp.nwindows, 256), 256, 0, st>>>(sc.wincount, sc.itemstart, gp.nwindows,
-                                                                   (unsigned)T::CH, sc.item_win, sc.item_seg);
+    spl_scan_kernel<<<1, 1024, 0, st>>>(sc.wincount, nbins, ch, sc.winstart, sc.itemstart, sc.meta);
+    spl_perm_kernel<NDIM, CELL><<<grid, 256, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.winstart, sc.wincursor,
+                                                      sc.perm);
+    spl_items_kernel<<<spl_div_up(nbins, 256), 256, 0, st>>>(sc.wincount, sc.itemstart, nbins, ch, sc.item_win,
+                                                             sc.item_seg);
     if (ev) cudaEventRecord(ev[2], st);
-    const size_t smem = sizeof(double) * (2 * (size_t)T::PB * T::RS + (size_t)D::LPGW * (T::R * 10 + D::APL));
-    auto kern = rhs_only ? spl_accumulate_kernel<NDIM, true> : spl_accumulate_kernel<NDIM, false>;
-    SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    SPL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T::NT + D::NP, smem));
-    if (per_sm < 1) per_sm = 1;
-    long long agrid = (long long)nsm * per_sm;
-    const long long max_items = gp.nwindows + n / T::CH + 1;
-    if (agrid > max_items) agrid = max_items;
-    kern<<<(unsigned)agrid, T::NT + D::NP, smem, st>>>(gp, d_x, l1x, d_y, d_w, weighted, sc.perm, sc.wincount,
-                                               sc.winstart, sc.item_win, sc.item_seg, sc.meta, d_S, d_g);
+    const long long max_items = nbins + n / ch + 1;
+    if constexpr (CELL) {
+        static_assert(NDIM == 3, "the moment path is 3-D");
+        const size_t smem = sizeof(double) * (size_t)MOM_PB * MOM_RS;
+        auto kern = rhs_only ? spl_moments_kernel<true> : spl_moments_kernel<false>;
+        SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        SPL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MOM_NT, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long agrid = (long long)nsm * per_sm;
+        if (agrid > max_items) agrid = max_items;
+        kern<<<(unsigned)agrid, MOM_NT, smem, st>>>(gp, d_x, l1x, d_y, d_w, weighted, sc.perm, sc.wincount, sc.winstart,
+                                                    sc.item_win, sc.item_seg, sc.meta, sc.cellmom);
+        if (rhs_only)
+            spl_cell_transform_kernel<true><<<(unsigned)nbins, 128, 0, st>>>(gp, sc.wincount, sc.celltab, sc.cellmom, d_S, d_g);
+        else
+            spl_cell_transform_kernel<false><<<(unsigned)nbins, 128, 0, st>>>(gp, sc.wincount, sc.celltab, sc.cellmom, d_S, d_g);
+        g_spl_launches += 6;
+    } else {
+        const size_t smem = sizeof(double) * (2 * (size_t)T::PB * T::RS + (size_t)D::LPGW * (T::R * 10 + D::APL));
+        auto kern = rhs_only ? spl_accumulate_kernel<NDIM, true> : spl_accumulate_kernel<NDIM, false>;
+        SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        SPL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T::NT + D::NP, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long agrid = (long long)nsm * per_sm;
+        if (agrid > max_items) agrid = max_items;
+        kern<<<(unsigned)agrid, T::NT + D::NP, smem, st>>>(gp, d_x, l1x, d_y, d_w, weighted, sc.perm, sc.wincount,
+                                                           sc.winstart, sc.item_win, sc.item_seg, sc.meta, d_S, d_g);
+        g_spl_launches += 5;
+    }
     if (ev) cudaEventRecord(ev[3], st);
-    g_spl_launches += 5;
     SPL_CUDA_TRY(cudaGetLastError());
     return SPLPAK_OK;
 }
@@ -717,10 +799,12 @@ int spl_assemble_chunk(const GridParams &gp, const real_t *d_x, int l1x, const r
                        const AssembleScratch &sc, double *d_S, double *d_g, double *d_cnt,
                        double *d_totals, cudaStream_t st, int nsm, cudaEvent_t *ev) {
     switch (gp.ndim) {
-    case 1: return assemble_chunk_t<1>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
-    case 2: return assemble_chunk_t<2>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
-    case 3: return assemble_chunk_t<3>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
-    case 4: return assemble_chunk_t<4>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 1: return assemble_chunk_t<1, false>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 2: return assemble_chunk_t<2, false>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 3:
+        if (sc.moments) return assemble_chunk_t<3, true>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+        return assemble_chunk_t<3, false>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 4: return assemble_chunk_t<4, false>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
     }
     return SPLPAK_ERR_NDIM;
 }

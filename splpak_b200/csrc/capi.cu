@@ -12,11 +12,8 @@
 unsigned long long g_spl_launches = 0;
 
 // ---- kernels' host launchers (other translation units) ----
-struct AssembleScratch {
-    unsigned *wincount, *winstart, *wincursor, *itemstart, *item_win, *item_seg, *meta;
-    unsigned *perm;
-    long long max_items;
-};
+int spl_assemble_scratch_init(const GridParams &gp, AssembleScratch &sc, cudaStream_t st);
+void spl_assemble_scratch_free(AssembleScratch &sc);
 int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, int l1x, long long nq,
                     const double *d_coef, long long ncol_padded, real_t *d_out, cudaStream_t stream,
                     int nsm, size_t smem_optin, unsigned long long *d_counter);
@@ -24,7 +21,7 @@ long long spl_grid_tmp_elems(const GridParams &gp, const long long *naxis);
 int spl_eval_grid_launch(const GridParams &gp, const int *nderiv, const real_t *const *d_axis, const long long *naxis,
                          const double *d_coef64, real_t *d_out, double *d_tmp, long long tmp_elems, int *d_iws,
                          double *d_w4, cudaStream_t st, int nsm);
-int spl_acc_chunk_points(int ndim);
+int spl_acc_chunk_points(int ndim, int moments);
 int spl_assemble_chunk(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y,
                        const real_t *d_w, int weighted, long long n, int do_hist, int rhs_only,
                        const AssembleScratch &sc, double *d_S, double *d_g, double *d_cnt,
@@ -572,11 +569,10 @@ static bool valid(splpak_b200_fit_t h) { return h && h->magic == FIT_MAGIC; }
 static void free_handle(splpak_b200_fit_t h) {
     if (!h) return;
     if (h->d_part) cudaFree(h->d_part);
-    unsigned *u[] = {h->sc.wincount, h->sc.winstart, h->sc.wincursor, h->sc.itemstart,
-                     h->sc.item_win, h->sc.item_seg, h->sc.meta};
+    unsigned *u[] = {h->sc.item_win, h->sc.item_seg, h->sc.perm};
     for (unsigned *p : u)
         if (p) cudaFree(p);
-    if (h->sc.perm) cudaFree(h->sc.perm);
+    spl_assemble_scratch_free(h->sc);
     for (int k = 0; k < 2; ++k) {
         for (int a = 0; a < 3; ++a)
             if (h->d_stage[k][a]) cudaFree(h->d_stage[k][a]);
@@ -681,14 +677,11 @@ static int ensure_scratch(splpak_b200_fit_t h, long long n) {
     sc.item_win = sc.item_seg = nullptr;
     h->chunk_cap = 0;
     if (!sc.wincount) {
-        SPL_CUDA_TRY(cudaMalloc((void **)&sc.wincount, sizeof(unsigned) * (size_t)gp.nwindows));
-        SPL_CUDA_TRY(cudaMalloc((void **)&sc.winstart, sizeof(unsigned) * (size_t)gp.nwindows));
-        SPL_CUDA_TRY(cudaMalloc((void **)&sc.wincursor, sizeof(unsigned) * (size_t)gp.nwindows));
-        SPL_CUDA_TRY(cudaMalloc((void **)&sc.itemstart, sizeof(unsigned) * (size_t)gp.nwindows));
-        SPL_CUDA_TRY(cudaMalloc((void **)&sc.meta, sizeof(unsigned) * 4));
+        const int rc = spl_assemble_scratch_init(gp, sc, h->st);
+        if (rc != SPLPAK_OK) return rc;
     }
-    const int ch = spl_acc_chunk_points(gp.ndim);
-    sc.max_items = gp.nwindows + n / ch + 2;
+    const int ch = spl_acc_chunk_points(gp.ndim, sc.moments);
+    sc.max_items = sc.nbins + n / ch + 2;
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.perm, sizeof(unsigned) * (size_t)n));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_win, sizeof(unsigned) * (size_t)sc.max_items));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_seg, sizeof(unsigned) * (size_t)sc.max_items));

@@ -45,6 +45,17 @@ __host__ __device__ __forceinline__ void spl_pair(int a, int &i, int &j) {
 
 __host__ __device__ constexpr int spl_ipow(int b, int e) { return e <= 0 ? 1 : b * spl_ipow(b, e - 1); }
 
+// Scratch of the chunk pipeline of assemble.cu (owned by a fit handle, sized by spl_assemble_scratch_*).
+struct AssembleScratch {
+    unsigned *wincount, *winstart, *wincursor, *itemstart, *item_win, *item_seg, *meta;
+    unsigned *perm;
+    long long max_items;
+    long long nbins;      // bins of the counting sort: windows (direct path) or cells (moment path)
+    int moments;          // 1: 3-D assembly by cell moments (moments.cuh)
+    double *celltab;      // moment path: per-(dimension, cell) coefficient tables
+    double *cellmom;      // moment path: per-cell moment sums of the chunk in flight (kept zero between chunks)
+};
+
 extern unsigned long long g_spl_launches;   // host-side launch counter (capi.cu)
 
 #define SPL_CUDA_TRY(expr)                                                              \

@@ -1,0 +1,361 @@
+// moments.cuh -- 3-D assembly by CELL MOMENTS (included by assemble.cu).
+//
+// Inside one grid cell (a node interval in every dimension, or an exterior half-line) every 1-D basis
+// function of bascmp (src/splpak.F90:206-389) is ONE polynomial of degree <= 3 in the local coordinate
+// t = dxin*(x - x_cell), so every entry of the cell's block of
+//     G = sum_p (w phi)(w phi)^T,   g = sum_p (w phi)(w y)              (:806, :837, suprls :1468-1549)
+// is a fixed linear function of the cell's power sums.  Per point we therefore accumulate only
+//     M[e3][e2][e1] = sum_p w^2   P_e3(t3) P_e2(t2) P_e1(t1),   e = 0..6   (343 values)
+//     R[f3][f2][f1] = sum_p w^2 y P_f3(t3) P_f2(t2) P_f1(t1),   f = 0..3   ( 64 values)
+// in the shifted Legendre basis P_e on [0,1] (orthogonal, so the change of basis below is well
+// conditioned, unlike raw powers), i.e. 407 FMAs per point instead of the 1064 of the direct
+// orthant-stencil accumulation -- and once per cell and chunk the moments are mapped to the 10^3 + 4^3
+// stencil entries with the per-cell coefficient tables
+//     b_i(t) b_j(t) = sum_e C_d[cell][a=(i,j)][e] P_e(t),    b_k(t) = sum_f D_d[cell][k][f] P_f(t),
+// which spl_cell_tables_kernel builds by 7-point Gauss projection of the SAME device basis function the
+// direct path evaluates (exact for the degree <= 12 integrands up to rounding).
+//
+// The result differs from the direct path only by rounding (the sums are re-associated), which the
+// parity tolerance 10*eps*cond(G) covers by a wide margin; tests/test_gpu_fit.py compares both paths.
+#pragma once
+
+#include "basis.cuh"
+
+#define MOM_NE 7                      // Legendre degrees of a pair product b_i b_j
+#define MOM_NF 4                      // Legendre degrees of one basis function
+#define MOM_CW (10 * MOM_NE + 4 * MOM_NF)   // doubles per (dimension, cell) of the coefficient table
+#define MOM_NM 343                    // moments of G per cell
+#define MOM_NR 64                     // moments of g per cell
+#define MOM_MG 408                    // doubles per cell of the moment array (407 used)
+#define MOM_NT 128                    // threads per CTA of the moment kernel (thread = point when staging)
+#define MOM_PB 128                    // points per staged batch
+#define MOM_RS 74                     // doubles per staged point: P1[7] . | OUT[49] . | ROUT[16];  RS/2 odd
+#define MOM_OFF_OUT 8
+#define MOM_OFF_ROUT 58
+#define MOM_CH 4096                   // max points per work item
+#define MOM_NWARP (MOM_NT / 32)
+
+// shifted Legendre polynomials P_0..P_{N-1} at t (z = 2t-1; Bonnet recurrence with constant factors)
+template <int N>
+__device__ __forceinline__ void spl_legendre(double t, double *P) {
+    const double z = fma(2.0, t, -1.0);
+    P[0] = 1.0;
+    if (N > 1) P[1] = z;
+#pragma unroll
+    for (int k = 1; k + 1 < N; ++k) {
+        const double a = (double)(2 * k + 1) / (double)(k + 1), b = (double)k / (double)(k + 1);
+        P[k + 1] = fma(a * z, P[k], -b * P[k - 1]);
+    }
+}
+
+// One thread per (dimension, cell): coefficient tables C[10][7], D[4][4].
+__global__ void __launch_bounds__(128)
+spl_cell_tables_kernel(const __grid_constant__ GridParams gp, double *__restrict__ tab) {
+    // 7-point Gauss-Legendre rule on [-1, 1]
+    const double gz[7] = {0.0, -0.4058451513773972, 0.4058451513773972, -0.7415311855993945,
+                          0.7415311855993945, -0.9491079123427585, 0.9491079123427585};
+    const double gw[7] = {0.4179591836734694, 0.3818300505051189, 0.3818300505051189, 0.2797053914892766,
+                          0.2797053914892766, 0.1294849661688697, 0.1294849661688697};
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int d = 0;
+    long long off = 0;
+    for (; d < gp.ndim; ++d) {
+        if (idx < gp.nodes[d] + 1) break;
+        idx -= gp.nodes[d] + 1;
+        off += (long long)(gp.nodes[d] + 1) * MOM_CW;
+    }
+    if (d >= gp.ndim) return;
+    const int nod = gp.nodes[d], ic = idx, it = ic - 1;
+    const int ws = min(max(it - 1, 0), nod - 4);
+    const bool exterior = (ic == 0) || (ic == nod);
+    double bq[7][4], Pq[7][MOM_NE];
+    const double x0 = gp.xmin[d] + (double)it * gp.dx[d];
+    for (int q = 0; q < 7; ++q) {
+        const double tq = 0.5 * (1.0 + gz[q]);
+        const double x = x0 + tq * gp.dx[d];
+        // local coordinate exactly as the moment kernel forms it, so the projection sees the same t
+        const double tl = spl_mul(gp.dxin[d], spl_sub(x, spl_add(gp.xmin[d], spl_mul((double)it, gp.dx[d]))));
+        for (int k = 0; k < 4; ++k) bq[q][k] = spl_bas1_value(ws + k, nod, x, gp.xmin[d], gp.dx[d], gp.dxin[d]);
+        spl_legendre<MOM_NE>(tl, Pq[q]);
+    }
+    double *C = tab + off + (long long)ic * MOM_CW;
+    double *D = C + 10 * MOM_NE;
+    for (int a = 0; a < 10; ++a) {
+        int i, j;
+        spl_pair(a, i, j);
+        for (int e = 0; e < MOM_NE; ++e) {
+            double s = 0.0;
+            for (int q = 0; q < 7; ++q) s += 0.5 * gw[q] * bq[q][i] * bq[q][j] * Pq[q][e];
+            // on an exterior half-line the basis is linear: degrees > 2 vanish identically (and their
+            // moments may overflow for far-away points, so they must not be touched)
+            C[a * MOM_NE + e] = (exterior && e > 2) ? 0.0 : (double)(2 * e + 1) * s;
+        }
+    }
+    for (int k = 0; k < 4; ++k)
+        for (int f = 0; f < MOM_NF; ++f) {
+            double s = 0.0;
+            for (int q = 0; q < 7; ++q) s += 0.5 * gw[q] * bq[q][k] * Pq[q][f];
+            D[k * MOM_NF + f] = (exterior && f > 1) ? 0.0 : (double)(2 * f + 1) * s;
+        }
+}
+
+// Persistent CTAs over work items (cell, segment of <= MOM_CH points).  Per batch of MOM_PB points:
+//   stage   thread = point: gather through the permutation (prefetched one batch ahead, the permutation
+//           two ahead), Legendre values of the three local coordinates, outer products
+//           OUT[e3*7+e2] = w^2 P3 P2 and ROUT[f3*4+f2] = w^2 y P3 P2 into shared memory;
+//   accumulate   warp k takes points k, k+4, ..; lane l owns outer rows l and l+32 (< 49) x 7 inner
+//           degrees, lanes 0..15 also one right-hand-side row x 4: 18 DFMA per lane and point.
+// Three CTAs are resident per SM, so one CTA's staging overlaps another's DFMA stream.
+template <bool RHS_ONLY>
+__global__ void __launch_bounds__(MOM_NT, 3)
+spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
+                   const real_t *__restrict__ y, const real_t *__restrict__ w, int weighted,
+                   const unsigned *__restrict__ perm, const unsigned *__restrict__ bincount,
+                   const unsigned *__restrict__ binstart, const unsigned *__restrict__ item_bin,
+                   const unsigned *__restrict__ item_seg, unsigned *__restrict__ meta,
+                   double *__restrict__ MG) {
+    extern __shared__ __align__(16) double s_pts[];          // MOM_PB x MOM_RS, reused for the reduction
+    __shared__ unsigned s_item;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned nitems = meta[0];
+    const int nc1 = gp.nodes[0] + 1, nc2 = gp.nodes[1] + 1;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(meta + 2, 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= nitems) break;
+        const unsigned cell = item_bin[item];
+        const unsigned seg = item_seg[item];
+        const long long first = (long long)binstart[cell] + (long long)seg * MOM_CH;
+        const int npts = (int)min((unsigned)MOM_CH, bincount[cell] - seg * (unsigned)MOM_CH);
+        const int nbatch = (npts + MOM_PB - 1) / MOM_PB;
+        double xc[3];                                        // left end of the cell per dimension (:246 form)
+        {
+            const int c1 = (int)(cell % (unsigned)nc1), c2 = (int)((cell / (unsigned)nc1) % (unsigned)nc2),
+                      c3 = (int)(cell / (unsigned)(nc1 * nc2));
+            xc[0] = spl_add(gp.xmin[0], spl_mul((double)(c1 - 1), gp.dx[0]));
+            xc[1] = spl_add(gp.xmin[1], spl_mul((double)(c2 - 1), gp.dx[1]));
+            xc[2] = spl_add(gp.xmin[2], spl_mul((double)(c3 - 1), gp.dx[2]));
+        }
+        double acc0[MOM_NE], acc1[MOM_NE], racc[MOM_NF];
+#pragma unroll
+        for (int e = 0; e < MOM_NE; ++e) acc0[e] = acc1[e] = 0.0;
+#pragma unroll
+        for (int f = 0; f < MOM_NF; ++f) racc[f] = 0.0;
+
+        unsigned pi;
+        double px[3], py, pw;
+        auto load_perm = [&](int b) {
+            const int p = b * MOM_PB + tid;
+            pi = (p < npts) ? perm[first + p] : 0xffffffffu;
+        };
+        auto load_data = [&]() {
+            px[0] = px[1] = px[2] = 0.0;
+            py = 0.0;
+            pw = 0.0;
+            if (pi != 0xffffffffu) {
+                const long long i = pi;
+                px[0] = (double)x[i * (long long)l1x + 0];
+                px[1] = (double)x[i * (long long)l1x + 1];
+                px[2] = (double)x[i * (long long)l1x + 2];
+                py = (double)y[i];
+                pw = weighted ? (double)w[i] : 1.0;
+            }
+        };
+        load_perm(0);
+        load_data();
+        if (nbatch > 1) load_perm(1);
+        for (int b = 0; b < nbatch; ++b) {
+            const int nb = min(MOM_PB, npts - b * MOM_PB);
+            // ---- stage ----
+            if (tid < nb) {
+                double P1[MOM_NE], P2[MOM_NE], P3[MOM_NE];
+                spl_legendre<MOM_NE>(spl_mul(gp.dxin[0], spl_sub(px[0], xc[0])), P1);
+                spl_legendre<MOM_NE>(spl_mul(gp.dxin[1], spl_sub(px[1], xc[1])), P2);
+                spl_legendre<MOM_NE>(spl_mul(gp.dxin[2], spl_sub(px[2], xc[2])), P3);
+                const double w2 = pw * pw;                       // row = w*phi, rhs = w*y (:806, :837)
+                const double w2y = w2 * py;
+                double *rec = s_pts + tid * MOM_RS;
+#pragma unroll
+                for (int e = 0; e < 8; e += 2)
+                    *reinterpret_cast<double2 *>(rec + e) = make_double2(P1[e], e + 1 < MOM_NE ? P1[e + 1] : 0.0);
+                if (!RHS_ONLY) {
+                    double o[50];
+#pragma unroll
+                    for (int e3 = 0; e3 < MOM_NE; ++e3) {
+                        const double h = w2 * P3[e3];
+#pragma unroll
+                        for (int e2 = 0; e2 < MOM_NE; ++e2) o[e3 * MOM_NE + e2] = h * P2[e2];
+                    }
+                    o[49] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 50; k += 2)
+                        *reinterpret_cast<double2 *>(rec + MOM_OFF_OUT + k) = make_double2(o[k], o[k + 1]);
+                }
+#pragma unroll
+                for (int f3 = 0; f3 < MOM_NF; ++f3) {
+                    const double h = w2y * P3[f3];
+                    *reinterpret_cast<double2 *>(rec + MOM_OFF_ROUT + f3 * 4) = make_double2(h * P2[0], h * P2[1]);
+                    *reinterpret_cast<double2 *>(rec + MOM_OFF_ROUT + f3 * 4 + 2) = make_double2(h * P2[2], h * P2[3]);
+                }
+            }
+            __syncthreads();
+            if (b + 1 < nbatch) load_data();                     // gathers of the next batch fly under the DFMAs
+            if (b + 2 < nbatch) load_perm(b + 2);
+            // ---- accumulate ----
+#pragma unroll 2
+            for (int p = warp; p < nb; p += MOM_NWARP) {
+                const double *rec = s_pts + p * MOM_RS;
+                double in[8];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(rec + e);
+                    in[e] = v.x;
+                    in[e + 1] = v.y;
+                }
+                const double r = (lane < 16) ? rec[MOM_OFF_ROUT + lane] : 0.0;
+#pragma unroll
+                for (int f = 0; f < MOM_NF; ++f) racc[f] = fma(r, in[f], racc[f]);
+                if (!RHS_ONLY) {
+                    const double h0 = rec[MOM_OFF_OUT + lane];
+                    const double h1 = (lane < 17) ? rec[MOM_OFF_OUT + 32 + lane] : 0.0;
+#pragma unroll
+                    for (int e = 0; e < MOM_NE; ++e) {
+                        acc0[e] = fma(h0, in[e], acc0[e]);
+                        acc1[e] = fma(h1, in[e], acc1[e]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- reduce the four warps through shared memory, flush once per work item ----
+        {
+            double *red = s_pts + warp * MOM_MG;
+            if (!RHS_ONLY) {
+#pragma unroll
+                for (int e = 0; e < MOM_NE; ++e) {
+                    red[lane * MOM_NE + e] = acc0[e];
+                    if (lane < 17) red[(32 + lane) * MOM_NE + e] = acc1[e];
+                }
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int f = 0; f < MOM_NF; ++f) red[MOM_NM + lane * MOM_NF + f] = racc[f];
+            }
+        }
+        __syncthreads();
+        double *dst = MG + (long long)cell * MOM_MG;
+        for (int k = (RHS_ONLY ? MOM_NM : 0) + tid; k < MOM_NM + MOM_NR; k += MOM_NT) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < MOM_NWARP; ++q) v += s_pts[q * MOM_MG + k];
+            if (v != 0.0) atomicAdd(dst + k, v);
+        }
+    }
+}
+
+// One CTA per non-empty cell: moments -> stencil entries (three 1-D changes of basis), added into S / g.
+// The cell's moments are zeroed after they are read, so the array is clean for the next chunk.
+template <bool RHS_ONLY>
+__global__ void __launch_bounds__(128)
+spl_cell_transform_kernel(const __grid_constant__ GridParams gp, const unsigned *__restrict__ bincount,
+                          const double *__restrict__ tab, double *__restrict__ MG, double *__restrict__ S,
+                          double *__restrict__ g) {
+    const unsigned cell = blockIdx.x;
+    if (bincount[cell] == 0u) return;
+    __shared__ double s_M[MOM_NM + MOM_NR];
+    __shared__ double s_C[3][MOM_CW];
+    __shared__ double s_T1[49 * 10], s_T2[7 * 100];
+    __shared__ double s_U1[16 * 4], s_U2[4 * 16];
+    const int tid = threadIdx.x;
+    const int nc1 = gp.nodes[0] + 1, nc2 = gp.nodes[1] + 1;
+    int c[3], ws[3];
+    c[0] = (int)(cell % (unsigned)nc1);
+    c[1] = (int)((cell / (unsigned)nc1) % (unsigned)nc2);
+    c[2] = (int)(cell / (unsigned)(nc1 * nc2));
+    long long toff = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        ws[d] = min(max(c[d] - 2, 0), gp.nodes[d] - 4);
+        const double *src = tab + toff + (long long)c[d] * MOM_CW;
+        for (int k = tid; k < MOM_CW; k += blockDim.x) s_C[d][k] = src[k];
+        toff += (long long)(gp.nodes[d] + 1) * MOM_CW;
+    }
+    double *mg = MG + (long long)cell * MOM_MG;
+    for (int k = (RHS_ONLY ? MOM_NM : 0) + tid; k < MOM_NM + MOM_NR; k += blockDim.x) {
+        s_M[k] = mg[k];
+        mg[k] = 0.0;
+    }
+    __syncthreads();
+    // a zero coefficient must skip its moment (it may be inf/NaN for a far exterior point)
+    auto mac = [](double cf, double m, double s) { return cf != 0.0 ? fma(cf, m, s) : s; };
+    if (!RHS_ONLY) {
+        for (int k = tid; k < 490; k += blockDim.x) {           // T1[o][a1]
+            const int o = k / 10, a1 = k - o * 10;
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[0][a1 * MOM_NE + e], s_M[o * MOM_NE + e], s);
+            s_T1[k] = s;
+        }
+    }
+    if (tid < 64) {                                              // U1[ro][i1]
+        const int ro = tid >> 2, i1 = tid & 3;
+        double s = 0.0;
+#pragma unroll
+        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[0][70 + i1 * MOM_NF + f], s_M[MOM_NM + ro * MOM_NF + f], s);
+        s_U1[tid] = s;
+    }
+    __syncthreads();
+    if (!RHS_ONLY) {
+        for (int k = tid; k < 700; k += blockDim.x) {           // T2[e3][a2][a1]
+            const int e3 = k / 100, r = k - e3 * 100, a2 = r / 10, a1 = r - a2 * 10;
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[1][a2 * MOM_NE + e], s_T1[(e3 * MOM_NE + e) * 10 + a1], s);
+            s_T2[k] = s;
+        }
+    }
+    if (tid < 64) {                                              // U2[f3][i2][i1]
+        const int f3 = tid >> 4, i2 = (tid >> 2) & 3, i1 = tid & 3;
+        double s = 0.0;
+#pragma unroll
+        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[1][70 + i2 * MOM_NF + f], s_U1[(f3 * 4 + f) * 4 + i1], s);
+        s_U2[tid] = s;
+    }
+    __syncthreads();
+    if (!RHS_ONLY) {
+        for (int k = tid; k < 1000; k += blockDim.x) {          // S[a3][a2][a1]
+            const int a3 = k / 100, r = k - a3 * 100;
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[2][a3 * MOM_NE + e], s_T2[e * 100 + r], s);
+            if (s != 0.0) {
+                const int a[3] = {r % 10, r / 10, a3};
+                long long node = 0, nstride = 1;
+                int sten = 0, sstride = 1;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    int i, j;
+                    spl_pair(a[d], i, j);
+                    node += (long long)(ws[d] + i) * nstride;
+                    sten += (j - i) * sstride;
+                    nstride *= gp.nodes[d];
+                    sstride *= 4;
+                }
+                atomicAdd(S + node * gp.nsten + sten, s);
+            }
+        }
+    }
+    if (tid < 64) {                                              // g[i3][i2][i1]
+        const int i3 = tid >> 4, r = tid & 15;
+        double s = 0.0;
+#pragma unroll
+        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[2][70 + i3 * MOM_NF + f], s_U2[f * 16 + r], s);
+        if (s != 0.0) {
+            const long long node = (long long)(ws[0] + (r & 3)) + (long long)(ws[1] + (r >> 2)) * gp.nodes[0] +
+                                   (long long)(ws[2] + i3) * gp.nodes[0] * gp.nodes[1];
+            atomicAdd(g + node, s);
+        }
+    }
+}
