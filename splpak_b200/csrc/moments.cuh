@@ -29,9 +29,13 @@
 #define MOM_MG 408                    // doubles per cell of the moment array (407 used)
 #define MOM_NT 128                    // threads per CTA of the moment kernel (thread = point when staging)
 #define MOM_PB 128                    // points per staged batch
-#define MOM_RS 74                     // doubles per staged point: P1[7] . | OUT[49] . | ROUT[16];  RS/2 odd
-#define MOM_OFF_OUT 8
-#define MOM_OFF_ROUT 58
+// staged record of one point (doubles; RS/2 odd so the 128-bit staging stores of neighbouring points do not collide):
+//   [0..7] P1[0..6], 0   [8..15] P2[0..6], 0   [16..23] (A3[g], A3[g+4]) g = 0..3, A3 = w^2 P3, A3[7] = 0
+//   [24..27] B3[0..3] = w^2 y P3
+#define MOM_RS 30
+#define MOM_OFF_P2 8
+#define MOM_OFF_A3 16
+#define MOM_OFF_B3 24
 #define MOM_CH 4096                   // max points per work item
 #define MOM_NWARP (MOM_NT / 32)
 
@@ -101,13 +105,16 @@ spl_cell_tables_kernel(const __grid_constant__ GridParams gp, double *__restrict
 
 // Persistent CTAs over work items (cell, segment of <= MOM_CH points).  Per batch of MOM_PB points:
 //   stage   thread = point: gather through the permutation (prefetched one batch ahead, the permutation
-//           two ahead), Legendre values of the three local coordinates, outer products
-//           OUT[e3*7+e2] = w^2 P3 P2 and ROUT[f3*4+f2] = w^2 y P3 P2 into shared memory;
-//   accumulate   warp k takes points k, k+4, ..; lane l owns outer rows l and l+32 (< 49) x 7 inner
-//           degrees, lanes 0..15 also one right-hand-side row x 4: 18 DFMA per lane and point.
-// Three CTAs are resident per SM, so one CTA's staging overlaps another's DFMA stream.
+//           two ahead), Legendre values of the three local coordinates -> P1, P2, w^2 P3, w^2 y P3 into
+//           shared memory (28 doubles per point);
+//   accumulate   warp k takes points k, k+4, ..; lane l = 7 g + e2 (28 active lanes) owns the moments
+//           (e3 in {g, g+4}, e2, e1 = 0..6) and, when e2 < 4, the right-hand-side row (f3 = g, f2 = e2,
+//           f1 = 0..3): 3 DMUL + 18 DFMA per lane and point.  Every shared-memory load of the inner loop
+//           is a SINGLE wavefront (broadcast, or <= 7 distinct addresses inside 64 bytes): the kernel is
+//           bound by the shared-memory pipe, and multi-wavefront loads cost ~2 cycles per wavefront.
+// Several CTAs are resident per SM, so one CTA's staging overlaps another's DFMA stream.
 template <bool RHS_ONLY>
-__global__ void __launch_bounds__(MOM_NT, 3)
+__global__ void __launch_bounds__(MOM_NT, 4)
 spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
                    const real_t *__restrict__ y, const real_t *__restrict__ w, int weighted,
                    const unsigned *__restrict__ perm, const unsigned *__restrict__ bincount,
@@ -117,6 +124,9 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
     extern __shared__ __align__(16) double s_pts[];          // MOM_PB x MOM_RS, reused for the reduction
     __shared__ unsigned s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // lanes 28..31 (lg = 4) run the same loads on in-record addresses and are never flushed
+    const int lg = lane / 7, le2 = lane - 7 * lg;
+    const int offP2 = MOM_OFF_P2 + le2, offA3 = MOM_OFF_A3 + 2 * lg, offB3 = MOM_OFF_B3 + lg;
     const unsigned nitems = meta[0];
     const int nc1 = gp.nodes[0] + 1, nc2 = gp.nodes[1] + 1;
     for (;;) {
@@ -144,18 +154,21 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
 #pragma unroll
         for (int f = 0; f < MOM_NF; ++f) racc[f] = 0.0;
 
-        unsigned pi;
+        // pn: permutation entry of the batch AFTER the one held in px/py/pw.  The entry a gather uses is
+        // first copied to a fresh register: overwriting the register the in-flight gathers were addressed
+        // from made the next permutation load wait on their scoreboard (a full memory latency per batch).
+        unsigned pn;
         double px[3], py, pw;
         auto load_perm = [&](int b) {
             const int p = b * MOM_PB + tid;
-            pi = (p < npts) ? perm[first + p] : 0xffffffffu;
+            pn = (b < nbatch && p < npts) ? perm[first + p] : 0xffffffffu;
         };
-        auto load_data = [&]() {
+        auto load_data = [&](unsigned pc) {
             px[0] = px[1] = px[2] = 0.0;
             py = 0.0;
             pw = 0.0;
-            if (pi != 0xffffffffu) {
-                const long long i = pi;
+            if (pc != 0xffffffffu) {
+                const long long i = pc;
                 px[0] = (double)x[i * (long long)l1x + 0];
                 px[1] = (double)x[i * (long long)l1x + 1];
                 px[2] = (double)x[i * (long long)l1x + 2];
@@ -164,8 +177,8 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
             }
         };
         load_perm(0);
-        load_data();
-        if (nbatch > 1) load_perm(1);
+        load_data(pn);
+        load_perm(1);
         for (int b = 0; b < nbatch; ++b) {
             const int nb = min(MOM_PB, npts - b * MOM_PB);
             // ---- stage ----
@@ -178,31 +191,23 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
                 const double w2y = w2 * py;
                 double *rec = s_pts + tid * MOM_RS;
 #pragma unroll
-                for (int e = 0; e < 8; e += 2)
+                for (int e = 0; e < 8; e += 2) {
                     *reinterpret_cast<double2 *>(rec + e) = make_double2(P1[e], e + 1 < MOM_NE ? P1[e + 1] : 0.0);
-                if (!RHS_ONLY) {
-                    double o[50];
-#pragma unroll
-                    for (int e3 = 0; e3 < MOM_NE; ++e3) {
-                        const double h = w2 * P3[e3];
-#pragma unroll
-                        for (int e2 = 0; e2 < MOM_NE; ++e2) o[e3 * MOM_NE + e2] = h * P2[e2];
-                    }
-                    o[49] = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 50; k += 2)
-                        *reinterpret_cast<double2 *>(rec + MOM_OFF_OUT + k) = make_double2(o[k], o[k + 1]);
+                    *reinterpret_cast<double2 *>(rec + MOM_OFF_P2 + e) = make_double2(P2[e], e + 1 < MOM_NE ? P2[e + 1] : 0.0);
                 }
 #pragma unroll
-                for (int f3 = 0; f3 < MOM_NF; ++f3) {
-                    const double h = w2y * P3[f3];
-                    *reinterpret_cast<double2 *>(rec + MOM_OFF_ROUT + f3 * 4) = make_double2(h * P2[0], h * P2[1]);
-                    *reinterpret_cast<double2 *>(rec + MOM_OFF_ROUT + f3 * 4 + 2) = make_double2(h * P2[2], h * P2[3]);
-                }
+                for (int gq = 0; gq < 4; ++gq)
+                    *reinterpret_cast<double2 *>(rec + MOM_OFF_A3 + 2 * gq) =
+                        make_double2(RHS_ONLY ? 0.0 : w2 * P3[gq], (RHS_ONLY || gq + 4 >= MOM_NE) ? 0.0 : w2 * P3[gq + 4]);
+                *reinterpret_cast<double2 *>(rec + MOM_OFF_B3) = make_double2(w2y * P3[0], w2y * P3[1]);
+                *reinterpret_cast<double2 *>(rec + MOM_OFF_B3 + 2) = make_double2(w2y * P3[2], w2y * P3[3]);
             }
             __syncthreads();
-            if (b + 1 < nbatch) load_data();                     // gathers of the next batch fly under the DFMAs
-            if (b + 2 < nbatch) load_perm(b + 2);
+            {
+                const unsigned pc = pn;
+                load_perm(b + 2);                                // permutation two batches ahead
+                if (b + 1 < nbatch) load_data(pc);               // gathers of the next batch fly under the DFMAs
+            }
             // ---- accumulate ----
 #pragma unroll 2
             for (int p = warp; p < nb; p += MOM_NWARP) {
@@ -214,12 +219,13 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
                     in[e] = v.x;
                     in[e + 1] = v.y;
                 }
-                const double r = (lane < 16) ? rec[MOM_OFF_ROUT + lane] : 0.0;
+                const double p2 = rec[offP2];
+                const double r = rec[offB3] * p2;
 #pragma unroll
                 for (int f = 0; f < MOM_NF; ++f) racc[f] = fma(r, in[f], racc[f]);
                 if (!RHS_ONLY) {
-                    const double h0 = rec[MOM_OFF_OUT + lane];
-                    const double h1 = (lane < 17) ? rec[MOM_OFF_OUT + 32 + lane] : 0.0;
+                    const double2 a3 = *reinterpret_cast<const double2 *>(rec + offA3);
+                    const double h0 = a3.x * p2, h1 = a3.y * p2;
 #pragma unroll
                     for (int e = 0; e < MOM_NE; ++e) {
                         acc0[e] = fma(h0, in[e], acc0[e]);
@@ -232,16 +238,16 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
         // ---- reduce the four warps through shared memory, flush once per work item ----
         {
             double *red = s_pts + warp * MOM_MG;
-            if (!RHS_ONLY) {
+            if (!RHS_ONLY && lg < 4) {
 #pragma unroll
                 for (int e = 0; e < MOM_NE; ++e) {
-                    red[lane * MOM_NE + e] = acc0[e];
-                    if (lane < 17) red[(32 + lane) * MOM_NE + e] = acc1[e];
+                    red[(lg * MOM_NE + le2) * MOM_NE + e] = acc0[e];
+                    if (lg < 3) red[((lg + 4) * MOM_NE + le2) * MOM_NE + e] = acc1[e];
                 }
             }
-            if (lane < 16) {
+            if (lg < 4 && le2 < 4) {
 #pragma unroll
-                for (int f = 0; f < MOM_NF; ++f) red[MOM_NM + lane * MOM_NF + f] = racc[f];
+                for (int f = 0; f < MOM_NF; ++f) red[MOM_NM + (lg * 4 + le2) * MOM_NF + f] = racc[f];
             }
         }
         __syncthreads();
