@@ -29,9 +29,10 @@
 #define MOM_MG 408                    // doubles per cell of the moment array (407 used)
 #define MOM_NT 128                    // threads per CTA of the moment kernel (thread = point when staging)
 #define MOM_PB 128                    // points per staged batch
-// staged record of one point (doubles; RS/2 odd so the 128-bit staging stores of neighbouring points do not collide):
-//   [0..7] P1[0..6], 0   [8..15] P2[0..6], 0   [16..23] (A3[g], A3[g+4]) g = 0..3, A3 = w^2 P3, A3[7] = 0
-//   [24..27] B3[0..3] = w^2 y P3
+// staged record of one point (doubles):
+//   [0..7] P1[0..6], 0   [8..15] P2[0..6], 0   [16..23] A3[0..6] = w^2 P3, 0   [24..27] B3[0..3] = w^2 y P3
+// RS/2 odd: the 128-bit staging stores of neighbouring points do not collide; RS = 14 mod 16: the four points
+// {q, q+2, q+4, q+6} of one MMA k-group start 4 (8-byte) banks apart, so the fragment loads are conflict-free.
 #define MOM_RS 30
 #define MOM_OFF_P2 8
 #define MOM_OFF_A3 16
@@ -103,16 +104,23 @@ spl_cell_tables_kernel(const __grid_constant__ GridParams gp, double *__restrict
         }
 }
 
+__device__ __forceinline__ void spl_mom_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 // Persistent CTAs over work items (cell, segment of <= MOM_CH points).  Per batch of MOM_PB points:
 //   stage   thread = point: gather through the permutation (prefetched one batch ahead, the permutation
 //           two ahead), Legendre values of the three local coordinates -> P1, P2, w^2 P3, w^2 y P3 into
 //           shared memory (28 doubles per point);
-//   accumulate   warp k takes points k, k+4, ..; lane l = 7 g + e2 (28 active lanes) owns the moments
-//           (e3 in {g, g+4}, e2, e1 = 0..6) and, when e2 < 4, the right-hand-side row (f3 = g, f2 = e2,
-//           f1 = 0..3): 3 DMUL + 18 DFMA per lane and point.  Every shared-memory load of the inner loop
-//           is a SINGLE wavefront (broadcast, or <= 7 distinct addresses inside 64 bytes): the kernel is
-//           bound by the shared-memory pipe, and multi-wavefront loads cost ~2 cycles per wavefront.
-// Several CTAs are resident per SM, so one CTA's staging overlaps another's DFMA stream.
+//   accumulate   the moment sums are a GEMM over the points, M[(e3,e2)][e1] = sum_p (A3[e3] P2[e2])_p P1[e1]_p,
+//           run on the FP64 tensor cores (mma.sync.m8n8k4.f64 -> DMMA.8x8x4): k = 4 points, n = e1 (7 of 8
+//           columns), one m-tile of rows e2 (7 of 8) per e3, plus two tiles (rows (f3, f2)) for the
+//           right-hand side.  Lane (r, k) multiplies its own A fragment A3[e3]*P2[r] of point k; the B
+//           fragment P1[r] is ONE shared-memory load per 4 points, where the DFMA form needed 7 broadcast
+//           loads per point -- the kernel is bound by the shared-memory pipe, not by FP64 issue.
+// Several CTAs are resident per SM, so one CTA's staging overlaps another's MMA stream.
 template <bool RHS_ONLY>
 __global__ void __launch_bounds__(MOM_NT, 4)
 spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
@@ -124,9 +132,8 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
     extern __shared__ __align__(16) double s_pts[];          // MOM_PB x MOM_RS, reused for the reduction
     __shared__ unsigned s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // lanes 28..31 (lg = 4) run the same loads on in-record addresses and are never flushed
-    const int lg = lane / 7, le2 = lane - 7 * lg;
-    const int offP2 = MOM_OFF_P2 + le2, offA3 = MOM_OFF_A3 + 2 * lg, offB3 = MOM_OFF_B3 + lg;
+    const int fr = lane >> 2, fk = lane & 3;                // MMA fragment coordinates of this lane
+    const int frr = fr & 3, frh = fr >> 2;
     const unsigned nitems = meta[0];
     const int nc1 = gp.nodes[0] + 1, nc2 = gp.nodes[1] + 1;
     for (;;) {
@@ -148,11 +155,10 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
             xc[1] = spl_add(gp.xmin[1], spl_mul((double)(c2 - 1), gp.dx[1]));
             xc[2] = spl_add(gp.xmin[2], spl_mul((double)(c3 - 1), gp.dx[2]));
         }
-        double acc0[MOM_NE], acc1[MOM_NE], racc[MOM_NF];
+        double acc[MOM_NE][2], racc[2][2];                   // C fragments: tile e3 (rows e2), rhs tiles
 #pragma unroll
-        for (int e = 0; e < MOM_NE; ++e) acc0[e] = acc1[e] = 0.0;
-#pragma unroll
-        for (int f = 0; f < MOM_NF; ++f) racc[f] = 0.0;
+        for (int e = 0; e < MOM_NE; ++e) acc[e][0] = acc[e][1] = 0.0;
+        racc[0][0] = racc[0][1] = racc[1][0] = racc[1][1] = 0.0;
 
         // pn: permutation entry of the batch AFTER the one held in px/py/pw.  The entry a gather uses is
         // first copied to a fresh register: overwriting the register the in-flight gathers were addressed
@@ -195,12 +201,19 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
                     *reinterpret_cast<double2 *>(rec + e) = make_double2(P1[e], e + 1 < MOM_NE ? P1[e + 1] : 0.0);
                     *reinterpret_cast<double2 *>(rec + MOM_OFF_P2 + e) = make_double2(P2[e], e + 1 < MOM_NE ? P2[e + 1] : 0.0);
                 }
+                if (!RHS_ONLY) {
 #pragma unroll
-                for (int gq = 0; gq < 4; ++gq)
-                    *reinterpret_cast<double2 *>(rec + MOM_OFF_A3 + 2 * gq) =
-                        make_double2(RHS_ONLY ? 0.0 : w2 * P3[gq], (RHS_ONLY || gq + 4 >= MOM_NE) ? 0.0 : w2 * P3[gq + 4]);
+                    for (int e = 0; e < 8; e += 2)
+                        *reinterpret_cast<double2 *>(rec + MOM_OFF_A3 + e) =
+                            make_double2(w2 * P3[e], e + 1 < MOM_NE ? w2 * P3[e + 1] : 0.0);
+                }
                 *reinterpret_cast<double2 *>(rec + MOM_OFF_B3) = make_double2(w2y * P3[0], w2y * P3[1]);
                 *reinterpret_cast<double2 *>(rec + MOM_OFF_B3 + 2) = make_double2(w2y * P3[2], w2y * P3[3]);
+            } else if (tid < ((nb + 7) & ~7)) {
+                // the MMA consumes whole groups of 8 points: pad the last group with zero records
+                double *rec = s_pts + tid * MOM_RS;
+#pragma unroll
+                for (int e = 0; e < 28; e += 2) *reinterpret_cast<double2 *>(rec + e) = make_double2(0.0, 0.0);
             }
             __syncthreads();
             {
@@ -209,27 +222,26 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
                 if (b + 1 < nbatch) load_data(pc);               // gathers of the next batch fly under the DFMAs
             }
             // ---- accumulate ----
-#pragma unroll 2
-            for (int p = warp; p < nb; p += MOM_NWARP) {
-                const double *rec = s_pts + p * MOM_RS;
-                double in[8];
+            for (int p0 = warp * 8; p0 < nb; p0 += MOM_NWARP * 8) {
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(rec + e);
-                    in[e] = v.x;
-                    in[e + 1] = v.y;
-                }
-                const double p2 = rec[offP2];
-                const double r = rec[offB3] * p2;
+                for (int half = 0; half < 2; ++half) {
+                    const double *rec = s_pts + (p0 + half + 2 * fk) * MOM_RS;      // point of this lane's k
+                    const double bfrag = rec[fr];                                    // B[k][n = fr] = P1[fr]
+                    const double p2r = rec[MOM_OFF_P2 + frr];
+                    const double b30 = rec[MOM_OFF_B3 + frh], b31 = rec[MOM_OFF_B3 + 2 + frh];
+                    spl_mom_dmma(racc[0][0], racc[0][1], b30 * p2r, bfrag);        // rows (f3 = frh, f2 = frr)
+                    spl_mom_dmma(racc[1][0], racc[1][1], b31 * p2r, bfrag);        // rows (f3 = 2 + frh, f2 = frr)
+                    if (!RHS_ONLY) {
+                        const double p2 = rec[MOM_OFF_P2 + fr];
+                        double a3[8];
 #pragma unroll
-                for (int f = 0; f < MOM_NF; ++f) racc[f] = fma(r, in[f], racc[f]);
-                if (!RHS_ONLY) {
-                    const double2 a3 = *reinterpret_cast<const double2 *>(rec + offA3);
-                    const double h0 = a3.x * p2, h1 = a3.y * p2;
+                        for (int e = 0; e < 8; e += 2) {
+                            const double2 v = *reinterpret_cast<const double2 *>(rec + MOM_OFF_A3 + e);
+                            a3[e] = v.x;
+                            a3[e + 1] = v.y;
+                        }
 #pragma unroll
-                    for (int e = 0; e < MOM_NE; ++e) {
-                        acc0[e] = fma(h0, in[e], acc0[e]);
-                        acc1[e] = fma(h1, in[e], acc1[e]);
+                        for (int e = 0; e < MOM_NE; ++e) spl_mom_dmma(acc[e][0], acc[e][1], a3[e] * p2, bfrag);
                     }
                 }
             }
@@ -237,17 +249,19 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
         }
         // ---- reduce the four warps through shared memory, flush once per work item ----
         {
+            // C fragment: rows fr, columns 2 fk + {0, 1}
             double *red = s_pts + warp * MOM_MG;
-            if (!RHS_ONLY && lg < 4) {
 #pragma unroll
-                for (int e = 0; e < MOM_NE; ++e) {
-                    red[(lg * MOM_NE + le2) * MOM_NE + e] = acc0[e];
-                    if (lg < 3) red[((lg + 4) * MOM_NE + le2) * MOM_NE + e] = acc1[e];
+            for (int j = 0; j < 2; ++j) {
+                const int col = 2 * fk + j;
+                if (!RHS_ONLY && fr < MOM_NE && col < MOM_NE) {
+#pragma unroll
+                    for (int e = 0; e < MOM_NE; ++e) red[(e * MOM_NE + fr) * MOM_NE + col] = acc[e][j];
                 }
-            }
-            if (lg < 4 && le2 < 4) {
-#pragma unroll
-                for (int f = 0; f < MOM_NF; ++f) red[MOM_NM + (lg * 4 + le2) * MOM_NF + f] = racc[f];
+                if (col < MOM_NF) {
+                    red[MOM_NM + (frh * 4 + frr) * MOM_NF + col] = racc[0][j];
+                    red[MOM_NM + ((2 + frh) * 4 + frr) * MOM_NF + col] = racc[1][j];
+                }
             }
         }
         __syncthreads();
