@@ -409,20 +409,28 @@ def run_ours(args):
                      "note": "uniform-random 3-D real64 queries are bound by the shared-memory gather (64 x 8 B per "
                              "query, ~3-way bank conflicts) and the FP64 pipe, not by HBM: DESIGN.md 4.5"}
         eval_roof["frac"] = eval_roof["achieved"] / hbm_peak
-        # accumulate: 1000 G + 64 rhs FMAs per point actually needed (Kronecker-symmetric form), flops = 2*FMA
-        acc_flops = npts * 2.0 * (1000 + 64)
-        acc_roof = {"kernel": "spl_accumulate_kernel<3>", "bound": "fp64", "unit": "TFLOP/s",
+        # accumulate stage = spl_moments_kernel (+ the per-cell change of basis, ~2% of it).  It gathers the
+        # cell-sorted points through the 4-byte permutation: on uniform-random data every gather of x / y / w pulls
+        # its own 128-byte line, so the kernel moves ~390 B of DRAM traffic per point for 44 algorithmic bytes
+        # (40 B point + 4 B permutation entry) and runs at the HBM roof on that TRAFFIC.
+        # FP64: 9 DMMA.8x8x4 tiles per 4 points = 576 FMA per point executed (407 needed).
+        asm_bytes = npts * ((NDIM + 2) * 8 + 4)
+        acc_flops = npts * 2.0 * 576
+        acc_traffic = traffic_for("spl_moments_kernel", npts)
+        acc_roof = {"kernel": "spl_moments_kernel", "bound": "hbm (gather traffic)", "unit": "TFLOP/s",
                     "achieved": acc_flops / (acc_ms * 1e-3) / 1e12 if acc_ms > 0 else None,
-                    "peak": dfma_tf, "peak_source": "DFMA micro-benchmark in this run (splpak_b200_measure_peaks)",
-                    "traffic": traffic_for("spl_accumulate_kernel<3>", npts), "algorithmic_bytes": asm_bytes,
+                    "peak": dmma_tf, "peak_source": "DMMA micro-benchmark in this run (splpak_b200_measure_peaks)",
+                    "traffic": acc_traffic, "algorithmic_bytes": asm_bytes,
                     "hbm_achieved_gbs": asm_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None,
-                    "hbm_frac": (asm_bytes / (acc_ms * 1e-3) / 1e9) / hbm_peak if acc_ms > 0 else None}
-        if acc_roof["achieved"] and dfma_tf:
-            acc_roof["frac"] = acc_roof["achieved"] / dfma_tf
+                    "hbm_frac": (asm_bytes / (acc_ms * 1e-3) / 1e9) / hbm_peak if acc_ms > 0 else None,
+                    "traffic_gbs": acc_traffic / (acc_ms * 1e-3) / 1e9 if (acc_ms > 0 and acc_traffic) else None,
+                    "traffic_frac": (acc_traffic / (acc_ms * 1e-3) / 1e9) / hbm_peak if (acc_ms > 0 and acc_traffic) else None}
+        if acc_roof["achieved"] and dmma_tf:
+            acc_roof["frac"] = acc_roof["achieved"] / dmma_tf
         dominant = eval_roof if eval_ms >= acc_ms else {
             "kernel": acc_roof["kernel"], "bound": "hbm", "achieved": acc_roof["hbm_achieved_gbs"], "peak": hbm_peak,
             "unit": "GB/s", "frac": acc_roof["hbm_frac"], "traffic": acc_roof["traffic"],
-            "note": "FP64-pipe-bound kernel; see roofline_fp64 for the binding roof"}
+            "note": "bound by the DRAM traffic of the permutation gathers; see roofline_fp64.traffic_frac"}
         dominant = dict(dominant)
         dominant["peak_source"] = peak_src
 

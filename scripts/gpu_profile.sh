@@ -16,7 +16,7 @@ echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:spl_eval -s 3 -c 1 -f -o $OUT/prof_${TAG}_eval \
     $CMD > $OUT/ncu_${TAG}_eval.log 2>&1
 echo "full capture eval rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:spl_accumulate -s 3 -c 1 -f -o $OUT/prof_${TAG}_accumulate \
+ncu --set full --clock-control none --import-source on -k regex:spl_moments -s 3 -c 1 -f -o $OUT/prof_${TAG}_accumulate \
     $CMD > $OUT/ncu_${TAG}_accumulate.log 2>&1
 echo "full capture accumulate rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:spl_panel -s 700 -c 1 -f -o $OUT/prof_${TAG}_panel \

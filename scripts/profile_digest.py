@@ -47,7 +47,7 @@ if os.path.exists(csvp):
     subprocess.run(["cp", csvp, os.path.join(PROF, "r01_launches.csv")])
 
 traffic = {}
-units = {"eval": ("spl_eval_kernel<3>", 1_000_000_000), "accumulate": ("spl_accumulate_kernel<3>", 100_000_000)}
+units = {"eval": ("spl_eval_kernel<3>", 1_000_000_000), "accumulate": ("spl_moments_kernel", 100_000_000)}
 for k in ("eval", "accumulate", "panel"):
     rep = os.path.join(OUT, f"prof_{tag}_{k}.ncu-rep")
     if not os.path.exists(rep):
@@ -57,7 +57,8 @@ for k in ("eval", "accumulate", "panel"):
                     if not any(s in ln for s in ("stalled_drain", "stalled_lg_", "stalled_membar", "stalled_misc",
                                                  "stalled_sleeping", "stalled_tex")))
     with open(os.path.join(PROF, f"r01_{k}.md"), "w") as f:
-        f.write(f"# r01 — `ncu --set full --clock-control none` of spl_{k}* inside `{CMD}` (bench size)\n\n```\n{txt}\n```\n")
+        kn = "spl_moments_kernel (the accumulate stage)" if k == "accumulate" else f"spl_{k}*"
+        f.write(f"# r01 — `ncu --set full --clock-control none` of {kn} inside `{CMD}` (bench size)\n\n```\n{txt}\n```\n")
     if k in units:
         m, _ = raw_metrics(rep)
         rd = float(m["dram__bytes_read.sum"].replace(",", ""))

@@ -207,6 +207,48 @@ def test_streaming_add_points_equals_one_shot(oracle):
     h.destroy()
 
 
+@pytest.mark.parametrize("nodes,ndata,outside,lo,hi", [
+    ([5, 4, 6], 6000, 0.0, 0.0, 1.0),
+    ([6, 7, 5], 20000, 0.3, 0.0, 1.0),          # exterior cells: linear continuation of the edge basis
+    ([4, 4, 4], 3000, 0.0, 0.0, 1.0),           # every cell touches an edge
+    ([9, 8, 10], 30000, 0.5, -3.0, 7.5),        # anisotropic box, far exterior points
+])
+def test_3d_moment_and_direct_assembly_agree(oracle, monkeypatch, nodes, ndata, outside, lo, hi):
+    """3-D assembles through per-cell Legendre moments (csrc/moments.cuh); SPLPAK_B200_ASSEMBLY=direct keeps the
+    per-point orthant-stencil accumulation.  Both against the oracle's rows, and against each other at the
+    rounding level of the re-associated sums; points exactly on nodes / box faces included."""
+    rng = np.random.default_rng(nodes[0] * 100 + ndata)
+    x, y, w, mn, mx = make_problem(3, nodes, ndata, seed=nodes[1] + ndata, weighted=True, outside=outside)
+    span = np.asarray(mx) - np.asarray(mn)
+    x = lo + (x - np.asarray(mn)) / span * (hi - lo)         # same relative positions in the box [lo, hi]^3
+    mn, mx = [lo] * 3, [hi] * 3
+    dx = (hi - lo) / (np.asarray(nodes) - 1)
+    x[:40] = lo + rng.integers(0, np.asarray(nodes), (40, 3)) * dx      # exactly on nodes (cell boundaries)
+    x[40] = [lo, lo, lo]
+    x[41] = [hi, hi, hi]
+    w[5::23] = 0.0
+    res = {}
+    for mode in ("direct", "moments"):
+        monkeypatch.setenv("SPLPAK_B200_ASSEMBLY", mode)
+        h = sp.FitHandle(3, mn, mx, nodes, 1.0)
+        assert h.add_points(x, y, w) == 0
+        S, g, cnt, totlwt, nrows = h.normal_equations()
+        res[mode] = (dense_from_stencil(S, nodes), g, cnt, totlwt, nrows)
+        h.destroy()
+    Gref, gref, A, r = _gram_from_oracle(oracle, 3, x, y, w, mn, mx, nodes, 0.0)
+    scale = np.abs(np.diag(Gref)).max()
+    gs = np.abs(gref).max()
+    for mode, (G, g, cnt, totlwt, nrows) in res.items():
+        np.testing.assert_allclose(G, Gref, rtol=0, atol=1e-12 * scale, err_msg=mode)
+        np.testing.assert_allclose(g, gref, rtol=0, atol=1e-12 * gs, err_msg=mode)
+        assert nrows == A.shape[0]
+    np.testing.assert_allclose(res["moments"][0], res["direct"][0], rtol=0, atol=2e-13 * scale)
+    np.testing.assert_allclose(res["moments"][1], res["direct"][1], rtol=0, atol=2e-13 * gs)
+    # nearest-node histogram: the same classify pass in both modes (atomic order differs run to run)
+    np.testing.assert_allclose(res["moments"][2], res["direct"][2], rtol=1e-13, atol=0)
+    assert abs(res["moments"][3] - res["direct"][3]) <= 1e-13 * res["direct"][3]
+
+
 def test_refinement_recovers_orthogonal_solver_accuracy(oracle):
     """Handle path: compute() alone is accurate to eps*cond(G); one refinement pass over the same points
     (fit_refine_*) brings the coefficients to eps*cond(A), where the reference's QR (suprls) works."""
