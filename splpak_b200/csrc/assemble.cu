@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(512, 2)
 spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
                     const real_t *__restrict__ w, int weighted, long long n, int nbins,
                     unsigned *__restrict__ wincount, int do_hist, double *__restrict__ cnt,
-                    double *__restrict__ totals) {
+                    double *__restrict__ totals, const real_t *__restrict__ y, double2 *__restrict__ yw) {
     extern __shared__ unsigned s_hist[];
     if (SMEMH) {
         for (int e = threadIdx.x; e < nbins; e += blockDim.x) s_hist[e] = 0u;
@@ -126,6 +126,10 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
                 wv[u] = weighted ? (double)w[i] : 1.0;
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) xp[u][d] = x[i * (long long)l1x + d];
+                // moment path, weighted: interleaved (y, w) copy, so the cell-sorted gather of the moment
+                // kernel pulls ONE 128-byte line for the pair instead of one each (streaming 16 B/point here
+                // against 128 B/point of gather traffic there)
+                if (CELL && yw) yw[i] = make_double2((double)y[i], wv[u]);
             } else {
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) xp[u][d] = (real_t)0;
@@ -733,6 +737,7 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
     const long long cap = (long long)nsm * 8;
     const int grid = (int)(nb < cap ? nb : cap);
 
+    double2 *yw = (CELL && weighted) ? reinterpret_cast<double2 *>(sc.yw) : nullptr;
     if (ev) cudaEventRecord(ev[0], st);
     {
         // two 512-thread CTAs per SM when the histogram is in shared memory (<= 2 x 96 KB), else 4
@@ -745,10 +750,10 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
             auto kern = spl_classify_kernel<NDIM, true, CELL>;
             SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
             kern<<<cgrid, 512, hist_bytes, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins, sc.wincount, do_hist,
-                                                 d_cnt, d_totals);
+                                                 d_cnt, d_totals, d_y, yw);
         } else {
             spl_classify_kernel<NDIM, false, CELL><<<cgrid, 512, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins,
-                                                                          sc.wincount, do_hist, d_cnt, d_totals);
+                                                                          sc.wincount, do_hist, d_cnt, d_totals, d_y, yw);
         }
     }
     if (ev) cudaEventRecord(ev[1], st);
@@ -769,7 +774,7 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
         if (per_sm < 1) per_sm = 1;
         long long agrid = (long long)nsm * per_sm;
         if (agrid > max_items) agrid = max_items;
-        kern<<<(unsigned)agrid, MOM_NT, smem, st>>>(gp, d_x, l1x, d_y, d_w, weighted, sc.perm, sc.wincount, sc.winstart,
+        kern<<<(unsigned)agrid, MOM_NT, smem, st>>>(gp, d_x, l1x, d_y, yw, sc.perm, sc.wincount, sc.winstart,
                                                     sc.item_win, sc.item_seg, sc.meta, sc.cellmom);
         if (rhs_only)
             spl_cell_transform_kernel<true><<<(unsigned)nbins, 128, 0, st>>>(gp, sc.wincount, sc.celltab, sc.cellmom, d_S, d_g);

@@ -569,6 +569,7 @@ static bool valid(splpak_b200_fit_t h) { return h && h->magic == FIT_MAGIC; }
 static void free_handle(splpak_b200_fit_t h) {
     if (!h) return;
     if (h->d_part) cudaFree(h->d_part);
+    if (h->sc.yw) cudaFree(h->sc.yw);
     unsigned *u[] = {h->sc.item_win, h->sc.item_seg, h->sc.perm};
     for (unsigned *p : u)
         if (p) cudaFree(p);
@@ -671,6 +672,8 @@ static int ensure_scratch(splpak_b200_fit_t h, long long n) {
     const GridParams &gp = h->gp;
     AssembleScratch &sc = h->sc;
     if (sc.perm) cudaFree(sc.perm);
+    if (sc.yw) cudaFree(sc.yw);
+    sc.yw = nullptr;
     if (sc.item_win) cudaFree(sc.item_win);
     if (sc.item_seg) cudaFree(sc.item_seg);
     sc.perm = nullptr;
@@ -683,6 +686,7 @@ static int ensure_scratch(splpak_b200_fit_t h, long long n) {
     const int ch = spl_acc_chunk_points(gp.ndim, sc.moments);
     sc.max_items = sc.nbins + n / ch + 2;
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.perm, sizeof(unsigned) * (size_t)n));
+    if (sc.moments) SPL_CUDA_TRY(cudaMalloc((void **)&sc.yw, 2 * sizeof(double) * (size_t)n));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_win, sizeof(unsigned) * (size_t)sc.max_items));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_seg, sizeof(unsigned) * (size_t)sc.max_items));
     h->chunk_cap = n;

@@ -54,6 +54,7 @@ struct AssembleScratch {
     int moments;          // 1: 3-D assembly by cell moments (moments.cuh)
     double *celltab;      // moment path: per-(dimension, cell) coefficient tables
     double *cellmom;      // moment path: per-cell moment sums of the chunk in flight (kept zero between chunks)
+    double *yw;           // moment path: interleaved (y, w) copy of the chunk, 2 doubles per point (sized with perm)
 };
 
 extern unsigned long long g_spl_launches;   // host-side launch counter (capi.cu)

@@ -124,7 +124,7 @@ __device__ __forceinline__ void spl_mom_dmma(double &c0, double &c1, double a, d
 template <bool RHS_ONLY>
 __global__ void __launch_bounds__(MOM_NT, 4)
 spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
-                   const real_t *__restrict__ y, const real_t *__restrict__ w, int weighted,
+                   const real_t *__restrict__ y, const double2 *__restrict__ yw,
                    const unsigned *__restrict__ perm, const unsigned *__restrict__ bincount,
                    const unsigned *__restrict__ binstart, const unsigned *__restrict__ item_bin,
                    const unsigned *__restrict__ item_seg, unsigned *__restrict__ meta,
@@ -178,8 +178,14 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
                 px[0] = (double)x[i * (long long)l1x + 0];
                 px[1] = (double)x[i * (long long)l1x + 1];
                 px[2] = (double)x[i * (long long)l1x + 2];
-                py = (double)y[i];
-                pw = weighted ? (double)w[i] : 1.0;
+                if (yw) {                                    // weighted: interleaved (y, w) copy written by classify
+                    const double2 v = __ldg(yw + i);
+                    py = v.x;
+                    pw = v.y;
+                } else {
+                    py = (double)y[i];
+                    pw = 1.0;
+                }
             }
         };
         load_perm(0);
