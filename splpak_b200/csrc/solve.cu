@@ -337,6 +337,50 @@ __device__ __forceinline__ void spl_cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
+#define PANEL_LDT 36    // 32 + 4, same bank argument as TILE_LD
+// One doubling level of the blocked triangular inversion: for every pair of SZ x SZ diagonal blocks (instance q)
+//   X21 = -X22 (L21 X11),
+// both products as 8 x 8 output tiles on the FP64 tensor cores (one or two tiles per warp).  L11 (sL) and X (sX) are
+// row-major with stride TILE_LD, T (sT) with stride PANEL_LDT, so every fragment load is conflict-free and a
+// "k-major" operand is just the other index order of the same array.  A scalar version of this level was bound by
+// shared-memory wavefronts (2,570 clocks per 32^3 product: an LDS.64 whose lanes share addresses still costs 2).
+template <int SZ>
+__device__ __forceinline__ void spl_inv_level(const double *__restrict__ sL, double *__restrict__ sX,
+                                              double *__restrict__ sT, int tid) {
+    constexpr int TR = SZ / 8, TPI = TR * TR, NTILE = (64 / (2 * SZ)) * TPI;     // 4, 8, 16 tiles
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
+    for (int tl = warp; tl < NTILE; tl += PANEL_THREADS / 32) {                  // T = L21 X11
+        const int q = tl / TPI, rem = tl % TPI, ti = rem / TR, tj = rem % TR;
+        const int rb = (2 * q + 1) * SZ, cb = 2 * q * SZ;
+        const double *pa = sL + (rb + ti * 8 + gq) * TILE_LD + cb + t4;
+        const double *pb = sX + (cb + t4) * TILE_LD + cb + tj * 8 + gq;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < SZ; k0 += 8) {
+            spl_dmma_8x8x4(c0, c1, pa[k0], pb[k0 * TILE_LD]);
+            spl_dmma_8x8x4(d0, d1, pa[k0 + 4], pb[(k0 + 4) * TILE_LD]);
+        }
+        *reinterpret_cast<double2 *>(sT + (q * SZ + ti * 8 + gq) * PANEL_LDT + tj * 8 + 2 * t4) =
+            make_double2(c0 + d0, c1 + d1);
+    }
+    __syncthreads();
+    for (int tl = warp; tl < NTILE; tl += PANEL_THREADS / 32) {                  // X21 = -X22 T
+        const int q = tl / TPI, rem = tl % TPI, ti = rem / TR, tj = rem % TR;
+        const int rb = (2 * q + 1) * SZ, cb = 2 * q * SZ;
+        const double *pa = sX + (rb + ti * 8 + gq) * TILE_LD + rb + t4;
+        const double *pb = sT + (q * SZ + t4) * PANEL_LDT + tj * 8 + gq;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < SZ; k0 += 8) {
+            spl_dmma_8x8x4(c0, c1, pa[k0], pb[k0 * PANEL_LDT]);
+            spl_dmma_8x8x4(d0, d1, pa[k0 + 4], pb[(k0 + 4) * PANEL_LDT]);
+        }
+        *reinterpret_cast<double2 *>(sX + (rb + ti * 8 + gq) * TILE_LD + cb + tj * 8 + 2 * t4) =
+            make_double2(-(c0 + d0), -(c1 + d1));
+    }
+    __syncthreads();
+}
+
 // Every CTA factors the nb x nb diagonal block A11 = L11 L11^T (four threads per row, 16 entries each in
 // registers, one barrier per pivot, pivot column broadcast through double-buffered shared memory) and
 // inverts L11.  Doing this redundantly in every CTA costs no time (it is a latency chain) and saves a
@@ -352,12 +396,13 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
 #define PANEL_STAMP(i) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
     PANEL_STAMP(0);
     double *sA = s_pan;                          // [k][row]  A21 tile, 64 x TILE_LD
-    double *sB = s_pan + 64 * TILE_LD;           // [k][n]    L11^-1 [n][k]
-    double *s_col = sB + 64 * TILE_LD;           // 2 x 64   pivot column (double buffered)
+    double *sX = s_pan + 64 * TILE_LD;           // [n][k]    L11^-1, row-major, stride TILE_LD
+    double *s_col = sX + 64 * TILE_LD;           // 2 x 64   pivot column (double buffered)
     double *s_g = s_col + 128;                   // 64       g1, then y1
     double *s_rd = s_g + 64;                     // 64       d_k, then 1 / L11[k][k]
-    double *s_lfac = s_rd + 64;                  // 64 x 64  L11, row-major
-    int *s_bad = reinterpret_cast<int *>(s_lfac + 64 * 64);
+    double *s_lfac = s_rd + 64;                  // 64 x TILE_LD  L11, row-major
+    double *sT = s_lfac + 64 * TILE_LD;          // 32 x PANEL_LDT  L21 X11 of the current inversion level
+    int *s_bad = reinterpret_cast<int *>(sT + 32 * PANEL_LDT);
     const int tid = threadIdx.x;
     if (*fail) return;                           // an earlier panel failed (uniform across the grid)
     const int R0 = blockIdx.x * 64;              // first row of this CTA's tile, relative to j0 + nb
@@ -449,37 +494,43 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
         const int k = 4 * kk + rc;
-        sL[ri * 64 + k] = (k <= ri) ? u[kk] * s_rd[k] : 0.0;
+        sL[ri * TILE_LD + k] = (k <= ri) ? u[kk] * s_rd[k] : 0.0;
     }
     __syncthreads();
-    // ---- X = L11^-1 by columns: thread j < 64 forward-substitutes e_j.  No barriers; rows of L11 are
-    //      broadcast reads; fully unrolled so X stays in registers (entries above the diagonal are 0) ----
-    if (tid < 64) {
-        double X[64];
+    // ---- X = L11^-1, blocked: the eight 8 x 8 diagonal blocks by forward substitution (64 threads, an 8-step
+    //      chain each), then three doubling levels  X21 = -X22 (L21 X11)  on the tensor cores.  One thread per
+    //      column running the whole 64-step substitution took 14.1k clocks. ----
+    {
+        for (int e = tid; e < 64 * TILE_LD; e += PANEL_THREADS) sX[e] = 0.0;
+        __syncthreads();
+        PANEL_STAMP(7);
+        if (tid < 64) {
+            const int b0 = tid & ~7, cj = tid & 7;
+            double X[8];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int i = 0; i < 8; ++i) {
+                double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-            for (int c = 0; c + 1 < i; c += 2) {
-                const double2 l = *reinterpret_cast<const double2 *>(sL + i * 64 + c);
-                if ((c >> 1) & 1) {
-                    s2 = fma(l.x, X[c], s2);
-                    s3 = fma(l.y, X[c + 1], s3);
-                } else {
-                    s0 = fma(l.x, X[c], s0);
-                    s1 = fma(l.y, X[c + 1], s1);
+                for (int c = 0; c < i; ++c) {
+                    const double l = sL[(b0 + i) * TILE_LD + b0 + c];
+                    if (c & 1) s1 = fma(l, X[c], s1);
+                    else s0 = fma(l, X[c], s0);
                 }
+                const double rhs = (i == cj) ? 1.0 : 0.0;
+                X[i] = (rhs - (s0 + s1)) * s_rd[b0 + i];
             }
-            if (i & 1) s0 = fma(sL[i * 64 + i - 1], X[i - 1], s0);
-            const double rhs = (i == tid) ? 1.0 : 0.0;
-            X[i] = (rhs - ((s0 + s1) + (s2 + s3))) * s_rd[i];
-        }
-        // stage L11^-1 as the B operand: sB[k][n] = Linv[n][k];  CTA 0 also stores it for the backsolve
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-            sB[tid * TILE_LD + i] = X[i];
-            if (blockIdx.x == 0) linv_blk[i * 64 + tid] = X[i];
+            for (int i = 0; i < 8; ++i) sX[(b0 + i) * TILE_LD + b0 + cj] = X[i];
         }
+        __syncthreads();
+        PANEL_STAMP(8);
+        spl_inv_level<8>(sL, sX, sT, tid);
+        spl_inv_level<16>(sL, sX, sT, tid);
+        spl_inv_level<32>(sL, sX, sT, tid);
+        PANEL_STAMP(9);
+        // CTA 0 stores L11^-1 for the back-substitution
+        if (blockIdx.x == 0)
+            for (int e = tid; e < 64 * 64; e += PANEL_THREADS) linv_blk[e] = sX[(e >> 6) * TILE_LD + (e & 63)];
     }
     PANEL_STAMP(3);
     spl_cp_async_wait_all();
@@ -489,7 +540,7 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     double y1c = 0.0;
     if (tid < 64) {
 #pragma unroll 8
-        for (int k = 0; k < 64; ++k) y1c = fma(sB[k * TILE_LD + tid], s_g[k], y1c);
+        for (int k = 0; k < 64; ++k) y1c = fma(sX[tid * TILE_LD + k], s_g[k], y1c);
     }
     __syncthreads();
     if (tid < 64) {
@@ -515,7 +566,7 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) af[mi] = sA[(k0 + t4) * TILE_LD + wy + mi * 8 + gq];
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) bf[ni] = sB[(k0 + t4) * TILE_LD + wx + ni * 8 + gq];
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = sX[(wx + ni * 8 + gq) * TILE_LD + k0 + t4];   // B[k][n] = Linv[n][k]
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -745,7 +796,7 @@ static long long *spl_panel_dbg_buffer() {
     if (!tried) {
         tried = true;
         if (getenv("SPLPAK_B200_PANELCLK")) {
-            if (cudaMalloc((void **)&buf, 64) != cudaSuccess) buf = nullptr;
+            if (cudaMalloc((void **)&buf, 128) != cudaSuccess) buf = nullptr;
         }
     }
     return buf;
@@ -832,7 +883,7 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     *d_coef_out = d_csol;
     (void)nsm;
     const size_t syrk_smem = sizeof(double) * 2 * 64 * TILE_LD;
-    const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 64 + 64 + 64 * 64 + 2);
+    const size_t panel_smem = sizeof(double) * (3 * 64 * TILE_LD + 128 + 64 + 64 + 32 * PANEL_LDT + 2);
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
 
@@ -897,9 +948,11 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     }
     g_spl_launches += nl;
     if (spl_panel_dbg_buffer()) {
-        long long hst[8];
+        long long hst[16];
         cudaStreamSynchronize(st);
         cudaMemcpy(hst, spl_panel_dbg_buffer(), sizeof(hst), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "inverse phases: scale+L %lld base %lld levels %lld store %lld\n", hst[7] - hst[2],
+                hst[8] - hst[7], hst[9] - hst[8], hst[3] - hst[9]);
         fprintf(stderr, "panel (mid) clocks: load %lld chol %lld inverse %lld wait %lld y1 %lld gemm+store %lld total %lld\n",
                 hst[1] - hst[0], hst[2] - hst[1], hst[3] - hst[2], hst[4] - hst[3], hst[5] - hst[4], hst[6] - hst[5],
                 hst[6] - hst[0]);
