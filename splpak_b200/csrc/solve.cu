@@ -408,14 +408,7 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     const int R0 = blockIdx.x * 64;              // first row of this CTA's tile, relative to j0 + nb
     const long long r0 = j0 + nb;
 
-    // ---- start streaming this CTA's A21 tile into shared memory; it lands under the factorization ----
-    for (int e = tid; e < 64 * 64; e += PANEL_THREADS) {
-        const int k = e >> 6, r = e & 63;
-        double *dst = sA + k * TILE_LD + r;
-        if (k < nb && R0 + r < m) spl_cp_async8(dst, AB + (r0 + R0 + r) + (j0 + k) * lda);
-        else *dst = 0.0;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int e = tid; e < 64 * TILE_LD; e += PANEL_THREADS) sX[e] = 0.0;     // upper triangle of L11^-1 (read by the MMAs)
 
     // ---- load A11: thread (i, c) = (tid / 4, tid % 4) owns u[kk] = A[i][4 kk + c], kk = 0..15 ----
     const int ri = tid >> 2, rc = tid & 3;
@@ -429,6 +422,15 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     }
     if (tid < 64) s_g[tid] = (tid < nb) ? g[j0 + tid] : 0.0;
     if (tid == 0) *s_bad = 0;
+
+    // ---- start streaming this CTA's A21 tile into shared memory; it lands under the factorization ----
+    for (int e = tid; e < 64 * 64; e += PANEL_THREADS) {
+        const int k = e >> 6, r = e & 63;
+        double *dst = sA + k * TILE_LD + r;
+        if (k < nb && R0 + r < m) spl_cp_async8(dst, AB + (r0 + R0 + r) + (j0 + k) * lda);
+        else *dst = 0.0;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
     PANEL_STAMP(1);
     // ---- right-looking Cholesky in the square-root-free form, one barrier per column.
@@ -454,13 +456,16 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
             // operations; two Newton steps are four, and FP64 latency is what this loop is made of)
             const double e = fma(-d, y0, 1.0);
             const double e2 = fma(e, e, e);
-            rinv = fma(y0, e2, y0);
+            // ci = col[ri] / d = t (1 + e2), t = col[ri] y0: t does not wait for e, so forming ci directly is
+            // one dependent FP64 operation shorter than rinv = y0 (1 + e2) followed by col[ri] * rinv
+            const double t = col[ri] * y0;
+            rinv = fma(t, e2, t);
         }
         if (tid == 0) {
             s_rd[j] = d;                                     // d_j for now; 1/L_jj after the loop
             if (!(d > 0.0)) *s_bad = 1;                      // non-positive (or NaN) pivot -> 107
         }
-        const double ci = col[ri] * rinv;
+        const double ci = rinv;
 #pragma unroll
         for (int kk = kj; kk < 16; ++kk) {
             const int k = 4 * kk + rc;
@@ -501,8 +506,6 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     //      chain each), then three doubling levels  X21 = -X22 (L21 X11)  on the tensor cores.  One thread per
     //      column running the whole 64-step substitution took 14.1k clocks. ----
     {
-        for (int e = tid; e < 64 * TILE_LD; e += PANEL_THREADS) sX[e] = 0.0;
-        __syncthreads();
         PANEL_STAMP(7);
         if (tid < 64) {
             const int b0 = tid & ~7, cj = tid & 7;
@@ -528,24 +531,35 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
         spl_inv_level<16>(sL, sX, sT, tid);
         spl_inv_level<32>(sL, sX, sT, tid);
         PANEL_STAMP(9);
-        // CTA 0 stores L11^-1 for the back-substitution
-        if (blockIdx.x == 0)
-            for (int e = tid; e < 64 * 64; e += PANEL_THREADS) linv_blk[e] = sX[(e >> 6) * TILE_LD + (e & 63)];
+        // L11^-1 for the back-substitution: every CTA has it, each stores a slice of its rows
+        {
+            const int rows = (64 + gridDim.x - 1) / gridDim.x;
+            const int rlo = blockIdx.x * rows, rhi = min(64, rlo + rows);
+            for (int e = rlo * 64 + tid; e < rhi * 64; e += PANEL_THREADS) linv_blk[e] = sX[(e >> 6) * TILE_LD + (e & 63)];
+        }
     }
     PANEL_STAMP(3);
     spl_cp_async_wait_all();
     __syncthreads();
     PANEL_STAMP(4);
     // y1[c] = sum_k Linv[c][k] g1[k]
+    // four threads per row (ri, rc): 16 products each (k = rc + 4 q: conflict-free), combined with two shuffles
     double y1c = 0.0;
-    if (tid < 64) {
-#pragma unroll 8
-        for (int k = 0; k < 64; ++k) y1c = fma(sX[tid * TILE_LD + k], s_g[k], y1c);
+    {
+        double y1d = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) {
+            y1c = fma(sX[ri * TILE_LD + rc + 4 * q], s_g[rc + 4 * q], y1c);
+            y1d = fma(sX[ri * TILE_LD + rc + 4 * q + 4], s_g[rc + 4 * q + 4], y1d);
+        }
+        y1c += y1d;
+        y1c += __shfl_xor_sync(0xffffffffu, y1c, 1);
+        y1c += __shfl_xor_sync(0xffffffffu, y1c, 2);
     }
     __syncthreads();
-    if (tid < 64) {
-        s_g[tid] = y1c;
-        if (blockIdx.x == 0 && tid < nb) ysol[j0 + tid] = y1c;
+    if (rc == 0) {
+        s_g[ri] = y1c;
+        if (blockIdx.x == 0 && ri < nb) ysol[j0 + ri] = y1c;
     }
     __syncthreads();
     PANEL_STAMP(5);
