@@ -340,13 +340,13 @@ __device__ __forceinline__ void spl_cp_async_wait_all() {
 #define PANEL_LDT 36    // 32 + 4, same bank argument as TILE_LD
 // One doubling level of the blocked triangular inversion: for every pair of SZ x SZ diagonal blocks (instance q)
 //   X21 = -X22 (L21 X11),
-// both products as 8 x 8 output tiles on the FP64 tensor cores (one or two tiles per warp).  L11 (sL) and X (sX) are
+// both products as 8 x 8 output tiles on the FP64 tensor cores (one or two tiles per warp).  The inversion is IN
+// PLACE (sL == sX): X11 and X22 already replaced their L blocks, L21 is dead once T = L21 X11 is formed.  The array is
 // row-major with stride TILE_LD, T (sT) with stride PANEL_LDT, so every fragment load is conflict-free and a
 // "k-major" operand is just the other index order of the same array.  A scalar version of this level was bound by
 // shared-memory wavefronts (2,570 clocks per 32^3 product: an LDS.64 whose lanes share addresses still costs 2).
 template <int SZ>
-__device__ __forceinline__ void spl_inv_level(const double *__restrict__ sL, double *__restrict__ sX,
-                                              double *__restrict__ sT, int tid) {
+__device__ __forceinline__ void spl_inv_level(const double *sL, double *sX, double *__restrict__ sT, int tid) {
     constexpr int TR = SZ / 8, TPI = TR * TR, NTILE = (64 / (2 * SZ)) * TPI;     // 4, 8, 16 tiles
     const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
     for (int tl = warp; tl < NTILE; tl += PANEL_THREADS / 32) {                  // T = L21 X11
@@ -400,15 +400,13 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     double *s_col = sX + 64 * TILE_LD;           // 2 x 64   pivot column (double buffered)
     double *s_g = s_col + 128;                   // 64       g1, then y1
     double *s_rd = s_g + 64;                     // 64       d_k, then 1 / L11[k][k]
-    double *s_lfac = s_rd + 64;                  // 64 x TILE_LD  L11, row-major
-    double *sT = s_lfac + 64 * TILE_LD;          // 32 x PANEL_LDT  L21 X11 of the current inversion level
+    double *s_lfac = sX;                         // L11, row-major, inverted in place
+    double *sT = s_rd + 64;                      // 32 x PANEL_LDT  L21 X11 of the current inversion level
     int *s_bad = reinterpret_cast<int *>(sT + 32 * PANEL_LDT);
     const int tid = threadIdx.x;
     if (*fail) return;                           // an earlier panel failed (uniform across the grid)
     const int R0 = blockIdx.x * 64;              // first row of this CTA's tile, relative to j0 + nb
     const long long r0 = j0 + nb;
-
-    for (int e = tid; e < 64 * TILE_LD; e += PANEL_THREADS) sX[e] = 0.0;     // upper triangle of L11^-1 (read by the MMAs)
 
     // ---- load A11: thread (i, c) = (tid / 4, tid % 4) owns u[kk] = A[i][4 kk + c], kk = 0..15 ----
     const int ri = tid >> 2, rc = tid & 3;
@@ -507,23 +505,31 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     //      column running the whole 64-step substitution took 14.1k clocks. ----
     {
         PANEL_STAMP(7);
-        if (tid < 64) {
-            const int b0 = tid & ~7, cj = tid & 7;
-            double X[8];
+        {
+            const int b0 = tid & 56, cj = tid & 7;            // threads >= 64 compute nothing
+            double Lb[8][8], X[8];
+            if (tid < 64) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double s0 = 0.0, s1 = 0.0;
+                for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int c = 0; c < i; ++c) {
-                    const double l = sL[(b0 + i) * TILE_LD + b0 + c];
-                    if (c & 1) s1 = fma(l, X[c], s1);
-                    else s0 = fma(l, X[c], s0);
-                }
-                const double rhs = (i == cj) ? 1.0 : 0.0;
-                X[i] = (rhs - (s0 + s1)) * s_rd[b0 + i];
+                    for (int c = 0; c < i; ++c) Lb[i][c] = sL[(b0 + i) * TILE_LD + b0 + c];
             }
+            __syncthreads();                                  // the block is in registers: X may overwrite it
+            if (tid < 64) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sX[(b0 + i) * TILE_LD + b0 + cj] = X[i];
+                for (int i = 0; i < 8; ++i) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < i; ++c) {
+                        if (c & 1) s1 = fma(Lb[i][c], X[c], s1);
+                        else s0 = fma(Lb[i][c], X[c], s0);
+                    }
+                    const double rhs = (i == cj) ? 1.0 : 0.0;
+                    X[i] = (rhs - (s0 + s1)) * s_rd[b0 + i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sX[(b0 + i) * TILE_LD + b0 + cj] = X[i];
+            }
         }
         __syncthreads();
         PANEL_STAMP(8);
@@ -897,7 +903,7 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     *d_coef_out = d_csol;
     (void)nsm;
     const size_t syrk_smem = sizeof(double) * 2 * 64 * TILE_LD;
-    const size_t panel_smem = sizeof(double) * (3 * 64 * TILE_LD + 128 + 64 + 64 + 32 * PANEL_LDT + 2);
+    const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 64 + 64 + 32 * PANEL_LDT + 2);
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
 
