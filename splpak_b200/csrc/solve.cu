@@ -404,7 +404,9 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     double *sT = s_rd + 64;                      // 32 x PANEL_LDT  L21 X11 of the current inversion level
     int *s_bad = reinterpret_cast<int *>(sT + 32 * PANEL_LDT);
     const int tid = threadIdx.x;
-    if (*fail) return;                           // an earlier panel failed (uniform across the grid)
+    // an earlier panel failed (uniform across the grid): the flag is loaded now and tested after this kernel's
+    // loads have been issued, so its L2 round trip is not on the chain
+    const int failed = *reinterpret_cast<const volatile int *>(fail);
     const int R0 = blockIdx.x * 64;              // first row of this CTA's tile, relative to j0 + nb
     const long long r0 = j0 + nb;
 
@@ -429,6 +431,10 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
         else *dst = 0.0;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    if (failed) {
+        spl_cp_async_wait_all();
+        return;
+    }
 
     PANEL_STAMP(1);
     // ---- right-looking Cholesky in the square-root-free form, one barrier per column.
