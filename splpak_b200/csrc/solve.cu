@@ -26,7 +26,9 @@
 // Back-substitution L^T c = y runs block by block from the end (spl_backsolve_kernel): every CTA
 // forms c_k = L11^-T y_k from the stored block inverse, then eliminates c_k from its slice of the b
 // preceding entries.
+#include <cooperative_groups.h>
 #include <stdlib.h>
+#include <string.h>
 #include <new>
 
 #include "basis.cuh"
@@ -388,12 +390,12 @@ __device__ __forceinline__ void spl_inv_level(const double *sL, double *sX, doub
 // Then  y1 = L11^-1 g1,  L21 = A21 L11^-T  for this CTA's 64 rows (FP64 tensor-core MMA against the
 // inverse, so no per-row substitution chain) and  g2 -= L21 y1.
 // CTA 0 stores L11^-1 (for the back-substitution) and y1.
-__global__ void __launch_bounds__(PANEL_THREADS)
-spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, int m,
-                 double *__restrict__ g, double *__restrict__ ysol, double *__restrict__ linv_blk,
-                 int *__restrict__ fail, long long *__restrict__ dbg) {
-    extern __shared__ __align__(16) double s_pan[];
-#define PANEL_STAMP(i) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
+// cta / ncta: this CTA's index among the CTAs working on the panel and their number (the stand-alone kernel passes
+// blockIdx.x / gridDim.x; the persistent factor kernel its first CTAs).  failed: an earlier panel failed.
+__device__ __forceinline__ void spl_panel_body(double *AB, long long lda, long long j0, int nb, int m, double *g,
+                                               double *ysol, double *linv_blk, int *fail, long long *dbg,
+                                               double *s_pan, const int cta, const int ncta, const int failed) {
+#define PANEL_STAMP(i) do { if (dbg && cta == 0 && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
     PANEL_STAMP(0);
     double *sA = s_pan;                          // [k][row]  A21 tile, 64 x TILE_LD
     double *sX = s_pan + 64 * TILE_LD;           // [n][k]    L11^-1, row-major, stride TILE_LD
@@ -404,10 +406,7 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     double *sT = s_rd + 64;                      // 32 x PANEL_LDT  L21 X11 of the current inversion level
     int *s_bad = reinterpret_cast<int *>(sT + 32 * PANEL_LDT);
     const int tid = threadIdx.x;
-    // an earlier panel failed (uniform across the grid): the flag is loaded now and tested after this kernel's
-    // loads have been issued, so its L2 round trip is not on the chain
-    const int failed = *reinterpret_cast<const volatile int *>(fail);
-    const int R0 = blockIdx.x * 64;              // first row of this CTA's tile, relative to j0 + nb
+    const int R0 = cta * 64;                     // first row of this CTA's tile, relative to j0 + nb
     const long long r0 = j0 + nb;
 
     // ---- load A11: thread (i, c) = (tid / 4, tid % 4) owns u[kk] = A[i][4 kk + c], kk = 0..15 ----
@@ -479,7 +478,7 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     __syncthreads();
     PANEL_STAMP(2);
     if (*s_bad) {
-        if (blockIdx.x == 0 && tid == 0) *fail = 1;
+        if (cta == 0 && tid == 0) *fail = 1;
         spl_cp_async_wait_all();
         return;
     }
@@ -545,8 +544,8 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
         PANEL_STAMP(9);
         // L11^-1 for the back-substitution: every CTA has it, each stores a slice of its rows
         {
-            const int rows = (64 + gridDim.x - 1) / gridDim.x;
-            const int rlo = blockIdx.x * rows, rhi = min(64, rlo + rows);
+            const int rows = (64 + ncta - 1) / ncta;
+            const int rlo = cta * rows, rhi = min(64, rlo + rows);
             for (int e = rlo * 64 + tid; e < rhi * 64; e += PANEL_THREADS) linv_blk[e] = sX[(e >> 6) * TILE_LD + (e & 63)];
         }
     }
@@ -571,7 +570,7 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     __syncthreads();
     if (rc == 0) {
         s_g[ri] = y1c;
-        if (blockIdx.x == 0 && ri < nb) ysol[j0 + ri] = y1c;
+        if (cta == 0 && ri < nb) ysol[j0 + ri] = y1c;
     }
     __syncthreads();
     PANEL_STAMP(5);
@@ -619,6 +618,17 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
     PANEL_STAMP(6);
 }
 
+__global__ void __launch_bounds__(PANEL_THREADS)
+spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, int m,
+                 double *__restrict__ g, double *__restrict__ ysol, double *__restrict__ linv_blk,
+                 int *__restrict__ fail, long long *__restrict__ dbg) {
+    extern __shared__ __align__(16) double s_pan[];
+    // the flag is loaded now and tested inside the body after the loads have been issued, so its L2 round trip is
+    // not on the chain
+    const int failed = *reinterpret_cast<const volatile int *>(fail);
+    spl_panel_body(AB, lda, j0, nb, m, g, ysol, linv_blk, fail, dbg, s_pan, (int)blockIdx.x, (int)gridDim.x, failed);
+}
+
 // ------------------------------------------------------------------------------------------
 // trailing update with FP64 tensor-core MMA
 // ------------------------------------------------------------------------------------------
@@ -632,30 +642,18 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
 // part 0: the first tile column (tj = 0, one CTA per tile row) -- all the next panel depends on;
 // part 1: every other lower-triangular tile (ti >= tj >= 1), launched on the auxiliary stream so that it
 // overlaps the next panel's latency chain (look-ahead).
-__global__ void __launch_bounds__(SYRK_THREADS)
-spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long j0, int nb, int m,
-                const int *__restrict__ fail, int part) {
-    extern __shared__ __align__(16) double s_ab[];
+// One 64 x 64 tile (ti, tj), ti >= tj, with NTHR threads (128: 2 x 2 warps of 32 x 32; 256: 4 x 2 warps of 16 x 32).
+template <int NTHR>
+__device__ __forceinline__ void spl_syrk_tile(double *AB, long long lda, long long r0, long long j0, int nb, int m,
+                                              int ti, int tj, double *s_ab) {
+    constexpr int MI = (NTHR == 128) ? 4 : 2;
     double *sA = s_ab;                          // [k][row]
     double *sB = s_ab + 64 * TILE_LD;
-    if (*fail) return;
-    int ti, tj;
-    if (part == 0) {
-        ti = blockIdx.x;
-        tj = 0;
-    } else {
-        const int tile = blockIdx.x;
-        ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
-        while ((long long)(ti + 1) * (ti + 2) / 2 <= tile) ++ti;
-        while ((long long)ti * (ti + 1) / 2 > tile) --ti;
-        tj = tile - ti * (ti + 1) / 2 + 1;
-        ti += 1;
-    }
     const int I0 = ti * SYRK_TILE, J0 = tj * SYRK_TILE;
     const int t = threadIdx.x;
     const bool diag = (ti == tj);
 
-    for (int e = t; e < 64 * 64; e += SYRK_THREADS) {
+    for (int e = t; e < 64 * 64; e += NTHR) {
         const int k = e >> 6, r = e & 63;
         double *da = sA + k * TILE_LD + r;
         if (k < nb && I0 + r < m) spl_cp_async8(da, AB + (r0 + I0 + r) + (j0 + k) * lda);
@@ -670,11 +668,11 @@ spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long 
 
     const int warp = t >> 5, lane = t & 31;
     const int g = lane >> 2, t4 = lane & 3;
-    const int wy = (warp >> 1) * 32, wx = (warp & 1) * 32;
+    const int wy = (warp >> 1) * (MI * 8), wx = (warp & 1) * 32;
     // prefetch the C tile into the accumulators (lower triangle, inside the window)
-    double acc[4][4][2];
+    double acc[MI][4][2];
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
@@ -689,18 +687,18 @@ spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long 
 
 #pragma unroll 4
     for (int k0 = 0; k0 < 64; k0 += 4) {
-        double a[4], b[4];
+        double a[MI], b[4];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) a[mi] = -sA[(k0 + t4) * TILE_LD + wy + mi * 8 + g];
+        for (int mi = 0; mi < MI; ++mi) a[mi] = -sA[(k0 + t4) * TILE_LD + wy + mi * 8 + g];
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) b[ni] = pB[(k0 + t4) * TILE_LD + wx + ni * 8 + g];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
@@ -709,6 +707,108 @@ spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long 
                 const int lj = J0 + wx + ni * 8 + 2 * t4 + h;
                 if (li < m && lj < m && li >= lj) AB[(r0 + li) + (r0 + lj) * lda] = acc[mi][ni][h];
             }
+}
+
+// rest-of-update tile number (0 .. (T-1) T / 2 - 1)  ->  (ti, tj) with ti >= tj >= 1
+__device__ __forceinline__ void spl_rest_tile(int tile, int &ti, int &tj) {
+    ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
+    while ((long long)(ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+    while ((long long)ti * (ti + 1) / 2 > tile) --ti;
+    tj = tile - ti * (ti + 1) / 2 + 1;
+    ti += 1;
+}
+
+__global__ void __launch_bounds__(SYRK_THREADS)
+spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long j0, int nb, int m,
+                const int *__restrict__ fail, int part) {
+    extern __shared__ __align__(16) double s_ab[];
+    if (*fail) return;
+    int ti, tj;
+    if (part == 0) {
+        ti = blockIdx.x;
+        tj = 0;
+    } else {
+        spl_rest_tile((int)blockIdx.x, ti, tj);
+    }
+    spl_syrk_tile<SYRK_THREADS>(AB, lda, r0, j0, nb, m, ti, tj, s_ab);
+}
+
+// ------------------------------------------------------------------------------------------
+// persistent factorisation: the whole right-looking loop in ONE cooperative kernel (one 256-thread CTA per SM),
+// phases separated by grid-wide barriers instead of kernel boundaries and cross-stream events:
+//   step kb, phase P:  CTAs [0, pblocks) run panel(kb)  ||  the other CTAs finish the trailing update of step kb-1
+//                      (tiles with tj >= 1: nothing panel(kb) reads -- the look-ahead of the two-stream version)
+//            grid barrier
+//            phase C:  tile column 0 of update kb (all panel(kb+1) needs) on CTAs [0, T); every other CTA takes ONE
+//                      tile of the rest of update kb, so the phase is one tile long for everyone
+//            grid barrier
+// The kernel-boundary version spent 11 us per step between its panel kernels (column-0 kernel + two boundaries)
+// and its two streams slowed each other down (6.8 ms for 216 steps at cfg3).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PANEL_THREADS, 1)
+spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, double *g, double *ysol, double *linv,
+                             int *fail, long long *dbg) {
+    extern __shared__ __align__(16) double s_dyn_f[];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    // trailing update still owed from the previous step: window (r0, j0, nb, m), first rest tile not yet done
+    long long pr0 = 0, pj0 = 0;
+    int pnb = 0, pm = 0, pfirst = 0, pntiles = 0;
+    for (long long kb = 0; kb < nblk; ++kb) {
+        const long long j0 = kb * SOLVE_NB;
+        const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
+        const long long r0 = j0 + nb;
+        long long mm = n - r0;
+        if (mm > bw) mm = bw;
+        const int m = (int)mm;
+        int pblocks = (m + 63) / 64;
+        if (pblocks < 1) pblocks = 1;
+        if (pblocks > G) pblocks = G;            // (never at the sizes this library targets: bw <= 64 G)
+        // ---- phase P ----
+        if (cta < pblocks) {
+            // every panel CTA covers rows cta, cta + pblocks, .. (one tile row each unless bw > 64 G)
+            for (int c = cta; c * 64 < (m > 0 ? m : 1); c += pblocks) {
+                spl_panel_body(AB, lda, j0, nb, m, g, ysol, linv + kb * 4096, fail,
+                               (kb == nblk / 2) ? dbg : nullptr, s_dyn_f, c, (m + 63) / 64 > 0 ? (m + 63) / 64 : 1, 0);
+                __syncthreads();
+            }
+        } else if (pntiles > pfirst) {
+            const int helpers = G - pblocks;
+            for (int tile = pfirst + (cta - pblocks); tile < pntiles; tile += helpers) {
+                int ti, tj;
+                spl_rest_tile(tile, ti, tj);
+                spl_syrk_tile<PANEL_THREADS>(AB, lda, pr0, pj0, pnb, pm, ti, tj, s_dyn_f);
+                __syncthreads();
+            }
+        }
+        grid.sync();
+        if (*reinterpret_cast<volatile int *>(fail)) return;     // uniform: everybody reads it after the barrier
+        // ---- phase C ----
+        const int T = (m + SYRK_TILE - 1) / SYRK_TILE;
+        const int ntiles = (T > 1) ? (T - 1) * T / 2 : 0;
+        int first = 0;
+        if (m > 0) {
+            if (cta < T) {
+                for (int ti = cta; ti < T; ti += G) {
+                    spl_syrk_tile<PANEL_THREADS>(AB, lda, r0, j0, nb, m, ti, 0, s_dyn_f);
+                    __syncthreads();
+                }
+            } else if (cta - T < ntiles) {
+                int ti, tj;
+                spl_rest_tile(cta - T, ti, tj);
+                spl_syrk_tile<PANEL_THREADS>(AB, lda, r0, j0, nb, m, ti, tj, s_dyn_f);
+            }
+            first = (G - T > 0) ? ((G - T < ntiles) ? G - T : ntiles) : 0;
+        }
+        pr0 = r0;
+        pj0 = j0;
+        pnb = nb;
+        pm = m;
+        pfirst = first;
+        pntiles = ntiles;
+        grid.sync();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -798,6 +898,7 @@ struct SolveGraphs {
     long long n = 0;
     int bw = 0;
     long long nfactor = 0, nback = 0;     // kernel nodes
+    bool persistent = false;              // the factor loop is the cooperative kernel: no factor graph
 };
 
 void spl_solve_cache_free(void *cache) {
@@ -907,29 +1008,51 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     double *d_ysol = d_work + nblk * 4096;
     double *d_csol = d_ysol + (n + 64);
     *d_coef_out = d_csol;
-    (void)nsm;
+
     const size_t syrk_smem = sizeof(double) * 2 * 64 * TILE_LD;
     const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 64 + 64 + 32 * PANEL_LDT + 2);
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
 
+    // The factor loop runs as ONE persistent cooperative kernel when the device can keep one CTA per SM resident
+    // (SPLPAK_B200_SOLVER=graph selects the kernel-per-phase version: two streams, CUDA graph).
+    const size_t pers_smem = panel_smem > syrk_smem ? panel_smem : syrk_smem;
+    bool persistent = false;
+    int pgrid = 0;
+    {
+        const char *mode = getenv("SPLPAK_B200_SOLVER");
+        int dev = 0, coop = 0, per_sm = 0;
+        if (!(mode && strcmp(mode, "graph") == 0) && cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop) {
+            if (cudaFuncSetAttribute(spl_factor_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)pers_smem) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spl_factor_persistent_kernel, PANEL_THREADS,
+                                                              pers_smem) == cudaSuccess &&
+                per_sm >= 1) {
+                persistent = true;
+                pgrid = nsm > 0 ? nsm : SPL_NSM_DEFAULT;
+            }
+        }
+        cudaGetLastError();
+    }
     (void)spl_panel_dbg_buffer();        // allocate (if asked for) outside stream capture
     // (re)build the graphs when the buffers or the problem changed
     SolveGraphs *sg = cache ? static_cast<SolveGraphs *>(*cache) : nullptr;
-    if (cache && (!sg || sg->key_AB != d_AB || sg->key_g != d_g || sg->n != n || sg->bw != bw)) {
+    if (cache && (!sg || sg->key_AB != d_AB || sg->key_g != d_g || sg->n != n || sg->bw != bw || sg->persistent != persistent)) {
         spl_solve_cache_free(sg);
         sg = new (std::nothrow) SolveGraphs();
         *cache = sg;
         if (sg) {
             cudaGraph_t gr = nullptr;
-            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
-            if (e == cudaSuccess) {
+            sg->persistent = persistent;
+            cudaError_t e = persistent ? cudaSuccess : cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess && !persistent) {
                 const cudaError_t eq = enqueue_factor(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux,
                                                       panel_smem, syrk_smem, &sg->nfactor);
                 e = cudaStreamEndCapture(st, &gr);
                 if (eq != cudaSuccess) e = eq;
             }
-            if (e == cudaSuccess) e = cudaGraphInstantiate(&sg->factor, gr, 0);
+            if (e == cudaSuccess && !persistent) e = cudaGraphInstantiate(&sg->factor, gr, 0);
             if (gr) cudaGraphDestroy(gr);
             gr = nullptr;
             if (e == cudaSuccess) e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
@@ -966,7 +1089,17 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     }
     if (ev) cudaEventRecord(ev[1], st);
     long long nl = 0;
-    if (sg && sg->factor) {
+    if (persistent) {
+        double *a_AB = d_AB, *a_g = d_g, *a_y = d_ysol, *a_li = d_linv;
+        long long a_lda = lda, a_n = n;
+        int a_bw = bw;
+        int *a_fail = d_fail;
+        long long *a_dbg = spl_panel_dbg_buffer();
+        void *args[] = {&a_AB, &a_lda, &a_n, &a_bw, &a_g, &a_y, &a_li, &a_fail, &a_dbg};
+        SPL_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)spl_factor_persistent_kernel, dim3(pgrid), dim3(PANEL_THREADS),
+                                                 args, pers_smem, st));
+        nl = 1;
+    } else if (sg && sg->factor) {
         SPL_CUDA_TRY(cudaGraphLaunch(sg->factor, st));
         nl = sg->nfactor;
     } else {
