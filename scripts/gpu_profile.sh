@@ -19,7 +19,8 @@ echo "full capture eval rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:spl_moments -s 3 -c 1 -f -o $OUT/prof_${TAG}_accumulate \
     $CMD > $OUT/ncu_${TAG}_accumulate.log 2>&1
 echo "full capture accumulate rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:spl_panel -s 700 -c 1 -f -o $OUT/prof_${TAG}_panel \
+# the panel code runs inside the persistent factor kernel by default; SPLPAK_B200_SOLVER=graph launches it per panel
+SPLPAK_B200_SOLVER=graph ncu --set full --clock-control none --import-source on -k regex:spl_panel -s 700 -c 1 -f -o $OUT/prof_${TAG}_panel \
     $CMD > $OUT/ncu_${TAG}_panel.log 2>&1
 echo "full capture panel rc=$?"
 ls -la $OUT | tail -8

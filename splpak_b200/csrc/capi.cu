@@ -629,7 +629,7 @@ extern "C" int splpak_b200_fit_create(int ndim, const real_t *xmin, const real_t
     ok = ok && cudaStreamCreateWithFlags(&h->st_aux, cudaStreamNonBlocking) == cudaSuccess;
     h->n_part = gp.ncol * gp.nsten + gp.ncol + gp.ncol + 2;
     ok = ok && cudaMalloc((void **)&h->d_part, sizeof(double) * (size_t)h->n_part) == cudaSuccess;
-    ok = ok && cudaMalloc((void **)&h->d_fail, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&h->d_fail, 2 * sizeof(int)) == cudaSuccess;   // [failure flag, grid-barrier counter of the persistent factor kernel]
     ok = ok && cudaMalloc((void **)&h->d_coef64, sizeof(double) * (size_t)(gp.ncol + 2)) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&h->d_dummy_tot, sizeof(double) * 2) == cudaSuccess;
     for (int k = 0; k < 8 && ok; ++k) ok = cudaEventCreate(&h->ev[k]) == cudaSuccess;

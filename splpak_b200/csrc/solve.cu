@@ -26,7 +26,6 @@
 // Back-substitution L^T c = y runs block by block from the end (spl_backsolve_kernel): every CTA
 // forms c_k = L11^-T y_k from the stored block inverse, then eliminates c_k from its slice of the b
 // preceding entries.
-#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
 #include <new>
@@ -394,7 +393,8 @@ __device__ __forceinline__ void spl_inv_level(const double *sL, double *sX, doub
 // blockIdx.x / gridDim.x; the persistent factor kernel its first CTAs).  failed: an earlier panel failed.
 __device__ __forceinline__ void spl_panel_body(double *AB, long long lda, long long j0, int nb, int m, double *g,
                                                double *ysol, double *linv_blk, int *fail, long long *dbg,
-                                               double *s_pan, const int cta, const int ncta, const int failed) {
+                                               double *s_pan, const int cta, const int ncta, const int failed,
+                                               const bool keep_l21 = false) {
 #define PANEL_STAMP(i) do { if (dbg && cta == 0 && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
     PANEL_STAMP(0);
     double *sA = s_pan;                          // [k][row]  A21 tile, 64 x TILE_LD
@@ -615,6 +615,18 @@ __device__ __forceinline__ void spl_panel_body(double *AB, long long lda, long l
         part += __shfl_xor_sync(0xffffffffu, part, 2);
         if (t4 == 0 && r < m && part != 0.0) atomicAdd(g + r0 + r, -part);
     }
+    if (keep_l21) {
+        // leave this CTA's L21 tile in shared memory, k-major, where spl_syrk_tile expects its A operand: the
+        // persistent kernel's column-0 update of the same tile row then loads only the other operand
+        __syncthreads();                                      // everyone is done reading sA (A21)
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    sA[(wx + ni * 8 + 2 * t4 + h) * TILE_LD + wy + mi * 8 + gq] = acc[mi][ni][h];
+    }
     PANEL_STAMP(6);
 }
 
@@ -643,7 +655,8 @@ spl_panel_kernel(double *__restrict__ AB, long long lda, long long j0, int nb, i
 // part 1: every other lower-triangular tile (ti >= tj >= 1), launched on the auxiliary stream so that it
 // overlaps the next panel's latency chain (look-ahead).
 // One 64 x 64 tile (ti, tj), ti >= tj, with NTHR threads (128: 2 x 2 warps of 32 x 32; 256: 4 x 2 warps of 16 x 32).
-template <int NTHR>
+// A_READY: the A operand (rows of tile row ti, k-major) is already in shared memory.
+template <int NTHR, bool A_READY = false>
 __device__ __forceinline__ void spl_syrk_tile(double *AB, long long lda, long long r0, long long j0, int nb, int m,
                                               int ti, int tj, double *s_ab) {
     constexpr int MI = (NTHR == 128) ? 4 : 2;
@@ -655,9 +668,11 @@ __device__ __forceinline__ void spl_syrk_tile(double *AB, long long lda, long lo
 
     for (int e = t; e < 64 * 64; e += NTHR) {
         const int k = e >> 6, r = e & 63;
-        double *da = sA + k * TILE_LD + r;
-        if (k < nb && I0 + r < m) spl_cp_async8(da, AB + (r0 + I0 + r) + (j0 + k) * lda);
-        else *da = 0.0;
+        if (!A_READY) {
+            double *da = sA + k * TILE_LD + r;
+            if (k < nb && I0 + r < m) spl_cp_async8(da, AB + (r0 + I0 + r) + (j0 + k) * lda);
+            else *da = 0.0;
+        }
         if (!diag) {
             double *db = sB + k * TILE_LD + r;
             if (k < nb && J0 + r < m) spl_cp_async8(db, AB + (r0 + J0 + r) + (j0 + k) * lda);
@@ -745,12 +760,30 @@ spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long 
 // The kernel-boundary version spent 11 us per step between its panel kernels (column-0 kernel + two boundaries)
 // and its two streams slowed each other down (6.8 ms for 216 steps at cfg3).
 // ------------------------------------------------------------------------------------------
+// Grid-wide barrier of the persistent kernel (all CTAs are co-resident: cooperative launch).  One monotonically
+// increasing counter; the k-th barrier is passed when it reaches k * G.  cooperative_groups' grid.sync() cost 3 us
+// per barrier here, a third of the step.
+__device__ __forceinline__ void spl_grid_barrier(unsigned *counter, unsigned &target, unsigned G) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += G;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
 spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, double *g, double *ysol, double *linv,
-                             int *fail, long long *dbg) {
+                             int *fail, long long *dbg, unsigned *bar) {
     extern __shared__ __align__(16) double s_dyn_f[];
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    unsigned bar_target = 0;
     const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
     // trailing update still owed from the previous step: window (r0, j0, nb, m), first rest tile not yet done
     long long pr0 = 0, pj0 = 0;
@@ -764,13 +797,15 @@ spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, dou
         const int m = (int)mm;
         int pblocks = (m + 63) / 64;
         if (pblocks < 1) pblocks = 1;
+        const bool one_row_each = pblocks <= G && m > 0;      // CTA c holds L21 of tile row c after the panel
         if (pblocks > G) pblocks = G;            // (never at the sizes this library targets: bw <= 64 G)
         // ---- phase P ----
         if (cta < pblocks) {
             // every panel CTA covers rows cta, cta + pblocks, .. (one tile row each unless bw > 64 G)
             for (int c = cta; c * 64 < (m > 0 ? m : 1); c += pblocks) {
                 spl_panel_body(AB, lda, j0, nb, m, g, ysol, linv + kb * 4096, fail,
-                               (kb == nblk / 2) ? dbg : nullptr, s_dyn_f, c, (m + 63) / 64 > 0 ? (m + 63) / 64 : 1, 0);
+                               (kb == nblk / 2) ? dbg : nullptr, s_dyn_f, c, (m + 63) / 64 > 0 ? (m + 63) / 64 : 1, 0,
+                               one_row_each);
                 __syncthreads();
             }
         } else if (pntiles > pfirst) {
@@ -782,7 +817,9 @@ spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, dou
                 __syncthreads();
             }
         }
-        grid.sync();
+        if (dbg && kb == nblk / 2 && cta == 0 && threadIdx.x == 0) dbg[12] = clock64();
+        spl_grid_barrier(bar, bar_target, (unsigned)G);
+        if (dbg && kb == nblk / 2 && cta == 0 && threadIdx.x == 0) dbg[13] = clock64();
         if (*reinterpret_cast<volatile int *>(fail)) return;     // uniform: everybody reads it after the barrier
         // ---- phase C ----
         const int T = (m + SYRK_TILE - 1) / SYRK_TILE;
@@ -791,7 +828,8 @@ spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, dou
         if (m > 0) {
             if (cta < T) {
                 for (int ti = cta; ti < T; ti += G) {
-                    spl_syrk_tile<PANEL_THREADS>(AB, lda, r0, j0, nb, m, ti, 0, s_dyn_f);
+                    if (one_row_each && ti == cta) spl_syrk_tile<PANEL_THREADS, true>(AB, lda, r0, j0, nb, m, ti, 0, s_dyn_f);
+                    else spl_syrk_tile<PANEL_THREADS>(AB, lda, r0, j0, nb, m, ti, 0, s_dyn_f);
                     __syncthreads();
                 }
             } else if (cta - T < ntiles) {
@@ -807,7 +845,9 @@ spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, dou
         pm = m;
         pfirst = first;
         pntiles = ntiles;
-        grid.sync();
+        if (dbg && kb == nblk / 2 && cta == 0 && threadIdx.x == 0) dbg[14] = clock64();
+        spl_grid_barrier(bar, bar_target, (unsigned)G);
+        if (dbg && kb == nblk / 2 && cta == 0 && threadIdx.x == 0) dbg[15] = clock64();
     }
 }
 
@@ -1095,7 +1135,10 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         int a_bw = bw;
         int *a_fail = d_fail;
         long long *a_dbg = spl_panel_dbg_buffer();
-        void *args[] = {&a_AB, &a_lda, &a_n, &a_bw, &a_g, &a_y, &a_li, &a_fail, &a_dbg};
+        // the barrier counter lives behind the failure flag (d_fail is allocated as two ints by the handle)
+        unsigned *a_bar = reinterpret_cast<unsigned *>(d_fail + 1);
+        SPL_CUDA_TRY(cudaMemsetAsync(a_bar, 0, sizeof(unsigned), st));
+        void *args[] = {&a_AB, &a_lda, &a_n, &a_bw, &a_g, &a_y, &a_li, &a_fail, &a_dbg, &a_bar};
         SPL_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)spl_factor_persistent_kernel, dim3(pgrid), dim3(PANEL_THREADS),
                                                  args, pers_smem, st));
         nl = 1;
@@ -1110,6 +1153,8 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         long long hst[16];
         cudaStreamSynchronize(st);
         cudaMemcpy(hst, spl_panel_dbg_buffer(), sizeof(hst), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "persistent step (CTA 0): panel body %lld, barrier 1 %lld, column-0 tile %lld, barrier 2 %lld\n",
+                hst[12] - hst[0], hst[13] - hst[12], hst[14] - hst[13], hst[15] - hst[14]);
         fprintf(stderr, "inverse phases: scale+L %lld base %lld levels %lld store %lld\n", hst[7] - hst[2],
                 hst[8] - hst[7], hst[9] - hst[8], hst[3] - hst[9]);
         fprintf(stderr, "panel (mid) clocks: load %lld chol %lld inverse %lld wait %lld y1 %lld gemm+store %lld total %lld\n",
