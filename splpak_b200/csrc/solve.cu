@@ -907,6 +907,111 @@ spl_backsolve_kernel(const double *__restrict__ AB, long long lda, long long j0,
 }
 
 // ------------------------------------------------------------------------------------------
+// persistent back-substitution: the whole block loop in ONE cooperative kernel (ceil(bw / 256) CTAs), one grid
+// barrier per 64-column block instead of one kernel launch (216 launches of 5.8 us at cfg3).  The next block's
+// inverse (cp.async, double-buffered) and every thread's next column of L (registers) are fetched before the barrier
+// they will be needed after: L and the block inverses are final, only y changes between the steps, and y is
+// read with ld.global.cg (other CTAs wrote it).
+// ------------------------------------------------------------------------------------------
+#define BACKP_THREADS 256
+#define BACKP_NC 8                                // columns per warp and step: grid = ceil(bw / (8 warps x 8))
+__global__ void __launch_bounds__(BACKP_THREADS, 1)
+spl_backsolve_persistent_kernel(const double *__restrict__ AB, long long lda, long long n, int bw,
+                                const double *__restrict__ linv, double *ysol, double *__restrict__ csol,
+                                const int *__restrict__ fail, unsigned *bar) {
+    extern __shared__ __align__(16) double s_bk[];
+    double *s_li = s_bk;                        // 2 x 64 x 64  block inverse, row-major [r][c]
+    double *s_y = s_bk + 2 * 4096;              // 64
+    double *s_c = s_y + 64;                     // 64
+    const int t = threadIdx.x, lane = t & 31;
+    const unsigned G = gridDim.x;
+    const int gw = (int)blockIdx.x * (BACKP_THREADS / 32) + (t >> 5), nw = (int)G * (BACKP_THREADS / 32);
+    unsigned target = 0;
+    if (*fail) return;                          // uniform across the grid
+    const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    auto fetch_inv = [&](long long kb, int buf) {
+        const double *src = linv + kb * 4096;
+        double *dst = s_li + buf * 4096;
+        for (int e = t; e < 4096; e += BACKP_THREADS) spl_cp_async8(dst + e, src + e);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // warp gw eliminates from the columns jlo + gw, jlo + gw + nw, ..: a column's 64 entries of the block rows are
+    // contiguous, lane l holds rows l and l + 32 (two coalesced 256-byte loads per column)
+    double colr[BACKP_NC][2];
+    auto fetch_col = [&](long long kb) {
+        const long long j0 = kb * SOLVE_NB;
+        const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
+        const long long jlo = (j0 - bw > 0) ? j0 - bw : 0;
+#pragma unroll
+        for (int q = 0; q < BACKP_NC; ++q) {
+            const long long j = jlo + gw + (long long)q * nw;
+            colr[q][0] = colr[q][1] = 0.0;
+            if (j < j0) {
+                const double *col = AB + j0 + j * lda;
+                if (lane < nb) colr[q][0] = col[lane];
+                if (lane + 32 < nb) colr[q][1] = col[lane + 32];
+            }
+        }
+    };
+    fetch_inv(nblk - 1, (int)((nblk - 1) & 1));
+    fetch_col(nblk - 1);
+    for (long long kb = nblk - 1; kb >= 0; --kb) {
+        const long long j0 = kb * SOLVE_NB;
+        const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
+        const long long jlo = (j0 - bw > 0) ? j0 - bw : 0;
+        const double *li = s_li + (kb & 1) * 4096;
+        if (t < 64) s_y[t] = (t < nb) ? __ldcg(ysol + j0 + t) : 0.0;
+        // the entries this warp will update, fetched now (other CTAs wrote them before the barrier)
+        double yold = 0.0;
+        if (lane < BACKP_NC) {
+            const long long j = jlo + gw + (long long)lane * nw;
+            if (j < j0) yold = __ldcg(ysol + j);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // c_k = L11^-T y_k:  c[i] = sum_r Linv[r][i] y[r]; thread (i, part) sums r = part, part + 4, ..
+        {
+            const int i = t >> 2, part = t & 3;
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; q += 2) {
+                c0 = fma(li[(part + 4 * q) * 64 + i], s_y[part + 4 * q], c0);
+                c1 = fma(li[(part + 4 * q + 4) * 64 + i], s_y[part + 4 * q + 4], c1);
+            }
+            double c = c0 + c1;
+            c += __shfl_xor_sync(0xffffffffu, c, 1);
+            c += __shfl_xor_sync(0xffffffffu, c, 2);
+            if (part == 0) {
+                s_c[i] = c;
+                if (blockIdx.x == 0 && i < nb) csol[j0 + i] = c;
+            }
+        }
+        __syncthreads();
+        // eliminate c_k from the bw preceding unknowns: y[j] -= sum_i L[i][j] c[i], i in the block
+        {
+            const double ca = s_c[lane], cb = s_c[lane + 32];
+            double mine = 0.0;
+#pragma unroll
+            for (int q = 0; q < BACKP_NC; ++q) {
+                double v = fma(colr[q][0], ca, colr[q][1] * cb);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == q) mine = v;
+            }
+            if (lane < BACKP_NC) {
+                const long long j = jlo + gw + (long long)lane * nw;
+                if (j < j0) ysol[j] = yold - mine;
+            }
+        }
+        if (kb > 0) {
+            fetch_inv(kb - 1, (int)((kb - 1) & 1));
+            fetch_col(kb - 1);
+            spl_grid_barrier(bar, target, G);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
 long long spl_band_lda(int bw) { return (long long)bw + SOLVE_NB; }
@@ -1075,6 +1180,17 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         }
         cudaGetLastError();
     }
+    const size_t back_smem = sizeof(double) * (2 * 4096 + 128);
+    int back_grid = 0;
+    if (persistent) {
+        const long long per_cta = (BACKP_THREADS / 32) * BACKP_NC;      // columns a CTA covers per step
+        const long long need = ((long long)bw + per_cta - 1) / per_cta;
+        if (need >= 1 && need <= pgrid &&
+            cudaFuncSetAttribute(spl_backsolve_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)back_smem) == cudaSuccess)
+            back_grid = (int)need;
+        cudaGetLastError();
+    }
     (void)spl_panel_dbg_buffer();        // allocate (if asked for) outside stream capture
     // (re)build the graphs when the buffers or the problem changed
     SolveGraphs *sg = cache ? static_cast<SolveGraphs *>(*cache) : nullptr;
@@ -1162,7 +1278,19 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
                 hst[6] - hst[0]);
     }
     if (ev) cudaEventRecord(ev[2], st);
-    if (sg && sg->back) {
+    if (persistent && back_grid > 0) {
+        const double *a_AB = d_AB, *a_li = d_linv;
+        double *a_y = d_ysol, *a_c = d_csol;
+        long long a_lda = lda, a_n = n;
+        int a_bw = bw;
+        const int *a_fail = d_fail;
+        unsigned *a_bar = reinterpret_cast<unsigned *>(d_fail + 1);
+        SPL_CUDA_TRY(cudaMemsetAsync(a_bar, 0, sizeof(unsigned), st));
+        void *args[] = {&a_AB, &a_lda, &a_n, &a_bw, &a_li, &a_y, &a_c, &a_fail, &a_bar};
+        SPL_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)spl_backsolve_persistent_kernel, dim3(back_grid),
+                                                 dim3(BACKP_THREADS), args, back_smem, st));
+        nl = 1;
+    } else if (sg && sg->back) {
         SPL_CUDA_TRY(cudaGraphLaunch(sg->back, st));
         nl = sg->nback;
     } else {
