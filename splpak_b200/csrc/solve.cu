@@ -1180,6 +1180,17 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         }
         cudaGetLastError();
     }
+    // The persistent FACTOR kernel keeps one CTA per SM and gives the trailing update only the CTAs that are not on
+    // the panel: right when the chain of panels dominates (cfg3: 29 tile rows, 406 update tiles per step for 119
+    // helper CTAs), wrong when the update does (cfg4: 89 tile rows, 3,916 tiles for 59 helpers: 94 ms against 40 ms
+    // for the kernel-per-phase version, which runs three update CTAs per SM on every SM).  Rule: the helpers must
+    // get through a step's update in about four tiles each.
+    bool persistent_factor = persistent;
+    if (persistent) {
+        const long long T = ((long long)bw + SYRK_TILE - 1) / SYRK_TILE;
+        const long long helpers = (long long)pgrid - T;
+        if (helpers <= 0 || (T - 1) * T / 2 > 4 * helpers) persistent_factor = false;
+    }
     const size_t back_smem = sizeof(double) * (2 * 4096 + 128);
     int back_grid = 0;
     if (persistent) {
@@ -1194,21 +1205,21 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     (void)spl_panel_dbg_buffer();        // allocate (if asked for) outside stream capture
     // (re)build the graphs when the buffers or the problem changed
     SolveGraphs *sg = cache ? static_cast<SolveGraphs *>(*cache) : nullptr;
-    if (cache && (!sg || sg->key_AB != d_AB || sg->key_g != d_g || sg->n != n || sg->bw != bw || sg->persistent != persistent)) {
+    if (cache && (!sg || sg->key_AB != d_AB || sg->key_g != d_g || sg->n != n || sg->bw != bw || sg->persistent != persistent_factor)) {
         spl_solve_cache_free(sg);
         sg = new (std::nothrow) SolveGraphs();
         *cache = sg;
         if (sg) {
             cudaGraph_t gr = nullptr;
-            sg->persistent = persistent;
-            cudaError_t e = persistent ? cudaSuccess : cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
-            if (e == cudaSuccess && !persistent) {
+            sg->persistent = persistent_factor;
+            cudaError_t e = persistent_factor ? cudaSuccess : cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess && !persistent_factor) {
                 const cudaError_t eq = enqueue_factor(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux,
                                                       panel_smem, syrk_smem, &sg->nfactor);
                 e = cudaStreamEndCapture(st, &gr);
                 if (eq != cudaSuccess) e = eq;
             }
-            if (e == cudaSuccess && !persistent) e = cudaGraphInstantiate(&sg->factor, gr, 0);
+            if (e == cudaSuccess && !persistent_factor) e = cudaGraphInstantiate(&sg->factor, gr, 0);
             if (gr) cudaGraphDestroy(gr);
             gr = nullptr;
             if (e == cudaSuccess) e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
@@ -1245,7 +1256,7 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     }
     if (ev) cudaEventRecord(ev[1], st);
     long long nl = 0;
-    if (persistent) {
+    if (persistent_factor) {
         double *a_AB = d_AB, *a_g = d_g, *a_y = d_ysol, *a_li = d_linv;
         long long a_lda = lda, a_n = n;
         int a_bw = bw;
