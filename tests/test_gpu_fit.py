@@ -182,6 +182,47 @@ def test_solver_failures_map_to_107(oracle):
     assert sp.splcc(1, xh, 1, xh[:, 0], 80, [0.0], [1.0], [20], 0.0, **a)[1] == 107
 
 
+@pytest.mark.parametrize("ndim,nodes,ndata", [(3, [9, 8, 10], 6000), (2, [24, 20], 5000), (1, [300], 5000)])
+def test_solver_paths_agree(oracle, monkeypatch, ndim, nodes, ndata):
+    """The factorisation / back-substitution run as persistent cooperative kernels where the panel chain dominates
+    and as one kernel per phase (CUDA graph, two streams) otherwise; SPLPAK_B200_SOLVER=graph forces the latter.
+    Same normal equations -> coefficients equal to the solver's own run-to-run spread, and both at oracle parity."""
+    x, y, w, mn, mx = make_problem(ndim, nodes, ndata, seed=ndim + ndata)
+    ref, ierr = oracle.initialize(ndim, x, y, w, mn, mx, nodes, 0.0)     # xtrap = 0: no constraint rows, no refinement
+    assert ierr == 0
+    got = {}
+    for mode in ("persistent", "graph"):
+        if mode == "graph":
+            monkeypatch.setenv("SPLPAK_B200_SOLVER", "graph")
+        else:
+            monkeypatch.delenv("SPLPAK_B200_SOLVER", raising=False)
+        h = sp.FitHandle(ndim, mn, mx, nodes, 0.0)
+        assert h.add_points(x, y, w) == 0
+        S = h.normal_equations()[0]
+        tol, cond = coef_tolerance(dense_from_stencil(S, nodes))
+        c, ierr = h.compute()
+        assert ierr == 0, mode
+        got[mode] = c
+        np.testing.assert_allclose(c, ref, rtol=0, atol=tol * np.abs(ref).max(), err_msg=f"{mode}, cond {cond:.2e}")
+        h.destroy()
+    np.testing.assert_allclose(got["persistent"], got["graph"], rtol=0, atol=tol * np.abs(ref).max())
+
+
+def test_solver_failure_is_reported_by_both_paths(monkeypatch):
+    """A fit without enough data and xtrap = 0 is rank deficient: non-positive pivot -> ierror 107 (:1634-1637),
+    from the persistent kernel (every CTA leaves at the next grid barrier) as from the per-phase kernels."""
+    rng = np.random.default_rng(3)
+    x = rng.random((20, 3)) * 0.1                      # 20 points in one corner of a 6^3 grid
+    y = rng.random(20)
+    for mode in ("persistent", "graph"):
+        if mode == "graph":
+            monkeypatch.setenv("SPLPAK_B200_SOLVER", "graph")
+        else:
+            monkeypatch.delenv("SPLPAK_B200_SOLVER", raising=False)
+        coef, ierr = sp.splcc(3, x, 3, y, len(x), [0] * 3, [1] * 3, [6] * 3, 0.0, quiet=True)
+        assert ierr == 107, mode
+
+
 def test_streaming_add_points_equals_one_shot(oracle):
     """add_points in several calls (host chunks) == one splcw call up to summation-order roundoff
     (amplified by cond(G) in the coefficients); compute() twice is refused."""
