@@ -724,6 +724,59 @@ __device__ __forceinline__ void spl_syrk_tile(double *AB, long long lda, long lo
             }
 }
 
+// Half of a 64 x 64 tile (rows half*32 .. +32) with 256 threads (4 x 2 warps of 8 x 32): the persistent factor kernel
+// splits the tiles of the last, partial round among its helper CTAs so that nobody carries a whole extra tile.
+__device__ __forceinline__ void spl_syrk_half_tile(double *AB, long long lda, long long r0, long long j0, int nb, int m,
+                                                   int ti, int tj, int half, double *s_ab) {
+    double *sA = s_ab;                          // [k][row 0..31]
+    double *sB = s_ab + 64 * TILE_LD;
+    const int I0 = ti * SYRK_TILE + half * 32, J0 = tj * SYRK_TILE;
+    const int t = threadIdx.x;
+    for (int e = t; e < 64 * 64; e += PANEL_THREADS) {
+        const int k = e >> 6, r = e & 63;
+        if (r < 32) {
+            double *da = sA + k * TILE_LD + r;
+            if (k < nb && I0 + r < m) spl_cp_async8(da, AB + (r0 + I0 + r) + (j0 + k) * lda);
+            else *da = 0.0;
+        }
+        double *db = sB + k * TILE_LD + r;
+        if (k < nb && J0 + r < m) spl_cp_async8(db, AB + (r0 + J0 + r) + (j0 + k) * lda);
+        else *db = 0.0;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int warp = t >> 5, lane = t & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wy = (warp >> 1) * 8, wx = (warp & 1) * 32;
+    double acc[4][2];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int li = I0 + wy + g;
+            const int lj = J0 + wx + ni * 8 + 2 * t4 + h;
+            acc[ni][h] = (li < m && lj < m && li >= lj) ? AB[(r0 + li) + (r0 + lj) * lda] : 0.0;
+        }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+#pragma unroll 4
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+        const double a = -sA[(k0 + t4) * TILE_LD + wy + g];
+        double b[4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = sB[(k0 + t4) * TILE_LD + wx + ni * 8 + g];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) spl_dmma_8x8x4(acc[ni][0], acc[ni][1], a, b[ni]);
+    }
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int li = I0 + wy + g;
+            const int lj = J0 + wx + ni * 8 + 2 * t4 + h;
+            if (li < m && lj < m && li >= lj) AB[(r0 + li) + (r0 + lj) * lda] = acc[ni][h];
+        }
+}
+
 // rest-of-update tile number (0 .. (T-1) T / 2 - 1)  ->  (ti, tj) with ti >= tj >= 1
 __device__ __forceinline__ void spl_rest_tile(int tile, int &ti, int &tj) {
     ti = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
@@ -809,12 +862,28 @@ spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, dou
                 __syncthreads();
             }
         } else if (pntiles > pfirst) {
-            const int helpers = G - pblocks;
-            for (int tile = pfirst + (cta - pblocks); tile < pntiles; tile += helpers) {
+            // whole rounds of full tiles; the tiles of the last, partial round are split into row halves when that
+            // lets every helper finish one half instead of some a whole tile (the barrier waits for the slowest)
+            const int helpers = G - pblocks, me = cta - pblocks;
+            const int todo = pntiles - pfirst;
+            const int nfull = (todo / helpers) * helpers, rem = todo - nfull;
+            for (int u = me; u < nfull; u += helpers) {
                 int ti, tj;
-                spl_rest_tile(tile, ti, tj);
+                spl_rest_tile(pfirst + u, ti, tj);
                 spl_syrk_tile<PANEL_THREADS>(AB, lda, pr0, pj0, pnb, pm, ti, tj, s_dyn_f);
                 __syncthreads();
+            }
+            if (2 * rem <= helpers) {
+                if (me < 2 * rem) {
+                    int ti, tj;
+                    spl_rest_tile(pfirst + nfull + (me >> 1), ti, tj);
+                    if (ti != tj) spl_syrk_half_tile(AB, lda, pr0, pj0, pnb, pm, ti, tj, me & 1, s_dyn_f);
+                    else if ((me & 1) == 0) spl_syrk_tile<PANEL_THREADS>(AB, lda, pr0, pj0, pnb, pm, ti, tj, s_dyn_f);
+                }
+            } else if (me < rem) {
+                int ti, tj;
+                spl_rest_tile(pfirst + nfull + me, ti, tj);
+                spl_syrk_tile<PANEL_THREADS>(AB, lda, pr0, pj0, pnb, pm, ti, tj, s_dyn_f);
             }
         }
         if (dbg && kb == nblk / 2 && cta == 0 && threadIdx.x == 0) dbg[12] = clock64();
