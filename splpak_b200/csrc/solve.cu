@@ -666,17 +666,30 @@ __device__ __forceinline__ void spl_syrk_tile(double *AB, long long lda, long lo
     const int t = threadIdx.x;
     const bool diag = (ti == tj);
 
-    for (int e = t; e < 64 * 64; e += NTHR) {
-        const int k = e >> 6, r = e & 63;
-        if (!A_READY) {
-            double *da = sA + k * TILE_LD + r;
-            if (k < nb && I0 + r < m) spl_cp_async8(da, AB + (r0 + I0 + r) + (j0 + k) * lda);
-            else *da = 0.0;
-        }
-        if (!diag) {
-            double *db = sB + k * TILE_LD + r;
-            if (k < nb && J0 + r < m) spl_cp_async8(db, AB + (r0 + J0 + r) + (j0 + k) * lda);
-            else *db = 0.0;
+    {
+        // thread t owns row r = t % 64 of both operand tiles and every (NTHR / 64)-th k: pointers advance by a constant,
+        // no index arithmetic per element (the per-element form made the tile issue-bound in its load phase)
+        constexpr int KS = NTHR / 64;
+        const int r = t & 63, kq = t >> 6;
+        const bool a_ok = I0 + r < m, b_ok = J0 + r < m;
+        const double *ga = AB + (r0 + I0 + r) + (j0 + kq) * lda;
+        const double *gb = AB + (r0 + J0 + r) + (j0 + kq) * lda;
+        double *da = sA + kq * TILE_LD + r, *db = sB + kq * TILE_LD + r;
+        const long long gstep = (long long)KS * lda;
+#pragma unroll 4
+        for (int k = kq; k < 64; k += KS) {
+            if (!A_READY) {
+                if (a_ok && k < nb) spl_cp_async8(da, ga);
+                else *da = 0.0;
+            }
+            if (!diag) {
+                if (b_ok && k < nb) spl_cp_async8(db, gb);
+                else *db = 0.0;
+            }
+            ga += gstep;
+            gb += gstep;
+            da += KS * TILE_LD;
+            db += KS * TILE_LD;
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -684,18 +697,30 @@ __device__ __forceinline__ void spl_syrk_tile(double *AB, long long lda, long lo
     const int warp = t >> 5, lane = t & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const int wy = (warp >> 1) * (MI * 8), wx = (warp & 1) * 32;
+    // the C tile: element (mi, ni, h) of this thread at pc[mi * 8 + (ni * 8 + h) * lda]
+    double *pc = AB + (r0 + I0 + wy + g) + (r0 + J0 + wx + 2 * t4) * lda;
+    const bool inside = !diag && I0 + 64 <= m && J0 + 64 <= m;     // every element valid: no per-element tests
     // prefetch the C tile into the accumulators (lower triangle, inside the window)
     double acc[MI][4][2];
+    if (inside) {
 #pragma unroll
-    for (int mi = 0; mi < MI; ++mi)
+        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
+            for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int li = I0 + wy + mi * 8 + g;
-                const int lj = J0 + wx + ni * 8 + 2 * t4 + h;
-                acc[mi][ni][h] = (li < m && lj < m && li >= lj) ? AB[(r0 + li) + (r0 + lj) * lda] : 0.0;
-            }
+                for (int h = 0; h < 2; ++h) acc[mi][ni][h] = pc[mi * 8 + (long long)(ni * 8 + h) * lda];
+    } else {
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int li = I0 + wy + mi * 8 + g;
+                    const int lj = J0 + wx + ni * 8 + 2 * t4 + h;
+                    acc[mi][ni][h] = (li < m && lj < m && li >= lj) ? pc[mi * 8 + (long long)(ni * 8 + h) * lda] : 0.0;
+                }
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     const double *pB = diag ? sA : sB;
@@ -712,16 +737,25 @@ __device__ __forceinline__ void spl_syrk_tile(double *AB, long long lda, long lo
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
+    if (inside) {
 #pragma unroll
-    for (int mi = 0; mi < MI; ++mi)
+        for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
+            for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int li = I0 + wy + mi * 8 + g;
-                const int lj = J0 + wx + ni * 8 + 2 * t4 + h;
-                if (li < m && lj < m && li >= lj) AB[(r0 + li) + (r0 + lj) * lda] = acc[mi][ni][h];
-            }
+                for (int h = 0; h < 2; ++h) pc[mi * 8 + (long long)(ni * 8 + h) * lda] = acc[mi][ni][h];
+    } else {
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int li = I0 + wy + mi * 8 + g;
+                    const int lj = J0 + wx + ni * 8 + 2 * t4 + h;
+                    if (li < m && lj < m && li >= lj) pc[mi * 8 + (long long)(ni * 8 + h) * lda] = acc[mi][ni][h];
+                }
+    }
 }
 
 // Half of a 64 x 64 tile (rows half*32 .. +32) with 256 threads (4 x 2 warps of 8 x 32): the persistent factor kernel
