@@ -1369,9 +1369,17 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         unsigned *a_bar = reinterpret_cast<unsigned *>(d_fail + 1);
         SPL_CUDA_TRY(cudaMemsetAsync(a_bar, 0, sizeof(unsigned), st));
         void *args[] = {&a_AB, &a_lda, &a_n, &a_bw, &a_g, &a_y, &a_li, &a_fail, &a_dbg, &a_bar};
-        SPL_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)spl_factor_persistent_kernel, dim3(pgrid), dim3(PANEL_THREADS),
-                                                 args, pers_smem, st));
-        nl = 1;
+        const cudaError_t ce = cudaLaunchCooperativeKernel((const void *)spl_factor_persistent_kernel, dim3(pgrid),
+                                                           dim3(PANEL_THREADS), args, pers_smem, st);
+        if (ce == cudaSuccess) {
+            nl = 1;
+        } else {
+            // e.g. the grid cannot be co-resident in this context: fall back to the kernel-per-phase loop
+            fprintf(stderr, "splpak_b200: cooperative launch of the factor kernel failed (%s); launching per phase\n",
+                    cudaGetErrorString(ce));
+            cudaGetLastError();
+            SPL_CUDA_TRY(enqueue_factor(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux, panel_smem, syrk_smem, &nl));
+        }
     } else if (sg && sg->factor) {
         SPL_CUDA_TRY(cudaGraphLaunch(sg->factor, st));
         nl = sg->nfactor;
@@ -1401,9 +1409,16 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         unsigned *a_bar = reinterpret_cast<unsigned *>(d_fail + 1);
         SPL_CUDA_TRY(cudaMemsetAsync(a_bar, 0, sizeof(unsigned), st));
         void *args[] = {&a_AB, &a_lda, &a_n, &a_bw, &a_li, &a_y, &a_c, &a_fail, &a_bar};
-        SPL_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)spl_backsolve_persistent_kernel, dim3(back_grid),
-                                                 dim3(BACKP_THREADS), args, back_smem, st));
-        nl = 1;
+        const cudaError_t ce = cudaLaunchCooperativeKernel((const void *)spl_backsolve_persistent_kernel, dim3(back_grid),
+                                                           dim3(BACKP_THREADS), args, back_smem, st);
+        if (ce == cudaSuccess) {
+            nl = 1;
+        } else {
+            fprintf(stderr, "splpak_b200: cooperative launch of the back-substitution failed (%s); launching per block\n",
+                    cudaGetErrorString(ce));
+            cudaGetLastError();
+            SPL_CUDA_TRY(enqueue_back(n, bw, lda, d_AB, d_linv, d_ysol, d_csol, d_fail, st, &nl));
+        }
     } else if (sg && sg->back) {
         SPL_CUDA_TRY(cudaGraphLaunch(sg->back, st));
         nl = sg->nback;
