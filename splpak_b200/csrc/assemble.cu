@@ -101,15 +101,22 @@ __device__ __forceinline__ long long spl_nearest_node(const GridParams &gp, cons
 // SMEMH: the per-window counts are first accumulated in a shared-memory histogram (native 32-bit
 // ATOMS) and flushed once per CTA -- the L2 atomic units, not HBM, bound this pass when every point
 // issues two global reductions.  Used when the window table fits (launcher decides).
-template <int NDIM, bool SMEMH, bool CELL>
-__global__ void __launch_bounds__(512, 2)
+// SMEMC (with SMEMH): the nearest-node weight histogram is privatised per CTA in shared memory as well (one
+// 1024-thread CTA per SM, shared-memory f64 atomic adds, one flush of the non-zero entries per CTA): with one
+// red.global.add.f64 per point the pass was bound by the L2 atomic units (1.45 ms per 1e8 points for 0.5 ms of HBM
+// traffic).  Used when both tables fit (launcher decides).
+template <int NDIM, bool SMEMH, bool CELL, bool SMEMC = false>
+__global__ void __launch_bounds__(SMEMC ? 1024 : 512, SMEMC ? 1 : 2)
 spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
                     const real_t *__restrict__ w, int weighted, long long n, int nbins,
                     unsigned *__restrict__ wincount, int do_hist, double *__restrict__ cnt,
                     double *__restrict__ totals, const real_t *__restrict__ y, double2 *__restrict__ yw) {
-    extern __shared__ unsigned s_hist[];
+    extern __shared__ __align__(8) unsigned s_hist[];
+    double *s_cnt = reinterpret_cast<double *>(s_hist + ((nbins + 1) & ~1));     // SMEMC: gp.ncol doubles
     if (SMEMH) {
         for (int e = threadIdx.x; e < nbins; e += blockDim.x) s_hist[e] = 0u;
+        if (SMEMC)
+            for (long long e = threadIdx.x; e < gp.ncol; e += blockDim.x) s_cnt[e] = 0.0;
         __syncthreads();
     }
     double tot = 0.0;
@@ -143,7 +150,8 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
                 else atomicAdd(wincount + key, 1u);
                 rows += 1.0;
                 if (do_hist) {
-                    atomicAdd(cnt + spl_nearest_node<NDIM>(gp, xp[u]), wv[u]);
+                    if (SMEMC) atomicAdd(s_cnt + spl_nearest_node<NDIM>(gp, xp[u]), wv[u]);
+                    else atomicAdd(cnt + spl_nearest_node<NDIM>(gp, xp[u]), wv[u]);
                     tot += wv[u];
                 }
             }
@@ -155,9 +163,14 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
             const unsigned c = s_hist[e];
             if (c) atomicAdd(wincount + e, c);
         }
+        if (SMEMC && do_hist)
+            for (long long e = threadIdx.x; e < gp.ncol; e += blockDim.x) {
+                const double c = s_cnt[e];
+                if (c != 0.0) atomicAdd(cnt + e, c);
+            }
     }
     // block reduction of totlwt and the row count
-    __shared__ double s_tot[16], s_rows[16];
+    __shared__ double s_tot[32], s_rows[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         tot += __shfl_xor_sync(0xffffffffu, tot, o);
@@ -746,7 +759,17 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
         long long cb = (n + 512LL * BIN_U - 1) / (512LL * BIN_U);
         const long long ccap = (long long)nsm * (smemh ? 2 : 4);
         const int cgrid = (int)(cb < ccap ? (cb < 1 ? 1 : cb) : ccap);
-        if (smemh) {
+        // both histograms in shared memory: one 1024-thread CTA per SM
+        const size_t both_bytes = sizeof(unsigned) * (size_t)((nbins + 1) & ~1LL) + sizeof(double) * (size_t)gp.ncol;
+        const bool smemc = smemh && do_hist && both_bytes <= 200 * 1024 && !getenv("SPLPAK_B200_GLOBAL_HIST");
+        if (smemc) {
+            auto kern = spl_classify_kernel<NDIM, true, CELL, true>;
+            SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)both_bytes));
+            long long cb1 = (n + 1024LL * BIN_U - 1) / (1024LL * BIN_U);
+            const int cgrid1 = (int)(cb1 < nsm ? (cb1 < 1 ? 1 : cb1) : nsm);
+            kern<<<cgrid1, 1024, both_bytes, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins, sc.wincount, do_hist,
+                                                   d_cnt, d_totals, d_y, yw);
+        } else if (smemh) {
             auto kern = spl_classify_kernel<NDIM, true, CELL>;
             SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
             kern<<<cgrid, 512, hist_bytes, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins, sc.wincount, do_hist,
