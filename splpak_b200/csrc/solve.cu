@@ -854,13 +854,14 @@ __device__ __forceinline__ void spl_grid_barrier(unsigned *counter, unsigned &ta
     __syncthreads();
     if (threadIdx.x == 0) {
         target += G;
-        __threadfence();
-        atomicAdd(counter, 1u);
+        // release: the CTA's writes (ordered before this thread by the bar.sync above) are visible to whoever
+        // observes the increment with an acquire load -- one instruction instead of a fence + a relaxed atomic,
+        // and the acquire poll needs no fence after it
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         unsigned v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
         } while (v < target);
-        __threadfence();
     }
     __syncthreads();
 }
