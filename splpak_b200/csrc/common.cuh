@@ -54,6 +54,7 @@ struct AssembleScratch {
     int moments;          // 1: 3-D assembly by cell moments (moments.cuh)
     double *celltab;      // moment path: per-(dimension, cell) coefficient tables
     double *cellmom;      // moment path: per-cell moment sums of the chunk in flight (kept zero between chunks)
+    int cursor_stride;    // 4-byte words between the per-bin cursors of the second binning pass
     double *yw;           // moment path: interleaved (y, w) copy of the chunk, 2 doubles per point (sized with perm)
 };
 
