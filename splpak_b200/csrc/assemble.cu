@@ -13,7 +13,10 @@
 //   3. spl_perm_kernel       second pass: counting sort of the point INDICES by window (4 bytes per
 //                            point; scattering 40-byte records instead was LSU-bound)
 //   4. spl_items_kernel      work-item table (window, segment of <= CH points)
-//   5. spl_accumulate_kernel persistent CTAs; per work item the points are gathered through the
+//   5. accumulate            3-D: spl_moments_kernel + spl_cell_transform_kernel (moments.cuh: per-cell Legendre
+//                            moments as an FP64 tensor-core GEMM over the points, then one change of basis per
+//                            cell); 1-D / 2-D / 4-D (and 3-D under SPLPAK_B200_ASSEMBLY=direct):
+//      spl_accumulate_kernel persistent CTAs; per work item the points are gathered through the
 //                            permutation (prefetched two batches ahead, hidden under the FP64 work),
 //                            the window-local block of G is accumulated in REGISTERS and flushed once
 //                            with red.global.add.f64

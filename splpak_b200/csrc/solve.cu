@@ -12,18 +12,24 @@
 // ldab = lda + 1 viewed as a dense column-major matrix with leading dimension lda = b + NB, so every
 // block kernel below is an ordinary dense column-major kernel on a sub-block (ncol*(lda+1) doubles).
 //
-// Right-looking blocked Cholesky, panel width NB = 64, two launches per panel:
-//   spl_panel_kernel   every CTA factors the NB x NB diagonal block AND inverts the factor in
-//                      registers (redundantly: it is a latency chain, and this saves a launch and a
-//                      dependency per panel), forward-solves the right-hand side of the block, then
+// Right-looking blocked Cholesky, panel width NB = 64.  The same device code runs in two drivers:
+//   * spl_factor_persistent_kernel / spl_backsolve_persistent_kernel: the whole loop in one cooperative
+//     kernel each, phases separated by a grid-wide barrier (default where the panel chain dominates);
+//   * one kernel per phase (spl_panel_kernel, spl_syrk_kernel, spl_backsolve_kernel), two streams with
+//     look-ahead, captured into CUDA graphs (update-bound shapes, SPLPAK_B200_SOLVER=graph, or when a
+//     cooperative launch is refused).
+// The phases:
+//   spl_panel_body     every CTA factors the NB x NB diagonal block AND inverts the factor (blocked
+//                      inversion on the tensor cores; redundantly in every CTA: it is a latency chain, and
+//                      this saves a dependency per panel), forward-solves the right-hand side of the block, then
 //                      forms its 64 rows of the sub-diagonal panel L21 = A21 L11^-T as a tensor-core
 //                      GEMM against the inverse and updates the right-hand side below: the forward
 //                      solve L y = g rides along with the factorization.
-//   spl_syrk_kernel    trailing update A22 -= L21 L21^T on the lower-triangular 64 x 64 tiles of
+//   spl_syrk_tile      trailing update A22 -= L21 L21^T on the lower-triangular 64 x 64 tiles of
 //                      the (<= b) x (<= b) window, with FP64 tensor-core MMA
 //                      (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), operands staged k-major in
 //                      shared memory.
-// Back-substitution L^T c = y runs block by block from the end (spl_backsolve_kernel): every CTA
+// Back-substitution L^T c = y runs block by block from the end: every CTA
 // forms c_k = L11^-T y_k from the stored block inverse, then eliminates c_k from its slice of the b
 // preceding entries.
 #include <stdlib.h>
