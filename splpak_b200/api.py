@@ -96,11 +96,16 @@ def splcw(ndim, xdata, l1xdat, ydata, wdata, ndata, xmin, xmax, nodes, xtrap, nc
     w = _vec(wdata, dt) if wdata is not None else np.array([-1.0], dtype=dt)
     keep, (mnp, mxp, nop) = _grid_args(lib, ndim, xmin, xmax, nodes, real32)
     coef = np.zeros(max(int(ncf), 1), dtype=dt)
+    if ndata >= 1 and l1xdat >= 1:
+        # the C ABI trusts (ndata, l1xdat) as Fortran explicit-shape dummies do: check the buffers here
+        if x.size < int(ndata) * int(l1xdat) or y.size < int(ndata) or (w[0] >= 0 and w.size < int(ndata)):
+            raise SplpakError(f"xdata/ydata/wdata are smaller than ndata={ndata} x l1xdat={l1xdat} requires")
     ierr = C.c_int(0)
-    lib.splpak_b200_splcw(int(ndim), _ptr(x), int(l1xdat), _ptr(y), _ptr(w), int(ndata), mnp, mxp, nop,
-                          lib._real(xtrap), _ptr(coef), int(ncf), None, int(nwrk), C.byref(ierr))
-    _report(ierr.value, False, quiet, real32)
-    return coef[:int(ncf)] if ncf >= 1 else coef[:0], ierr.value
+    rc = lib.splpak_b200_splcw(int(ndim), _ptr(x), int(l1xdat), _ptr(y), _ptr(w), int(ndata), mnp, mxp, nop,
+                               lib._real(xtrap), _ptr(coef), int(ncf), None, int(nwrk), C.byref(ierr))
+    ie = ierr.value if ierr.value != 0 else int(rc)          # a failure that could not write ierror still surfaces
+    _report(ie, False, quiet, real32)
+    return coef[:int(ncf)] if ncf >= 1 else coef[:0], ie
 
 
 def splcc(ndim, xdata, l1xdat, ydata, ndata, xmin, xmax, nodes, xtrap, ncf=None, nwrk=None, *,
@@ -370,7 +375,11 @@ class FitHandle:
         if rc != 0:
             return rc
         if allreduce is not None:
-            allreduce(self.rhs_tensor())
+            # the collective must be ordered against the handle's private stream: issue it there
+            import torch
+
+            with torch.cuda.stream(torch.cuda.ExternalStream(self.stream())):
+                allreduce(self.rhs_tensor())
         ierr = C.c_int(0)
         self.lib.splpak_b200_fit_refine_compute_device(self.h, _dev_ptr(d_coef), self.ncol, C.byref(ierr))
         return ierr.value

@@ -36,6 +36,8 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
                      double **d_coef_out, int *d_fail, cudaStream_t st, cudaStream_t st_aux, int nsm, cudaEvent_t *ev,
                      void **cache);
 void spl_solve_cache_free(void *cache);
+int spl_resolve_launch(const GridParams &gp, const double *d_AB, double *d_g, double *d_work, double **d_coef_out,
+                       int *d_fail, cudaStream_t st, int nsm);
 int spl_constraints_residual_launch(const GridParams &gp, double xtrap, const double *d_cnt,
                                     const double *d_totals_in, const double *d_coef, double *d_g,
                                     cudaStream_t st, int nsm);
@@ -540,7 +542,8 @@ struct splpak_b200_fit_s {
     AssembleScratch sc;
     long long chunk_cap;          // points the scratch can take
     real_t *d_stage[2][3];        // host-path staging: x, y, w double-buffered
-    long long stage_cap;
+    long long stage_cap;          // points the y / w staging buffers hold
+    long long stage_xcap;         // reals the x staging buffers hold (chunk * l1x of the call that sized them)
     cudaEvent_t ev_stage_in[2], ev_stage_free[2];
     // solve
     double *d_AB;
@@ -551,13 +554,15 @@ struct splpak_b200_fit_s {
     double *d_coef64;             // ncol: solution of the last compute / refine step
     real_t *d_res;                // residuals y - s(x) of the chunk being re-assembled
     long long res_cap;
-    double *d_dummy_tot;          // classify's row/weight totals of refinement passes (discarded)
+    double *d_dummy_tot;          // [0,1] classify's row/weight totals of refinement passes (discarded); [2] row count before the constraint rows
     int solved;                   // compute succeeded: d_coef64 is valid
+    int factor_valid;             // d_AB / the workspace behind it hold the Cholesky factor of the current G
+    real_t *d_out_tmp;            // ncol reals: working-precision copy of the solution for the D2H of real32 builds
     int refining;
     int constraints_fired;        // derivative-constraint rows were added by compute
     // timing: accumulated event pairs
     double ms[NTIMER];
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[12];           // 0-3 assembly, 4-5 constraints, 8-11 solve stages
     unsigned long long launches0;
     int finalized;
     int timers_pending;           // ev[0..3] hold an unharvested assembly measurement
@@ -582,13 +587,14 @@ static void free_handle(splpak_b200_fit_t h) {
     }
     if (h->d_AB) cudaFree(h->d_AB);
     if (h->d_fail) cudaFree(h->d_fail);
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < 12; ++k)
         if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     if (h->st) cudaStreamDestroy(h->st);
     if (h->solve_cache) spl_solve_cache_free(h->solve_cache);
     if (h->d_coef64) cudaFree(h->d_coef64);
     if (h->d_res) cudaFree(h->d_res);
     if (h->d_dummy_tot) cudaFree(h->d_dummy_tot);
+    if (h->d_out_tmp) cudaFree(h->d_out_tmp);
     if (h->st_copy) cudaStreamDestroy(h->st_copy);
     if (h->st_aux) cudaStreamDestroy(h->st_aux);
     h->magic = 0;
@@ -631,8 +637,10 @@ extern "C" int splpak_b200_fit_create(int ndim, const real_t *xmin, const real_t
     ok = ok && cudaMalloc((void **)&h->d_part, sizeof(double) * (size_t)h->n_part) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&h->d_fail, 2 * sizeof(int)) == cudaSuccess;   // [failure flag, grid-barrier counter of the persistent factor kernel]
     ok = ok && cudaMalloc((void **)&h->d_coef64, sizeof(double) * (size_t)(gp.ncol + 2)) == cudaSuccess;
-    ok = ok && cudaMalloc((void **)&h->d_dummy_tot, sizeof(double) * 2) == cudaSuccess;
-    for (int k = 0; k < 8 && ok; ++k) ok = cudaEventCreate(&h->ev[k]) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&h->d_dummy_tot, sizeof(double) * 4) == cudaSuccess;
+    if (sizeof(real_t) != sizeof(double))
+        ok = ok && cudaMalloc((void **)&h->d_out_tmp, sizeof(real_t) * (size_t)(gp.ncol + 2)) == cudaSuccess;
+    for (int k = 0; k < 12 && ok; ++k) ok = cudaEventCreate(&h->ev[k]) == cudaSuccess;
     for (int k = 0; k < 2 && ok; ++k) {
         ok = ok && cudaEventCreateWithFlags(&h->ev_stage_in[k], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->ev_stage_free[k], cudaEventDisableTiming) == cudaSuccess;
@@ -663,7 +671,7 @@ extern "C" int splpak_b200_fit_reset(splpak_b200_fit_t h) {
     h->finalized = 0;
     h->timers_pending = 0;
     h->total_points = 0;
-    h->solved = h->refining = h->constraints_fired = 0;
+    h->solved = h->refining = h->constraints_fired = h->factor_valid = 0;
     return SPLPAK_OK;
 }
 
@@ -743,6 +751,36 @@ extern "C" int splpak_b200_fit_add_points_device(splpak_b200_fit_t h, const real
     return SPLPAK_OK;   // asynchronous: timers are harvested by the next chunk / compute / fit_timings
 }
 
+// Host-path staging buffers, grow-only.  The x buffer is sized in REALS (chunk * l1x): a later call with
+// a larger leading dimension must not reuse a buffer sized for a smaller one.
+static int ensure_stage(splpak_b200_fit_t h, long long chunk, int l1x) {
+    const long long xneed = chunk * (long long)l1x;
+    if (chunk > h->stage_cap) {
+        for (int k = 0; k < 2; ++k)
+            for (int a = 1; a < 3; ++a) {
+                if (h->d_stage[k][a]) cudaFree(h->d_stage[k][a]);
+                h->d_stage[k][a] = nullptr;
+            }
+        h->stage_cap = 0;
+        for (int k = 0; k < 2; ++k) {
+            SPL_CUDA_TRY(cudaMalloc((void **)&h->d_stage[k][1], sizeof(real_t) * (size_t)chunk));
+            SPL_CUDA_TRY(cudaMalloc((void **)&h->d_stage[k][2], sizeof(real_t) * (size_t)chunk));
+        }
+        h->stage_cap = chunk;
+    }
+    if (xneed > h->stage_xcap) {
+        for (int k = 0; k < 2; ++k) {
+            if (h->d_stage[k][0]) cudaFree(h->d_stage[k][0]);
+            h->d_stage[k][0] = nullptr;
+        }
+        h->stage_xcap = 0;
+        for (int k = 0; k < 2; ++k)
+            SPL_CUDA_TRY(cudaMalloc((void **)&h->d_stage[k][0], sizeof(real_t) * (size_t)xneed));
+        h->stage_xcap = xneed;
+    }
+    return SPLPAK_OK;
+}
+
 extern "C" int splpak_b200_fit_add_points(splpak_b200_fit_t h, const real_t *x, int l1x,
                                           const real_t *y, const real_t *w, int weighted, int64_t n) {
     if (!valid(h) || h->finalized) return SPLPAK_ERR_HANDLE;
@@ -750,20 +788,8 @@ extern "C" int splpak_b200_fit_add_points(splpak_b200_fit_t h, const real_t *x, 
     if (l1x < h->gp.ndim) return SPLPAK_ERR_HANDLE;
     if (!w) weighted = 0;
     const long long chunk = n < HOST_CHUNK ? n : HOST_CHUNK;
-    if (chunk > h->stage_cap) {
-        for (int k = 0; k < 2; ++k)
-            for (int a = 0; a < 3; ++a) {
-                if (h->d_stage[k][a]) cudaFree(h->d_stage[k][a]);
-                h->d_stage[k][a] = nullptr;
-            }
-        h->stage_cap = 0;
-        for (int k = 0; k < 2; ++k) {
-            SPL_CUDA_TRY(cudaMalloc((void **)&h->d_stage[k][0], sizeof(real_t) * (size_t)chunk * l1x));
-            SPL_CUDA_TRY(cudaMalloc((void **)&h->d_stage[k][1], sizeof(real_t) * (size_t)chunk));
-            SPL_CUDA_TRY(cudaMalloc((void **)&h->d_stage[k][2], sizeof(real_t) * (size_t)chunk));
-        }
-        h->stage_cap = chunk;
-    }
+    int rcs = ensure_stage(h, chunk, l1x);
+    if (rcs != SPLPAK_OK) return rcs;
     int k = 0;
     for (long long i0 = 0; i0 < n; i0 += chunk, k ^= 1) {
         const long long nc = (n - i0 < chunk) ? n - i0 : chunk;
@@ -854,51 +880,61 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
         }
         h->ab_elems = need;
     }
-    double rows_before = 0.0;
-    if (h->xtrap != 0.0) {
-        SPL_CUDA_TRY(cudaMemcpyAsync(&rows_before, h->d_totals + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
-        SPL_CUDA_TRY(cudaStreamSynchronize(st));
-    }
-    SPL_CUDA_TRY(cudaEventRecord(h->ev[4], st));
+    // A CUDA failure below must reach the caller through *ierror (the Fortran shim and api.py read nothing
+    // else) and leave the handle finalized.
+#define FC_TRY(expr)                                                                        \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            fprintf(stderr, "splpak_b200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorString(_e), __FILE__, \
+                    __LINE__, #expr);                                                       \
+            h->finalized = 1;                                                               \
+            h->solved = 0;                                                                  \
+            if (ierror) *ierror = SPLPAK_ERR_CUDA;                                          \
+            return SPLPAK_ERR_CUDA;                                                         \
+        }                                                                                   \
+    } while (0)
+    // row count before the constraint rows, kept on the device until the one synchronisation after the solve
+    FC_TRY(cudaMemcpyAsync(h->d_dummy_tot + 2, h->d_totals + 1, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    FC_TRY(cudaEventRecord(h->ev[4], st));
     if (h->xtrap != 0.0) {
         rc = spl_constraints_launch(gp, h->xtrap, h->d_cnt, h->d_totals, h->d_S, h->d_totals, st, h->di.nsm);
         if (rc != SPLPAK_OK) {
+            h->finalized = 1;
             if (ierror) *ierror = rc;
             return rc;
         }
     }
-    SPL_CUDA_TRY(cudaEventRecord(h->ev[5], st));
-    SPL_CUDA_TRY(cudaMemsetAsync(h->d_AB, 0, sizeof(double) * (size_t)need, st));
-    SPL_CUDA_TRY(cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
-    cudaEvent_t sev[4];
-    for (int k = 0; k < 4; ++k) SPL_CUDA_TRY(cudaEventCreate(&sev[k]));
+    FC_TRY(cudaEventRecord(h->ev[5], st));
+    FC_TRY(cudaMemsetAsync(h->d_AB, 0, sizeof(double) * (size_t)need, st));
+    FC_TRY(cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
+    cudaEvent_t *sev = h->ev + 8;
     // the solve destroys g; the solution comes back in the workspace behind the band matrix
     double *d_sol = nullptr;
     rc = spl_solve_launch(gp, h->d_S, h->d_AB, h->d_g, h->d_AB + band_elems, &d_sol, h->d_fail, st, h->st_aux, h->di.nsm, sev,
                           &h->solve_cache);
     int fail = 0;
-    double totals[2] = {0.0, 0.0};
+    double totals[2] = {0.0, 0.0}, rows_before = 0.0;
     if (rc == SPLPAK_OK) {
-        SPL_CUDA_TRY(cudaMemcpyAsync(h->d_coef64, d_sol, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToDevice, st));
+        FC_TRY(cudaMemcpyAsync(h->d_coef64, d_sol, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToDevice, st));
         if (coef_on_device) {
             spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(d_sol, coef, gp.ncol);
             ++g_spl_launches;
         }
-        SPL_CUDA_TRY(cudaMemcpyAsync(&fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
-        SPL_CUDA_TRY(cudaMemcpyAsync(totals, h->d_totals, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+        FC_TRY(cudaMemcpyAsync(&fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FC_TRY(cudaMemcpyAsync(totals, h->d_totals, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+        FC_TRY(cudaMemcpyAsync(&rows_before, h->d_dummy_tot + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
         if (!coef_on_device) {
             if (sizeof(real_t) == sizeof(double)) {
-                SPL_CUDA_TRY(cudaMemcpyAsync(coef, d_sol, sizeof(double) * (size_t)gp.ncol,
-                                             cudaMemcpyDeviceToHost, st));
+                FC_TRY(cudaMemcpyAsync(coef, d_sol, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
             } else {
-                real_t *tmp = reinterpret_cast<real_t *>(h->d_AB);   // band storage is dead now
+                real_t *tmp = h->d_out_tmp;                           // d_AB keeps the factor for refinement steps
                 spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(d_sol, tmp, gp.ncol);
                 ++g_spl_launches;
-                SPL_CUDA_TRY(cudaMemcpyAsync(coef, tmp, sizeof(real_t) * (size_t)gp.ncol,
-                                             cudaMemcpyDeviceToHost, st));
+                FC_TRY(cudaMemcpyAsync(coef, tmp, sizeof(real_t) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
             }
         }
-        SPL_CUDA_TRY(cudaStreamSynchronize(st));
+        FC_TRY(cudaStreamSynchronize(st));
         collect_assemble_timers(h);
         add_ms(h, 3, h->ev[4], h->ev[5]);
         add_ms(h, 4, sev[0], sev[1]);
@@ -907,9 +943,10 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
         // fewer rows than columns (suprls error 33, :1650) or a non-positive pivot -> 107
         if (fail || totals[1] < (double)gp.ncol) rc = SPLPAK_ERR_SOLVER;
         h->solved = (rc == SPLPAK_OK);
+        h->factor_valid = h->solved;
         h->constraints_fired = (h->xtrap != 0.0) && (totals[1] > rows_before);
     }
-    for (int k = 0; k < 4; ++k) cudaEventDestroy(sev[k]);
+#undef FC_TRY
     h->finalized = 1;
     if (ierror) *ierror = rc;
     return rc;
@@ -984,7 +1021,11 @@ extern "C" int splpak_b200_fit_refine_add_points(splpak_b200_fit_t h, const real
     if (l1x < h->gp.ndim) return SPLPAK_ERR_HANDLE;
     if (!w) weighted = 0;
     const long long chunk = n < HOST_CHUNK ? n : HOST_CHUNK;
-    if (chunk > h->stage_cap) return SPLPAK_ERR_HANDLE;                // the staging buffers of add_points are reused
+    {   // the staging buffers of add_points are reused (and grown if this call needs more)
+        // the kernels of a previous call may still read them: frees are ordered by cudaFree's implicit sync
+        const int rcs = ensure_stage(h, chunk, l1x);
+        if (rcs != SPLPAK_OK) return rcs;
+    }
     int k = 0;
     for (long long i0 = 0; i0 < n; i0 += chunk, k ^= 1) {
         const long long nc = (n - i0 < chunk) ? n - i0 : chunk;
@@ -1017,6 +1058,17 @@ static int fit_refine_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_o
     const GridParams &gp = h->gp;
     cudaStream_t st = h->st;
     h->refining = 0;
+#define RC_TRY(expr)                                                                        \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            fprintf(stderr, "splpak_b200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorString(_e), __FILE__, \
+                    __LINE__, #expr);                                                       \
+            h->factor_valid = 0;                                                            \
+            if (ierror) *ierror = SPLPAK_ERR_CUDA;                                          \
+            return SPLPAK_ERR_CUDA;                                                         \
+        }                                                                                   \
+    } while (0)
     if (sizeof(real_t) == sizeof(double)) {
         if (h->xtrap != 0.0) {
             rc = spl_constraints_residual_launch(gp, h->xtrap, h->d_cnt, h->d_totals, h->d_coef64, h->d_g, st, h->di.nsm);
@@ -1031,11 +1083,21 @@ static int fit_refine_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_o
         const long long need = band_elems + spl_solve_workspace(gp);
         if (need > h->ab_elems) rc = SPLPAK_ERR_HANDLE;               // compute allocated it
         if (rc == SPLPAK_OK) {
-            SPL_CUDA_TRY(cudaMemsetAsync(h->d_AB, 0, sizeof(double) * (size_t)need, st));
-            SPL_CUDA_TRY(cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
             double *d_sol = nullptr;
-            rc = spl_solve_launch(gp, h->d_S, h->d_AB, h->d_g, h->d_AB + band_elems, &d_sol, h->d_fail, st, h->st_aux,
-                                  h->di.nsm, nullptr, &h->solve_cache);
+            // G is unchanged: reuse its factor (forward + back substitution only); re-factor only where the persistent
+            // substitution kernels are not available for this shape
+            int rs = h->factor_valid ? spl_resolve_launch(gp, h->d_AB, h->d_g, h->d_AB + band_elems, &d_sol, h->d_fail, st,
+                                                          h->di.nsm)
+                                     : SPLPAK_ERR_HANDLE;
+            if (rs != SPLPAK_OK) {
+                h->factor_valid = 0;
+                RC_TRY(cudaMemsetAsync(h->d_AB, 0, sizeof(double) * (size_t)need, st));
+                RC_TRY(cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
+                rs = spl_solve_launch(gp, h->d_S, h->d_AB, h->d_g, h->d_AB + band_elems, &d_sol, h->d_fail, st, h->st_aux,
+                                      h->di.nsm, nullptr, &h->solve_cache);
+                if (rs == SPLPAK_OK) h->factor_valid = 1;
+            }
+            rc = rs;
             if (rc == SPLPAK_OK) {
                 spl_axpy_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(h->d_coef64, d_sol, gp.ncol);
                 ++g_spl_launches;
@@ -1044,24 +1106,25 @@ static int fit_refine_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_o
     }
     if (rc == SPLPAK_OK) {
         int fail = 0;
-        SPL_CUDA_TRY(cudaMemcpyAsync(&fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RC_TRY(cudaMemcpyAsync(&fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
         if (coef_on_device) {
             spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(h->d_coef64, coef, gp.ncol);
             ++g_spl_launches;
         } else if (sizeof(real_t) == sizeof(double)) {
-            SPL_CUDA_TRY(cudaMemcpyAsync(coef, h->d_coef64, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
+            RC_TRY(cudaMemcpyAsync(coef, h->d_coef64, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
         } else {
-            real_t *tmp = reinterpret_cast<real_t *>(h->d_AB);
+            real_t *tmp = h->d_out_tmp;
             spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(h->d_coef64, tmp, gp.ncol);
             ++g_spl_launches;
-            SPL_CUDA_TRY(cudaMemcpyAsync(coef, tmp, sizeof(real_t) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
+            RC_TRY(cudaMemcpyAsync(coef, tmp, sizeof(real_t) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
         }
-        SPL_CUDA_TRY(cudaStreamSynchronize(st));
+        RC_TRY(cudaStreamSynchronize(st));
         if (fail) rc = SPLPAK_ERR_SOLVER;
     }
     if (ierror) *ierror = rc;
     return rc;
 }
+#undef RC_TRY
 
 extern "C" int splpak_b200_fit_refine_compute(splpak_b200_fit_t h, real_t *coef, int64_t ncf, int *ierror) {
     return fit_refine_compute_impl(h, coef, 0, ncf, ierror);

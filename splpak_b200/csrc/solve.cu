@@ -1122,6 +1122,104 @@ spl_backsolve_persistent_kernel(const double *__restrict__ AB, long long lda, lo
 }
 
 // ------------------------------------------------------------------------------------------
+// persistent forward substitution L y = g against the STORED factor (refinement steps, capi.cu: the
+// factorisation of G is reused, only the right-hand side is new).  Mirror image of the kernel above: per 64-column
+// block every CTA forms y_k = L11^-1 g_k from the stored block inverse, then warp pairs eliminate y_k from the (<= bw)
+// rows below -- lane = row, the two warps of a pair take 32 columns each (a column's rows are contiguous: coalesced
+// 256-byte loads, prefetched before the barrier because L is final) and are combined in a fixed order, so the
+// result is deterministic.  One grid barrier per block.
+// ------------------------------------------------------------------------------------------
+#define FWDP_THREADS 256
+#define FWDP_LD 65
+__global__ void __launch_bounds__(FWDP_THREADS, 1)
+spl_forwardsolve_persistent_kernel(const double *__restrict__ AB, long long lda, long long n, int bw,
+                                   const double *__restrict__ linv, double *g, double *__restrict__ ysol,
+                                   const int *__restrict__ fail, unsigned *bar) {
+    extern __shared__ __align__(16) double s_fw[];
+    double *s_li = s_fw;                        // 2 x 64 x FWDP_LD  block inverse, row-major [r][c], padded
+    double *s_g = s_fw + 2 * 64 * FWDP_LD;      // 64  g_k
+    double *s_y = s_g + 64;                     // 64  y_k
+    double *s_part = s_y + 64;                  // 8 x 32 partial row sums of the warps
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned G = gridDim.x;
+    const int gw = (int)blockIdx.x * (FWDP_THREADS / 32) + warp;
+    const int pair = gw >> 1, hc = gw & 1;      // rows r0 + 32 pair + lane, columns 32 hc .. 32 hc + 31 of the block
+    unsigned target = 0;
+    if (*fail) return;                          // uniform across the grid
+    const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    auto fetch_inv = [&](long long kb, int buf) {
+        const double *src = linv + kb * 4096;
+        double *dst = s_li + buf * 64 * FWDP_LD;
+        for (int e = t; e < 4096; e += FWDP_THREADS) spl_cp_async8(dst + (e >> 6) * FWDP_LD + (e & 63), src + e);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double lreg[32];
+    auto fetch_rows = [&](long long kb) {
+        const long long j0 = kb * SOLVE_NB;
+        const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
+        const long long r0 = j0 + nb;
+        long long mm = n - r0;
+        if (mm > bw) mm = bw;
+        const long long rl = (long long)pair * 32 + lane;
+        const bool ok = rl < mm;
+        const double *src = AB + (r0 + rl) + (j0 + hc * 32) * lda;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) lreg[c] = (ok && hc * 32 + c < nb) ? src[(long long)c * lda] : 0.0;
+    };
+    fetch_inv(0, 0);
+    fetch_rows(0);
+    for (long long kb = 0; kb < nblk; ++kb) {
+        const long long j0 = kb * SOLVE_NB;
+        const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
+        const long long r0 = j0 + nb;
+        long long mm = n - r0;
+        if (mm > bw) mm = bw;
+        const double *li = s_li + (kb & 1) * 64 * FWDP_LD;
+        if (t < 64) s_g[t] = (t < nb) ? __ldcg(g + j0 + t) : 0.0;
+        const long long rl = (long long)pair * 32 + lane;
+        double gold = 0.0;
+        if (hc == 0 && rl < mm) gold = __ldcg(g + r0 + rl);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // y_k = L11^-1 g_k: thread (r, part) sums c = part, part + 4, ..
+        {
+            const int r = t >> 2, part = t & 3;
+            double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; q += 2) {
+                y0 = fma(li[r * FWDP_LD + part + 4 * q], s_g[part + 4 * q], y0);
+                y1 = fma(li[r * FWDP_LD + part + 4 * q + 4], s_g[part + 4 * q + 4], y1);
+            }
+            double y = y0 + y1;
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            if (part == 0) {
+                s_y[r] = y;
+                if (blockIdx.x == 0 && r < nb) ysol[j0 + r] = y;
+            }
+        }
+        __syncthreads();
+        // g[i] -= sum_c L[i][j0 + c] y[c] for the rows below the block
+        {
+            double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                p0 = fma(lreg[c], s_y[hc * 32 + c], p0);
+                p1 = fma(lreg[c + 1], s_y[hc * 32 + c + 1], p1);
+            }
+            s_part[warp * 32 + lane] = p0 + p1;
+        }
+        __syncthreads();
+        if (hc == 0 && rl < mm) g[r0 + rl] = gold - (s_part[warp * 32 + lane] + s_part[(warp + 1) * 32 + lane]);
+        if (kb + 1 < nblk) {
+            fetch_inv(kb + 1, (int)((kb + 1) & 1));
+            fetch_rows(kb + 1);
+            spl_grid_barrier(bar, target, G);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
 long long spl_band_lda(int bw) { return (long long)bw + SOLVE_NB; }
@@ -1435,5 +1533,72 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     g_spl_launches += nl;
     if (ev) cudaEventRecord(ev[3], st);
     SPL_CUDA_TRY(cudaGetLastError());
+    return SPLPAK_OK;
+}
+
+// Solve G c = g again with the factor left in d_AB / d_work by spl_solve_launch (same layout of d_work); g is
+// destroyed.  Only the two persistent substitution kernels run: returns SPLPAK_ERR_HANDLE when they are not
+// available for this shape (the caller then re-factors).
+int spl_resolve_launch(const GridParams &gp, const double *d_AB, double *d_g, double *d_work, double **d_coef_out,
+                       int *d_fail, cudaStream_t st, int nsm) {
+    const long long n = gp.ncol;
+    const int bw = spl_half_bandwidth(gp);
+    const long long lda = spl_band_lda(bw);
+    const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    double *d_linv = d_work;
+    double *d_ysol = d_work + nblk * 4096;
+    double *d_csol = d_ysol + (n + 64);
+    *d_coef_out = d_csol;
+    const char *mode = getenv("SPLPAK_B200_SOLVER");
+    if (mode && strcmp(mode, "graph") == 0) return SPLPAK_ERR_HANDLE;
+    int dev = 0, coop = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) {
+        cudaGetLastError();
+        return SPLPAK_ERR_HANDLE;
+    }
+    const int pgrid = nsm > 0 ? nsm : SPL_NSM_DEFAULT;
+    const size_t back_smem = sizeof(double) * (2 * 4096 + 128);
+    const size_t fwd_smem = sizeof(double) * (2 * 64 * FWDP_LD + 128 + 8 * 32);
+    const long long per_cta = (BACKP_THREADS / 32) * BACKP_NC;
+    const long long back_grid = ((long long)bw + per_cta - 1) / per_cta;
+    long long fwd_grid = ((((long long)bw + 31) / 32) * 2 + FWDP_THREADS / 32 - 1) / (FWDP_THREADS / 32);
+    if (fwd_grid < 1) fwd_grid = 1;
+    if (back_grid < 1 || back_grid > pgrid || fwd_grid > pgrid) return SPLPAK_ERR_HANDLE;
+    if (cudaFuncSetAttribute(spl_backsolve_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)back_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(spl_forwardsolve_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)fwd_smem) != cudaSuccess) {
+        cudaGetLastError();
+        return SPLPAK_ERR_HANDLE;
+    }
+    unsigned *a_bar = reinterpret_cast<unsigned *>(d_fail + 1);
+    {
+        const double *a_AB = d_AB, *a_li = d_linv;
+        double *a_g = d_g, *a_y = d_ysol;
+        long long a_lda = lda, a_n = n;
+        int a_bw = bw;
+        const int *a_fail = d_fail;
+        SPL_CUDA_TRY(cudaMemsetAsync(a_bar, 0, sizeof(unsigned), st));
+        void *args[] = {&a_AB, &a_lda, &a_n, &a_bw, &a_li, &a_g, &a_y, &a_fail, &a_bar};
+        if (cudaLaunchCooperativeKernel((const void *)spl_forwardsolve_persistent_kernel, dim3((unsigned)fwd_grid),
+                                        dim3(FWDP_THREADS), args, fwd_smem, st) != cudaSuccess) {
+            cudaGetLastError();
+            return SPLPAK_ERR_HANDLE;
+        }
+        ++g_spl_launches;
+    }
+    {
+        const double *a_AB = d_AB, *a_li = d_linv;
+        double *a_y = d_ysol, *a_c = d_csol;
+        long long a_lda = lda, a_n = n;
+        int a_bw = bw;
+        const int *a_fail = d_fail;
+        SPL_CUDA_TRY(cudaMemsetAsync(a_bar, 0, sizeof(unsigned), st));
+        void *args[] = {&a_AB, &a_lda, &a_n, &a_bw, &a_li, &a_y, &a_c, &a_fail, &a_bar};
+        SPL_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)spl_backsolve_persistent_kernel, dim3((unsigned)back_grid),
+                                                 dim3(BACKP_THREADS), args, back_smem, st));
+        ++g_spl_launches;
+    }
     return SPLPAK_OK;
 }

@@ -39,10 +39,34 @@ def allreduce_partials(buf, group=None):
     return buf
 
 
-def fit_sharded(handle, x, y, w, weighted=True, device_resident=False, l1x=None, n=None, group=None, stream=None):
-    """Every rank adds ITS shard to `handle`, the partial sums are all-reduced, every rank solves.
-    Returns (coef, ierror); coef is identical on every rank (identical inputs to a deterministic solve)."""
+def _on_handle_stream(handle, fn, stream=None):
+    """Run the collective `fn()` ordered against the handle's private stream (on which assembly, compute and refine
+    run).  Default: issue it ON that stream.  A caller-chosen `stream` is fenced with events on both sides."""
     import torch
+
+    hs = torch.cuda.ExternalStream(handle.stream())
+    if stream is None or getattr(stream, "cuda_stream", None) == hs.cuda_stream:
+        with torch.cuda.stream(hs):
+            fn()
+        return
+    before, after = torch.cuda.Event(), torch.cuda.Event()
+    before.record(hs)
+    stream.wait_event(before)
+    with torch.cuda.stream(stream):
+        fn()
+    after.record(stream)
+    hs.wait_event(after)
+
+
+def fit_sharded(handle, x, y, w, weighted=True, device_resident=False, l1x=None, n=None, group=None, stream=None,
+                broadcast_coef=False):
+    """Every rank adds ITS shard to `handle`, the partial sums are all-reduced, every rank solves.
+    Returns (coef, ierror).  The all-reduce is ordered against the handle's stream (see _on_handle_stream), so no
+    host synchronisation is needed around it.  The replicated solves see identical inputs; their constraint rows
+    are added with unordered FP64 atomics, so coefficients may differ by ~eps*cond(G) between ranks unless the handle
+    is deterministic or `broadcast_coef` is set (rank 0's coefficients are then broadcast, 8*ncol bytes)."""
+    import torch
+    import torch.distributed as dist
 
     if device_resident:
         rc = handle.add_points_device(x, l1x, y, w, n, weighted)
@@ -51,11 +75,10 @@ def fit_sharded(handle, x, y, w, weighted=True, device_resident=False, l1x=None,
     if rc != 0:
         return None, rc
     part = handle.partial_tensor()
-    if stream is not None:
-        with torch.cuda.stream(stream):
-            allreduce_partials(part, group)
-    else:
-        handle.synchronize()
-        allreduce_partials(part, group)
-        torch.cuda.synchronize()
-    return handle.compute()
+    _on_handle_stream(handle, lambda: allreduce_partials(part, group), stream)
+    coef, ierr = handle.compute()
+    if broadcast_coef and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.from_numpy(np.ascontiguousarray(coef, dtype=np.float64)).cuda()
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        coef = t.cpu().numpy().astype(coef.dtype, copy=False)
+    return coef, ierr
