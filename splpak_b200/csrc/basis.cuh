@@ -148,16 +148,24 @@ __device__ __forceinline__ double spl_clamp0(double s) {
     return __hiloint2double(hi & keep, __double2loint(s) & keep);
 }
 
-// The four window weights of one dimension for nder = 0 -- the hot-path form used by evaluation
-// (splfe) and assembly.  Arithmetic per node is EXACTLY that of spl_bas1_value (same operations, same
-// order, no FMA), so the values are bit-identical to the reference's bascmp; what is different is the
-// plumbing around it, which the instruction mix of the evaluation kernel showed to dominate:
-//   * it = trunc(t) through the saturating F2I (NaN -> 0) instead of a floating clamp;
-//   * sign manipulation (-u, -|u|), max(.,0), the alpha select and the s >= 2 test on the high word
-//     with integer-pipe instructions instead of FP64-pipe DADD/DSETP + paired FSELs;
-//   * no box mask: a window node outside the reference's box [ibmn, ibmx] is >= 2 cells away from x,
-//     so s <= 0 (up to one ulp of u, i.e. a term <= 1e-47 instead of an exact 0) and the value formula
-//     returns 0 for it anyway.
+// The four window weights of one dimension for nder = 0 -- the hot-path form used by evaluation (splfe) and
+// assembly.  Every value is bit-identical to the reference's bascmp (same operations on the same operands, every
+// product that is not rounded in the reference is an exact power-of-two scaling here); what differs is the plumbing,
+// which the instruction mix of the evaluation kernel showed to dominate (613 instructions per 3-D query, 267 FP64):
+//   * it = trunc(t) through the saturating F2I (NaN -> 0);
+//   * the sign of u is STATIC in the window position k: a chapeau node at k <= 1 has x >= xb (it >= ws + 1 >= ib
+//     whenever the window is not clamped from below -- and then the node is a left-edge node), one at k >= 2 has
+//     x < xb; left-edge nodes (ib <= 1) only ever sit at k <= 1, right-edge nodes (ib >= nod-2) at k >= 2.  So
+//     s = 2 - u for k < 2 and s = 2 + u for k >= 2 is bascmp's -z / z in all three node types (:253, :352, :358);
+//     a rounding disagreement between t and u can flip the sign only at |u| ~ 1e-15 at the peak of the node's
+//     function, where the value changes by O(u^2) < 1e-28;
+//   * max(s, 0) as (s + |s|) / 2 with the division deferred: sq = s + |s| is exact, sq^3 = 8 max(s,0)^3 with the
+//     reference's two roundings, and alpha * sq^3 - tq^3 is ONE rounding in the reference too (alpha is a power of
+//     two), so a single FMA gives 8 x the reference value bit for bit; no integer-pipe clamps, no FSEL pairs;
+//   * no box mask: a window node outside the reference's box [ibmn, ibmx] is >= 2 cells away from x, so s <= 0 (up
+//     to one ulp of u, i.e. a term <= 1e-47 instead of an exact 0) and the formula returns 0 for it.
+// SCALE8: return 8 x the values (the caller multiplies its final sum by 8^-ndim, exact) and save one multiply each.
+template <bool SCALE8 = false>
 __device__ __forceinline__ void spl_window_weights_value(double x, double xmin, double dx, double dxin,
                                                          int nod, int &ws, double b[4]) {
     const double t = spl_mul(dxin, spl_sub(x, xmin));
@@ -166,25 +174,20 @@ __device__ __forceinline__ void spl_window_weights_value(double x, double xmin, 
     const double wsf = (double)ws;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int ib = ws + k;
         const double xb = spl_add(xmin, spl_mul(wsf + (double)k, dx));     // :246 (wsf + k is exact)
         const double u = spl_mul(dxin, spl_sub(x, xb));
-        const bool is_l = ib <= 1;
-        const bool edge = is_l || ib >= nod - 2;
-        // w = -u (left edge), u (right edge), -|u| (chapeau): flip / keep / set the sign bit
-        const unsigned flip = is_l ? 0x80000000u : 0u;
-        const unsigned set = edge ? 0u : 0x80000000u;
-        const double w = __hiloint2double((int)(((unsigned)__double2hiint(u) ^ flip) | set), __double2loint(u));
-        const double s = spl_add(2.0, w);
-        const double sp = spl_clamp0(s);
-        const double s3 = spl_mul(spl_mul(sp, sp), sp);
-        const double m = spl_clamp0(spl_sub(s, 1.0));
-        const double m3 = spl_mul(spl_mul(m, m), m);
+        const double s = (k < 2) ? spl_sub(2.0, u) : spl_add(2.0, u);
+        const bool edge = (k < 2) ? (ws + k <= 1) : (ws + k >= nod - 2);
+        const double sq = spl_add(s, fabs(s));                             // 2 max(s, 0), exact
+        const double sq3 = spl_mul(spl_mul(sq, sq), sq);                   // 8 max(s, 0)^3
+        const double s1 = spl_sub(s, 1.0);
+        const double tq = spl_add(s1, fabs(s1));                           // 2 max(s - 1, 0), exact
+        const double tq3 = spl_mul(spl_mul(tq, tq), tq);                   // 8 max(s - 1, 0)^3
         const double alpha = __hiloint2double(edge ? 0x3fe00000 : 0x3fd00000, 0);   // 1/2 : 1/4
-        double v = spl_sub(spl_mul(alpha, s3), m3);
-        const double lin = spl_sub(spl_mul(3.0, s), 3.0);
-        if (edge && __double2hiint(s) >= 0x40000000) v = lin;                      // s >= 2 (s < 0 has the sign bit set)
-        b[k] = v;
+        double v = __fma_rn(sq3, alpha, -tq3);                             // product exact: one rounding, as :262/:371
+        const double lin = spl_sub(spl_mul(24.0, s), 24.0);                // 8 (3 s - 3), :376
+        if (edge && __double2hiint(s) >= 0x40000000) v = lin;              // s >= 2 (s < 0 has the sign bit set)
+        b[k] = SCALE8 ? v : spl_mul(v, 0.125);
     }
 }
 

@@ -2,10 +2,14 @@
 // device-memory ownership, host<->device staging, and the launch sequences of the kernels in
 // eval.cu / assemble.cu / solve.cu.  There is no CPU fallback anywhere in this file: without a
 // usable CUDA device every compute entry point returns SPLPAK_ERR_CUDA.
+#include <condition_variable>
 #include <dlfcn.h>
 #include <mutex>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -16,7 +20,8 @@ int spl_assemble_scratch_init(const GridParams &gp, AssembleScratch &sc, cudaStr
 void spl_assemble_scratch_free(AssembleScratch &sc);
 int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, int l1x, long long nq,
                     const double *d_coef, long long ncol_padded, real_t *d_out, cudaStream_t stream,
-                    int nsm, size_t smem_optin, unsigned long long *d_counter);
+                    int nsm, size_t smem_optin, unsigned long long *d_counter, double *d_pad);
+long long spl_eval_regroup_elems(const GridParams &gp, long long nq, int nsm, size_t smem_optin);
 long long spl_grid_tmp_elems(const GridParams &gp, const long long *naxis);
 int spl_eval_grid_launch(const GridParams &gp, const int *nderiv, const real_t *const *d_axis, const long long *naxis,
                          const double *d_coef64, real_t *d_out, double *d_tmp, long long tmp_elems, int *d_iws,
@@ -105,6 +110,194 @@ static int get_device(DeviceInfo &di) {
     }
     di.ok = 1;
     return SPLPAK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Pageable host memory.  The reference's caller arrays are ordinary Fortran arrays (src/splpak.F90:537-559), i.e.
+// pageable: cudaMemcpyAsync from/to them is staged by the driver through one internal bounce buffer by ONE thread
+// and serialises with everything else.  The host-array entry points therefore stage pageable ranges themselves:
+// a small per-device ring of pinned slots, filled (or drained) by a pool of host threads, one cudaMemcpyAsync per
+// slot, so the host-side memcpy of piece k+1 overlaps the DMA of piece k.  Ranges that are already pinned
+// (cudaHostAlloc / cudaHostRegister / torch pin_memory) are copied directly.
+// ------------------------------------------------------------------------------------------
+class CopyPool {
+  public:
+    static CopyPool &get() {
+        static CopyPool *pool = new CopyPool();      // leaked on purpose: its detached workers outlive static destructors
+        return *pool;
+    }
+    void copy(void *dst, const void *src, size_t bytes) {
+        if (nthr_ <= 1 || bytes < (1u << 20)) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        dst_ = static_cast<char *>(dst);
+        src_ = static_cast<const char *>(src);
+        bytes_ = bytes;
+        pending_ = nthr_;
+        ++gen_;
+        cv_work_.notify_all();
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+  private:
+    CopyPool() {
+        int n = 0;
+        if (const char *e = getenv("SPLPAK_B200_COPY_THREADS")) n = atoi(e);
+        if (n <= 0) {
+            int hw = (int)std::thread::hardware_concurrency();
+            int ranks = 1;
+            if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+            n = hw / ranks;
+            if (n > 8) n = 8;
+        }
+        if (n < 1) n = 1;
+        nthr_ = n;
+        for (int t = 0; t < nthr_; ++t) workers_.emplace_back([this, t] { run(t); });
+        for (auto &w : workers_) w.detach();         // process-lifetime pool
+    }
+    void run(int t) {
+        unsigned long long seen = 0;
+        for (;;) {
+            const char *src;
+            char *dst;
+            size_t bytes;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                src = src_;
+                dst = dst_;
+                bytes = bytes_;
+            }
+            const size_t per = ((bytes + nthr_ - 1) / nthr_ + 4095) & ~(size_t)4095;
+            const size_t lo = per * t, hi = lo + per < bytes ? lo + per : bytes;
+            if (lo < bytes) memcpy(dst + lo, src + lo, hi - lo);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) cv_done_.notify_all();
+            }
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> workers_;
+    int nthr_ = 1, pending_ = 0;
+    unsigned long long gen_ = 0;
+    char *dst_ = nullptr;
+    const char *src_ = nullptr;
+    size_t bytes_ = 0;
+};
+
+#define STAGE_SLOTS 4
+#define STAGE_SLOT_BYTES ((size_t)16 << 20)
+struct HostStager {
+    std::mutex mu;
+    char *up[STAGE_SLOTS] = {nullptr}, *down[STAGE_SLOTS] = {nullptr};
+    cudaEvent_t up_ev[STAGE_SLOTS] = {nullptr}, down_ev[STAGE_SLOTS] = {nullptr};
+    int up_next = 0, down_next = 0;
+    // device -> pageable host copies whose DMA into the pinned slot has been issued but not yet drained
+    struct Pending {
+        void *dst = nullptr;
+        size_t bytes = 0;
+    } down_pending[STAGE_SLOTS];
+    bool ok = false, tried = false;
+};
+static HostStager &host_stager(int device) {
+    static HostStager st[64];
+    return st[(device >= 0 && device < 64) ? device : 0];
+}
+static bool stager_init(HostStager &hs) {
+    if (hs.tried) return hs.ok;
+    hs.tried = true;
+    bool ok = true;
+    for (int k = 0; k < STAGE_SLOTS && ok; ++k) {
+        ok = ok && cudaHostAlloc((void **)&hs.up[k], STAGE_SLOT_BYTES, cudaHostAllocDefault) == cudaSuccess;
+        ok = ok && cudaHostAlloc((void **)&hs.down[k], STAGE_SLOT_BYTES, cudaHostAllocDefault) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&hs.up_ev[k], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&hs.down_ev[k], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) cudaGetLastError();
+    hs.ok = ok;
+    return ok;
+}
+// true when the driver can DMA straight from/to p (pinned or registered host memory, or managed/device memory)
+static bool host_range_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type != cudaMemoryTypeUnregistered;
+}
+static bool stage_disabled() {
+    static int v = -1;
+    if (v < 0) v = getenv("SPLPAK_B200_NO_STAGING") ? 1 : 0;
+    return v == 1;
+}
+
+// host -> device, asynchronous on st for pinned sources; pageable sources go through the pinned ring (the call then
+// returns once the LAST piece has been handed to the DMA engine; the source may be reused immediately)
+static cudaError_t spl_h2d(void *d_dst, const void *h_src, size_t bytes, cudaStream_t st, int dev) {
+    if (bytes == 0) return cudaSuccess;
+    if (bytes < (256u << 10) || stage_disabled() || host_range_is_pinned(h_src))
+        return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st);
+    HostStager &hs = host_stager(dev);
+    std::lock_guard<std::mutex> lk(hs.mu);
+    if (!stager_init(hs)) return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaSuccess;
+    for (size_t off = 0; off < bytes && e == cudaSuccess; off += STAGE_SLOT_BYTES) {
+        const size_t nb = bytes - off < STAGE_SLOT_BYTES ? bytes - off : STAGE_SLOT_BYTES;
+        const int k = hs.up_next;
+        hs.up_next = (k + 1) % STAGE_SLOTS;
+        if ((e = cudaEventSynchronize(hs.up_ev[k])) != cudaSuccess) break;        // the slot's previous DMA is done
+        CopyPool::get().copy(hs.up[k], static_cast<const char *>(h_src) + off, nb);
+        if ((e = cudaMemcpyAsync(static_cast<char *>(d_dst) + off, hs.up[k], nb, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        e = cudaEventRecord(hs.up_ev[k], st);
+    }
+    return e;
+}
+
+static cudaError_t drain_slot(HostStager &hs, int k) {
+    if (!hs.down_pending[k].dst) return cudaSuccess;
+    cudaError_t e = cudaEventSynchronize(hs.down_ev[k]);
+    if (e == cudaSuccess) CopyPool::get().copy(hs.down_pending[k].dst, hs.down[k], hs.down_pending[k].bytes);
+    hs.down_pending[k].dst = nullptr;
+    return e;
+}
+// device -> host on st.  Pageable destinations: the DMA lands in a pinned slot and the host-side copy is DEFERRED
+// until the slot is needed again or spl_d2h_flush() is called -- callers must flush before they return.
+static cudaError_t spl_d2h(void *h_dst, const void *d_src, size_t bytes, cudaStream_t st, int dev) {
+    if (bytes == 0) return cudaSuccess;
+    if (bytes < (256u << 10) || stage_disabled() || host_range_is_pinned(h_dst))
+        return cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st);
+    HostStager &hs = host_stager(dev);
+    std::lock_guard<std::mutex> lk(hs.mu);
+    if (!stager_init(hs)) return cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaSuccess;
+    for (size_t off = 0; off < bytes && e == cudaSuccess; off += STAGE_SLOT_BYTES) {
+        const size_t nb = bytes - off < STAGE_SLOT_BYTES ? bytes - off : STAGE_SLOT_BYTES;
+        const int k = hs.down_next;
+        hs.down_next = (k + 1) % STAGE_SLOTS;
+        if ((e = drain_slot(hs, k)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(hs.down[k], static_cast<const char *>(d_src) + off, nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        if ((e = cudaEventRecord(hs.down_ev[k], st)) != cudaSuccess) break;
+        hs.down_pending[k].dst = static_cast<char *>(h_dst) + off;
+        hs.down_pending[k].bytes = nb;
+    }
+    return e;
+}
+static cudaError_t spl_d2h_flush(int dev) {
+    HostStager &hs = host_stager(dev);
+    std::lock_guard<std::mutex> lk(hs.mu);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < STAGE_SLOTS; ++i) {
+        const int k = (hs.down_next + i) % STAGE_SLOTS;       // oldest first
+        const cudaError_t ek = drain_slot(hs, k);
+        if (e == cudaSuccess) e = ek;
+    }
+    return e;
 }
 
 // Grid validation shared by fit and evaluation, in the reference's order
@@ -247,7 +440,20 @@ static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const in
     // on its own stream)
     unsigned long long *counter = eval_counter_slot(di.dev);
     if (!counter) return SPLPAK_ERR_ALLOC;
-    int rc = spl_eval_launch(gp, nderiv, d_x, l1x, nq, coef64, npad, d_out, st, di.nsm, di.smem_optin, counter);
+    // padded copy of the table for the regrouping kernel (2-D..4-D, large batches)
+    double *pad = nullptr;
+    const long long pad_elems = spl_eval_regroup_elems(gp, nq, di.nsm, di.smem_optin);
+    if (pad_elems > 0) {
+        cudaMemPool_t pool = eval_scratch_pool(di.dev);
+        cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&pad, sizeof(double) * (size_t)pad_elems, pool, st)
+                             : cudaMallocAsync((void **)&pad, sizeof(double) * (size_t)pad_elems, st);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            pad = nullptr;                                     // the plain kernel needs no scratch
+        }
+    }
+    int rc = spl_eval_launch(gp, nderiv, d_x, l1x, nq, coef64, npad, d_out, st, di.nsm, di.smem_optin, counter, pad);
+    if (pad) cudaFreeAsync(pad, st);
     if (tmp) cudaFreeAsync(tmp, st);
     return rc;
 }
@@ -487,15 +693,15 @@ extern "C" int splpak_b200_eval(int ndim, const real_t *x, int l1x, int64_t nq, 
     for (long long q0 = 0; q0 < nq; q0 += chunk, k ^= 1) {
         const long long nc = (nq - q0 < chunk) ? nq - q0 : chunk;
         EV_TRY(cudaStreamWaitEvent(st2, cx.ev_done[k], 0));      // buffer k free again
-        EV_TRY(cudaMemcpyAsync(cx.d_x[k], x + q0 * (long long)l1x, sizeof(real_t) * (size_t)nc * l1x,
-                               cudaMemcpyHostToDevice, st2));
+        EV_TRY(spl_h2d(cx.d_x[k], x + q0 * (long long)l1x, sizeof(real_t) * (size_t)nc * l1x, st2, di.dev));
         EV_TRY(cudaEventRecord(cx.ev_in[k], st2));
         EV_TRY(cudaStreamWaitEvent(st, cx.ev_in[k], 0));
         rc = eval_device_impl(gp, di, nderiv, cx.d_x[k], l1x, nc, d_coef, cx.d_out[k], st);
         if (rc != SPLPAK_OK) break;
-        EV_TRY(cudaMemcpyAsync(out + q0, cx.d_out[k], sizeof(real_t) * (size_t)nc, cudaMemcpyDeviceToHost, st));
+        EV_TRY(spl_d2h(out + q0, cx.d_out[k], sizeof(real_t) * (size_t)nc, st, di.dev));
         EV_TRY(cudaEventRecord(cx.ev_done[k], st));
     }
+    EV_TRY(spl_d2h_flush(di.dev));
     EV_TRY(cudaStreamSynchronize(st));
     EV_TRY(cudaStreamSynchronize(st2));
 #undef EV_TRY
@@ -795,13 +1001,11 @@ extern "C" int splpak_b200_fit_add_points(splpak_b200_fit_t h, const real_t *x, 
         const long long nc = (n - i0 < chunk) ? n - i0 : chunk;
         // copy stream: wait until the kernels that read staging buffer k have finished
         SPL_CUDA_TRY(cudaStreamWaitEvent(h->st_copy, h->ev_stage_free[k], 0));
-        SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][0], x + i0 * (long long)l1x,
-                                     sizeof(real_t) * (size_t)nc * l1x, cudaMemcpyHostToDevice, h->st_copy));
-        SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][1], y + i0, sizeof(real_t) * (size_t)nc,
-                                     cudaMemcpyHostToDevice, h->st_copy));
+        SPL_CUDA_TRY(spl_h2d(h->d_stage[k][0], x + i0 * (long long)l1x, sizeof(real_t) * (size_t)nc * l1x, h->st_copy,
+                             h->di.dev));
+        SPL_CUDA_TRY(spl_h2d(h->d_stage[k][1], y + i0, sizeof(real_t) * (size_t)nc, h->st_copy, h->di.dev));
         if (weighted)
-            SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][2], w + i0, sizeof(real_t) * (size_t)nc,
-                                         cudaMemcpyHostToDevice, h->st_copy));
+            SPL_CUDA_TRY(spl_h2d(h->d_stage[k][2], w + i0, sizeof(real_t) * (size_t)nc, h->st_copy, h->di.dev));
         SPL_CUDA_TRY(cudaEventRecord(h->ev_stage_in[k], h->st_copy));
         SPL_CUDA_TRY(cudaStreamWaitEvent(h->st, h->ev_stage_in[k], 0));
         int rc = add_device_chunk(h, h->d_stage[k][0], l1x, h->d_stage[k][1],
@@ -1030,13 +1234,11 @@ extern "C" int splpak_b200_fit_refine_add_points(splpak_b200_fit_t h, const real
     for (long long i0 = 0; i0 < n; i0 += chunk, k ^= 1) {
         const long long nc = (n - i0 < chunk) ? n - i0 : chunk;
         SPL_CUDA_TRY(cudaStreamWaitEvent(h->st_copy, h->ev_stage_free[k], 0));
-        SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][0], x + i0 * (long long)l1x, sizeof(real_t) * (size_t)nc * l1x,
-                                     cudaMemcpyHostToDevice, h->st_copy));
-        SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][1], y + i0, sizeof(real_t) * (size_t)nc, cudaMemcpyHostToDevice,
-                                     h->st_copy));
+        SPL_CUDA_TRY(spl_h2d(h->d_stage[k][0], x + i0 * (long long)l1x, sizeof(real_t) * (size_t)nc * l1x, h->st_copy,
+                             h->di.dev));
+        SPL_CUDA_TRY(spl_h2d(h->d_stage[k][1], y + i0, sizeof(real_t) * (size_t)nc, h->st_copy, h->di.dev));
         if (weighted)
-            SPL_CUDA_TRY(cudaMemcpyAsync(h->d_stage[k][2], w + i0, sizeof(real_t) * (size_t)nc, cudaMemcpyHostToDevice,
-                                         h->st_copy));
+            SPL_CUDA_TRY(spl_h2d(h->d_stage[k][2], w + i0, sizeof(real_t) * (size_t)nc, h->st_copy, h->di.dev));
         SPL_CUDA_TRY(cudaEventRecord(h->ev_stage_in[k], h->st_copy));
         SPL_CUDA_TRY(cudaStreamWaitEvent(h->st, h->ev_stage_in[k], 0));
         int rc = refine_device_chunk(h, h->d_stage[k][0], l1x, h->d_stage[k][1], weighted ? h->d_stage[k][2] : nullptr,

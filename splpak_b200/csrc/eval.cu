@@ -11,18 +11,24 @@
 // reference), then the nested contraction  sum_k b3[k] sum_j b2[j] sum_i coef[..]*b1[i]  with
 // dimension 1 innermost (4 contiguous coefficients).
 //
-// What binds this kernel for scattered queries is the GATHER of the 4^ndim coefficients: 64 8-byte
-// shared-memory loads per 3-D query at random addresses, ~3 bank-conflict wavefronts per half-warp
-// each (measured: 12 crossbar cycles per query per SM; 4 would be the conflict-free floor).  Queries
-// that arrive in coherent runs (raster order of an output grid) broadcast and are bound by
-// instruction issue and the FP64 pipe instead.  Two regrouping schemes that make half-warps
-// conflict-free by construction (a per-tile counting sort by bank class, then a persistent ring of
-// per-bank-class FIFOs) were built and measured in round 1; both lost more to CTA-wide barriers and
-// bookkeeping than they saved in wavefronts (experiments/eval_ring_r01.cu.txt,
-// profiles/r01_eval_ring_experiment.md).
+// What binds the plain kernel for scattered queries is the GATHER of the 4^ndim coefficients: 64 8-byte
+// shared-memory loads per 3-D query at random addresses, ~3 bank-conflict wavefronts per half-warp each (measured
+// in round 1: 12.9 crossbar cycles per query per SM; 4 is the conflict-free floor).  Queries that arrive in
+// coherent runs (raster order of an output grid) broadcast and are bound by instruction issue and the FP64 pipe.
+//
+// spl_eval_regroup_kernel (2-D..4-D, large batches) removes the conflicts by construction, without any CTA-wide
+// barrier: the gather offsets i + s1 j + s2 k are the same for every query, so two queries whose BASE addresses
+// differ mod 16 (8-byte banks per half-warp phase) never collide on any of the 4^ndim loads.  Lane l of a warp is
+// DEDICATED to bank class l mod 16; every warp keeps 16 small per-class FIFOs in shared memory (its own, warp
+// private: only __syncwarp), inserts the raw queries it streams (class from the window index; rank among same-class
+// lanes from four ballots; the FIFO cursors live in registers of the dedicated lanes), and every round each lane
+// pops one query of ITS class and evaluates it.  Queries whose FIFO is full stay pending in their lane and retry next
+// round; coherent batches (raster order: all lanes in one class) bypass the FIFOs.  The table is padded to strides
+// chosen so that the class distribution is uniform (24^3: s1 = 25, s2 = 603 -> within 1.4 %).
 //
 // Algorithmic HBM traffic: (ndim + 1) reals per query.
 #include <stdlib.h>
+#include <string.h>
 
 #include "basis.cuh"
 
@@ -149,12 +155,13 @@ __device__ __forceinline__ double spl_eval_point(const GridParams &gp, const Der
 #pragma unroll
     for (int d = 0; d < NDIM; ++d) {
         if (VALUE)
-            spl_window_weights_value(xv[d], gp.xmin[d], gp.dx[d], gp.dxin[d], gp.nodes[d], ws[d], b[d]);
+            spl_window_weights_value<true>(xv[d], gp.xmin[d], gp.dx[d], gp.dxin[d], gp.nodes[d], ws[d], b[d]);   // 8 x
         else
             spl_window_weights(xv[d], gp.xmin[d], gp.dx[d], gp.dxin[d], gp.nodes[d], dp.nd[d], ws[d], b[d]);
     }
     double sum = spl_contract<NDIM>(tl, cf, ws, b);
     if (VALUE) {
+        sum *= 1.0 / (double)spl_ipow(8, NDIM);      // the weights carry a factor 8 per dimension (exact scaling)
         // a NaN coordinate fails every comparison of bascmp, so every basis value stays 0 (:253-379)
         bool isnan_q = false;
 #pragma unroll
@@ -231,6 +238,297 @@ spl_eval_kernel(const __grid_constant__ GridParams gp, const DerivParams dp,
 }
 
 // ------------------------------------------------------------------------------------------
+// regrouping kernel: conflict-free gathers through warp-private per-bank-class FIFOs (see the file header)
+// ------------------------------------------------------------------------------------------
+#define RG_CHUNK 256u     // raw queries a warp claims from its CTA's range per shared-memory atomic
+#define RG_BYPASS 12      // a batch with >= this many lanes in ONE class is coherent (raster order): evaluate it directly
+
+template <int NDIM> struct RegroupCfg {
+    // warps per CTA (one CTA per SM): the register budget per thread is 64 K / threads
+    static constexpr int NWARPS = (NDIM <= 2) ? 32 : (NDIM == 3 ? 24 : 16);
+};
+
+// coefficient table -> padded image (strides tl.s1/s2/s3, zero-filled gaps), so that the CTAs can bulk-copy it
+__global__ void spl_pad_table_kernel(const __grid_constant__ GridParams gp, const TableLayout tl,
+                                     const double *__restrict__ coef, double *__restrict__ padded, long long total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long st[5] = {1, tl.s1, tl.s2, tl.s3, total};
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        long long src = 0, mul = 1;
+        bool ok = true;
+        for (int d = 0; d < gp.ndim; ++d) {
+            const long long hi = (d + 1 < gp.ndim) ? st[d + 1] : total;
+            const long long id = (e % hi) / st[d];
+            if (id >= gp.nodes[d]) ok = false;
+            src += id * mul;
+            mul *= gp.nodes[d];
+        }
+        padded[e] = ok ? coef[src] : 0.0;
+    }
+}
+
+template <int NDIM, bool VALUE>
+__global__ void __launch_bounds__(RegroupCfg<NDIM>::NWARPS * 32, 1)
+spl_eval_regroup_kernel(const __grid_constant__ GridParams gp, const DerivParams dp, const TableLayout tl,
+                        const real_t *__restrict__ x, int l1x, long long nq,
+                        const double *__restrict__ coef_padded, unsigned table_doubles, int cap,
+                        real_t *__restrict__ out) {
+    extern __shared__ __align__(128) double s_dyn[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ unsigned s_chunk;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_chunk = 0;
+        mbar_init(&mbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&mbar, table_doubles * (unsigned)sizeof(double));
+        bulk_g2s(s_dyn, coef_padded, table_doubles * (unsigned)sizeof(double), &mbar);
+    }
+    __syncthreads();
+    mbar_wait(&mbar, 0);
+    const double *cf = s_dyn;
+    // warp-private FIFOs: fx[d][slot][class] (doubles), ftag[slot][class] (query offset inside the CTA's range)
+    const int per_warp = cap * 16 * NDIM + cap * 8;                  // doubles (tags: 16 x 4 bytes per slot)
+    double *fx = s_dyn + table_doubles + (size_t)warp * per_warp;
+    unsigned *ftag = reinterpret_cast<unsigned *>(fx + cap * 16 * NDIM);
+
+    // this CTA's contiguous range of queries (offsets inside it fit 32 bits: checked by the launcher)
+    const long long q_lo = nq * (long long)blockIdx.x / (long long)gridDim.x;
+    const long long q_hi = nq * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
+    const unsigned range = (unsigned)(q_hi - q_lo);
+    const real_t *xb = x + q_lo * (long long)l1x;
+    real_t *ob = out + q_lo;
+
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+    const int dc = lane & 15, hf = lane >> 4;                        // dedicated class, half-warp
+    int stride16[NDIM];                                              // table strides mod 16
+    stride16[0] = 1;
+    if (NDIM > 1) stride16[1] = tl.s1 & 15;
+    if (NDIM > 2) stride16[2] = tl.s2 & 15;
+    if (NDIM > 3) stride16[NDIM - 1] = (int)(tl.s3 & 15);
+    int head = 0, cnt = 0;                                           // FIFO cursor of class dc (same in both halves)
+    bool pend = false;                                               // this lane holds a raw query not yet in a FIFO
+    double px[NDIM];
+    unsigned ptag = 0;
+    unsigned cpos = 0, cend = 0;                                     // warp-uniform: the warp's current chunk
+    bool done = false;                                               // warp-uniform: the CTA's range is exhausted
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) px[d] = 0.0;
+
+    // lanes without a pending query take the next raw queries of the warp's chunk (loads consumed one round later)
+    auto refill = [&]() {
+        const unsigned nm = __ballot_sync(full, !pend);
+        if (done || nm == 0u) return;
+        if (cpos == cend) {
+            unsigned c = 0;
+            if (lane == 0) c = atomicAdd(&s_chunk, 1u);
+            c = __shfl_sync(full, c, 0);
+            const unsigned long long b0 = (unsigned long long)c * RG_CHUNK;
+            if (b0 >= (unsigned long long)range) {
+                done = true;
+                return;
+            }
+            cpos = (unsigned)b0;
+            cend = (range - cpos < RG_CHUNK) ? range : cpos + RG_CHUNK;
+        }
+        const unsigned my = cpos + (unsigned)__popc(nm & lt);
+        if (!pend && my < cend) {
+            ptag = my;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) px[d] = (double)xb[(long long)my * l1x + d];
+            pend = true;
+        }
+        const unsigned adv = cpos + (unsigned)__popc(nm);
+        cpos = adv < cend ? adv : cend;
+    };
+
+    refill();
+    for (;;) {
+        // ---- insert: bank class of the pending query = its base address in the table mod 16 ----
+        int cls = 0;
+        if (pend) {
+            int lin = 0;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                const double t = spl_mul(gp.dxin[d], spl_sub(px[d], gp.xmin[d]));
+                const int it = max(__double2int_rz(t), -4);
+                const int ws = min(max(it - 1, 0), gp.nodes[d] - 4);
+                lin += ws * stride16[d];
+            }
+            cls = lin & 15;
+        }
+        const unsigned bp = __ballot_sync(full, pend);
+        const unsigned v0 = __ballot_sync(full, pend && (cls & 1));
+        const unsigned v1 = __ballot_sync(full, pend && (cls & 2));
+        const unsigned v2 = __ballot_sync(full, pend && (cls & 4));
+        const unsigned v3 = __ballot_sync(full, pend && (cls & 8));
+        const unsigned peers = bp & ((cls & 1) ? v0 : ~v0) & ((cls & 2) ? v1 : ~v1) & ((cls & 4) ? v2 : ~v2) &
+                               ((cls & 8) ? v3 : ~v3);              // pending lanes of my query's class
+        const unsigned arr = bp & ((dc & 1) ? v0 : ~v0) & ((dc & 2) ? v1 : ~v1) & ((dc & 4) ? v2 : ~v2) &
+                             ((dc & 8) ? v3 : ~v3);                  // pending lanes of my DEDICATED class
+        const int big = __reduce_max_sync(full, pend ? __popc(peers) : 0);
+        bool take = false;
+        double ex[NDIM];
+        unsigned etag = 0;
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) ex[d] = 0.0;
+        if (big >= RG_BYPASS) {
+            // coherent batch (raster order): the lanes evaluate their own queries, the gathers broadcast
+            take = pend;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) ex[d] = px[d];
+            etag = ptag;
+            pend = false;
+        } else {
+            const int st = __shfl_sync(full, (head << 8) | cnt, cls);           // cursor of my query's class
+            const int qh = st >> 8, qc = st & 255;
+            const int rank = __popc(peers & lt);
+            if (pend && qc + rank < cap) {
+                int slot = qh + qc + rank;
+                if (slot >= cap) slot -= cap;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) fx[(d * cap + slot) * 16 + cls] = px[d];
+                ftag[slot * 16 + cls] = ptag;
+                pend = false;
+            }
+            cnt += min(__popc(arr), cap - cnt);
+            __syncwarp();
+            // ---- pop: one query of my class (two per class and round: one per half-warp) ----
+            take = cnt > hf;
+            if (take) {
+                int slot = head + hf;
+                if (slot >= cap) slot -= cap;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) ex[d] = fx[(d * cap + slot) * 16 + dc];
+                etag = ftag[slot * 16 + dc];
+            }
+            const int n = min(cnt, 2);
+            head += n;
+            if (head >= cap) head -= cap;
+            cnt -= n;
+            __syncwarp();
+        }
+        refill();
+        if (take) ob[etag] = (real_t)spl_eval_point<NDIM, VALUE>(gp, dp, tl, cf, ex);
+        if (done && !__any_sync(full, pend || cnt > 0)) break;
+    }
+}
+
+// Padded table strides for the regrouping kernel: the class (base address mod 16) of a query must be uniformly
+// distributed, or the dedicated lanes of the hot classes limit the throughput to 1 / (16 p_max).  For window starts
+// distributed as for uniformly scattered data, the class distribution is the cyclic convolution of the per-dimension
+// ones; a small search over the paddings picks the flattest.  Cached for the last grid seen.
+struct RegroupPlan {
+    bool ok = false;
+    TableLayout tl;
+    long long table_doubles = 0;
+    int cap = 0, nwarps = 0;
+    size_t smem = 0;
+    int key_ndim = 0, key_nodes[SPL_MAXDIM] = {0, 0, 0, 0};
+    size_t key_smem = 0;
+};
+static double class_pmax(const GridParams &gp, const long long *st) {
+    double dist[16] = {1.0};
+    for (int c = 1; c < 16; ++c) dist[c] = 0.0;
+    for (int d = 0; d < gp.ndim; ++d) {
+        double pd[16] = {0.0};
+        const int nod = gp.nodes[d];
+        for (int it = 0; it < nod - 1; ++it) {
+            int ws = it - 1;
+            if (ws < 0) ws = 0;
+            if (ws > nod - 4) ws = nod - 4;
+            pd[(int)((ws * (st[d] & 15)) & 15)] += 1.0 / (double)(nod - 1);
+        }
+        double nx[16] = {0.0};
+        for (int a = 0; a < 16; ++a)
+            for (int b = 0; b < 16; ++b) nx[(a + b) & 15] += dist[a] * pd[b];
+        for (int c = 0; c < 16; ++c) dist[c] = nx[c];
+    }
+    double m = 0.0;
+    for (int c = 0; c < 16; ++c) m = dist[c] > m ? dist[c] : m;
+    return m;
+}
+static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin) {
+    static thread_local RegroupPlan plan;
+    bool same = plan.key_ndim == gp.ndim && plan.key_smem == smem_optin;
+    for (int d = 0; d < SPL_MAXDIM && same; ++d) same = plan.key_nodes[d] == gp.nodes[d];
+    if (same) return plan;
+    plan = RegroupPlan();
+    plan.key_ndim = gp.ndim;
+    plan.key_smem = smem_optin;
+    for (int d = 0; d < SPL_MAXDIM; ++d) plan.key_nodes[d] = gp.nodes[d];
+    if (gp.ndim < 2) return plan;
+    const int nwarps = gp.ndim == 2 ? RegroupCfg<2>::NWARPS : (gp.ndim == 3 ? RegroupCfg<3>::NWARPS : RegroupCfg<4>::NWARPS);
+    const long long n0 = gp.nodes[0], n1 = gp.nodes[1], n2 = gp.ndim > 2 ? gp.nodes[2] : 1, n3 = gp.ndim > 3 ? gp.nodes[3] : 1;
+    const size_t reserve = 1024;                                       // static shared memory + alignment
+    const size_t per_slot = (size_t)nwarps * 16 * (8 * gp.ndim + 4);   // bytes of FIFO per unit of cap
+    double best = 1e30;
+    const int r1 = gp.ndim == 4 ? 4 : 8, r2 = gp.ndim == 4 ? 8 : 16;
+    for (long long s1 = n0; s1 < n0 + r1; ++s1)
+        for (long long s2 = s1 * n1; s2 < s1 * n1 + (gp.ndim > 2 ? r2 : 1); ++s2)
+            for (long long s3 = s2 * n2; s3 < s2 * n2 + (gp.ndim > 3 ? 16 : 1); ++s3) {
+                long long total = gp.ndim == 2 ? s1 * n1 : (gp.ndim == 3 ? s2 * n2 : s3 * n3);
+                total = (total + 1) & ~1LL;
+                const size_t tbytes = (size_t)total * sizeof(double);
+                if (tbytes + reserve + 4 * per_slot > smem_optin || total >= (1LL << 28)) continue;
+                const long long st[4] = {1, s1, s2, s3};
+                const double pm = class_pmax(gp, st);
+                long long cap = (long long)((smem_optin - reserve - tbytes) / per_slot);
+                if (cap > 16) cap = 16;
+                // estimated lane efficiency: the hottest class bounds it; short FIFOs lose a little more
+                const double eff = (1.0 / (16.0 * pm)) * (1.0 - 0.6 / (double)cap);
+                const double score = -eff;
+                if (score < best) {
+                    best = score;
+                    plan.ok = true;
+                    plan.tl.s1 = (int)s1;
+                    plan.tl.s2 = (int)s2;
+                    plan.tl.s3 = s3;
+                    plan.table_doubles = total;
+                    plan.cap = (int)cap;
+                    plan.nwarps = nwarps;
+                    plan.smem = tbytes + (size_t)cap * per_slot;
+                }
+            }
+    return plan;
+}
+
+// 0: the plain kernel will run; otherwise the number of doubles of padded-table scratch the regrouping kernel needs
+long long spl_eval_regroup_elems(const GridParams &gp, long long nq, int nsm, size_t smem_optin) {
+    const char *mode = getenv("SPLPAK_B200_EVAL");
+    if (mode && strcmp(mode, "plain") == 0) return 0;
+    const bool force = mode && strcmp(mode, "regroup") == 0;
+    if (gp.ndim < 2 || (!force && nq < (1LL << 18))) return 0;
+    if (nq / (nsm > 0 ? nsm : 1) >= (1LL << 32) - 1024) return 0;
+    const RegroupPlan &pl = regroup_plan(gp, smem_optin);
+    return pl.ok ? pl.table_doubles : 0;
+}
+
+template <int NDIM, bool VALUE>
+static int launch_eval_regroup(const GridParams &gp, const DerivParams &dp, const real_t *d_x, int l1x, long long nq,
+                               const double *d_coef, double *d_pad, real_t *d_out, cudaStream_t stream, int nsm,
+                               size_t smem_optin) {
+    const RegroupPlan &pl = regroup_plan(gp, smem_optin);
+    {
+        long long blocks = (pl.table_doubles + 255) / 256;
+        if (blocks > 1024) blocks = 1024;
+        spl_pad_table_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gp, pl.tl, d_coef, d_pad, pl.table_doubles);
+        ++g_spl_launches;
+    }
+    auto kern = spl_eval_regroup_kernel<NDIM, VALUE>;
+    SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    long long grid = nsm;
+    const long long per_cta_min = 4096;                 // tiny batches: fewer CTAs, each with a useful range
+    if (grid > (nq + per_cta_min - 1) / per_cta_min) grid = (nq + per_cta_min - 1) / per_cta_min;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, RegroupCfg<NDIM>::NWARPS * 32, pl.smem, stream>>>(gp, dp, pl.tl, d_x, l1x, nq, d_pad,
+                                                                             (unsigned)pl.table_doubles, pl.cap, d_out);
+    ++g_spl_launches;
+    SPL_CUDA_TRY(cudaGetLastError());
+    return SPLPAK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 template <int NDIM, bool VALUE>
@@ -263,10 +561,11 @@ static int launch_eval(const GridParams &gp, const DerivParams &dp, const real_t
     return SPLPAK_OK;
 }
 
-// d_coef: float64 device table with ncol_padded (even, >= ncol) entries; d_counter: 8-byte scratch.
+// d_coef: float64 device table with ncol_padded (even, >= ncol) entries; d_counter: 8-byte scratch; d_pad: scratch of
+// spl_eval_regroup_elems() doubles (or NULL: the plain kernel runs).
 int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, int l1x, long long nq,
                     const double *d_coef, long long ncol_padded, real_t *d_out, cudaStream_t stream,
-                    int nsm, size_t smem_optin, unsigned long long *d_counter) {
+                    int nsm, size_t smem_optin, unsigned long long *d_counter, double *d_pad) {
     DerivParams dp;
     bool value = true;
     for (int d = 0; d < SPL_MAXDIM; ++d) {
@@ -274,6 +573,18 @@ int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, 
         if (dp.nd[d] != 0) value = false;
     }
     if (nq <= 0) return SPLPAK_OK;
+    if (d_pad && spl_eval_regroup_elems(gp, nq, nsm, smem_optin) > 0) {
+#define SPL_RG_CASE(N)                                                                                              \
+    case N:                                                                                                         \
+        return value ? launch_eval_regroup<N, true>(gp, dp, d_x, l1x, nq, d_coef, d_pad, d_out, stream, nsm, smem_optin) \
+                     : launch_eval_regroup<N, false>(gp, dp, d_x, l1x, nq, d_coef, d_pad, d_out, stream, nsm, smem_optin);
+        switch (gp.ndim) {
+            SPL_RG_CASE(2)
+            SPL_RG_CASE(3)
+            SPL_RG_CASE(4)
+        }
+#undef SPL_RG_CASE
+    }
 #define SPL_EVAL_CASE(N)                                                                                  \
     case N:                                                                                               \
         return value ? launch_eval<N, true>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, \
