@@ -252,16 +252,18 @@ template <int NDIM> struct RegroupCfg {
 __global__ void spl_pad_table_kernel(const __grid_constant__ GridParams gp, const TableLayout tl,
                                      const double *__restrict__ coef, double *__restrict__ padded, long long total) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long st[5] = {1, tl.s1, tl.s2, tl.s3, total};
+    const long long st[4] = {1, tl.s1, tl.s2, tl.s3};
+    long long mulv[4] = {1, 1, 1, 1};
+    for (int d = 1; d < gp.ndim; ++d) mulv[d] = mulv[d - 1] * gp.nodes[d - 1];
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        long long src = 0, mul = 1;
+        // e = sum_d id_d st[d]: peel the indices off from the slowest dimension down (st[d+1] need not be a multiple of st[d])
+        long long src = 0, rem = e;
         bool ok = true;
-        for (int d = 0; d < gp.ndim; ++d) {
-            const long long hi = (d + 1 < gp.ndim) ? st[d + 1] : total;
-            const long long id = (e % hi) / st[d];
+        for (int d = gp.ndim - 1; d >= 0; --d) {
+            const long long id = rem / st[d];
+            rem -= id * st[d];
             if (id >= gp.nodes[d]) ok = false;
-            src += id * mul;
-            mul *= gp.nodes[d];
+            src += id * mulv[d];
         }
         padded[e] = ok ? coef[src] : 0.0;
     }
@@ -498,7 +500,9 @@ long long spl_eval_regroup_elems(const GridParams &gp, long long nq, int nsm, si
     const char *mode = getenv("SPLPAK_B200_EVAL");
     if (mode && strcmp(mode, "plain") == 0) return 0;
     const bool force = mode && strcmp(mode, "regroup") == 0;
-    if (gp.ndim < 2 || (!force && nq < (1LL << 18))) return 0;
+    // measured (profiles/r02_eval_ab.md): 3-D 45.5 -> 30.0 ms and 4-D 201 -> 84 ms per 1e9 random queries; 2-D gathers only
+    // 16 values per query and is faster in the plain kernel (12.1 vs 17.2 ms), so it regroups only when forced
+    if (gp.ndim < 2 || (!force && (gp.ndim < 3 || nq < (1LL << 18)))) return 0;
     if (nq / (nsm > 0 ? nsm : 1) >= (1LL << 32) - 1024) return 0;
     const RegroupPlan &pl = regroup_plan(gp, smem_optin);
     return pl.ok ? pl.table_doubles : 0;
@@ -539,7 +543,9 @@ static int launch_eval(const GridParams &gp, const DerivParams &dp, const real_t
     const size_t coef_bytes = (size_t)ncol_padded * sizeof(double);
     const size_t static_reserve = 2048;
     SPL_CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
-    const bool use_smem = coef_bytes + static_reserve <= smem_optin && coef_bytes < (1u << 20);
+    // a handful of queries (scalar splfe / splde calls): gathering 4^ndim values from L2 is cheaper than staging the table
+    const bool use_smem = coef_bytes + static_reserve <= smem_optin && coef_bytes < (1u << 20) &&
+                          nq * (long long)spl_ipow(4, NDIM) * 64 > (long long)coef_bytes / 8;
     long long chunks = (nq + EVAL_WCHUNK - 1) / EVAL_WCHUNK;
     long long ctas = (chunks + THREADS / 32 - 1) / (THREADS / 32);
     if (ctas < 1) ctas = 1;
