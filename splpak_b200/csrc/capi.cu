@@ -445,8 +445,8 @@ static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const in
     const long long pad_elems = spl_eval_regroup_elems(gp, nq, di.nsm, di.smem_optin);
     if (pad_elems > 0) {
         cudaMemPool_t pool = eval_scratch_pool(di.dev);
-        cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&pad, sizeof(double) * (size_t)pad_elems, pool, st)
-                             : cudaMallocAsync((void **)&pad, sizeof(double) * (size_t)pad_elems, st);
+        cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&pad, sizeof(double) * (size_t)(pad_elems + 2), pool, st)
+                             : cudaMallocAsync((void **)&pad, sizeof(double) * (size_t)(pad_elems + 2), st);   // + the order flag
         if (e != cudaSuccess) {
             cudaGetLastError();
             pad = nullptr;                                     // the plain kernel needs no scratch

@@ -187,9 +187,11 @@ __global__ void __launch_bounds__(EvalCfg<NDIM>::THREADS, 1)
 spl_eval_kernel(const __grid_constant__ GridParams gp, const DerivParams dp,
                 const real_t *__restrict__ x, int l1x, long long nq,
                 const double *__restrict__ coef, long long ncol_padded, real_t *__restrict__ out,
-                unsigned long long *__restrict__ chunk_counter) {
+                unsigned long long *__restrict__ chunk_counter, const int *__restrict__ order_flag) {
     extern __shared__ __align__(128) double s_dyn[];
     __shared__ __align__(8) uint64_t mbar;
+    // order_flag (spl_eval_probe_kernel): 1 = the batch is scattered and the regrouping kernel evaluates it
+    if (order_flag && *order_flag == 1) return;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const double *cf = coef;
@@ -241,12 +243,45 @@ spl_eval_kernel(const __grid_constant__ GridParams gp, const DerivParams dp,
 // regrouping kernel: conflict-free gathers through warp-private per-bank-class FIFOs (see the file header)
 // ------------------------------------------------------------------------------------------
 #define RG_CHUNK 256u     // raw queries a warp claims from its CTA's range per shared-memory atomic
-#define RG_BYPASS 12      // a batch with >= this many lanes in ONE class is coherent (raster order): evaluate it directly
 
 template <int NDIM> struct RegroupCfg {
     // warps per CTA (one CTA per SM): the register budget per thread is 64 K / threads
     static constexpr int NWARPS = (NDIM <= 2) ? 32 : (NDIM == 3 ? 24 : 16);
 };
+
+// Order probe: are the queries scattered (regrouping kernel) or do they arrive in coherent runs, e.g. the raster order of
+// an output grid (plain kernel: its gathers broadcast, and it runs 12 % faster than the regrouping kernel's bypass)?
+// One CTA samples 32 groups of 32 CONSECUTIVE queries spread over the batch and counts the groups in which at least
+// RG_BYPASS queries share one bank class.  Both evaluation kernels are launched; the one the flag rules out exits at once.
+#define RG_BYPASS 12      // a batch with >= this many lanes in ONE class is coherent (raster order): evaluate it directly
+template <int NDIM>
+__global__ void __launch_bounds__(1024)
+spl_eval_probe_kernel(const __grid_constant__ GridParams gp, const TableLayout tl, const real_t *__restrict__ x, int l1x,
+                      long long nq, int *__restrict__ order_flag) {
+    __shared__ int s_coherent;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_coherent = 0;
+    __syncthreads();
+    const long long q = (nq / 32) * warp + lane;           // group `warp` starts at warp/32 of the batch
+    int cls = 0;
+    if (q < nq) {
+        const long long st[4] = {1, tl.s1, tl.s2, tl.s3};
+        int lin = 0;
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) {
+            const double t = spl_mul(gp.dxin[d], spl_sub((double)x[q * (long long)l1x + d], gp.xmin[d]));
+            const int it = max(__double2int_rz(t), -4);
+            const int ws = min(max(it - 1, 0), gp.nodes[d] - 4);
+            lin += ws * (int)(st[d] & 15);
+        }
+        cls = lin & 15;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, cls);
+    const int big = __reduce_max_sync(0xffffffffu, __popc(peers));
+    if (lane == 0 && big >= RG_BYPASS) atomicAdd(&s_coherent, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) *order_flag = (s_coherent >= 16) ? 0 : 1;
+}
 
 // coefficient table -> padded image (strides tl.s1/s2/s3, zero-filled gaps), so that the CTAs can bulk-copy it
 __global__ void spl_pad_table_kernel(const __grid_constant__ GridParams gp, const TableLayout tl,
@@ -269,15 +304,17 @@ __global__ void spl_pad_table_kernel(const __grid_constant__ GridParams gp, cons
     }
 }
 
-template <int NDIM, bool VALUE>
-__global__ void __launch_bounds__(RegroupCfg<NDIM>::NWARPS * 32, 1)
+template <int NDIM, bool VALUE, int NWARPS = RegroupCfg<NDIM>::NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
 spl_eval_regroup_kernel(const __grid_constant__ GridParams gp, const DerivParams dp, const TableLayout tl,
                         const real_t *__restrict__ x, int l1x, long long nq,
                         const double *__restrict__ coef_padded, unsigned table_doubles, int cap,
-                        real_t *__restrict__ out) {
+                        real_t *__restrict__ out, const int *__restrict__ order_flag) {
     extern __shared__ __align__(128) double s_dyn[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ unsigned s_chunk;
+    // order_flag (spl_eval_probe_kernel): 0 = the batch arrives in coherent runs and the plain kernel evaluates it
+    if (order_flag && *order_flag == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         s_chunk = 0;
@@ -426,7 +463,7 @@ struct RegroupPlan {
     long long table_doubles = 0;
     int cap = 0, nwarps = 0;
     size_t smem = 0;
-    int key_ndim = 0, key_nodes[SPL_MAXDIM] = {0, 0, 0, 0};
+    int key_ndim = 0, key_nodes[SPL_MAXDIM] = {0, 0, 0, 0}, key_warps = 0;
     size_t key_smem = 0;
 };
 static double class_pmax(const GridParams &gp, const long long *st) {
@@ -450,17 +487,27 @@ static double class_pmax(const GridParams &gp, const long long *st) {
     for (int c = 0; c < 16; ++c) m = dist[c] > m ? dist[c] : m;
     return m;
 }
+// warps per CTA of the regrouping kernel (SPLPAK_B200_RG_WARPS = 16 | 24 | 32 overrides the default for experiments)
+static int regroup_warps(int ndim) {
+    int nw = ndim == 2 ? RegroupCfg<2>::NWARPS : (ndim == 3 ? RegroupCfg<3>::NWARPS : RegroupCfg<4>::NWARPS);
+    if (const char *e = getenv("SPLPAK_B200_RG_WARPS")) {
+        const int v = atoi(e);
+        if (ndim == 3 && (v == 16 || v == 24 || v == 32)) nw = v;
+    }
+    return nw;
+}
 static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin) {
     static thread_local RegroupPlan plan;
-    bool same = plan.key_ndim == gp.ndim && plan.key_smem == smem_optin;
+    const int nwarps = regroup_warps(gp.ndim);
+    bool same = plan.key_ndim == gp.ndim && plan.key_smem == smem_optin && plan.key_warps == nwarps;
     for (int d = 0; d < SPL_MAXDIM && same; ++d) same = plan.key_nodes[d] == gp.nodes[d];
     if (same) return plan;
     plan = RegroupPlan();
     plan.key_ndim = gp.ndim;
     plan.key_smem = smem_optin;
+    plan.key_warps = nwarps;
     for (int d = 0; d < SPL_MAXDIM; ++d) plan.key_nodes[d] = gp.nodes[d];
     if (gp.ndim < 2) return plan;
-    const int nwarps = gp.ndim == 2 ? RegroupCfg<2>::NWARPS : (gp.ndim == 3 ? RegroupCfg<3>::NWARPS : RegroupCfg<4>::NWARPS);
     const long long n0 = gp.nodes[0], n1 = gp.nodes[1], n2 = gp.ndim > 2 ? gp.nodes[2] : 1, n3 = gp.ndim > 3 ? gp.nodes[3] : 1;
     const size_t reserve = 1024;                                       // static shared memory + alignment
     const size_t per_slot = (size_t)nwarps * 16 * (8 * gp.ndim + 4);   // bytes of FIFO per unit of cap
@@ -511,22 +558,29 @@ long long spl_eval_regroup_elems(const GridParams &gp, long long nq, int nsm, si
 template <int NDIM, bool VALUE>
 static int launch_eval_regroup(const GridParams &gp, const DerivParams &dp, const real_t *d_x, int l1x, long long nq,
                                const double *d_coef, double *d_pad, real_t *d_out, cudaStream_t stream, int nsm,
-                               size_t smem_optin) {
+                               size_t smem_optin, int *d_flag) {
     const RegroupPlan &pl = regroup_plan(gp, smem_optin);
+    if (d_flag) {
+        spl_eval_probe_kernel<NDIM><<<1, 1024, 0, stream>>>(gp, pl.tl, d_x, l1x, nq, d_flag);
+        ++g_spl_launches;
+    }
     {
         long long blocks = (pl.table_doubles + 255) / 256;
         if (blocks > 1024) blocks = 1024;
         spl_pad_table_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gp, pl.tl, d_coef, d_pad, pl.table_doubles);
         ++g_spl_launches;
     }
-    auto kern = spl_eval_regroup_kernel<NDIM, VALUE>;
+    void (*kern)(GridParams, DerivParams, TableLayout, const real_t *, int, long long, const double *, unsigned, int,
+                 real_t *, const int *) = spl_eval_regroup_kernel<NDIM, VALUE>;
+    if (NDIM == 3 && pl.nwarps == 16) kern = spl_eval_regroup_kernel<NDIM, VALUE, (NDIM == 3 ? 16 : RegroupCfg<NDIM>::NWARPS)>;
+    if (NDIM == 3 && pl.nwarps == 32) kern = spl_eval_regroup_kernel<NDIM, VALUE, (NDIM == 3 ? 32 : RegroupCfg<NDIM>::NWARPS)>;
     SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     long long grid = nsm;
     const long long per_cta_min = 4096;                 // tiny batches: fewer CTAs, each with a useful range
     if (grid > (nq + per_cta_min - 1) / per_cta_min) grid = (nq + per_cta_min - 1) / per_cta_min;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, RegroupCfg<NDIM>::NWARPS * 32, pl.smem, stream>>>(gp, dp, pl.tl, d_x, l1x, nq, d_pad,
-                                                                             (unsigned)pl.table_doubles, pl.cap, d_out);
+    kern<<<(unsigned)grid, pl.nwarps * 32, pl.smem, stream>>>(gp, dp, pl.tl, d_x, l1x, nq, d_pad,
+                                                                             (unsigned)pl.table_doubles, pl.cap, d_out, d_flag);
     ++g_spl_launches;
     SPL_CUDA_TRY(cudaGetLastError());
     return SPLPAK_OK;
@@ -538,7 +592,8 @@ static int launch_eval_regroup(const GridParams &gp, const DerivParams &dp, cons
 template <int NDIM, bool VALUE>
 static int launch_eval(const GridParams &gp, const DerivParams &dp, const real_t *d_x, int l1x,
                        long long nq, const double *d_coef, long long ncol_padded, real_t *d_out,
-                       cudaStream_t stream, int nsm, size_t smem_optin, unsigned long long *d_counter) {
+                       cudaStream_t stream, int nsm, size_t smem_optin, unsigned long long *d_counter,
+                       const int *d_flag = nullptr) {
     constexpr int THREADS = EvalCfg<NDIM>::THREADS;
     const size_t coef_bytes = (size_t)ncol_padded * sizeof(double);
     const size_t static_reserve = 2048;
@@ -555,12 +610,12 @@ static int launch_eval(const GridParams &gp, const DerivParams &dp, const real_t
         long long grid = nsm;
         if (grid > ctas) grid = ctas;
         kern<<<(unsigned)grid, THREADS, coef_bytes, stream>>>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out,
-                                                              d_counter);
+                                                              d_counter, d_flag);
     } else {
         auto kern = spl_eval_kernel<NDIM, false, VALUE>;
         long long grid = (long long)nsm * (2048 / THREADS);
         if (grid > ctas) grid = ctas;
-        kern<<<(unsigned)grid, THREADS, 0, stream>>>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out, d_counter);
+        kern<<<(unsigned)grid, THREADS, 0, stream>>>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out, d_counter, d_flag);
     }
     ++g_spl_launches;
     SPL_CUDA_TRY(cudaGetLastError());
@@ -580,16 +635,29 @@ int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, 
     }
     if (nq <= 0) return SPLPAK_OK;
     if (d_pad && spl_eval_regroup_elems(gp, nq, nsm, smem_optin) > 0) {
+        // forced ("regroup"): the regrouping kernel alone.  Default: order probe, then BOTH kernels -- the probe's flag
+        // (behind the padded table in d_pad) makes the wrong one exit immediately.
+        const char *mode = getenv("SPLPAK_B200_EVAL");
+        const bool force = mode && strcmp(mode, "regroup") == 0;
+        int *d_flag = force ? nullptr : reinterpret_cast<int *>(d_pad + spl_eval_regroup_elems(gp, nq, nsm, smem_optin));
+        int rc = SPLPAK_ERR_NDIM;
 #define SPL_RG_CASE(N)                                                                                              \
     case N:                                                                                                         \
-        return value ? launch_eval_regroup<N, true>(gp, dp, d_x, l1x, nq, d_coef, d_pad, d_out, stream, nsm, smem_optin) \
-                     : launch_eval_regroup<N, false>(gp, dp, d_x, l1x, nq, d_coef, d_pad, d_out, stream, nsm, smem_optin);
+        rc = value ? launch_eval_regroup<N, true>(gp, dp, d_x, l1x, nq, d_coef, d_pad, d_out, stream, nsm, smem_optin, d_flag) \
+                   : launch_eval_regroup<N, false>(gp, dp, d_x, l1x, nq, d_coef, d_pad, d_out, stream, nsm, smem_optin, d_flag); \
+        if (rc == SPLPAK_OK && d_flag)                                                                              \
+            rc = value ? launch_eval<N, true>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, smem_optin, \
+                                              d_counter, d_flag)                                                    \
+                       : launch_eval<N, false>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, smem_optin, \
+                                               d_counter, d_flag);                                                  \
+        return rc;
         switch (gp.ndim) {
             SPL_RG_CASE(2)
             SPL_RG_CASE(3)
             SPL_RG_CASE(4)
         }
 #undef SPL_RG_CASE
+        return rc;
     }
 #define SPL_EVAL_CASE(N)                                                                                  \
     case N:                                                                                               \

@@ -103,8 +103,9 @@ def test_regroup_matches_oracle(oracle):
     assert (np.abs(got[idx] - ref) <= np.maximum(64 * eps * np.abs(coef).max() * 216, 128 * eps * np.abs(bound))).all()
 
 
-def test_default_dispatch_uses_regroup_for_large_batches():
-    """Without the override, large 3-D batches go through the regrouping kernel (two launches: pad + evaluate)."""
+def test_default_dispatch_probes_the_query_order():
+    """Without the override, large 3-D batches launch the order probe, the table padding and BOTH evaluation kernels
+    (the probe's flag makes one of them exit at once): scattered queries -> regrouping kernel, raster order -> plain."""
     rng = np.random.default_rng(1)
     nodes = [24, 24, 24]
     coef = rng.standard_normal(24 ** 3)
@@ -112,5 +113,10 @@ def test_default_dispatch_uses_regroup_for_large_batches():
     os.environ.pop("SPLPAK_B200_EVAL", None)
     n0 = sp.total_launches()
     out, ierr = sp.eval_batch(3, q, coef, [0, 0, 0], [1, 1, 1], nodes)
-    assert ierr == 0 and sp.total_launches() - n0 == 2
+    assert ierr == 0 and sp.total_launches() - n0 == 4
     assert np.array_equal(out, _eval("plain", 3, q, coef, [0, 0, 0], [1, 1, 1], nodes))
+    ax = np.linspace(0.0, 1.0, 81)
+    g = np.stack(np.meshgrid(ax, ax, ax, indexing="ij")[::-1], axis=-1).reshape(-1, 3)      # 531,441 raster-ordered points
+    out, ierr = sp.eval_batch(3, g, coef, [0, 0, 0], [1, 1, 1], nodes)
+    assert ierr == 0
+    assert np.array_equal(out, _eval("plain", 3, g, coef, [0, 0, 0], [1, 1, 1], nodes))
