@@ -156,6 +156,19 @@ int splpak_b200_fit_partial_buffer(splpak_b200_fit_t h, void **d_ptr, int64_t *c
 /* In-place ncclAllReduce(sum, float64) of that buffer on the handle's stream; comm is an
  * ncclComm_t passed as void*.  libnccl.so.2 is loaded lazily; 202 if that or the call fails. */
 int splpak_b200_fit_allreduce(splpak_b200_fit_t h, void *nccl_comm);
+/* Same for the ncol-long right-hand side of a refinement step (between refine_add_points and refine_compute). */
+int splpak_b200_fit_allreduce_rhs(splpak_b200_fit_t h, void *nccl_comm);
+/* NCCL communicators for hosts without torch.distributed (a Fortran or C program) -- (new), thin re-exports of
+ * ncclCommInitAll / ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy / ncclGroupStart / ncclGroupEnd through the
+ * lazily loaded libnccl.so.2; communicators are passed as void*, the ncclUniqueId as its 128 raw bytes.
+ *   one process, ndev GPUs : comm_init_all; wrap the per-device fit_allreduce calls in comm_group_start/end
+ *   one process per GPU    : rank 0 calls comm_unique_id and distributes the bytes; every rank calls comm_init_rank */
+int splpak_b200_comm_init_all(int ndev, const int *devs, void **comms);
+int splpak_b200_comm_unique_id(char id[128]);
+int splpak_b200_comm_init_rank(int nranks, int rank, const char id[128], void **comm);
+int splpak_b200_comm_destroy(void *comm);
+int splpak_b200_comm_group_start(void);
+int splpak_b200_comm_group_end(void);
 
 /* Add the data-sparse derivative-constraint rows (xtrap != 0), factor and solve.
  * coef/ncf as in splcw (104 if ncf < ncol); nwrk < 0 skips the reference's workspace checks.

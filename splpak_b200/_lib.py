@@ -32,6 +32,13 @@ SYMBOLS = [
     "splpak_b200_fit_add_points_device",
     "splpak_b200_fit_partial_buffer",
     "splpak_b200_fit_allreduce",
+    "splpak_b200_fit_allreduce_rhs",
+    "splpak_b200_comm_init_all",
+    "splpak_b200_comm_unique_id",
+    "splpak_b200_comm_init_rank",
+    "splpak_b200_comm_destroy",
+    "splpak_b200_comm_group_start",
+    "splpak_b200_comm_group_end",
     "splpak_b200_fit_compute",
     "splpak_b200_fit_compute_device",
     "splpak_b200_fit_refine_begin",
@@ -112,6 +119,13 @@ def load(real32: bool = False) -> C.CDLL:
         "splpak_b200_fit_add_points_device": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, i64]),
         "splpak_b200_fit_partial_buffer": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "splpak_b200_fit_allreduce": (C.c_int, [vp, vp]),
+        "splpak_b200_fit_allreduce_rhs": (C.c_int, [vp, vp]),
+        "splpak_b200_comm_init_all": (C.c_int, [C.c_int, ip, C.POINTER(vp)]),
+        "splpak_b200_comm_unique_id": (C.c_int, [C.c_char_p]),
+        "splpak_b200_comm_init_rank": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]),
+        "splpak_b200_comm_destroy": (C.c_int, [vp]),
+        "splpak_b200_comm_group_start": (C.c_int, []),
+        "splpak_b200_comm_group_end": (C.c_int, []),
         "splpak_b200_fit_compute": (C.c_int, [vp, vp, i64, i64, ip]),
         "splpak_b200_fit_compute_device": (C.c_int, [vp, vp, i64, i64, ip]),
         "splpak_b200_fit_refine_begin": (C.c_int, [vp]),

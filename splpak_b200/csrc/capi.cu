@@ -1053,20 +1053,91 @@ extern "C" int splpak_b200_fit_partial_buffer(splpak_b200_fit_t h, void **d_ptr,
 }
 
 // ---- lazily bound NCCL (libnccl.so.2), so the library has no link-time NCCL dependency ----
-typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
-extern "C" int splpak_b200_fit_allreduce(splpak_b200_fit_t h, void *nccl_comm) {
-    if (!valid(h) || !nccl_comm) return SPLPAK_ERR_HANDLE;
-    static nccl_allreduce_fn fn = nullptr;
-    if (!fn) {
+// A Fortran / C host has no torch.distributed to create communicators for it, so the few NCCL calls a
+// one-process-per-GPU (or one-process-many-GPUs) fit needs are re-exported with plain C types.
+struct Id128 {
+    char b[128];
+};
+struct NcclApi {
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Bcast)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    bool ok = false;
+};
+static NcclApi &nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
         void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        if (!lib) return SPLPAK_ERR_NCCL;
-        fn = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
-        if (!fn) return SPLPAK_ERR_NCCL;
-    }
+        if (!lib) return;
+        api.AllReduce = (decltype(api.AllReduce))dlsym(lib, "ncclAllReduce");
+        api.Bcast = (decltype(api.Bcast))dlsym(lib, "ncclBcast");
+        api.CommInitAll = (decltype(api.CommInitAll))dlsym(lib, "ncclCommInitAll");
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
+        api.GroupStart = (decltype(api.GroupStart))dlsym(lib, "ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))dlsym(lib, "ncclGroupEnd");
+        api.ok = api.AllReduce && api.Bcast && api.CommInitAll && api.GetUniqueId && api.CommInitRank && api.CommDestroy &&
+                 api.GroupStart && api.GroupEnd;
+    });
+    return api;
+}
+extern "C" int splpak_b200_fit_allreduce(splpak_b200_fit_t h, void *nccl_comm) {
+    if (!valid(h) || !nccl_comm) return SPLPAK_ERR_HANDLE;
+    NcclApi &api = nccl_api();
+    if (!api.ok) return SPLPAK_ERR_NCCL;
     // ncclFloat64 = 8, ncclSum = 0 (nccl.h)
-    const int rc = fn(h->d_part, h->d_part, (size_t)h->n_part, 8, 0, nccl_comm, h->st);
+    const int rc = api.AllReduce(h->d_part, h->d_part, (size_t)h->n_part, 8, 0, nccl_comm, h->st);
     return rc == 0 ? SPLPAK_OK : SPLPAK_ERR_NCCL;
+}
+// refinement steps: the ncol-long right-hand side A^T r is what the ranks have to sum
+extern "C" int splpak_b200_fit_allreduce_rhs(splpak_b200_fit_t h, void *nccl_comm) {
+    if (!valid(h) || !nccl_comm) return SPLPAK_ERR_HANDLE;
+    NcclApi &api = nccl_api();
+    if (!api.ok) return SPLPAK_ERR_NCCL;
+    const int rc = api.AllReduce(h->d_g, h->d_g, (size_t)h->gp.ncol, 8, 0, nccl_comm, h->st);
+    return rc == 0 ? SPLPAK_OK : SPLPAK_ERR_NCCL;
+}
+// one process driving ndev GPUs: comms[i] belongs to device devs[i] (ncclCommInitAll)
+extern "C" int splpak_b200_comm_init_all(int ndev, const int *devs, void **comms) {
+    NcclApi &api = nccl_api();
+    if (!api.ok || ndev < 1 || !comms) return SPLPAK_ERR_NCCL;
+    return api.CommInitAll(comms, ndev, devs) == 0 ? SPLPAK_OK : SPLPAK_ERR_NCCL;
+}
+// one process per GPU: rank 0 calls comm_unique_id and hands the 128 bytes to the others (MPI, a file, a socket);
+// then every rank calls comm_init_rank on its own device
+extern "C" int splpak_b200_comm_unique_id(char id[128]) {
+    NcclApi &api = nccl_api();
+    if (!api.ok || !id) return SPLPAK_ERR_NCCL;
+    return api.GetUniqueId(id) == 0 ? SPLPAK_OK : SPLPAK_ERR_NCCL;
+}
+extern "C" int splpak_b200_comm_init_rank(int nranks, int rank, const char id[128], void **comm) {
+    NcclApi &api = nccl_api();
+    if (!api.ok || !id || !comm) return SPLPAK_ERR_NCCL;
+    Id128 v;
+    memcpy(v.b, id, 128);
+    return api.CommInitRank(comm, nranks, v, rank) == 0 ? SPLPAK_OK : SPLPAK_ERR_NCCL;
+}
+extern "C" int splpak_b200_comm_destroy(void *comm) {
+    NcclApi &api = nccl_api();
+    if (!api.ok || !comm) return SPLPAK_ERR_NCCL;
+    return api.CommDestroy(comm) == 0 ? SPLPAK_OK : SPLPAK_ERR_NCCL;
+}
+// several handles of ONE process (one per device) must issue their all-reduces inside a group
+extern "C" int splpak_b200_comm_group_start(void) {
+    NcclApi &api = nccl_api();
+    return api.ok && api.GroupStart() == 0 ? SPLPAK_OK : SPLPAK_ERR_NCCL;
+}
+extern "C" int splpak_b200_comm_group_end(void) {
+    NcclApi &api = nccl_api();
+    return api.ok && api.GroupEnd() == 0 ? SPLPAK_OK : SPLPAK_ERR_NCCL;
 }
 
 static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_device, int64_t ncf,
