@@ -191,6 +191,37 @@ __device__ __forceinline__ void spl_window_weights_value(double x, double xmin, 
     }
 }
 
+// The same in WORKING PRECISION real32 (the reference built with -DREAL32, src/splpak.F90:33-34, evaluates bascmp in
+// float): identical formulas with unfused float operations (__fmul_rn / __fadd_rn), so the 1-D values are bit-identical
+// to a float evaluation of bascmp.  Used by the REAL32 library's splfe path: FP32 pipe instead of the FP64 pipe.
+__device__ __forceinline__ float spl_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float spl_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float spl_sub(float a, float b) { return __fsub_rn(a, b); }
+template <bool SCALE8 = false>
+__device__ __forceinline__ void spl_window_weights_value_f32(float x, float xmin, float dx, float dxin, int nod, int &ws,
+                                                             float b[4]) {
+    const float t = spl_mul(dxin, spl_sub(x, xmin));
+    const int it = max(__float2int_rz(t), -4);               // saturating; NaN -> 0
+    ws = min(max(it - 1, 0), nod - 4);
+    const float wsf = (float)ws;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float xb = spl_add(xmin, spl_mul(wsf + (float)k, dx));
+        const float u = spl_mul(dxin, spl_sub(x, xb));
+        const float s = (k < 2) ? spl_sub(2.0f, u) : spl_add(2.0f, u);
+        const bool edge = (k < 2) ? (ws + k <= 1) : (ws + k >= nod - 2);
+        const float sq = spl_add(s, fabsf(s));
+        const float sq3 = spl_mul(spl_mul(sq, sq), sq);
+        const float s1 = spl_sub(s, 1.0f);
+        const float tq = spl_add(s1, fabsf(s1));
+        const float tq3 = spl_mul(spl_mul(tq, tq), tq);
+        float v = __fmaf_rn(sq3, edge ? 0.5f : 0.25f, -tq3);
+        const float lin = spl_sub(spl_mul(24.0f, s), 24.0f);
+        if (edge && __float_as_int(s) >= 0x40000000) v = lin;                 // s >= 2
+        b[k] = SCALE8 ? v : spl_mul(v, 0.125f);
+    }
+}
+
 // The four window weights of one dimension: b[k] = basis of node ws+k at x (0 outside the box).
 __device__ __forceinline__ void spl_window_weights(double x, double xmin, double dx, double dxin,
                                                    int nod, int nder, int &ws, double b[4]) {

