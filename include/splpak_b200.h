@@ -179,6 +179,20 @@ int splpak_b200_fit_compute(splpak_b200_fit_t h, splpak_real *coef, int64_t ncf,
 int splpak_b200_fit_compute_device(splpak_b200_fit_t h, splpak_real *d_coef, int64_t ncf,
                                    int64_t nwrk, int *ierror);
 
+/* Solver selection -- (new).  SPLPAK_SOLVER_CHOLESKY (default): band Cholesky of the normal equations (+ refinement).
+ * SPLPAK_SOLVER_ORTHOGONAL: the rows are reduced by Householder reflections only, like the reference's suprls
+ * (src/splpak.F90:1375-1695): per-window QR of the data and constraint rows, band QR of the stacked triangles,
+ * back-substitution -- accurate at cond(A) instead of cond(A)^2, slower; 1-D..3-D, single GPU.  Must be called before
+ * the first add_points (203 otherwise, or when the variant is not available for this grid).  The one-shot splcw /
+ * splcc switch to it by themselves when the Cholesky factor reports a non-positive pivot or a pivot-ratio bound of
+ * eps*cond(G) above 1e-3 (SPLPAK_B200_FIT=cholesky|orthogonal in the environment forces one). */
+#define SPLPAK_SOLVER_CHOLESKY   0
+#define SPLPAK_SOLVER_ORTHOGONAL 1
+int splpak_b200_fit_set_solver(splpak_b200_fit_t h, int solver);
+int splpak_b200_fit_get_solver(splpak_b200_fit_t h);
+/* (max L_jj / min L_jj)^2 of the last Cholesky factor: a cheap LOWER bound of cond(G); 0 when unknown. */
+int splpak_b200_fit_condition_estimate(splpak_b200_fit_t h, double *cond_lower_bound);
+
 /* Refinement by corrected semi-normal equations -- (new) no counterpart in the reference, whose orthogonal
  * solver (suprls, src/splpak.F90:1375-1695) does not need it.  The Cholesky solve works at cond(G) =
  * cond(A)^2; when derivative-constraint rows fire (xtrap != 0 and data holes) that is what separates its

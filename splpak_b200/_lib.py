@@ -46,6 +46,9 @@ SYMBOLS = [
     "splpak_b200_fit_refine_add_points_device",
     "splpak_b200_fit_refine_compute",
     "splpak_b200_fit_refine_compute_device",
+    "splpak_b200_fit_set_solver",
+    "splpak_b200_fit_get_solver",
+    "splpak_b200_fit_condition_estimate",
     "splpak_b200_fit_constraints_fired",
     "splpak_b200_fit_rhs_buffer",
     "splpak_b200_fit_reset",
@@ -133,6 +136,9 @@ def load(real32: bool = False) -> C.CDLL:
         "splpak_b200_fit_refine_add_points_device": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, i64]),
         "splpak_b200_fit_refine_compute": (C.c_int, [vp, vp, i64, ip]),
         "splpak_b200_fit_refine_compute_device": (C.c_int, [vp, vp, i64, ip]),
+        "splpak_b200_fit_set_solver": (C.c_int, [vp, C.c_int]),
+        "splpak_b200_fit_get_solver": (C.c_int, [vp]),
+        "splpak_b200_fit_condition_estimate": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "splpak_b200_fit_constraints_fired": (C.c_int, [vp]),
         "splpak_b200_fit_rhs_buffer": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "splpak_b200_fit_reset": (C.c_int, [vp]),

@@ -254,7 +254,9 @@ def total_launches():
 class FitHandle:
     """create -> add_points* -> [all-reduce partial buffer] -> compute."""
 
-    def __init__(self, ndim, xmin, xmax, nodes, xtrap, *, real32=False):
+    def __init__(self, ndim, xmin, xmax, nodes, xtrap, *, real32=False, solver=None):
+        """solver: None / "cholesky" (band Cholesky of the normal equations, default) or "orthogonal" (Householder
+        path matching the reference's suprls numerics; 1-D..3-D)."""
         self.lib = _lib.load(real32)
         self.real32 = real32
         self.dt = _np_dtype(real32)
@@ -267,6 +269,22 @@ class FitHandle:
         self.lib.splpak_b200_fit_create(int(ndim), mnp, mxp, nop, self.lib._real(xtrap), C.byref(h), C.byref(ierr))
         self.ierror = ierr.value
         self.h = h if ierr.value == 0 else None
+        if self.h is not None and solver is not None:
+            code = {"cholesky": 0, "orthogonal": 1}[solver]
+            rc = self.lib.splpak_b200_fit_set_solver(self.h, code)
+            if rc != 0:
+                raise SplpakError(f"solver {solver!r} is not available for this grid (rc {rc})")
+
+    def solver(self):
+        self._check()
+        return {0: "cholesky", 1: "orthogonal"}.get(self.lib.splpak_b200_fit_get_solver(self.h))
+
+    def condition_estimate(self):
+        """Pivot-ratio LOWER bound of cond(G) from the last Cholesky factor (0.0 when unknown)."""
+        self._check()
+        v = C.c_double(0.0)
+        self.lib.splpak_b200_fit_condition_estimate(self.h, C.byref(v))
+        return v.value
 
     def _check(self):
         if self.h is None:

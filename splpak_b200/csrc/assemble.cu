@@ -847,3 +847,5 @@ int spl_assemble_chunk(const GridParams &gp, const real_t *d_x, int l1x, const r
     }
     return SPLPAK_ERR_NDIM;
 }
+
+#include "ortho.cuh"

@@ -51,6 +51,16 @@ int spl_constraints_residual_launch(const GridParams &gp, double xtrap, const do
                                     const double *d_totals_in, const double *d_coef, double *d_g,
                                     cudaStream_t st, int nsm);
 int spl_measure_peaks_impl(double *out, int n);
+int spl_ortho_supported(const GridParams &gp);
+void spl_ortho_free(OrthoScratch &os);
+int spl_ortho_init(const GridParams &gp, OrthoScratch &os, cudaStream_t st, size_t smem_optin);
+int spl_ortho_reset(const GridParams &gp, OrthoScratch &os, cudaStream_t st);
+int spl_ortho_add_chunk(const GridParams &gp, const real_t *d_x, int l1x, const real_t *d_y, const real_t *d_w,
+                        int weighted, long long n, int do_hist, OrthoScratch &os, double *d_cnt, double *d_totals,
+                        cudaStream_t st, int nsm);
+int spl_ortho_compute(const GridParams &gp, double xtrap, OrthoScratch &os, const double *d_cnt, double *d_totals,
+                      int *d_fail, cudaStream_t st, int nsm);
+int spl_pivot_range_launch(const GridParams &gp, const double *d_work, double *d_out2, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // small conversion kernels
@@ -807,6 +817,9 @@ struct splpak_b200_fit_s {
     long long res_cap;
     double *d_dummy_tot;          // [0,1] classify's row/weight totals of refinement passes (discarded); [2] row count before the constraint rows
     int solved;                   // compute succeeded: d_coef64 is valid
+    int solver;                   // SPLPAK_SOLVER_CHOLESKY (default) or SPLPAK_SOLVER_ORTHOGONAL (ortho.cuh)
+    OrthoScratch *os;             // scratch of the orthogonal path (allocated on first use)
+    double cond_est;              // (max L_jj / min L_jj)^2 of the last Cholesky factor: a LOWER bound of cond(G); 0: unknown
     int factor_valid;             // d_AB / the workspace behind it hold the Cholesky factor of the current G
     real_t *d_out_tmp;            // ncol reals: working-precision copy of the solution for the D2H of real32 builds
     int refining;
@@ -846,6 +859,11 @@ static void free_handle(splpak_b200_fit_t h) {
     if (h->d_res) cudaFree(h->d_res);
     if (h->d_dummy_tot) cudaFree(h->d_dummy_tot);
     if (h->d_out_tmp) cudaFree(h->d_out_tmp);
+    if (h->os) {
+        spl_ortho_free(*h->os);
+        delete h->os;
+        h->os = nullptr;
+    }
     if (h->st_copy) cudaStreamDestroy(h->st_copy);
     if (h->st_aux) cudaStreamDestroy(h->st_aux);
     h->magic = 0;
@@ -880,6 +898,10 @@ extern "C" int splpak_b200_fit_create(int ndim, const real_t *xmin, const real_t
     h->di = di;
     h->xtrap = (double)xtrap;
     h->launches0 = g_spl_launches;
+    {
+        const char *mode = getenv("SPLPAK_B200_FIT");
+        if (mode && strcmp(mode, "orthogonal") == 0 && spl_ortho_supported(gp)) h->solver = SPLPAK_SOLVER_ORTHOGONAL;
+    }
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking) == cudaSuccess;
@@ -923,6 +945,8 @@ extern "C" int splpak_b200_fit_reset(splpak_b200_fit_t h) {
     h->timers_pending = 0;
     h->total_points = 0;
     h->solved = h->refining = h->constraints_fired = h->factor_valid = 0;
+    h->cond_est = 0.0;
+    if (h->os) return spl_ortho_reset(h->gp, *h->os, h->st);
     return SPLPAK_OK;
 }
 
@@ -965,6 +989,16 @@ static void add_ms(splpak_b200_fit_t h, int slot, cudaEvent_t a, cudaEvent_t b) 
 static int add_device_chunk(splpak_b200_fit_t h, const real_t *d_x, int l1x, const real_t *d_y,
                             const real_t *d_w, int weighted, long long n) {
     collect_assemble_timers(h);   // the events are re-recorded below
+    if (h->solver == SPLPAK_SOLVER_ORTHOGONAL) {
+        if (!h->os) {
+            h->os = new (std::nothrow) OrthoScratch();
+            if (!h->os) return SPLPAK_ERR_ALLOC;
+        }
+        int ro = spl_ortho_init(h->gp, *h->os, h->st, h->di.smem_optin);
+        if (ro != SPLPAK_OK) return ro;
+        return spl_ortho_add_chunk(h->gp, d_x, l1x, d_y, d_w, weighted, n, h->xtrap != 0.0, *h->os, h->d_cnt, h->d_totals,
+                                   h->st, h->di.nsm);
+    }
     int rc = ensure_scratch(h, n);
     if (rc != SPLPAK_OK) return rc;
     h->timers_pending = 1;
@@ -1184,6 +1218,59 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
         return SPLPAK_ERR_HANDLE;
     }
     cudaStream_t st = h->st;
+    if (h->solver == SPLPAK_SOLVER_ORTHOGONAL) {
+        // Householder path (ortho.cuh): constraint rows, band QR of the stacked window triangles, back-substitution
+#define FO_TRY(expr)                                                                        \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            fprintf(stderr, "splpak_b200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorString(_e), __FILE__, \
+                    __LINE__, #expr);                                                       \
+            h->finalized = 1;                                                               \
+            h->solved = 0;                                                                  \
+            if (ierror) *ierror = SPLPAK_ERR_CUDA;                                          \
+            return SPLPAK_ERR_CUDA;                                                         \
+        }                                                                                   \
+    } while (0)
+        h->finalized = 1;
+        double totals[2] = {0.0, 0.0}, rows_before = 0.0;
+        int fail = 0;
+        if (!h->os || !h->os->ready) {
+            // no point was ever added: fewer rows than columns (suprls error 33)
+            if (ierror) *ierror = SPLPAK_ERR_SOLVER;
+            return SPLPAK_ERR_SOLVER;
+        }
+        FO_TRY(cudaMemcpyAsync(h->d_dummy_tot + 2, h->d_totals + 1, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        FO_TRY(cudaMemsetAsync(h->d_fail, 0, sizeof(int), st));
+        FO_TRY(cudaEventRecord(h->ev[8], st));
+        rc = spl_ortho_compute(gp, h->xtrap, *h->os, h->d_cnt, h->d_totals, h->d_fail, st, h->di.nsm);
+        FO_TRY(cudaEventRecord(h->ev[9], st));
+        if (rc == SPLPAK_OK) {
+            const double *d_sol = h->os->csol;
+            FO_TRY(cudaMemcpyAsync(h->d_coef64, d_sol, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToDevice, st));
+            if (coef_on_device) {
+                spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(d_sol, coef, gp.ncol);
+                ++g_spl_launches;
+            } else if (sizeof(real_t) == sizeof(double)) {
+                FO_TRY(cudaMemcpyAsync(coef, d_sol, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
+            } else {
+                spl_from_double_kernel<<<spl_div_up(gp.ncol, 256), 256, 0, st>>>(d_sol, h->d_out_tmp, gp.ncol);
+                ++g_spl_launches;
+                FO_TRY(cudaMemcpyAsync(coef, h->d_out_tmp, sizeof(real_t) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
+            }
+            FO_TRY(cudaMemcpyAsync(&fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+            FO_TRY(cudaMemcpyAsync(totals, h->d_totals, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+            FO_TRY(cudaMemcpyAsync(&rows_before, h->d_dummy_tot + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
+            FO_TRY(cudaStreamSynchronize(st));
+            add_ms(h, 5, h->ev[8], h->ev[9]);                      // reported in the "factor" slot
+            if (fail || totals[1] < (double)gp.ncol) rc = SPLPAK_ERR_SOLVER;     // :1650 (33), :1662 (34)
+            h->solved = (rc == SPLPAK_OK);
+            h->constraints_fired = (h->xtrap != 0.0) && (totals[1] > rows_before);
+        }
+#undef FO_TRY
+        if (ierror) *ierror = rc;
+        return rc;
+    }
     const int bw = spl_half_bandwidth(gp);
     const long long lda = spl_band_lda(bw);
     // element (i, j) lives at i + j*lda, so the last one, (n-1, n-1), is at (n-1)*(lda+1)
@@ -1244,6 +1331,10 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
         FC_TRY(cudaMemcpyAsync(&fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
         FC_TRY(cudaMemcpyAsync(totals, h->d_totals, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
         FC_TRY(cudaMemcpyAsync(&rows_before, h->d_dummy_tot + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
+        // smallest / largest diagonal entry of L (from the stored block inverses): a cheap LOWER bound of cond(G)
+        double prange[2] = {0.0, 0.0};
+        if (spl_pivot_range_launch(gp, h->d_AB + band_elems, h->d_dummy_tot, st) == SPLPAK_OK)
+            FC_TRY(cudaMemcpyAsync(prange, h->d_dummy_tot, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
         if (!coef_on_device) {
             if (sizeof(real_t) == sizeof(double)) {
                 FC_TRY(cudaMemcpyAsync(coef, d_sol, sizeof(double) * (size_t)gp.ncol, cudaMemcpyDeviceToHost, st));
@@ -1263,6 +1354,7 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
         // fewer rows than columns (suprls error 33, :1650) or a non-positive pivot -> 107
         if (fail || totals[1] < (double)gp.ncol) rc = SPLPAK_ERR_SOLVER;
         h->solved = (rc == SPLPAK_OK);
+        h->cond_est = (prange[0] > 0.0 && prange[1] > 0.0) ? (prange[1] / prange[0]) * (prange[1] / prange[0]) : 0.0;
         h->factor_valid = h->solved;
         h->constraints_fired = (h->xtrap != 0.0) && (totals[1] > rows_before);
     }
@@ -1291,6 +1383,7 @@ extern "C" int splpak_b200_fit_compute_device(splpak_b200_fit_t h, real_t *d_coe
 // ------------------------------------------------------------------------------------------
 extern "C" int splpak_b200_fit_refine_begin(splpak_b200_fit_t h) {
     if (!valid(h) || !h->finalized || !h->solved) return SPLPAK_ERR_HANDLE;
+    if (h->solver == SPLPAK_SOLVER_ORTHOGONAL) return SPLPAK_ERR_HANDLE;   // already at cond(A): nothing to refine
     if (sizeof(real_t) != sizeof(double)) return SPLPAK_OK;            // fp32 I/O: nothing to gain
     SPL_CUDA_TRY(cudaMemsetAsync(h->d_g, 0, sizeof(double) * (size_t)h->gp.ncol, h->st));
     h->refining = 1;
@@ -1450,6 +1543,24 @@ extern "C" int splpak_b200_fit_refine_compute(splpak_b200_fit_t h, real_t *coef,
 extern "C" int splpak_b200_fit_refine_compute_device(splpak_b200_fit_t h, real_t *d_coef, int64_t ncf, int *ierror) {
     return fit_refine_compute_impl(h, d_coef, 1, ncf, ierror);
 }
+extern "C" int splpak_b200_fit_set_solver(splpak_b200_fit_t h, int solver) {
+    if (!valid(h) || h->total_points != 0 || h->finalized) return SPLPAK_ERR_HANDLE;    // before the first point
+    if (solver == SPLPAK_SOLVER_CHOLESKY) {
+        h->solver = solver;
+        return SPLPAK_OK;
+    }
+    if (solver == SPLPAK_SOLVER_ORTHOGONAL && spl_ortho_supported(h->gp)) {
+        h->solver = solver;
+        return SPLPAK_OK;
+    }
+    return SPLPAK_ERR_HANDLE;
+}
+extern "C" int splpak_b200_fit_get_solver(splpak_b200_fit_t h) { return valid(h) ? h->solver : -1; }
+extern "C" int splpak_b200_fit_condition_estimate(splpak_b200_fit_t h, double *cond_lower_bound) {
+    if (!valid(h) || !cond_lower_bound) return SPLPAK_ERR_HANDLE;
+    *cond_lower_bound = h->cond_est;
+    return SPLPAK_OK;
+}
 extern "C" int splpak_b200_fit_constraints_fired(splpak_b200_fit_t h) {
     return valid(h) ? h->constraints_fired : 0;
 }
@@ -1521,13 +1632,34 @@ extern "C" int splpak_b200_splcw(int ndim, const real_t *xdata, int l1xdat, cons
     rc = splpak_b200_fit_create(ndim, xmin, xmax, nodes, xtrap, &h, ierror);
     if (rc != SPLPAK_OK) return rc;
     const int weighted = (wdata != nullptr) && (wdata[0] >= (real_t)0);        // :796
+    const int first_solver = splpak_b200_fit_get_solver(h);
     rc = splpak_b200_fit_add_points(h, xdata, l1xdat, ydata, wdata, weighted, ndata);
     if (rc == SPLPAK_OK) rc = splpak_b200_fit_compute(h, coef, ncf, nwrk, ierror);
     else if (ierror) *ierror = rc;
+    // The reference reduces the rows with orthogonal transformations (suprls), i.e. at cond(A); the Cholesky path works
+    // at cond(A)^2.  When the factor says that is too much -- a non-positive pivot (107 from the solver although there
+    // are enough rows), or eps * (pivot-ratio bound of cond(G)) above 1e-3, where the refinement below no longer
+    // contracts -- the fit is repeated with the Householder path (ortho.cuh) over the same, still valid, host arrays.
+    // SPLPAK_B200_FIT=cholesky disables the fallback.
+    if (first_solver == SPLPAK_SOLVER_CHOLESKY && sizeof(real_t) == sizeof(double)) {
+        const char *mode = getenv("SPLPAK_B200_FIT");
+        const bool allow = !(mode && strcmp(mode, "cholesky") == 0);
+        double est = 0.0;
+        splpak_b200_fit_condition_estimate(h, &est);
+        const bool pivot_failed = (rc == SPLPAK_ERR_SOLVER) && h->total_points >= h->gp.ncol;
+        const bool too_ill = (rc == SPLPAK_OK) && est * 2.220446049250313e-16 > 1e-3;
+        if (allow && (pivot_failed || too_ill) && splpak_b200_fit_reset(h) == SPLPAK_OK &&
+            splpak_b200_fit_set_solver(h, SPLPAK_SOLVER_ORTHOGONAL) == SPLPAK_OK) {
+            rc = splpak_b200_fit_add_points(h, xdata, l1xdat, ydata, wdata, weighted, ndata);
+            if (rc == SPLPAK_OK) rc = splpak_b200_fit_compute(h, coef, ncf, nwrk, ierror);
+            else if (ierror) *ierror = rc;
+        }
+    }
     // Data-sparse constraint rows fired: their weights make cond(G) = cond(A)^2 explode, so two refinement
     // steps over the same (still valid) host arrays bring the coefficients back to the accuracy of the
     // reference's orthogonal solver (see the refinement section above).
-    if (rc == SPLPAK_OK && sizeof(real_t) == sizeof(double) && splpak_b200_fit_constraints_fired(h)) {
+    if (rc == SPLPAK_OK && sizeof(real_t) == sizeof(double) && splpak_b200_fit_get_solver(h) == SPLPAK_SOLVER_CHOLESKY &&
+        splpak_b200_fit_constraints_fired(h)) {
         for (int step = 0; step < SPLPAK_REFINE_STEPS && rc == SPLPAK_OK; ++step) {
             rc = splpak_b200_fit_refine_begin(h);
             if (rc == SPLPAK_OK) rc = splpak_b200_fit_refine_add_points(h, xdata, l1xdat, ydata, wdata, weighted, ndata);

@@ -58,6 +58,22 @@ struct AssembleScratch {
     double *yw;           // moment path: interleaved (y, w) copy of the chunk, 2 doubles per point (sized with perm)
 };
 
+// Scratch of the orthogonal fit path (ortho.cuh), owned by a fit handle.
+struct OrthoScratch {
+    unsigned *wincount = nullptr, *winstart = nullptr, *wincursor = nullptr, *itemstart = nullptr, *meta = nullptr;
+    unsigned *perm = nullptr;
+    long long perm_cap = 0;
+    double *Rw = nullptr;          // nwindows x ncw x (ncw + 1)
+    unsigned *blist = nullptr;     // non-zero stage-2 blocks, in order; meta2[0] = their number
+    unsigned *meta2 = nullptr;
+    double *Rb = nullptr;          // ncol x (bw + 2): band row + transformed rhs
+    long long *progress = nullptr; // pipeline flags, one per block
+    double *csol = nullptr;        // ncol
+    int ncw = 0, nrb = 0, nblk_win = 0, bw = 0;
+    long long max_blocks = 0;
+    int ready = 0;
+};
+
 extern unsigned long long g_spl_launches;   // host-side launch counter (capi.cu)
 
 #define SPL_CUDA_TRY(expr)                                                              \
