@@ -190,6 +190,9 @@ int splpak_b200_fit_compute_device(splpak_b200_fit_t h, splpak_real *d_coef, int
 #define SPLPAK_SOLVER_ORTHOGONAL 1
 int splpak_b200_fit_set_solver(splpak_b200_fit_t h, int solver);
 int splpak_b200_fit_get_solver(splpak_b200_fit_t h);
+/* Parity-test hook of the orthogonal path: which = 0 -> per-window triangles [nwindows][4^ndim][4^ndim + 1] (R_w | z_w),
+ * which = 1 -> band factor [ncol][b + 2] (row i: R[i][i..i+b], then (Q^T r)_i).  out may be NULL to query *count. */
+int splpak_b200_fit_get_orthogonal_factor(splpak_b200_fit_t h, int which, double *out, int64_t capacity, int64_t *count);
 /* (max L_jj / min L_jj)^2 of the last Cholesky factor: a cheap LOWER bound of cond(G); 0 when unknown. */
 int splpak_b200_fit_condition_estimate(splpak_b200_fit_t h, double *cond_lower_bound);
 

@@ -48,6 +48,7 @@ SYMBOLS = [
     "splpak_b200_fit_refine_compute_device",
     "splpak_b200_fit_set_solver",
     "splpak_b200_fit_get_solver",
+    "splpak_b200_fit_get_orthogonal_factor",
     "splpak_b200_fit_condition_estimate",
     "splpak_b200_fit_constraints_fired",
     "splpak_b200_fit_rhs_buffer",
@@ -138,6 +139,7 @@ def load(real32: bool = False) -> C.CDLL:
         "splpak_b200_fit_refine_compute_device": (C.c_int, [vp, vp, i64, ip]),
         "splpak_b200_fit_set_solver": (C.c_int, [vp, C.c_int]),
         "splpak_b200_fit_get_solver": (C.c_int, [vp]),
+        "splpak_b200_fit_get_orthogonal_factor": (C.c_int, [vp, C.c_int, vp, i64, C.POINTER(i64)]),
         "splpak_b200_fit_condition_estimate": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "splpak_b200_fit_constraints_fired": (C.c_int, [vp]),
         "splpak_b200_fit_rhs_buffer": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),

@@ -279,6 +279,19 @@ class FitHandle:
         self._check()
         return {0: "cholesky", 1: "orthogonal"}.get(self.lib.splpak_b200_fit_get_solver(self.h))
 
+    def orthogonal_factor(self, which):
+        """Parity-test hook: which = 0 -> per-window triangles (nwindows, 4^ndim, 4^ndim + 1); 1 -> band factor (ncol, b + 2)."""
+        self._check()
+        n = C.c_int64(0)
+        if self.lib.splpak_b200_fit_get_orthogonal_factor(self.h, int(which), None, 0, C.byref(n)) != 0:
+            raise SplpakError("no orthogonal factor on this handle")
+        out = np.zeros(n.value)
+        rc = self.lib.splpak_b200_fit_get_orthogonal_factor(self.h, int(which), _ptr(out), n.value, C.byref(n))
+        if rc != 0:
+            raise SplpakError(f"get_orthogonal_factor failed: {rc}")
+        ncw = 4 ** self.ndim
+        return out.reshape(-1, ncw, ncw + 1) if which == 0 else out.reshape(self.ncol, -1)
+
     def condition_estimate(self):
         """Pivot-ratio LOWER bound of cond(G) from the last Cholesky factor (0.0 when unknown)."""
         self._check()

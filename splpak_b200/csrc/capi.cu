@@ -1556,6 +1556,20 @@ extern "C" int splpak_b200_fit_set_solver(splpak_b200_fit_t h, int solver) {
     return SPLPAK_ERR_HANDLE;
 }
 extern "C" int splpak_b200_fit_get_solver(splpak_b200_fit_t h) { return valid(h) ? h->solver : -1; }
+// Parity-test hook of the orthogonal path: which = 0 -> the per-window triangles [nwindows][ncw][ncw + 1] (R_w | z_w),
+// which = 1 -> the band factor [ncol][bw + 2] (row i: R[i][i..i+bw], then (Q^T r)_i).  *count returns the size.
+extern "C" int splpak_b200_fit_get_orthogonal_factor(splpak_b200_fit_t h, int which, double *out, int64_t capacity,
+                                                     int64_t *count) {
+    if (!valid(h) || !h->os || !h->os->ready) return SPLPAK_ERR_HANDLE;
+    const OrthoScratch &os = *h->os;
+    const int64_t n = which == 0 ? (int64_t)h->gp.nwindows * os.ncw * (os.ncw + 1) : (int64_t)h->gp.ncol * (os.bw + 2);
+    if (count) *count = n;
+    if (!out) return SPLPAK_OK;
+    if (capacity < n) return SPLPAK_ERR_HANDLE;
+    SPL_CUDA_TRY(cudaStreamSynchronize(h->st));
+    SPL_CUDA_TRY(cudaMemcpy(out, which == 0 ? os.Rw : os.Rb, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    return SPLPAK_OK;
+}
 extern "C" int splpak_b200_fit_condition_estimate(splpak_b200_fit_t h, double *cond_lower_bound) {
     if (!valid(h) || !cond_lower_bound) return SPLPAK_ERR_HANDLE;
     *cond_lower_bound = h->cond_est;

@@ -33,6 +33,7 @@
 #define ORTHO_BR 64            // rows generated / absorbed per batch in stage 1
 #define ORTHO_NRB_MAX 16       // rows of one stage-2 block
 #define ORTHO_S2_THREADS 256
+#define ORTHO_TINY2 1e-280     // squared magnitude below which a column of new rows counts as zero (see ortho_absorb)
 
 
 // ------------------------------------------------------------------------------------------
@@ -56,7 +57,10 @@ __device__ __forceinline__ void ortho_absorb(double *s_R, double *s_B, int nb, d
         }
         __syncthreads();
         const double sigma = s_red[0] + s_red[1];
-        if (sigma != 0.0) {                                            // :1527 `if (s==0) cycle`
+        // :1527 `if (s==0) cycle`.  A column whose batch entries are all below 1e-140 holds nothing but the rounding residue
+        // of rows that were already absorbed (each step shrinks it by ~eps, down into the subnormals, where 1 / (v0 beta)
+        // overflows): it is skipped like an exactly zero one.
+        if (sigma > ORTHO_TINY2) {
             const double alpha = s_R[j * LD + j];
             double beta = sqrt(alpha * alpha + sigma);
             if (alpha > 0.0) beta = -beta;                              // :1530
@@ -355,7 +359,7 @@ spl_band_qr_kernel(const __grid_constant__ GridParams gp, const double *__restri
                 wj[r] = (r < nr) ? s_W[r * ldw + j] : 0.0;
                 sigma = fma(wj[r], wj[r], sigma);
             }
-            if (sigma != 0.0) {                               // uniform: every thread read the same values
+            if (sigma > ORTHO_TINY2) {                        // uniform: every thread read the same values
                 const double alpha = __ldcg(rc);                 // rows of Rb are written by other CTAs: L2 loads
                 double beta = sqrt(alpha * alpha + sigma);
                 if (alpha > 0.0) beta = -beta;
