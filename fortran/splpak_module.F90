@@ -58,6 +58,7 @@
         procedure,public :: add_points                   !! (new) streaming fit: accumulate points
         procedure,public :: compute                      !! (new) streaming fit: constraints + solve
         procedure,public :: refine                       !! (new) streaming fit: one refinement pass over the same points
+        procedure,public :: set_solver                   !! (new) streaming fit: 0 = band Cholesky (default), 1 = orthogonal (Householder)
         procedure,private :: splcc
         procedure,private :: splcw
         procedure,private :: splfe
@@ -175,6 +176,12 @@
             integer(c_int),intent(out) :: ierror
             integer(c_int) :: rc
         end function c_fit_refine_compute
+        function c_fit_set_solver(h,solver) bind(C,name='splpak_b200_fit_set_solver') result(rc)
+            import :: c_int, c_ptr
+            type(c_ptr),value :: h
+            integer(c_int),value :: solver
+            integer(c_int) :: rc
+        end function c_fit_set_solver
         function c_fit_destroy(h) bind(C,name='splpak_b200_fit_destroy') result(rc)
             import :: c_int, c_ptr
             type(c_ptr),value :: h
@@ -337,6 +344,16 @@
         ierror = ie
         call cfaerr(ierror,.false.)
     end subroutine create
+
+    !> (new) choose the solver of a streaming fit, after create and before the first add_points:
+    !  0 = band Cholesky of the normal equations (default), 1 = Householder reductions only, like the
+    !  reference's suprls (accurate at cond(A); 1-D..3-D).  ierror = 203 when not available.
+    subroutine set_solver(me,solver,ierror)
+        class(splpak_type),intent(inout) :: me
+        integer,intent(in) :: solver
+        integer,intent(out) :: ierror
+        ierror = int(c_fit_set_solver(me%handle,int(solver,c_int)))
+    end subroutine set_solver
 
     !> (new) accumulate n more points; wdata absent (or wdata(1)<0) => all weights 1.
     subroutine add_points(me,xdata,l1xdat,ydata,ndata,ierror,wdata)

@@ -37,18 +37,21 @@ csvp = os.path.join(OUT, f"launches_{tag}.csv")
 if os.path.exists(csvp):
     txt = capture(lambda: launch_shares.main(csvp, 2))
     plain = json.load(open(os.path.join(OUT, "prof_plain.json")))
-    with open(os.path.join(PROF, "r01_launches.md"), "w") as f:
-        f.write(f"# r01 — ncu launch list of `{CMD}` (the two timed steps)\n\n"
+    rt = tag.split("_")[0][:3] if tag.startswith("r0") else "r01"
+    with open(os.path.join(PROF, f"{rt}_launches.md"), "w") as f:
+        f.write(f"# {rt} — ncu launch list of `{CMD}` (the two timed steps)\n\n"
                 f"`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:spl_ -s <3 warm-up steps> -c <2 steps>`;\n"
-                f"raw csv: `profiles/r01_launches.csv`.  Per-launch times under ncu are cold-cache and serialised: compare SHARES.\n"
+                f"raw csv: `profiles/{rt}_launches.csv`.  Per-launch times under ncu are cold-cache and serialised: compare SHARES.\n"
                 f"The same command without ncu printed fit {plain['fit_ms']:.2f} ms + eval {plain['eval_ms']:.2f} ms per step "
                 f"(stages: {json.dumps({k: round(v, 3) for k, v in plain['stages_ms'].items()})}).\n\n")
         f.write(txt)
-    subprocess.run(["cp", csvp, os.path.join(PROF, "r01_launches.csv")])
+    subprocess.run(["cp", csvp, os.path.join(PROF, f"{rt}_launches.csv")])
 
 traffic = {}
-units = {"eval": ("spl_eval_kernel<3>", 1_000_000_000), "accumulate": ("spl_moments_kernel", 100_000_000)}
-for k in ("eval", "accumulate", "panel"):
+rt = tag.split("_")[0][:3] if tag.startswith("r0") else "r01"
+units = {"eval": ("spl_eval_regroup_kernel<3>" if rt != "r01" else "spl_eval_kernel<3>", 1_000_000_000),
+         "accumulate": ("spl_moments_kernel", 100_000_000)}
+for k in ("eval", "accumulate", "panel", "factor"):
     rep = os.path.join(OUT, f"prof_{tag}_{k}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -56,9 +59,9 @@ for k in ("eval", "accumulate", "panel"):
     txt = "\n".join(ln for ln in txt.splitlines()
                     if not any(s in ln for s in ("stalled_drain", "stalled_lg_", "stalled_membar", "stalled_misc",
                                                  "stalled_sleeping", "stalled_tex")))
-    with open(os.path.join(PROF, f"r01_{k}.md"), "w") as f:
+    with open(os.path.join(PROF, f"{rt}_{k}_bench.md" if rt != "r01" else f"r01_{k}.md"), "w") as f:
         kn = "spl_moments_kernel (the accumulate stage)" if k == "accumulate" else f"spl_{k}*"
-        f.write(f"# r01 — `ncu --set full --clock-control none` of {kn} inside `{CMD}` (bench size)\n\n```\n{txt}\n```\n")
+        f.write(f"# {rt} — `ncu --set full --clock-control none` of {kn} inside `{CMD}` (bench size)\n\n```\n{txt}\n```\n")
     if k in units:
         m, _ = raw_metrics(rep)
         rd = float(m["dram__bytes_read.sum"].replace(",", ""))
@@ -73,5 +76,5 @@ for k in ("eval", "accumulate", "panel"):
         traffic[units[k][0]] = {"dram_bytes": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr, "units": units[k][1],
                                 "source": f"ncu --set full of `{CMD}`, one launch"}
 if traffic:
-    json.dump(traffic, open(os.path.join(PROF, "r01_traffic.json"), "w"), indent=1)
+    json.dump(traffic, open(os.path.join(PROF, f"{rt}_traffic.json"), "w"), indent=1)
     print(json.dumps(traffic, indent=1))

@@ -1604,11 +1604,11 @@ int spl_resolve_launch(const GridParams &gp, const double *d_AB, double *d_g, do
 }
 
 // min / max of diag(L) over all panels, from the stored block inverses (L_jj = 1 / Linv_jj): out2 = {min, max}
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 spl_pivot_range_kernel(const double *__restrict__ linv, long long n, double *__restrict__ out2) {
-    __shared__ double s_mn[256], s_mx[256];
+    __shared__ double s_mn[1024], s_mx[1024];
     double mn = 1e300, mx = 0.0;
-    for (long long j = threadIdx.x; j < n; j += 256) {
+    for (long long j = threadIdx.x; j < n; j += 1024) {
         const long long kb = j / SOLVE_NB;
         const int r = (int)(j % SOLVE_NB);
         const double li = fabs(linv[kb * 4096 + r * 64 + r]);
@@ -1623,7 +1623,7 @@ spl_pivot_range_kernel(const double *__restrict__ linv, long long n, double *__r
     s_mn[threadIdx.x] = mn;
     s_mx[threadIdx.x] = mx;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = 512; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
             s_mn[threadIdx.x] = fmin(s_mn[threadIdx.x], s_mn[threadIdx.x + o]);
             s_mx[threadIdx.x] = fmax(s_mx[threadIdx.x], s_mx[threadIdx.x + o]);
@@ -1636,7 +1636,7 @@ spl_pivot_range_kernel(const double *__restrict__ linv, long long n, double *__r
     }
 }
 int spl_pivot_range_launch(const GridParams &gp, const double *d_work, double *d_out2, cudaStream_t st) {
-    spl_pivot_range_kernel<<<1, 256, 0, st>>>(d_work, gp.ncol, d_out2);
+    spl_pivot_range_kernel<<<1, 1024, 0, st>>>(d_work, gp.ncol, d_out2);
     ++g_spl_launches;
     SPL_CUDA_TRY(cudaGetLastError());
     return SPLPAK_OK;
