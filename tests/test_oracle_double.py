@@ -182,3 +182,21 @@ def test_error_codes_agree():
     v1, e1 = o.evaluate(1, [0.3], coef, [0.0], [1.0], [5], nderiv=[3])
     v2, e2 = m.splde(1, [0.3], [3], coef, [0.0], [1.0], [5])
     assert e1 == e2 == 104 and v1 == v2
+
+
+def test_algorithm_matched_cpu_baseline_is_a_correct_fit():
+    """bench.py's optional 'algorithm-matched' CPU row (oracle/cpu_matched.py: sparse normal equations by window +
+    LAPACK band Cholesky) must solve the same problem: its coefficients agree with the oracle's suprls."""
+    from oracle import cpu_matched
+
+    rng = np.random.default_rng(4)
+    for ndim, nodes, n in [(1, [9], 300), (2, [6, 7], 2500), (3, [5, 6, 5], 6000)]:
+        x = rng.random((n, ndim)) * 1.1 - 0.05
+        y = np.cos(x.sum(axis=1))
+        w = rng.uniform(0.5, 1.5, n)
+        mn, mx = [0.0] * ndim, [1.0] * ndim
+        c, _, _ = cpu_matched.fit(ndim, x, y, w, mn, mx, nodes)
+        ref, ie = Oracle().initialize(ndim, x, y, w, mn, mx, nodes, 0.0)
+        assert ie == 0
+        A, _ = Oracle().rows(ndim, x, y, w, mn, mx, nodes, 0.0)
+        assert np.abs(c - ref).max() <= 10 * EPS * np.linalg.cond(A) ** 2 * np.abs(ref).max()
