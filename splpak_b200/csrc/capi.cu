@@ -1672,8 +1672,14 @@ extern "C" int splpak_b200_splcw(int ndim, const real_t *xdata, int l1xdat, cons
     // Data-sparse constraint rows fired: their weights make cond(G) = cond(A)^2 explode, so two refinement
     // steps over the same (still valid) host arrays bring the coefficients back to the accuracy of the
     // reference's orthogonal solver (see the refinement section above).
+    // Round 2: the same when NO constraint row fired but the factor says the system is ill-conditioned
+    // (clustered data, tiny weights, xtrap = 0).  Calibration on 29 1-D..3-D problems (scripts/cond_calib.py): the
+    // pivot-ratio bound `est` is 0.01..0.5 x cond(G), and the unrefined coefficients differ from the oracle's by
+    // <= 1e-16 x est -- so below est = 3e6 they are good to 3e-10 as they are (cfg3's dense data: est ~ 1e6).
+    double est_now = 0.0;
+    splpak_b200_fit_condition_estimate(h, &est_now);
     if (rc == SPLPAK_OK && sizeof(real_t) == sizeof(double) && splpak_b200_fit_get_solver(h) == SPLPAK_SOLVER_CHOLESKY &&
-        splpak_b200_fit_constraints_fired(h)) {
+        (splpak_b200_fit_constraints_fired(h) || est_now > 3e6)) {
         for (int step = 0; step < SPLPAK_REFINE_STEPS && rc == SPLPAK_OK; ++step) {
             rc = splpak_b200_fit_refine_begin(h);
             if (rc == SPLPAK_OK) rc = splpak_b200_fit_refine_add_points(h, xdata, l1xdat, ydata, wdata, weighted, ndata);

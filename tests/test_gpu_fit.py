@@ -436,3 +436,25 @@ def test_pageable_host_arrays_are_staged(oracle):
     sub = np.arange(0, len(q), 1501)
     ref, _ = oracle.evaluate_batch(3, q[sub], cq, mn, mx, nodes)
     np.testing.assert_allclose(out_pageable[sub], ref, rtol=0, atol=1e-12 * max(1.0, np.abs(cq).max()))
+
+
+def test_ill_conditioned_fit_without_constraints(oracle):
+    """xtrap = 0 (no constraint rows, so round 1 never refined) with clustered data: the one-shot splcw now
+    refines when the pivot-ratio bound of cond(G) exceeds 3e6, and switches to the Householder path when the Cholesky
+    factor breaks down; either way the coefficients match the oracle's suprls at 20 eps cond(A)."""
+    for seed, ndim, nodes, n, sharp in [(77, 2, [12, 12], 6000, 4.0), (77, 3, [8, 7, 9], 20000, 4.0), (77, 2, [14, 14], 4000, 9.0),
+                                        (78, 2, [14, 14], 4000, 14.0)]:        # last: cond(A) = 9.6e8 -> Householder path
+        rng = np.random.default_rng(seed)
+        u = rng.random((n, ndim))
+        x = 0.5 + 0.5 * np.tanh(sharp * (u - 0.5))             # dense in the middle, thin towards the faces
+        y = np.sin(3 * x.sum(axis=1))
+        w = rng.uniform(1e-3, 1.0, n)                           # three decades of weights
+        mn, mx = np.zeros(ndim), np.ones(ndim)
+        ref, ie = oracle.initialize(ndim, x, y, w, mn, mx, nodes, 0.0)
+        assert ie == 0
+        A, _ = oracle.rows(ndim, x, y, w, mn, mx, nodes, 0.0)
+        cond = np.linalg.cond(A)
+        got, ierr = sp.splcw(ndim, x, ndim, y, w, n, mn, mx, nodes, 0.0, quiet=True)
+        assert ierr == 0
+        err = np.abs(got - ref).max() / np.abs(ref).max()
+        assert err <= max(1e-11, 20 * np.finfo(float).eps * cond), (ndim, nodes, err, cond)
