@@ -1674,7 +1674,7 @@ extern "C" int splpak_b200_splcw(int ndim, const real_t *xdata, int l1xdat, cons
     // reference's orthogonal solver (see the refinement section above).
     // Round 2: the same when NO constraint row fired but the factor says the system is ill-conditioned
     // (clustered data, tiny weights, xtrap = 0).  Calibration on 29 1-D..3-D problems (scripts/cond_calib.py): the
-    // pivot-ratio bound `est` is 0.01..0.5 x cond(G), and the unrefined coefficients differ from the oracle's by
+    // pivot-ratio bound `est` is 0.01..0.5 x cond(G), and the unrefined coefficients differ from the reference's suprls solution by
     // <= 1e-16 x est -- so below est = 3e6 they are good to 3e-10 as they are (cfg3's dense data: est ~ 1e6).
     double est_now = 0.0;
     splpak_b200_fit_condition_estimate(h, &est_now);
