@@ -724,7 +724,12 @@ extern "C" int splpak_b200_eval(int ndim, const real_t *x, int l1x, int64_t nq, 
         const size_t cbytes = sizeof(real_t) * (size_t)gp.ncol;
         if (!(cx.coef_valid && cx.coef_shadow.size() == cbytes && memcmp(cx.coef_shadow.data(), coef, cbytes) == 0)) {
             cx.coef_valid = false;
-            cx.coef_shadow.assign(reinterpret_cast<const char *>(coef), reinterpret_cast<const char *>(coef) + cbytes);
+            try {
+                cx.coef_shadow.assign(reinterpret_cast<const char *>(coef), reinterpret_cast<const char *>(coef) + cbytes);
+            } catch (...) {                                        // no C++ exception may cross the C ABI
+                if (ierror) *ierror = SPLPAK_ERR_ALLOC;
+                return SPLPAK_ERR_ALLOC;
+            }
             // from the shadow, not from the caller's array: the copy may still be in flight when we return on an error path
             EV_TRY(cudaMemcpyAsync(d_coef, cx.coef_shadow.data(), cbytes, cudaMemcpyHostToDevice, st));
             EV_TRY(cudaStreamSynchronize(st));                   // pageable source: complete before the shadow can change
