@@ -25,6 +25,9 @@ long long spl_eval_regroup_elems(const GridParams &gp, long long nq, int nsm, si
 #ifdef SPLPAK_REAL32
 int spl_eval_f32_launch(const GridParams &gp, const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
                         real_t *d_out, cudaStream_t stream, int nsm, size_t smem_optin, unsigned long long *d_counter);
+int spl_eval_f32_mixed4_launch(const GridParams &gp, const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
+                               const double *d_coef64, double *d_pad, real_t *d_out, cudaStream_t stream, int nsm,
+                               size_t smem_optin, unsigned long long *d_counter);
 #endif
 long long spl_grid_tmp_elems(const GridParams &gp, const long long *naxis);
 int spl_eval_grid_launch(const GridParams &gp, const int *nderiv, const real_t *const *d_axis, const long long *naxis,
@@ -442,6 +445,24 @@ static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const in
         if (value && !(mode && strcmp(mode, "f64") == 0)) {
             unsigned long long *counter = eval_counter_slot(di.dev);
             if (!counter) return SPLPAK_ERR_ALLOC;
+            const long long pad_elems4 = (gp.ndim == 4) ? spl_eval_regroup_elems(gp, nq, di.nsm, di.smem_optin) : 0;
+            if (pad_elems4 > 0) {
+                // 4-D, large batch: scattered queries go to the float64 regrouping kernel (order probe decides)
+                const long long npad4 = (gp.ncol + 1) & ~1LL;
+                cudaMemPool_t pool = eval_scratch_pool(di.dev);
+                double *blk = nullptr;
+                const size_t bytes = sizeof(double) * (size_t)(npad4 + pad_elems4 + 2);
+                cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&blk, bytes, pool, st) : cudaMallocAsync((void **)&blk, bytes, st);
+                if (e == cudaSuccess) {
+                    spl_to_double_kernel<<<spl_div_up(npad4, 256), 256, 0, st>>>(d_coef, blk, gp.ncol, npad4);
+                    ++g_spl_launches;
+                    const int rc4 = spl_eval_f32_mixed4_launch(gp, d_x, l1x, nq, d_coef, blk, blk + npad4, d_out, st, di.nsm,
+                                                               di.smem_optin, counter);
+                    cudaFreeAsync(blk, st);
+                    return rc4;
+                }
+                cudaGetLastError();
+            }
             return spl_eval_f32_launch(gp, d_x, l1x, nq, d_coef, d_out, st, di.nsm, di.smem_optin, counter);
         }
     }

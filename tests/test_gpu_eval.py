@@ -181,7 +181,13 @@ def test_real32_splfe_runs_in_working_precision(oracle32, ndim, nodes):
     # large batch (dynamic scheduler, shared-memory table) == small batch results for the same points
     big = np.tile(q, (200, 1))
     gotb, ierr = sp.eval_batch(ndim, big, coef, mn, mx, nodes, real32=True)
-    assert ierr == 0 and np.array_equal(gotb[: len(q)], got) and np.array_equal(gotb[-len(q):], got)
+    assert ierr == 0
+    if ndim < 4:
+        assert np.array_equal(gotb[: len(q)], got) and np.array_equal(gotb[-len(q):], got)
+    else:
+        # 4-D, >= 2^18 scattered queries: the order probe hands the batch to the float64 regrouping kernel (float I/O)
+        assert (np.abs(gotb[: len(q)].astype(np.float64) - ref.astype(np.float64)) <= tol).all()
+        assert np.array_equal(gotb[: len(q)], gotb[-len(q):])
 
 
 @pytest.mark.parametrize("ndim,nodes,naxis,nderiv", [
