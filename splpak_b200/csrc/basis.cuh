@@ -234,3 +234,66 @@ __device__ __forceinline__ void spl_window_weights(double x, double xmin, double
         b[k] = (ib >= ibmn && ib <= ibmx) ? v : 0.0;
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// Uniform ("phantom node") form of the same spline, used by batched evaluation when the extended table fits in
+// shared memory.  The reference's natural spline with its linear edge functions (bascmp :302-379) is a plain uniform
+// cubic B-spline series on the grid EXTENDED by one phantom node per side:
+//     s(x) = sum_{j=-1}^{n} a_j C((x - xmin)/dx - j),     C = the chapeau function of bascmp (:253-270),
+//     a_0 = 2 c_0 + 4 c_1,  a_1 = 2 c_1,  a_j = c_j (2 <= j <= n-3),  a_{n-2} = 2 c_{n-2},  a_{n-1} = 2 c_{n-1} + 4 c_{n-2},
+//     a_{-1} = 2 a_0 - a_1,  a_n = 2 a_{n-1} - a_{n-2}            (zero second derivative at both ends),
+// because L_0 = 2 (C_0 + 2 C_{-1}) and L_1 = 6 C_{-1} + 4 C_0 + 2 C_1 on x >= xmin (mirror image on the right), for every
+// n >= 4.  Outside [xmin, xmax] the reference's functions continue linearly, so the four weights there are the
+// first-order Taylor expansion of the boundary cell's weights.  With f = t - cell in [0, 1], g = 1 - f the weights of
+// the nodes cell-1 .. cell+2 are  C(f+1), C(f), C(f-1), C(f-2) = g^3/4, 1 - 3/2 f^2 + 3/4 f^3, 1 - 3/2 g^2 + 3/4 g^3, f^3/4:
+// 9 FP64 operations per dimension instead of the 56 of the node-by-node formulas.  Not bit-identical to bascmp: the
+// node positions of the reference carry their own rounding of eps*node index in u (:246), this form does not; the
+// difference is bounded by ~nod eps |phi'| (tests/test_gpu_eval.py states the tolerance).
+// All weights carry a factor 4 (value), 4*dx (1st) or 4*dx^2 (2nd derivative); the caller scales its final sum.
+// ------------------------------------------------------------------------------------------
+#define SPL_UNI_OOB 0x40000000u     // flag bit: the coordinate lies outside [xmin, xmax] (linear continuation)
+
+// cell index (0 .. nod-2), fractional coordinate f = t - cell and the out-of-range flag of one dimension
+__device__ __forceinline__ void spl_uni_cell(double x, double xmin, double dxin, int nod, int &cell, double &f, bool &oob) {
+    const double t = (x - xmin) * dxin;
+    const int it = __double2int_rd(t);                        // saturating; NaN -> 0
+    oob = (unsigned)it > (unsigned)(nod - 2);
+    cell = min(max(it, 0), nod - 2);
+    f = t - (double)cell;
+}
+
+// weights (x 4 / dxin^nder) of the extended-table entries cell .. cell+3 (nodes cell-1 .. cell+2); nder in 0..2
+template <bool VALUE>
+__device__ __forceinline__ void spl_uni_weights(double f, bool oob, int nder, double b[4]) {
+    const double g = 1.0 - f;
+    if (VALUE || nder == 0) {
+        const double f2 = f * f, g2 = g * g;
+        b[0] = g2 * g;
+        b[1] = fma(f2, fma(3.0, f, -6.0), 4.0);
+        b[2] = fma(g2, fma(3.0, g, -6.0), 4.0);
+        b[3] = f2 * f;
+        if (oob) {
+            if (f < 0.0) {                                    // left of xmin: value + slope at f = 0
+                b[0] = fma(-3.0, f, 1.0); b[1] = 4.0; b[2] = fma(3.0, f, 1.0); b[3] = 0.0;
+            } else if (f > 1.0) {                             // right of xmax: value + slope at f = 1
+                const double e = f - 1.0;
+                b[0] = 0.0; b[1] = fma(-3.0, e, 1.0); b[2] = 4.0; b[3] = fma(3.0, e, 1.0);
+            }
+        }
+    } else if (nder == 1) {
+        b[0] = -3.0 * g * g;
+        b[1] = f * fma(9.0, f, -12.0);
+        b[2] = -g * fma(9.0, g, -12.0);
+        b[3] = 3.0 * f * f;
+        if (oob) {
+            if (f < 0.0) { b[0] = -3.0; b[1] = 0.0; b[2] = 3.0; b[3] = 0.0; }
+            else if (f > 1.0) { b[0] = 0.0; b[1] = -3.0; b[2] = 0.0; b[3] = 3.0; }
+        }
+    } else {
+        b[0] = 6.0 * g;
+        b[1] = fma(18.0, f, -12.0);
+        b[2] = fma(18.0, g, -12.0);
+        b[3] = 6.0 * f;
+        if (oob && (f < 0.0 || f > 1.0)) { b[0] = 0.0; b[1] = 0.0; b[2] = 0.0; b[3] = 0.0; }
+    }
+}

@@ -22,6 +22,7 @@ int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, 
                     const double *d_coef, long long ncol_padded, real_t *d_out, cudaStream_t stream,
                     int nsm, size_t smem_optin, unsigned long long *d_counter, double *d_pad);
 long long spl_eval_regroup_elems(const GridParams &gp, long long nq, int nsm, size_t smem_optin);
+long long spl_eval_scratch_elems(const GridParams &gp, const int *nderiv, long long nq, int nsm, size_t smem_optin);
 #ifdef SPLPAK_REAL32
 int spl_eval_f32_launch(const GridParams &gp, const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
                         real_t *d_out, cudaStream_t stream, int nsm, size_t smem_optin, unsigned long long *d_counter);
@@ -489,16 +490,16 @@ static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const in
     // on its own stream)
     unsigned long long *counter = eval_counter_slot(di.dev);
     if (!counter) return SPLPAK_ERR_ALLOC;
-    // padded copy of the table for the regrouping kernel (2-D..4-D, large batches)
+    // image of the table the kernels read: extended (uniform form) and/or padded (regrouping kernel) copy
     double *pad = nullptr;
-    const long long pad_elems = spl_eval_regroup_elems(gp, nq, di.nsm, di.smem_optin);
+    const long long pad_elems = spl_eval_scratch_elems(gp, nderiv, nq, di.nsm, di.smem_optin);
     if (pad_elems > 0) {
         cudaMemPool_t pool = eval_scratch_pool(di.dev);
         cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&pad, sizeof(double) * (size_t)(pad_elems + 2), pool, st)
                              : cudaMallocAsync((void **)&pad, sizeof(double) * (size_t)(pad_elems + 2), st);   // + the order flag
         if (e != cudaSuccess) {
             cudaGetLastError();
-            pad = nullptr;                                     // the plain kernel needs no scratch
+            pad = nullptr;                                     // the exact plain kernel needs no scratch
         }
     }
     int rc = spl_eval_launch(gp, nderiv, d_x, l1x, nq, coef64, npad, d_out, st, di.nsm, di.smem_optin, counter, pad);

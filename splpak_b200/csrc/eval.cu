@@ -81,18 +81,15 @@ struct TableLayout {
     long long s3;
 };
 
-// Nested contraction over the 4^NDIM window, dimension 1 innermost.
+// Nested contraction over the 4^NDIM window starting at p0, dimension 1 innermost.
 template <int NDIM, typename T = double>
-__device__ __forceinline__ T spl_contract(const TableLayout &tl, const T *__restrict__ cf,
-                                          const int *ws, const T (*b)[4]) {
+__device__ __forceinline__ T spl_contract_at(const TableLayout &tl, const T *__restrict__ p0, const T (*b)[4]) {
     T sum = (T)0;
     if constexpr (NDIM == 1) {
-        const T *p = cf + ws[0];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sum = fma(p[i], b[0][i], sum);
+        for (int i = 0; i < 4; ++i) sum = fma(p0[i], b[0][i], sum);
     } else if constexpr (NDIM == 2) {
         const int n0 = tl.s1;
-        const T *p0 = cf + ws[0] + n0 * ws[1];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const T *p = p0 + n0 * j;
@@ -104,7 +101,6 @@ __device__ __forceinline__ T spl_contract(const TableLayout &tl, const T *__rest
     } else if constexpr (NDIM == 3) {
         const int n0 = tl.s1;
         const int n01 = tl.s2;
-        const T *p0 = cf + ws[0] + n0 * ws[1] + (long long)n01 * ws[2];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             T sk = (T)0;
@@ -122,7 +118,6 @@ __device__ __forceinline__ T spl_contract(const TableLayout &tl, const T *__rest
         const int n0 = tl.s1;
         const int n01 = tl.s2;
         const long long n012 = tl.s3;
-        const T *p0 = cf + ws[0] + n0 * ws[1] + (long long)n01 * ws[2] + n012 * ws[3];
 #pragma unroll 1
         for (int l = 0; l < 4; ++l) {
             T sl = (T)0;
@@ -143,6 +138,17 @@ __device__ __forceinline__ T spl_contract(const TableLayout &tl, const T *__rest
         }
     }
     return sum;
+}
+
+// window start from the per-dimension first nodes ws[]
+template <int NDIM, typename T = double>
+__device__ __forceinline__ T spl_contract(const TableLayout &tl, const T *__restrict__ cf,
+                                          const int *ws, const T (*b)[4]) {
+    const T *p0 = cf + ws[0];
+    if constexpr (NDIM >= 2) p0 += tl.s1 * ws[1];
+    if constexpr (NDIM >= 3) p0 += (long long)tl.s2 * ws[2];
+    if constexpr (NDIM >= 4) p0 += tl.s3 * ws[3];
+    return spl_contract_at<NDIM, T>(tl, p0, b);
 }
 
 // One query: weights of every dimension, then the contraction.  VALUE: every nderiv is 0 (splfe).
@@ -171,6 +177,60 @@ __device__ __forceinline__ double spl_eval_point(const GridParams &gp, const Der
     return sum;
 }
 
+// Uniform (phantom-node) form, basis.cuh: the same query against the EXTENDED table (nodes + 2 per dimension,
+// spl_uni_table_kernel), window = extended entries cell .. cell+3 per dimension.
+template <int NDIM>
+__device__ __forceinline__ double spl_uni_scale(const GridParams &gp, const DerivParams &dp, bool value) {
+    double sc = 1.0 / (double)spl_ipow(4, NDIM);
+    if (!value) {
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) {
+            if (dp.nd[d] >= 1) sc *= gp.dxin[d];
+            if (dp.nd[d] >= 2) sc *= gp.dxin[d];
+        }
+    }
+    return sc;
+}
+// from the fractional coordinates f[] and the window's base offset (flag SPL_UNI_OOB: some coordinate is out of range)
+template <int NDIM, bool VALUE>
+__device__ __forceinline__ double spl_eval_point_uni_at(const DerivParams &dp, const TableLayout &tl,
+                                                        const double *__restrict__ cf, const double *f, unsigned base,
+                                                        double scale) {
+    double b[NDIM][4];
+    const bool oob = (base & SPL_UNI_OOB) != 0u;
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) spl_uni_weights<VALUE>(f[d], oob, VALUE ? 0 : dp.nd[d], b[d]);
+    double sum = spl_contract_at<NDIM>(tl, cf + (base & ~SPL_UNI_OOB), b) * scale;
+    // a NaN coordinate fails every comparison of bascmp, so every basis value stays 0 (:253-379)
+    bool isnan_q = false;
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) isnan_q |= (f[d] != f[d]);
+    if (isnan_q) sum = 0.0;
+    return sum;
+}
+template <int NDIM>
+__device__ __forceinline__ unsigned spl_uni_locate(const GridParams &gp, const TableLayout &tl, const double *xv, double *f) {
+    unsigned base = 0u;
+    bool any = false;
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) {
+        int cell;
+        bool oob;
+        spl_uni_cell(xv[d], gp.xmin[d], gp.dxin[d], gp.nodes[d], cell, f[d], oob);
+        any |= oob;
+        const unsigned st = d == 0 ? 1u : (d == 1 ? (unsigned)tl.s1 : (d == 2 ? (unsigned)tl.s2 : (unsigned)tl.s3));
+        base += (unsigned)cell * st;
+    }
+    return base | (any ? SPL_UNI_OOB : 0u);
+}
+template <int NDIM, bool VALUE>
+__device__ __forceinline__ double spl_eval_point_uni(const GridParams &gp, const DerivParams &dp, const TableLayout &tl,
+                                                     const double *__restrict__ cf, const double *xv, double scale) {
+    double f[NDIM];
+    const unsigned base = spl_uni_locate<NDIM>(gp, tl, xv, f);
+    return spl_eval_point_uni_at<NDIM, VALUE>(dp, tl, cf, f, base, scale);
+}
+
 template <int NDIM> struct EvalCfg {
     static constexpr int THREADS = (NDIM <= 3) ? 1024 : 512;
 };
@@ -182,9 +242,9 @@ template <int NDIM> struct EvalCfg {
 // ------------------------------------------------------------------------------------------
 #define EVAL_WCHUNK 256   // queries a warp claims per atomic (8 per lane)
 
-template <int NDIM, bool SMEM, bool VALUE>
+template <int NDIM, bool SMEM, bool VALUE, bool UNI = false>
 __global__ void __launch_bounds__(EvalCfg<NDIM>::THREADS, 1)
-spl_eval_kernel(const __grid_constant__ GridParams gp, const DerivParams dp,
+spl_eval_kernel(const __grid_constant__ GridParams gp, const DerivParams dp, const TableLayout tl,
                 const real_t *__restrict__ x, int l1x, long long nq,
                 const double *__restrict__ coef, long long ncol_padded, real_t *__restrict__ out,
                 unsigned long long *__restrict__ chunk_counter, const int *__restrict__ order_flag) {
@@ -195,10 +255,7 @@ spl_eval_kernel(const __grid_constant__ GridParams gp, const DerivParams dp,
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const double *cf = coef;
-    TableLayout tl;
-    tl.s1 = gp.nodes[0];
-    tl.s2 = gp.nodes[0] * gp.nodes[1];
-    tl.s3 = (long long)tl.s2 * gp.nodes[2];
+    const double uscale = UNI ? spl_uni_scale<NDIM>(gp, dp, VALUE) : 1.0;
     if (SMEM) {
         if (tid == 0) {
             mbar_init(&mbar, 1);
@@ -234,7 +291,9 @@ spl_eval_kernel(const __grid_constant__ GridParams gp, const DerivParams dp,
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) xn[d] = (q2 < nq) ? (double)x[q2 * (long long)l1x + d] : 0.0;
             }
-            if (q < nq) out[q] = (real_t)spl_eval_point<NDIM, VALUE>(gp, dp, tl, cf, xv);
+            if (q < nq)
+                out[q] = UNI ? (real_t)spl_eval_point_uni<NDIM, VALUE>(gp, dp, tl, cf, xv, uscale)
+                             : (real_t)spl_eval_point<NDIM, VALUE>(gp, dp, tl, cf, xv);
         }
     }
 }
@@ -254,7 +313,7 @@ template <int NDIM> struct RegroupCfg {
 // One CTA samples 32 groups of 32 CONSECUTIVE queries spread over the batch and counts the groups in which at least
 // RG_BYPASS queries share one bank class.  Both evaluation kernels are launched; the one the flag rules out exits at once.
 #define RG_BYPASS 12      // a batch with >= this many lanes in ONE class is coherent (raster order): evaluate it directly
-template <int NDIM>
+template <int NDIM, bool UNI = false>
 __global__ void __launch_bounds__(1024)
 spl_eval_probe_kernel(const __grid_constant__ GridParams gp, const TableLayout tl, const real_t *__restrict__ x, int l1x,
                       long long nq, int *__restrict__ order_flag) {
@@ -269,9 +328,16 @@ spl_eval_probe_kernel(const __grid_constant__ GridParams gp, const TableLayout t
         int lin = 0;
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) {
-            const double t = spl_mul(gp.dxin[d], spl_sub((double)x[q * (long long)l1x + d], gp.xmin[d]));
-            const int it = max(__double2int_rz(t), -4);
-            const int ws = min(max(it - 1, 0), gp.nodes[d] - 4);
+            int ws;
+            if (UNI) {
+                double f;
+                bool oob;
+                spl_uni_cell((double)x[q * (long long)l1x + d], gp.xmin[d], gp.dxin[d], gp.nodes[d], ws, f, oob);
+            } else {
+                const double t = spl_mul(gp.dxin[d], spl_sub((double)x[q * (long long)l1x + d], gp.xmin[d]));
+                const int it = max(__double2int_rz(t), -4);
+                ws = min(max(it - 1, 0), gp.nodes[d] - 4);
+            }
             lin += ws * (int)(st[d] & 15);
         }
         cls = lin & 15;
@@ -304,7 +370,56 @@ __global__ void spl_pad_table_kernel(const __grid_constant__ GridParams gp, cons
     }
 }
 
-template <int NDIM, bool VALUE, int NWARPS = RegroupCfg<NDIM>::NWARPS>
+// coefficient table -> EXTENDED table of the uniform form (basis.cuh): nodes + 2 entries per dimension (extended index
+// r = node + 1, r = 0 and r = nodes + 1 are the phantom nodes), strides tl.s1/s2/s3, zero-filled gaps.  Every entry is
+// a fixed-order sum of <= 2^ndim coefficients with exact weights (1, 2, 4, 6 per dimension).
+__device__ __forceinline__ void spl_uni_row(int r, int n, int &j0, double &w0, int &j1, double &w1) {
+    const int j = r - 1;
+    j1 = 0;
+    w1 = 0.0;
+    if (j == -1)          { j0 = 0; w0 = 4.0; j1 = 1; w1 = 6.0; }
+    else if (j == 0)      { j0 = 0; w0 = 2.0; j1 = 1; w1 = 4.0; }
+    else if (j == 1)      { j0 = 1; w0 = 2.0; }
+    else if (j == n)      { j0 = n - 1; w0 = 4.0; j1 = n - 2; w1 = 6.0; }
+    else if (j == n - 1)  { j0 = n - 1; w0 = 2.0; j1 = n - 2; w1 = 4.0; }
+    else if (j == n - 2)  { j0 = n - 2; w0 = 2.0; }
+    else                  { j0 = j; w0 = 1.0; }
+}
+__global__ void spl_uni_table_kernel(const __grid_constant__ GridParams gp, const TableLayout tl,
+                                     const double *__restrict__ coef, double *__restrict__ ext, long long total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long st[4] = {1, tl.s1, tl.s2, tl.s3};
+    long long mulv[4] = {1, 1, 1, 1};
+    for (int d = 1; d < gp.ndim; ++d) mulv[d] = mulv[d - 1] * gp.nodes[d - 1];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        long long rem = e;
+        bool ok = true;
+        int j0[SPL_MAXDIM], j1[SPL_MAXDIM];
+        double w0[SPL_MAXDIM], w1[SPL_MAXDIM];
+        for (int d = gp.ndim - 1; d >= 0; --d) {
+            const long long id = rem / st[d];
+            rem -= id * st[d];
+            if (id >= gp.nodes[d] + 2) ok = false;
+            spl_uni_row((int)id, gp.nodes[d], j0[d], w0[d], j1[d], w1[d]);
+        }
+        double v = 0.0;
+        if (ok) {
+            for (int m = 0; m < (1 << gp.ndim); ++m) {
+                double w = 1.0;
+                long long src = 0;
+                for (int d = 0; d < gp.ndim; ++d) {
+                    const bool second = (m >> d) & 1;
+                    w *= second ? w1[d] : w0[d];
+                    src += (second ? j1[d] : j0[d]) * mulv[d];
+                }
+                if (w != 0.0) v = fma(w, coef[src], v);
+            }
+        }
+        ext[e] = v;
+    }
+}
+
+template <int NDIM, bool VALUE, int NWARPS = RegroupCfg<NDIM>::NWARPS, bool UNI = false>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 spl_eval_regroup_kernel(const __grid_constant__ GridParams gp, const DerivParams dp, const TableLayout tl,
                         const real_t *__restrict__ x, int l1x, long long nq,
@@ -326,10 +441,14 @@ spl_eval_regroup_kernel(const __grid_constant__ GridParams gp, const DerivParams
     __syncthreads();
     mbar_wait(&mbar, 0);
     const double *cf = s_dyn;
-    // warp-private FIFOs: fx[d][slot][class] (doubles), ftag[slot][class] (query offset inside the CTA's range)
-    const int per_warp = cap * 16 * NDIM + cap * 8;                  // doubles (tags: 16 x 4 bytes per slot)
+    // warp-private FIFOs: fx[d][slot][class] (doubles: the coordinates, or their fractional parts in the uniform form),
+    // then per (slot, class) the query's offset inside the CTA's range (exact form: 4 bytes) or the pair
+    // (window base offset | out-of-range flag, query offset) (uniform form: 8 bytes)
+    const int per_warp = cap * 16 * NDIM + (UNI ? cap * 16 : cap * 8);
     double *fx = s_dyn + table_doubles + (size_t)warp * per_warp;
     unsigned *ftag = reinterpret_cast<unsigned *>(fx + cap * 16 * NDIM);
+    uint2 *fbt = reinterpret_cast<uint2 *>(fx + cap * 16 * NDIM);
+    const double uscale = UNI ? spl_uni_scale<NDIM>(gp, dp, VALUE) : 1.0;
 
     // this CTA's contiguous range of queries (offsets inside it fit 32 bits: checked by the launcher)
     const long long q_lo = nq * (long long)blockIdx.x / (long long)gridDim.x;
@@ -385,16 +504,25 @@ spl_eval_regroup_kernel(const __grid_constant__ GridParams gp, const DerivParams
     for (;;) {
         // ---- insert: bank class of the pending query = its base address in the table mod 16 ----
         int cls = 0;
-        if (pend) {
-            int lin = 0;
+        unsigned pbase = 0u;                                         // uniform form: base offset | out-of-range flag
+        double pf[NDIM];                                             // what goes into the FIFO
 #pragma unroll
-            for (int d = 0; d < NDIM; ++d) {
-                const double t = spl_mul(gp.dxin[d], spl_sub(px[d], gp.xmin[d]));
-                const int it = max(__double2int_rz(t), -4);
-                const int ws = min(max(it - 1, 0), gp.nodes[d] - 4);
-                lin += ws * stride16[d];
+        for (int d = 0; d < NDIM; ++d) pf[d] = px[d];
+        if (pend) {
+            if (UNI) {
+                pbase = spl_uni_locate<NDIM>(gp, tl, px, pf);
+                cls = (int)(pbase & 15u);
+            } else {
+                int lin = 0;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    const double t = spl_mul(gp.dxin[d], spl_sub(px[d], gp.xmin[d]));
+                    const int it = max(__double2int_rz(t), -4);
+                    const int ws = min(max(it - 1, 0), gp.nodes[d] - 4);
+                    lin += ws * stride16[d];
+                }
+                cls = lin & 15;
             }
-            cls = lin & 15;
         }
         const unsigned bp = __ballot_sync(full, pend);
         const unsigned v0 = __ballot_sync(full, pend && (cls & 1));
@@ -408,15 +536,16 @@ spl_eval_regroup_kernel(const __grid_constant__ GridParams gp, const DerivParams
         const int big = __reduce_max_sync(full, pend ? __popc(peers) : 0);
         bool take = false;
         double ex[NDIM];
-        unsigned etag = 0;
+        unsigned etag = 0, ebase = 0u;
 #pragma unroll
         for (int d = 0; d < NDIM; ++d) ex[d] = 0.0;
         if (big >= RG_BYPASS) {
             // coherent batch (raster order): the lanes evaluate their own queries, the gathers broadcast
             take = pend;
 #pragma unroll
-            for (int d = 0; d < NDIM; ++d) ex[d] = px[d];
+            for (int d = 0; d < NDIM; ++d) ex[d] = pf[d];
             etag = ptag;
+            ebase = pbase;
             pend = false;
         } else {
             const int st = __shfl_sync(full, (head << 8) | cnt, cls);           // cursor of my query's class
@@ -426,8 +555,9 @@ spl_eval_regroup_kernel(const __grid_constant__ GridParams gp, const DerivParams
                 int slot = qh + qc + rank;
                 if (slot >= cap) slot -= cap;
 #pragma unroll
-                for (int d = 0; d < NDIM; ++d) fx[(d * cap + slot) * 16 + cls] = px[d];
-                ftag[slot * 16 + cls] = ptag;
+                for (int d = 0; d < NDIM; ++d) fx[(d * cap + slot) * 16 + cls] = pf[d];
+                if (UNI) fbt[slot * 16 + cls] = make_uint2(pbase, ptag);
+                else ftag[slot * 16 + cls] = ptag;
                 pend = false;
             }
             cnt += min(__popc(arr), cap - cnt);
@@ -439,7 +569,13 @@ spl_eval_regroup_kernel(const __grid_constant__ GridParams gp, const DerivParams
                 if (slot >= cap) slot -= cap;
 #pragma unroll
                 for (int d = 0; d < NDIM; ++d) ex[d] = fx[(d * cap + slot) * 16 + dc];
-                etag = ftag[slot * 16 + dc];
+                if (UNI) {
+                    const uint2 bt = fbt[slot * 16 + dc];
+                    ebase = bt.x;
+                    etag = bt.y;
+                } else {
+                    etag = ftag[slot * 16 + dc];
+                }
             }
             const int n = min(cnt, 2);
             head += n;
@@ -448,7 +584,10 @@ spl_eval_regroup_kernel(const __grid_constant__ GridParams gp, const DerivParams
             __syncwarp();
         }
         refill();
-        if (take) ob[etag] = (real_t)spl_eval_point<NDIM, VALUE>(gp, dp, tl, cf, ex);
+        if (take) {
+            if (UNI) ob[etag] = (real_t)spl_eval_point_uni_at<NDIM, VALUE>(dp, tl, cf, ex, ebase, uscale);
+            else ob[etag] = (real_t)spl_eval_point<NDIM, VALUE>(gp, dp, tl, cf, ex);
+        }
         if (done && !__any_sync(full, pend || cnt > 0)) break;
     }
 }
@@ -466,16 +605,19 @@ struct RegroupPlan {
     int key_ndim = 0, key_nodes[SPL_MAXDIM] = {0, 0, 0, 0}, key_warps = 0;
     size_t key_smem = 0;
 };
-static double class_pmax(const GridParams &gp, const long long *st) {
+// uni: the table is the extended one of the uniform form (nodes + 2 per dimension, window base = cell index)
+static double class_pmax(const GridParams &gp, const long long *st, bool uni) {
     double dist[16] = {1.0};
     for (int c = 1; c < 16; ++c) dist[c] = 0.0;
     for (int d = 0; d < gp.ndim; ++d) {
         double pd[16] = {0.0};
         const int nod = gp.nodes[d];
         for (int it = 0; it < nod - 1; ++it) {
-            int ws = it - 1;
-            if (ws < 0) ws = 0;
-            if (ws > nod - 4) ws = nod - 4;
+            int ws = uni ? it : it - 1;
+            if (!uni) {
+                if (ws < 0) ws = 0;
+                if (ws > nod - 4) ws = nod - 4;
+            }
             pd[(int)((ws * (st[d] & 15)) & 15)] += 1.0 / (double)(nod - 1);
         }
         double nx[16] = {0.0};
@@ -496,8 +638,9 @@ static int regroup_warps(int ndim) {
     }
     return nw;
 }
-static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin) {
-    static thread_local RegroupPlan plan;
+static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin, bool uni) {
+    static thread_local RegroupPlan plans[2];
+    RegroupPlan &plan = plans[uni ? 1 : 0];
     const int nwarps = regroup_warps(gp.ndim);
     bool same = plan.key_ndim == gp.ndim && plan.key_smem == smem_optin && plan.key_warps == nwarps;
     for (int d = 0; d < SPL_MAXDIM && same; ++d) same = plan.key_nodes[d] == gp.nodes[d];
@@ -508,9 +651,11 @@ static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin) 
     plan.key_warps = nwarps;
     for (int d = 0; d < SPL_MAXDIM; ++d) plan.key_nodes[d] = gp.nodes[d];
     if (gp.ndim < 2) return plan;
-    const long long n0 = gp.nodes[0], n1 = gp.nodes[1], n2 = gp.ndim > 2 ? gp.nodes[2] : 1, n3 = gp.ndim > 3 ? gp.nodes[3] : 1;
+    const int ext = uni ? 2 : 0;
+    const long long n0 = gp.nodes[0] + ext, n1 = gp.nodes[1] + ext, n2 = gp.ndim > 2 ? gp.nodes[2] + ext : 1,
+                    n3 = gp.ndim > 3 ? gp.nodes[3] + ext : 1;
     const size_t reserve = 1024;                                       // static shared memory + alignment
-    const size_t per_slot = (size_t)nwarps * 16 * (8 * gp.ndim + 4);   // bytes of FIFO per unit of cap
+    const size_t per_slot = (size_t)nwarps * 16 * (8 * gp.ndim + (uni ? 8 : 4));   // bytes of FIFO per unit of cap
     double best = 1e30;
     const int r1 = gp.ndim == 4 ? 4 : 8, r2 = gp.ndim == 4 ? 8 : 16;
     for (long long s1 = n0; s1 < n0 + r1; ++s1)
@@ -521,7 +666,7 @@ static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin) 
                 const size_t tbytes = (size_t)total * sizeof(double);
                 if (tbytes + reserve + 4 * per_slot > smem_optin || total >= (1LL << 28)) continue;
                 const long long st[4] = {1, s1, s2, s3};
-                const double pm = class_pmax(gp, st);
+                const double pm = class_pmax(gp, st, uni);
                 long long cap = (long long)((smem_optin - reserve - tbytes) / per_slot);
                 if (cap > 16) cap = 16;
                 // estimated lane efficiency: the hottest class bounds it; short FIFOs lose a little more
@@ -542,44 +687,118 @@ static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin) 
     return plan;
 }
 
-// 0: the plain kernel will run; otherwise the number of doubles of padded-table scratch the regrouping kernel needs
+static TableLayout natural_layout(const GridParams &gp, int ext) {
+    TableLayout tl;
+    tl.s1 = gp.nodes[0] + ext;
+    tl.s2 = tl.s1 * (gp.ndim > 1 ? gp.nodes[1] + ext : 1);
+    tl.s3 = (long long)tl.s2 * (gp.ndim > 2 ? gp.nodes[2] + ext : 1);
+    return tl;
+}
+static long long natural_doubles(const GridParams &gp, int ext) {
+    long long t = 1;
+    for (int d = 0; d < gp.ndim; ++d) t *= gp.nodes[d] + ext;
+    return (t + 1) & ~1LL;
+}
+
+// How a batch is evaluated (decided once on the host, the same way by the scratch sizing and by the launcher):
+//   uni      uniform (phantom-node) form: extended table in shared memory, 9-operation basis (basis.cuh).  Chosen for
+//            every batch large enough to pay for the table transform whose extended table fits in shared memory and
+//            whose nderiv is valid (0..2); SPLPAK_B200_BASIS=exact forces the node-by-node formulas of bascmp.
+//   regroup  scattered-order kernel with warp-private bank-class FIFOs (+ order probe unless forced)
+struct EvalRoute {
+    bool uni = false, regroup = false, force_regroup = false;
+    TableLayout tl;                 // layout of the table the kernels read (extended and/or padded)
+    long long table_doubles = 0;    // its size; 0: the caller's table is read directly
+};
+static EvalRoute eval_route(const GridParams &gp, const int *nderiv, long long nq, int nsm, size_t smem_optin) {
+    EvalRoute r;
+    r.tl = natural_layout(gp, 0);
+    const char *mode = getenv("SPLPAK_B200_EVAL");
+    const char *basis = getenv("SPLPAK_B200_BASIS");
+    const bool plain_only = mode && strcmp(mode, "plain") == 0;
+    r.force_regroup = mode && strcmp(mode, "regroup") == 0;
+    bool valid = true;
+    for (int d = 0; d < gp.ndim; ++d)
+        if (nderiv && (nderiv[d] < 0 || nderiv[d] > 2)) valid = false;
+    const long long ext_doubles = natural_doubles(gp, 2);
+    const bool force_uni = basis && strcmp(basis, "uniform") == 0;
+    bool uni = valid && !(basis && strcmp(basis, "exact") == 0) && (size_t)ext_doubles * 8 + 2048 <= smem_optin &&
+               (force_uni || nq * (long long)spl_ipow(4, gp.ndim) * 16 > ext_doubles);
+    // measured (profiles/r02_eval_ab.md): 3-D 45.5 -> 30.0 ms and 4-D 201 -> 84 ms per 1e9 random queries; 2-D gathers only
+    // 16 values per query and is faster in the plain kernel (12.1 vs 17.2 ms), so it regroups only when forced
+    bool rg = !plain_only && gp.ndim >= 2 && (r.force_regroup || (gp.ndim >= 3 && nq >= (1LL << 18))) &&
+              nq / (nsm > 0 ? nsm : 1) < (1LL << 32) - 1024;
+    if (rg) {
+        const RegroupPlan &pl = regroup_plan(gp, smem_optin, uni);
+        if (pl.ok) {
+            r.regroup = true;
+            r.tl = pl.tl;
+            r.table_doubles = pl.table_doubles;
+        } else if (uni) {
+            // the extended table leaves no room for the FIFOs: scattered batches keep the exact form if that regroups
+            const RegroupPlan &pe = regroup_plan(gp, smem_optin, false);
+            if (pe.ok) {
+                uni = false;
+                r.regroup = true;
+                r.tl = pe.tl;
+                r.table_doubles = pe.table_doubles;
+            }
+        }
+    }
+    r.uni = uni;
+    if (uni && !r.regroup) {
+        r.tl = natural_layout(gp, 2);
+        r.table_doubles = ext_doubles;
+    }
+    return r;
+}
+
+// doubles of device scratch the evaluation of this batch needs behind the caller's table (+ 2 for the order flag): the
+// extended and/or padded copy of the table.  0: none.
+long long spl_eval_scratch_elems(const GridParams &gp, const int *nderiv, long long nq, int nsm, size_t smem_optin) {
+    return eval_route(gp, nderiv, nq, nsm, smem_optin).table_doubles;
+}
+// the exact-form regrouping kernel alone (REAL32 library, 4-D): 0 or the number of doubles of its padded table
 long long spl_eval_regroup_elems(const GridParams &gp, long long nq, int nsm, size_t smem_optin) {
     const char *mode = getenv("SPLPAK_B200_EVAL");
     if (mode && strcmp(mode, "plain") == 0) return 0;
     const bool force = mode && strcmp(mode, "regroup") == 0;
-    // measured (profiles/r02_eval_ab.md): 3-D 45.5 -> 30.0 ms and 4-D 201 -> 84 ms per 1e9 random queries; 2-D gathers only
-    // 16 values per query and is faster in the plain kernel (12.1 vs 17.2 ms), so it regroups only when forced
     if (gp.ndim < 2 || (!force && (gp.ndim < 3 || nq < (1LL << 18)))) return 0;
     if (nq / (nsm > 0 ? nsm : 1) >= (1LL << 32) - 1024) return 0;
-    const RegroupPlan &pl = regroup_plan(gp, smem_optin);
+    const RegroupPlan &pl = regroup_plan(gp, smem_optin, false);
     return pl.ok ? pl.table_doubles : 0;
 }
 
-template <int NDIM, bool VALUE>
+// table image for the kernels: padded copy (exact form) or extended table (uniform form)
+static void launch_table(const GridParams &gp, const TableLayout &tl, long long total, bool uni, const double *d_coef,
+                         double *d_tab, cudaStream_t stream) {
+    long long blocks = (total + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    if (uni) spl_uni_table_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gp, tl, d_coef, d_tab, total);
+    else spl_pad_table_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gp, tl, d_coef, d_tab, total);
+    ++g_spl_launches;
+}
+
+// d_tab: the table image launch_table() made for this plan
+template <int NDIM, bool VALUE, bool UNI>
 static int launch_eval_regroup(const GridParams &gp, const DerivParams &dp, const real_t *d_x, int l1x, long long nq,
-                               const double *d_coef, double *d_pad, real_t *d_out, cudaStream_t stream, int nsm,
+                               const double *d_tab, real_t *d_out, cudaStream_t stream, int nsm,
                                size_t smem_optin, int *d_flag) {
-    const RegroupPlan &pl = regroup_plan(gp, smem_optin);
+    const RegroupPlan &pl = regroup_plan(gp, smem_optin, UNI);
     if (d_flag) {
-        spl_eval_probe_kernel<NDIM><<<1, 1024, 0, stream>>>(gp, pl.tl, d_x, l1x, nq, d_flag);
-        ++g_spl_launches;
-    }
-    {
-        long long blocks = (pl.table_doubles + 255) / 256;
-        if (blocks > 1024) blocks = 1024;
-        spl_pad_table_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gp, pl.tl, d_coef, d_pad, pl.table_doubles);
+        spl_eval_probe_kernel<NDIM, UNI><<<1, 1024, 0, stream>>>(gp, pl.tl, d_x, l1x, nq, d_flag);
         ++g_spl_launches;
     }
     void (*kern)(GridParams, DerivParams, TableLayout, const real_t *, int, long long, const double *, unsigned, int,
-                 real_t *, const int *) = spl_eval_regroup_kernel<NDIM, VALUE>;
-    if (NDIM == 3 && pl.nwarps == 16) kern = spl_eval_regroup_kernel<NDIM, VALUE, (NDIM == 3 ? 16 : RegroupCfg<NDIM>::NWARPS)>;
-    if (NDIM == 3 && pl.nwarps == 32) kern = spl_eval_regroup_kernel<NDIM, VALUE, (NDIM == 3 ? 32 : RegroupCfg<NDIM>::NWARPS)>;
+                 real_t *, const int *) = spl_eval_regroup_kernel<NDIM, VALUE, RegroupCfg<NDIM>::NWARPS, UNI>;
+    if (NDIM == 3 && pl.nwarps == 16) kern = spl_eval_regroup_kernel<NDIM, VALUE, (NDIM == 3 ? 16 : RegroupCfg<NDIM>::NWARPS), UNI>;
+    if (NDIM == 3 && pl.nwarps == 32) kern = spl_eval_regroup_kernel<NDIM, VALUE, (NDIM == 3 ? 32 : RegroupCfg<NDIM>::NWARPS), UNI>;
     SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     long long grid = nsm;
     const long long per_cta_min = 4096;                 // tiny batches: fewer CTAs, each with a useful range
     if (grid > (nq + per_cta_min - 1) / per_cta_min) grid = (nq + per_cta_min - 1) / per_cta_min;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, pl.nwarps * 32, pl.smem, stream>>>(gp, dp, pl.tl, d_x, l1x, nq, d_pad,
+    kern<<<(unsigned)grid, pl.nwarps * 32, pl.smem, stream>>>(gp, dp, pl.tl, d_x, l1x, nq, d_tab,
                                                                              (unsigned)pl.table_doubles, pl.cap, d_out, d_flag);
     ++g_spl_launches;
     SPL_CUDA_TRY(cudaGetLastError());
@@ -712,7 +931,9 @@ int spl_eval_f32_mixed4_launch(const GridParams &gp, const real_t *d_x, int l1x,
     DerivParams dp;
     for (int d = 0; d < SPL_MAXDIM; ++d) dp.nd[d] = 0;
     int *d_flag = reinterpret_cast<int *>(d_pad + pad_elems);
-    int rc = launch_eval_regroup<4, true>(gp, dp, d_x, l1x, nq, d_coef64, d_pad, d_out, stream, nsm, smem_optin, d_flag);
+    const RegroupPlan &pl = regroup_plan(gp, smem_optin, false);
+    launch_table(gp, pl.tl, pl.table_doubles, false, d_coef64, d_pad, stream);
+    int rc = launch_eval_regroup<4, true, false>(gp, dp, d_x, l1x, nq, d_pad, d_out, stream, nsm, smem_optin, d_flag);
     if (rc != SPLPAK_OK) return rc;
     return launch_eval_f32<4>(gp, d_x, l1x, nq, d_coef, d_out, stream, nsm, smem_optin, d_counter, d_flag);
 }
@@ -721,44 +942,74 @@ int spl_eval_f32_mixed4_launch(const GridParams &gp, const real_t *d_x, int l1x,
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int NDIM, bool VALUE>
-static int launch_eval(const GridParams &gp, const DerivParams &dp, const real_t *d_x, int l1x,
-                       long long nq, const double *d_coef, long long ncol_padded, real_t *d_out,
+// d_tab: the table the kernel reads, tab_doubles (even) entries laid out as tl
+template <int NDIM, bool VALUE, bool UNI>
+static int launch_eval(const GridParams &gp, const DerivParams &dp, const TableLayout &tl, const real_t *d_x, int l1x,
+                       long long nq, const double *d_tab, long long tab_doubles, real_t *d_out,
                        cudaStream_t stream, int nsm, size_t smem_optin, unsigned long long *d_counter,
                        const int *d_flag = nullptr) {
     constexpr int THREADS = EvalCfg<NDIM>::THREADS;
-    const size_t coef_bytes = (size_t)ncol_padded * sizeof(double);
+    const size_t coef_bytes = (size_t)tab_doubles * sizeof(double);
     const size_t static_reserve = 2048;
     SPL_CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
     // a handful of queries (scalar splfe / splde calls): gathering 4^ndim values from L2 is cheaper than staging the table
     const bool use_smem = coef_bytes + static_reserve <= smem_optin && coef_bytes < (1u << 20) &&
-                          nq * (long long)spl_ipow(4, NDIM) * 64 > (long long)coef_bytes / 8;
+                          (UNI || nq * (long long)spl_ipow(4, NDIM) * 64 > (long long)coef_bytes / 8);
     long long chunks = (nq + EVAL_WCHUNK - 1) / EVAL_WCHUNK;
     long long ctas = (chunks + THREADS / 32 - 1) / (THREADS / 32);
     if (ctas < 1) ctas = 1;
     if (use_smem) {
-        auto kern = spl_eval_kernel<NDIM, true, VALUE>;
+        auto kern = spl_eval_kernel<NDIM, true, VALUE, UNI>;
         SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coef_bytes));
         long long grid = nsm;
         if (grid > ctas) grid = ctas;
-        kern<<<(unsigned)grid, THREADS, coef_bytes, stream>>>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out,
+        kern<<<(unsigned)grid, THREADS, coef_bytes, stream>>>(gp, dp, tl, d_x, l1x, nq, d_tab, tab_doubles, d_out,
                                                               d_counter, d_flag);
     } else {
-        auto kern = spl_eval_kernel<NDIM, false, VALUE>;
+        auto kern = spl_eval_kernel<NDIM, false, VALUE, UNI>;
         long long grid = (long long)nsm * (2048 / THREADS);
         if (grid > ctas) grid = ctas;
-        kern<<<(unsigned)grid, THREADS, 0, stream>>>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out, d_counter, d_flag);
+        kern<<<(unsigned)grid, THREADS, 0, stream>>>(gp, dp, tl, d_x, l1x, nq, d_tab, tab_doubles, d_out, d_counter, d_flag);
     }
     ++g_spl_launches;
     SPL_CUDA_TRY(cudaGetLastError());
     return SPLPAK_OK;
 }
 
-// d_coef: float64 device table with ncol_padded (even, >= ncol) entries; d_counter: 8-byte scratch; d_pad: scratch of
-// spl_eval_regroup_elems() doubles (or NULL: the plain kernel runs).
+template <int NDIM, bool VALUE, bool UNI>
+static int eval_dispatch(const GridParams &gp, const DerivParams &dp, const EvalRoute &rt, const real_t *d_x, int l1x,
+                         long long nq, const double *d_coef, long long ncol_padded, real_t *d_out, cudaStream_t stream,
+                         int nsm, size_t smem_optin, unsigned long long *d_counter, double *d_scratch) {
+    const double *tab = d_coef;
+    long long tab_doubles = ncol_padded;
+    if (rt.table_doubles > 0) {
+        launch_table(gp, rt.tl, rt.table_doubles, UNI, d_coef, d_scratch, stream);
+        tab = d_scratch;
+        tab_doubles = rt.table_doubles;
+    }
+    if (rt.regroup) {
+        if constexpr (NDIM >= 2) {
+            // forced ("regroup"): the regrouping kernel alone.  Default: order probe, then BOTH kernels -- the probe's flag
+            // (behind the table image in d_scratch) makes the wrong one exit immediately.
+            int *d_flag = rt.force_regroup ? nullptr : reinterpret_cast<int *>(d_scratch + rt.table_doubles);
+            int rc = launch_eval_regroup<NDIM, VALUE, UNI>(gp, dp, d_x, l1x, nq, tab, d_out, stream, nsm, smem_optin, d_flag);
+            if (rc != SPLPAK_OK || !d_flag) return rc;
+            // the plain kernel reads the same (padded) image when it is the extended table; the exact form reads the caller's
+            if (UNI) return launch_eval<NDIM, VALUE, UNI>(gp, dp, rt.tl, d_x, l1x, nq, tab, tab_doubles, d_out, stream, nsm,
+                                                          smem_optin, d_counter, d_flag);
+            return launch_eval<NDIM, VALUE, false>(gp, dp, natural_layout(gp, 0), d_x, l1x, nq, d_coef, ncol_padded, d_out,
+                                                   stream, nsm, smem_optin, d_counter, d_flag);
+        }
+    }
+    return launch_eval<NDIM, VALUE, UNI>(gp, dp, rt.tl, d_x, l1x, nq, tab, tab_doubles, d_out, stream, nsm, smem_optin,
+                                         d_counter);
+}
+
+// d_coef: float64 device table with ncol_padded (even, >= ncol) entries; d_counter: 8-byte scratch; d_scratch: scratch of
+// spl_eval_scratch_elems() + 2 doubles (or NULL when that is 0, or when the allocation failed: exact plain kernel).
 int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, int l1x, long long nq,
                     const double *d_coef, long long ncol_padded, real_t *d_out, cudaStream_t stream,
-                    int nsm, size_t smem_optin, unsigned long long *d_counter, double *d_pad) {
+                    int nsm, size_t smem_optin, unsigned long long *d_counter, double *d_scratch) {
     DerivParams dp;
     bool value = true;
     for (int d = 0; d < SPL_MAXDIM; ++d) {
@@ -766,37 +1017,22 @@ int spl_eval_launch(const GridParams &gp, const int *nderiv, const real_t *d_x, 
         if (dp.nd[d] != 0) value = false;
     }
     if (nq <= 0) return SPLPAK_OK;
-    if (d_pad && spl_eval_regroup_elems(gp, nq, nsm, smem_optin) > 0) {
-        // forced ("regroup"): the regrouping kernel alone.  Default: order probe, then BOTH kernels -- the probe's flag
-        // (behind the padded table in d_pad) makes the wrong one exit immediately.
-        const char *mode = getenv("SPLPAK_B200_EVAL");
-        const bool force = mode && strcmp(mode, "regroup") == 0;
-        int *d_flag = force ? nullptr : reinterpret_cast<int *>(d_pad + spl_eval_regroup_elems(gp, nq, nsm, smem_optin));
-        int rc = SPLPAK_ERR_NDIM;
-#define SPL_RG_CASE(N)                                                                                              \
-    case N:                                                                                                         \
-        rc = value ? launch_eval_regroup<N, true>(gp, dp, d_x, l1x, nq, d_coef, d_pad, d_out, stream, nsm, smem_optin, d_flag) \
-                   : launch_eval_regroup<N, false>(gp, dp, d_x, l1x, nq, d_coef, d_pad, d_out, stream, nsm, smem_optin, d_flag); \
-        if (rc == SPLPAK_OK && d_flag)                                                                              \
-            rc = value ? launch_eval<N, true>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, smem_optin, \
-                                              d_counter, d_flag)                                                    \
-                       : launch_eval<N, false>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, smem_optin, \
-                                               d_counter, d_flag);                                                  \
-        return rc;
-        switch (gp.ndim) {
-            SPL_RG_CASE(2)
-            SPL_RG_CASE(3)
-            SPL_RG_CASE(4)
-        }
-#undef SPL_RG_CASE
-        return rc;
+    EvalRoute rt = eval_route(gp, nderiv, nq, nsm, smem_optin);
+    if (!d_scratch && rt.table_doubles > 0) {
+        rt = EvalRoute();                         // no scratch: the exact plain kernel on the caller's table
+        rt.tl = natural_layout(gp, 0);
     }
-#define SPL_EVAL_CASE(N)                                                                                  \
-    case N:                                                                                               \
-        return value ? launch_eval<N, true>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, \
-                                            smem_optin, d_counter)                                        \
-                     : launch_eval<N, false>(gp, dp, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, \
-                                             smem_optin, d_counter);
+#define SPL_EVAL_CASE(N)                                                                                              \
+    case N:                                                                                                           \
+        if (rt.uni)                                                                                                   \
+            return value ? eval_dispatch<N, true, true>(gp, dp, rt, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, \
+                                                        smem_optin, d_counter, d_scratch)                             \
+                         : eval_dispatch<N, false, true>(gp, dp, rt, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, \
+                                                         smem_optin, d_counter, d_scratch);                           \
+        return value ? eval_dispatch<N, true, false>(gp, dp, rt, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, \
+                                                     smem_optin, d_counter, d_scratch)                                \
+                     : eval_dispatch<N, false, false>(gp, dp, rt, d_x, l1x, nq, d_coef, ncol_padded, d_out, stream, nsm, \
+                                                      smem_optin, d_counter, d_scratch);
     switch (gp.ndim) {
         SPL_EVAL_CASE(1)
         SPL_EVAL_CASE(2)
