@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import splpak_b200 as sp
 from splpak_b200 import synth
-GRIDS = {2: [64, 64], 3: [24, 24, 24], 4: [12, 12, 12, 12]}
+GRIDS = {1: [50], 2: [64, 64], 3: [24, 24, 24], 4: [12, 12, 12, 12]}
 nq0 = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000_000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 dims = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [3, 2, 4]

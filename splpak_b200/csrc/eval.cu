@@ -250,10 +250,13 @@ spl_eval_kernel(const __grid_constant__ GridParams gp, const DerivParams dp, con
                 unsigned long long *__restrict__ chunk_counter, const int *__restrict__ order_flag) {
     extern __shared__ __align__(128) double s_dyn[];
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ unsigned long long s_chunk;
     // order_flag (spl_eval_probe_kernel): 1 = the batch is scattered and the regrouping kernel evaluates it
     if (order_flag && *order_flag == 1) return;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    if (tid == 0) s_chunk = 0ULL;
+    if (!SMEM) __syncthreads();
     const double *cf = coef;
     const double uscale = UNI ? spl_uni_scale<NDIM>(gp, dp, VALUE) : 1.0;
     if (SMEM) {
@@ -267,18 +270,79 @@ spl_eval_kernel(const __grid_constant__ GridParams gp, const DerivParams dp, con
         mbar_wait(&mbar, 0);
         cf = s_dyn;
     }
+    if constexpr (NDIM <= 2 && UNI) {
+        // 1-D / 2-D in the uniform form are bound by HBM, not by arithmetic: keep a whole chunk of coordinates per warp in
+        // flight (KQ queries per lane, the NEXT chunk's loads issued before the current chunk is evaluated; 16-byte loads
+        // for packed 2-D float64 points) -- one 8-byte load per lane in flight reaches only ~57 % of the HBM roof.
+        constexpr int KQ = NDIM == 1 ? 8 : (VALUE ? 4 : 3);
+        constexpr int CH = KQ * 32;
+        const bool vec2 = NDIM == 2 && l1x == 2 && sizeof(real_t) == 8 && ((uintptr_t)x % 16 == 0);
+        double cur[KQ][NDIM], nxt[KQ][NDIM];
+        long long cbase = -1, nbase = -1;
+        // static schedule (every query costs the same): CTA b owns a contiguous range, its warps take the chunks of that
+        // range round robin -- no atomics (3.9e6 same-address atomics per 1e9 queries cost as much as the kernel itself)
+        const long long q_lo = nq * (long long)blockIdx.x / (long long)gridDim.x;
+        const long long q_hi = nq * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
+        long long next_chunk = q_lo + (long long)(tid >> 5) * CH;
+        auto claim = [&]() -> long long {
+            const long long b = next_chunk;
+            next_chunk += (long long)(blockDim.x >> 5) * CH;
+            return b < q_hi ? b : -1;
+        };
+        auto issue = [&](long long b) {
+            if (b < 0) return;
+#pragma unroll
+            for (int k = 0; k < KQ; ++k) {
+                const long long q = b + k * 32 + lane;
+                if (q < q_hi) {
+                    if (NDIM == 2 && vec2) {
+                        const double2 v = reinterpret_cast<const double2 *>(x)[q];
+                        nxt[k][0] = v.x;
+                        nxt[k][NDIM - 1] = v.y;
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < NDIM; ++d) nxt[k][d] = (double)x[q * (long long)l1x + d];
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < NDIM; ++d) nxt[k][d] = 0.0;
+                }
+            }
+        };
+        nbase = claim();
+        issue(nbase);
+        while (nbase >= 0) {
+            cbase = nbase;
+#pragma unroll
+            for (int k = 0; k < KQ; ++k)
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) cur[k][d] = nxt[k][d];
+            nbase = claim();
+            issue(nbase);
+#pragma unroll
+            for (int k = 0; k < KQ; ++k) {
+                const long long q = cbase + k * 32 + lane;
+                if (q < q_hi) out[q] = (real_t)spl_eval_point_uni<NDIM, VALUE>(gp, dp, tl, cf, cur[k], uscale);
+            }
+        }
+        return;
+    }
+    // CTA b owns a contiguous range of the batch; its warps claim chunks of that range from a SHARED-memory counter
+    // (one same-address global atomic per 256 queries, 3.9e6 per 1e9, serialises in L2 for milliseconds)
+    const long long q_lo = nq * (long long)blockIdx.x / (long long)gridDim.x;
+    const long long q_hi = nq * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
     for (;;) {
         unsigned long long c = 0;
-        if (lane == 0) c = atomicAdd(chunk_counter, 1ULL);
+        if (lane == 0) c = atomicAdd(&s_chunk, 1ULL);
         c = __shfl_sync(0xffffffffu, c, 0);
-        const long long base = (long long)c * EVAL_WCHUNK;
-        if (base >= nq) break;
+        const long long base = q_lo + (long long)c * EVAL_WCHUNK;
+        if (base >= q_hi) break;
         // software pipeline: the coordinates of the next sub-step are in flight while this one is evaluated
         double xn[NDIM];
         {
             const long long q = base + lane;
 #pragma unroll
-            for (int d = 0; d < NDIM; ++d) xn[d] = (q < nq) ? (double)x[q * (long long)l1x + d] : 0.0;
+            for (int d = 0; d < NDIM; ++d) xn[d] = (q < q_hi) ? (double)x[q * (long long)l1x + d] : 0.0;
         }
 #pragma unroll 1
         for (int sub = 0; sub < EVAL_WCHUNK / 32; ++sub) {
@@ -289,9 +353,9 @@ spl_eval_kernel(const __grid_constant__ GridParams gp, const DerivParams dp, con
             const long long q2 = q + 32;
             if (sub + 1 < EVAL_WCHUNK / 32) {
 #pragma unroll
-                for (int d = 0; d < NDIM; ++d) xn[d] = (q2 < nq) ? (double)x[q2 * (long long)l1x + d] : 0.0;
+                for (int d = 0; d < NDIM; ++d) xn[d] = (q2 < q_hi) ? (double)x[q2 * (long long)l1x + d] : 0.0;
             }
-            if (q < nq)
+            if (q < q_hi)
                 out[q] = UNI ? (real_t)spl_eval_point_uni<NDIM, VALUE>(gp, dp, tl, cf, xv, uscale)
                              : (real_t)spl_eval_point<NDIM, VALUE>(gp, dp, tl, cf, xv);
         }
@@ -630,18 +694,21 @@ static double class_pmax(const GridParams &gp, const long long *st, bool uni) {
     return m;
 }
 // warps per CTA of the regrouping kernel (SPLPAK_B200_RG_WARPS = 16 | 24 | 32 overrides the default for experiments)
-static int regroup_warps(int ndim) {
+static int regroup_warps(int ndim, bool uni) {
     int nw = ndim == 2 ? RegroupCfg<2>::NWARPS : (ndim == 3 ? RegroupCfg<3>::NWARPS : RegroupCfg<4>::NWARPS);
+    // uniform form, 3-D: the larger extended table leaves less room for the FIFOs; 16 warps keep them 9 deep
+    // (measured 8 / 12 / 16 / 24 / 32 warps: 28.4 / 24.2 / 22.9 / 24.3 / 24.1 ms per 1e9 scattered queries)
+    if (ndim == 3 && uni) nw = 16;
     if (const char *e = getenv("SPLPAK_B200_RG_WARPS")) {
         const int v = atoi(e);
-        if (ndim == 3 && (v == 16 || v == 24 || v == 32)) nw = v;
+        if (ndim == 3 && (v == 8 || v == 12 || v == 16 || v == 24 || v == 32)) nw = v;
     }
     return nw;
 }
 static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin, bool uni) {
     static thread_local RegroupPlan plans[2];
     RegroupPlan &plan = plans[uni ? 1 : 0];
-    const int nwarps = regroup_warps(gp.ndim);
+    const int nwarps = regroup_warps(gp.ndim, uni);
     bool same = plan.key_ndim == gp.ndim && plan.key_smem == smem_optin && plan.key_warps == nwarps;
     for (int d = 0; d < SPL_MAXDIM && same; ++d) same = plan.key_nodes[d] == gp.nodes[d];
     if (same) return plan;
@@ -668,7 +735,7 @@ static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin, 
                 const long long st[4] = {1, s1, s2, s3};
                 const double pm = class_pmax(gp, st, uni);
                 long long cap = (long long)((smem_optin - reserve - tbytes) / per_slot);
-                if (cap > 16) cap = 16;
+                if (cap > 24) cap = 24;
                 // estimated lane efficiency: the hottest class bounds it; short FIFOs lose a little more
                 const double eff = (1.0 / (16.0 * pm)) * (1.0 - 0.6 / (double)cap);
                 const double score = -eff;
@@ -726,7 +793,8 @@ static EvalRoute eval_route(const GridParams &gp, const int *nderiv, long long n
                (force_uni || nq * (long long)spl_ipow(4, gp.ndim) * 16 > ext_doubles);
     // measured (profiles/r02_eval_ab.md): 3-D 45.5 -> 30.0 ms and 4-D 201 -> 84 ms per 1e9 random queries; 2-D gathers only
     // 16 values per query and is faster in the plain kernel (12.1 vs 17.2 ms), so it regroups only when forced
-    bool rg = !plain_only && gp.ndim >= 2 && (r.force_regroup || (gp.ndim >= 3 && nq >= (1LL << 18))) &&
+    // uniform form (profiles/r02_eval_uniform.md): 2-D scattered 10.2 (regrouped) vs 11.9 ms (plain), so 2-D regroups as well
+    bool rg = !plain_only && gp.ndim >= 2 && (r.force_regroup || ((gp.ndim >= 3 || uni) && nq >= (1LL << 18))) &&
               nq / (nsm > 0 ? nsm : 1) < (1LL << 32) - 1024;
     if (rg) {
         const RegroupPlan &pl = regroup_plan(gp, smem_optin, uni);
@@ -791,6 +859,8 @@ static int launch_eval_regroup(const GridParams &gp, const DerivParams &dp, cons
     }
     void (*kern)(GridParams, DerivParams, TableLayout, const real_t *, int, long long, const double *, unsigned, int,
                  real_t *, const int *) = spl_eval_regroup_kernel<NDIM, VALUE, RegroupCfg<NDIM>::NWARPS, UNI>;
+    if (NDIM == 3 && pl.nwarps == 8) kern = spl_eval_regroup_kernel<NDIM, VALUE, (NDIM == 3 ? 8 : RegroupCfg<NDIM>::NWARPS), UNI>;
+    if (NDIM == 3 && pl.nwarps == 12) kern = spl_eval_regroup_kernel<NDIM, VALUE, (NDIM == 3 ? 12 : RegroupCfg<NDIM>::NWARPS), UNI>;
     if (NDIM == 3 && pl.nwarps == 16) kern = spl_eval_regroup_kernel<NDIM, VALUE, (NDIM == 3 ? 16 : RegroupCfg<NDIM>::NWARPS), UNI>;
     if (NDIM == 3 && pl.nwarps == 32) kern = spl_eval_regroup_kernel<NDIM, VALUE, (NDIM == 3 ? 32 : RegroupCfg<NDIM>::NWARPS), UNI>;
     SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
