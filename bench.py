@@ -499,10 +499,15 @@ def run_ours(args):
                      "peak": hbm_peak, "unit": "GB/s",
                      "traffic": traffic_for("spl_eval_regroup_kernel<3>", nq) or traffic_for("spl_eval_kernel<3>", nq),
                      "algorithmic_bytes": eval_bytes,
-                     "note": "uniform-random 3-D real64 queries: conflict-free shared-memory gathers through warp-private "
-                             "bank-class FIFOs (5.75 wavefronts/query, 9 % conflicts); the kernel is bound by instruction "
-                             "issue and the FP64 pipe (256 FP64 instructions/query for the bit-exact basis + contraction: "
-                             "13.7 ms per 1e9 at the FP64 peak), not by HBM: DESIGN.md 4.5"}
+                     "note": "uniform-random 3-D real64 queries, uniform (phantom-node) form of the basis: conflict-free "
+                             "shared-memory gathers through warp-private bank-class FIFOs.  NOT HBM-bound: the kernel "
+                             "saturates the shared-memory crossbar (ncu l1tex data pipe 95.6 % of peak: 5.84 shared "
+                             "wavefronts per query -- 4.0 are the 64 coefficients x 8 B at 128 B/clk/SM, i.e. a 13.8 ms "
+                             "floor per 1e9 queries on 148 SMs -- plus FIFO traffic and 13 % idle lanes); FP64 pipe 33 %: "
+                             "DESIGN.md 4.5, profiles/r02_eval_uniform.md",
+                     "smem_crossbar": {"wavefronts_per_query_floor": 4.0, "wavefronts_per_query_measured": 5.84,
+                                       "floor_ms_per_1e9": 13.8,
+                                       "frac_of_floor": 13.8 / (eval_ms * 1e9 / nq) if eval_ms > 0 else None}}
         eval_roof["frac"] = eval_roof["achieved"] / hbm_peak
         # accumulate stage = spl_moments_kernel (+ the per-cell change of basis, ~2% of it).  It gathers the
         # cell-sorted points through the 4-byte permutation: on uniform-random data every gather of x / y / w pulls

@@ -297,3 +297,21 @@ __device__ __forceinline__ void spl_uni_weights(double f, bool oob, int nder, do
         if (oob && (f < 0.0 || f > 1.0)) { b[0] = 0.0; b[1] = 0.0; b[2] = 0.0; b[3] = 0.0; }
     }
 }
+
+// value weights of the uniform form in float (REAL32 library); f is the float64-formed fractional coordinate rounded once
+__device__ __forceinline__ void spl_uni_weights_f32(float f, bool oob, float b[4]) {
+    const float g = 1.0f - f;
+    const float f2 = f * f, g2 = g * g;
+    b[0] = g2 * g;
+    b[1] = fmaf(f2, fmaf(3.0f, f, -6.0f), 4.0f);
+    b[2] = fmaf(g2, fmaf(3.0f, g, -6.0f), 4.0f);
+    b[3] = f2 * f;
+    if (oob) {
+        if (f < 0.0f) {
+            b[0] = fmaf(-3.0f, f, 1.0f); b[1] = 4.0f; b[2] = fmaf(3.0f, f, 1.0f); b[3] = 0.0f;
+        } else if (f > 1.0f) {
+            const float e = f - 1.0f;
+            b[0] = 0.0f; b[1] = fmaf(-3.0f, e, 1.0f); b[2] = 4.0f; b[3] = fmaf(3.0f, e, 1.0f);
+        }
+    }
+}

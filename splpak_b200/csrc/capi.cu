@@ -29,6 +29,9 @@ int spl_eval_f32_launch(const GridParams &gp, const real_t *d_x, int l1x, long l
 int spl_eval_f32_mixed4_launch(const GridParams &gp, const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
                                const double *d_coef64, double *d_pad, real_t *d_out, cudaStream_t stream, int nsm,
                                size_t smem_optin, unsigned long long *d_counter);
+long long spl_eval_uni_f32_elems(const GridParams &gp, long long nq, int nsm, size_t smem_optin);
+int spl_eval_uni_f32_launch(const GridParams &gp, const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
+                            real_t *d_ext, real_t *d_out, cudaStream_t stream, int nsm, size_t smem_optin);
 #endif
 long long spl_grid_tmp_elems(const GridParams &gp, const long long *naxis);
 int spl_eval_grid_launch(const GridParams &gp, const int *nderiv, const real_t *const *d_axis, const long long *naxis,
@@ -446,11 +449,24 @@ static int eval_device_impl(const GridParams &gp, const DeviceInfo &di, const in
         if (value && !(mode && strcmp(mode, "f64") == 0)) {
             unsigned long long *counter = eval_counter_slot(di.dev);
             if (!counter) return SPLPAK_ERR_ALLOC;
+            cudaMemPool_t pool = eval_scratch_pool(di.dev);
+            // uniform (phantom-node) form in float: extended float table (padded when the 32-class regrouping kernel runs)
+            const long long ext_floats = spl_eval_uni_f32_elems(gp, nq, di.nsm, di.smem_optin);
+            if (ext_floats > 0) {
+                real_t *ext = nullptr;
+                cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&ext, sizeof(float) * (size_t)ext_floats, pool, st)
+                                     : cudaMallocAsync((void **)&ext, sizeof(float) * (size_t)ext_floats, st);
+                if (e == cudaSuccess) {
+                    const int rcu = spl_eval_uni_f32_launch(gp, d_x, l1x, nq, d_coef, ext, d_out, st, di.nsm, di.smem_optin);
+                    cudaFreeAsync(ext, st);
+                    return rcu;
+                }
+                cudaGetLastError();
+            }
             const long long pad_elems4 = (gp.ndim == 4) ? spl_eval_regroup_elems(gp, nq, di.nsm, di.smem_optin) : 0;
             if (pad_elems4 > 0) {
-                // 4-D, large batch: scattered queries go to the float64 regrouping kernel (order probe decides)
+                // 4-D, large batch, exact form: scattered queries go to the float64 regrouping kernel (order probe decides)
                 const long long npad4 = (gp.ncol + 1) & ~1LL;
-                cudaMemPool_t pool = eval_scratch_pool(di.dev);
                 double *blk = nullptr;
                 const size_t bytes = sizeof(double) * (size_t)(npad4 + pad_elems4 + 2);
                 cudaError_t e = pool ? cudaMallocFromPoolAsync((void **)&blk, bytes, pool, st) : cudaMallocAsync((void **)&blk, bytes, st);

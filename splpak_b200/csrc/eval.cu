@@ -377,7 +377,7 @@ template <int NDIM> struct RegroupCfg {
 // One CTA samples 32 groups of 32 CONSECUTIVE queries spread over the batch and counts the groups in which at least
 // RG_BYPASS queries share one bank class.  Both evaluation kernels are launched; the one the flag rules out exits at once.
 #define RG_BYPASS 12      // a batch with >= this many lanes in ONE class is coherent (raster order): evaluate it directly
-template <int NDIM, bool UNI = false>
+template <int NDIM, bool UNI = false, int NCLS = 16>
 __global__ void __launch_bounds__(1024)
 spl_eval_probe_kernel(const __grid_constant__ GridParams gp, const TableLayout tl, const real_t *__restrict__ x, int l1x,
                       long long nq, int *__restrict__ order_flag) {
@@ -402,9 +402,9 @@ spl_eval_probe_kernel(const __grid_constant__ GridParams gp, const TableLayout t
                 const int it = max(__double2int_rz(t), -4);
                 ws = min(max(it - 1, 0), gp.nodes[d] - 4);
             }
-            lin += ws * (int)(st[d] & 15);
+            lin += ws * (int)(st[d] & (NCLS - 1));
         }
-        cls = lin & 15;
+        cls = lin & (NCLS - 1);
     }
     const unsigned peers = __match_any_sync(0xffffffffu, cls);
     const int big = __reduce_max_sync(0xffffffffu, __popc(peers));
@@ -449,8 +449,9 @@ __device__ __forceinline__ void spl_uni_row(int r, int n, int &j0, double &w0, i
     else if (j == n - 2)  { j0 = n - 2; w0 = 2.0; }
     else                  { j0 = j; w0 = 1.0; }
 }
+template <typename TI, typename TO>
 __global__ void spl_uni_table_kernel(const __grid_constant__ GridParams gp, const TableLayout tl,
-                                     const double *__restrict__ coef, double *__restrict__ ext, long long total) {
+                                     const TI *__restrict__ coef, TO *__restrict__ ext, long long total) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long st[4] = {1, tl.s1, tl.s2, tl.s3};
     long long mulv[4] = {1, 1, 1, 1};
@@ -476,10 +477,10 @@ __global__ void spl_uni_table_kernel(const __grid_constant__ GridParams gp, cons
                     w *= second ? w1[d] : w0[d];
                     src += (second ? j1[d] : j0[d]) * mulv[d];
                 }
-                if (w != 0.0) v = fma(w, coef[src], v);
+                if (w != 0.0) v = fma(w, (double)coef[src], v);
             }
         }
-        ext[e] = v;
+        ext[e] = (TO)v;
     }
 }
 
@@ -670,11 +671,12 @@ struct RegroupPlan {
     size_t key_smem = 0;
 };
 // uni: the table is the extended one of the uniform form (nodes + 2 per dimension, window base = cell index)
-static double class_pmax(const GridParams &gp, const long long *st, bool uni) {
-    double dist[16] = {1.0};
-    for (int c = 1; c < 16; ++c) dist[c] = 0.0;
+static double class_pmax(const GridParams &gp, const long long *st, bool uni, int ncls = 16) {
+    double dist[32] = {1.0};
+    for (int c = 1; c < 32; ++c) dist[c] = 0.0;
+    const int msk = ncls - 1;
     for (int d = 0; d < gp.ndim; ++d) {
-        double pd[16] = {0.0};
+        double pd[32] = {0.0};
         const int nod = gp.nodes[d];
         for (int it = 0; it < nod - 1; ++it) {
             int ws = uni ? it : it - 1;
@@ -682,15 +684,15 @@ static double class_pmax(const GridParams &gp, const long long *st, bool uni) {
                 if (ws < 0) ws = 0;
                 if (ws > nod - 4) ws = nod - 4;
             }
-            pd[(int)((ws * (st[d] & 15)) & 15)] += 1.0 / (double)(nod - 1);
+            pd[(int)((ws * (st[d] & msk)) & msk)] += 1.0 / (double)(nod - 1);
         }
-        double nx[16] = {0.0};
-        for (int a = 0; a < 16; ++a)
-            for (int b = 0; b < 16; ++b) nx[(a + b) & 15] += dist[a] * pd[b];
-        for (int c = 0; c < 16; ++c) dist[c] = nx[c];
+        double nx[32] = {0.0};
+        for (int a = 0; a < ncls; ++a)
+            for (int b = 0; b < ncls; ++b) nx[(a + b) & msk] += dist[a] * pd[b];
+        for (int c = 0; c < ncls; ++c) dist[c] = nx[c];
     }
     double m = 0.0;
-    for (int c = 0; c < 16; ++c) m = dist[c] > m ? dist[c] : m;
+    for (int c = 0; c < ncls; ++c) m = dist[c] > m ? dist[c] : m;
     return m;
 }
 // warps per CTA of the regrouping kernel (SPLPAK_B200_RG_WARPS = 16 | 24 | 32 overrides the default for experiments)
@@ -705,10 +707,12 @@ static int regroup_warps(int ndim, bool uni) {
     }
     return nw;
 }
-static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin, bool uni) {
-    static thread_local RegroupPlan plans[2];
-    RegroupPlan &plan = plans[uni ? 1 : 0];
-    const int nwarps = regroup_warps(gp.ndim, uni);
+// f32: the float kernel of the REAL32 library (uniform form only): 4-byte table entries, 32 bank classes, one FIFO
+// column per lane
+static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin, bool uni, bool f32 = false) {
+    static thread_local RegroupPlan plans[3];
+    RegroupPlan &plan = plans[f32 ? 2 : (uni ? 1 : 0)];
+    const int nwarps = f32 ? 16 : regroup_warps(gp.ndim, uni);
     bool same = plan.key_ndim == gp.ndim && plan.key_smem == smem_optin && plan.key_warps == nwarps;
     for (int d = 0; d < SPL_MAXDIM && same; ++d) same = plan.key_nodes[d] == gp.nodes[d];
     if (same) return plan;
@@ -722,22 +726,25 @@ static const RegroupPlan &regroup_plan(const GridParams &gp, size_t smem_optin, 
     const long long n0 = gp.nodes[0] + ext, n1 = gp.nodes[1] + ext, n2 = gp.ndim > 2 ? gp.nodes[2] + ext : 1,
                     n3 = gp.ndim > 3 ? gp.nodes[3] + ext : 1;
     const size_t reserve = 1024;                                       // static shared memory + alignment
-    const size_t per_slot = (size_t)nwarps * 16 * (8 * gp.ndim + (uni ? 8 : 4));   // bytes of FIFO per unit of cap
+    const int ncls = f32 ? 32 : 16;
+    const size_t esz = f32 ? sizeof(float) : sizeof(double);
+    const size_t per_slot = f32 ? (size_t)nwarps * 32 * (4 * gp.ndim + 8)
+                                : (size_t)nwarps * 16 * (8 * gp.ndim + (uni ? 8 : 4));   // bytes of FIFO per unit of cap
     double best = 1e30;
-    const int r1 = gp.ndim == 4 ? 4 : 8, r2 = gp.ndim == 4 ? 8 : 16;
+    const int r1 = gp.ndim == 4 ? 4 : 8, r2 = f32 ? (gp.ndim == 4 ? 16 : 32) : (gp.ndim == 4 ? 8 : 16);
     for (long long s1 = n0; s1 < n0 + r1; ++s1)
         for (long long s2 = s1 * n1; s2 < s1 * n1 + (gp.ndim > 2 ? r2 : 1); ++s2)
-            for (long long s3 = s2 * n2; s3 < s2 * n2 + (gp.ndim > 3 ? 16 : 1); ++s3) {
+            for (long long s3 = s2 * n2; s3 < s2 * n2 + (gp.ndim > 3 ? (f32 ? 32 : 16) : 1); ++s3) {
                 long long total = gp.ndim == 2 ? s1 * n1 : (gp.ndim == 3 ? s2 * n2 : s3 * n3);
-                total = (total + 1) & ~1LL;
-                const size_t tbytes = (size_t)total * sizeof(double);
+                total = f32 ? ((total + 3) & ~3LL) : ((total + 1) & ~1LL);
+                const size_t tbytes = (size_t)total * esz;
                 if (tbytes + reserve + 4 * per_slot > smem_optin || total >= (1LL << 28)) continue;
                 const long long st[4] = {1, s1, s2, s3};
-                const double pm = class_pmax(gp, st, uni);
+                const double pm = class_pmax(gp, st, uni, ncls);
                 long long cap = (long long)((smem_optin - reserve - tbytes) / per_slot);
                 if (cap > 24) cap = 24;
                 // estimated lane efficiency: the hottest class bounds it; short FIFOs lose a little more
-                const double eff = (1.0 / (16.0 * pm)) * (1.0 - 0.6 / (double)cap);
+                const double eff = (1.0 / ((double)ncls * pm)) * (1.0 - 0.6 / (double)cap);
                 const double score = -eff;
                 if (score < best) {
                     best = score;
@@ -842,7 +849,7 @@ static void launch_table(const GridParams &gp, const TableLayout &tl, long long 
                          double *d_tab, cudaStream_t stream) {
     long long blocks = (total + 255) / 256;
     if (blocks > 1024) blocks = 1024;
-    if (uni) spl_uni_table_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gp, tl, d_coef, d_tab, total);
+    if (uni) spl_uni_table_kernel<double, double><<<(unsigned)blocks, 256, 0, stream>>>(gp, tl, d_coef, d_tab, total);
     else spl_pad_table_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gp, tl, d_coef, d_tab, total);
     ++g_spl_launches;
 }
@@ -984,6 +991,361 @@ int spl_eval_f32_launch(const GridParams &gp, const real_t *d_x, int l1x, long l
     case 2: return launch_eval_f32<2>(gp, d_x, l1x, nq, d_coef, d_out, stream, nsm, smem_optin, d_counter);
     case 3: return launch_eval_f32<3>(gp, d_x, l1x, nq, d_coef, d_out, stream, nsm, smem_optin, d_counter);
     case 4: return launch_eval_f32<4>(gp, d_x, l1x, nq, d_coef, d_out, stream, nsm, smem_optin, d_counter);
+    }
+    return SPLPAK_ERR_NDIM;
+}
+
+// splfe of the REAL32 library in the uniform (phantom-node) form: extended FLOAT table in shared memory, float weights
+// (9 FP32 operations per dimension) and FFMA contraction; only the cell index / fractional coordinate are formed in
+// float64 from the float inputs (3 operations per dimension), so f carries no eps32 * node-index error.  CTA-static
+// ranges, a whole chunk of coordinates per warp in flight (as spl_eval_kernel's 1-D / 2-D uniform loop).
+template <int NDIM>
+__global__ void __launch_bounds__(1024, 1)
+spl_eval_uni_f32_kernel(const __grid_constant__ GridParams gp, const TableLayout tl, const float *__restrict__ x, int l1x,
+                        long long nq, const float *__restrict__ ext, unsigned table_floats, float *__restrict__ out,
+                        const int *__restrict__ order_flag) {
+    extern __shared__ __align__(128) float s_ext[];
+    __shared__ __align__(8) uint64_t mbar;
+    if (order_flag && *order_flag == 1) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&mbar, table_floats * (unsigned)sizeof(float));
+        bulk_g2s(s_ext, ext, table_floats * (unsigned)sizeof(float), &mbar);
+    }
+    __syncthreads();
+    mbar_wait(&mbar, 0);
+    const float *cf = s_ext;
+    constexpr int KQ = NDIM == 1 ? 8 : (NDIM == 2 ? 4 : 2);
+    constexpr int CH = KQ * 32;
+    const bool vec2 = NDIM == 2 && l1x == 2 && ((uintptr_t)x % 8 == 0);
+    float cur[KQ][NDIM], nxt[KQ][NDIM];
+    const long long q_lo = nq * (long long)blockIdx.x / (long long)gridDim.x;
+    const long long q_hi = nq * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
+    long long next_chunk = q_lo + (long long)(tid >> 5) * CH;
+    auto claim = [&]() -> long long {
+        const long long b = next_chunk;
+        next_chunk += (long long)(blockDim.x >> 5) * CH;
+        return b < q_hi ? b : -1;
+    };
+    auto issue = [&](long long b) {
+        if (b < 0) return;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+            const long long q = b + k * 32 + lane;
+            if (q < q_hi) {
+                if (NDIM == 2 && vec2) {
+                    const float2 v = reinterpret_cast<const float2 *>(x)[q];
+                    nxt[k][0] = v.x;
+                    nxt[k][NDIM - 1] = v.y;
+                } else {
+#pragma unroll
+                    for (int d = 0; d < NDIM; ++d) nxt[k][d] = x[q * (long long)l1x + d];
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) nxt[k][d] = 0.0f;
+            }
+        }
+    };
+    const float scale = 1.0f / (float)spl_ipow(4, NDIM);
+    long long nbase = claim();
+    issue(nbase);
+    while (nbase >= 0) {
+        const long long cbase = nbase;
+#pragma unroll
+        for (int k = 0; k < KQ; ++k)
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) cur[k][d] = nxt[k][d];
+        nbase = claim();
+        issue(nbase);
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) {
+            const long long q = cbase + k * 32 + lane;
+            if (q < q_hi) {
+                float b[NDIM][4];
+                unsigned base = 0u;
+                bool isnan_q = false;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) {
+                    int cell;
+                    double fd;
+                    bool oob;
+                    spl_uni_cell((double)cur[k][d], gp.xmin[d], gp.dxin[d], gp.nodes[d], cell, fd, oob);
+                    spl_uni_weights_f32((float)fd, oob, b[d]);
+                    isnan_q |= (cur[k][d] != cur[k][d]);
+                    const unsigned st = d == 0 ? 1u : (d == 1 ? (unsigned)tl.s1 : (d == 2 ? (unsigned)tl.s2 : (unsigned)tl.s3));
+                    base += (unsigned)cell * st;
+                }
+                const float sum = spl_contract_at<NDIM, float>(tl, cf + base, b) * scale;
+                out[q] = isnan_q ? 0.0f : sum;
+            }
+        }
+    }
+}
+
+// Regrouping kernel of the REAL32 library (uniform form, splfe): the float table has 4-byte entries, so a WARP-wide
+// LDS.32 is conflict-free when its 32 lanes read 32 distinct banks -- 32 bank classes (window base mod 32), lane l
+// DEDICATED to class l, one FIFO column per lane, one pop per lane and round.  Otherwise the scheme of
+// spl_eval_regroup_kernel: warp-private FIFOs, ranks from ballots, cursors in registers, coherent batches bypass.
+// Half the crossbar wavefronts per query of the float64 kernel (64 x 4 B = 2 instead of 4).
+template <int NDIM, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+spl_eval_regroup_f32_kernel(const __grid_constant__ GridParams gp, const TableLayout tl, const float *__restrict__ x, int l1x,
+                            long long nq, const float *__restrict__ ext_padded, unsigned table_floats, int cap,
+                            float *__restrict__ out, const int *__restrict__ order_flag) {
+    extern __shared__ __align__(128) float s_ext[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ unsigned s_chunk;
+    if (order_flag && *order_flag == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_chunk = 0;
+        mbar_init(&mbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&mbar, table_floats * (unsigned)sizeof(float));
+        bulk_g2s(s_ext, ext_padded, table_floats * (unsigned)sizeof(float), &mbar);
+    }
+    __syncthreads();
+    mbar_wait(&mbar, 0);
+    const float *cf = s_ext;
+    // warp-private FIFOs: fbt[slot][class] = (window base | out-of-range flag, query offset) (8 bytes), then
+    // ff[d][slot][class] = fractional coordinates (floats)
+    const int per_warp = cap * 32 * (NDIM + 2);                     // floats
+    float *wbase = s_ext + table_floats + (size_t)warp * per_warp;
+    uint2 *fbt = reinterpret_cast<uint2 *>(wbase);
+    float *ff = wbase + cap * 64;
+    const float scale = 1.0f / (float)spl_ipow(4, NDIM);
+
+    const long long q_lo = nq * (long long)blockIdx.x / (long long)gridDim.x;
+    const long long q_hi = nq * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
+    const unsigned range = (unsigned)(q_hi - q_lo);
+    const float *xb = x + q_lo * (long long)l1x;
+    float *ob = out + q_lo;
+
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+    int head = 0, cnt = 0;                                           // FIFO cursor of class `lane`
+    bool pend = false;
+    float px[NDIM];
+    unsigned ptag = 0;
+    unsigned cpos = 0, cend = 0;
+    bool done = false;
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) px[d] = 0.0f;
+
+    auto refill = [&]() {
+        const unsigned nm = __ballot_sync(full, !pend);
+        if (done || nm == 0u) return;
+        if (cpos == cend) {
+            unsigned c = 0;
+            if (lane == 0) c = atomicAdd(&s_chunk, 1u);
+            c = __shfl_sync(full, c, 0);
+            const unsigned long long b0 = (unsigned long long)c * RG_CHUNK;
+            if (b0 >= (unsigned long long)range) {
+                done = true;
+                return;
+            }
+            cpos = (unsigned)b0;
+            cend = (range - cpos < RG_CHUNK) ? range : cpos + RG_CHUNK;
+        }
+        const unsigned my = cpos + (unsigned)__popc(nm & lt);
+        if (!pend && my < cend) {
+            ptag = my;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) px[d] = xb[(long long)my * l1x + d];
+            pend = true;
+        }
+        const unsigned adv = cpos + (unsigned)__popc(nm);
+        cpos = adv < cend ? adv : cend;
+    };
+
+    refill();
+    for (;;) {
+        int cls = 0;
+        unsigned pbase = 0u;
+        float pf[NDIM];
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) pf[d] = 0.0f;
+        if (pend) {
+            bool any = false;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                int cell;
+                double fd;
+                bool oob;
+                spl_uni_cell((double)px[d], gp.xmin[d], gp.dxin[d], gp.nodes[d], cell, fd, oob);
+                pf[d] = (px[d] != px[d]) ? px[d] : (float)fd;        // NaN stays NaN
+                any |= oob;
+                const unsigned st = d == 0 ? 1u : (d == 1 ? (unsigned)tl.s1 : (d == 2 ? (unsigned)tl.s2 : (unsigned)tl.s3));
+                pbase += (unsigned)cell * st;
+            }
+            cls = (int)(pbase & 31u);
+            if (any) pbase |= SPL_UNI_OOB;
+        }
+        const unsigned bp = __ballot_sync(full, pend);
+        const unsigned v0 = __ballot_sync(full, pend && (cls & 1));
+        const unsigned v1 = __ballot_sync(full, pend && (cls & 2));
+        const unsigned v2 = __ballot_sync(full, pend && (cls & 4));
+        const unsigned v3 = __ballot_sync(full, pend && (cls & 8));
+        const unsigned v4 = __ballot_sync(full, pend && (cls & 16));
+        const unsigned peers = bp & ((cls & 1) ? v0 : ~v0) & ((cls & 2) ? v1 : ~v1) & ((cls & 4) ? v2 : ~v2) &
+                               ((cls & 8) ? v3 : ~v3) & ((cls & 16) ? v4 : ~v4);
+        const unsigned arr = bp & ((lane & 1) ? v0 : ~v0) & ((lane & 2) ? v1 : ~v1) & ((lane & 4) ? v2 : ~v2) &
+                             ((lane & 8) ? v3 : ~v3) & ((lane & 16) ? v4 : ~v4);
+        const int big = __reduce_max_sync(full, pend ? __popc(peers) : 0);
+        bool take = false;
+        float ex[NDIM];
+        unsigned etag = 0, ebase = 0u;
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) ex[d] = 0.0f;
+        if (big >= RG_BYPASS) {
+            take = pend;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) ex[d] = pf[d];
+            etag = ptag;
+            ebase = pbase;
+            pend = false;
+        } else {
+            const int st = __shfl_sync(full, (head << 8) | cnt, cls);
+            const int qh = st >> 8, qc = st & 255;
+            const int rank = __popc(peers & lt);
+            if (pend && qc + rank < cap) {
+                int slot = qh + qc + rank;
+                if (slot >= cap) slot -= cap;
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) ff[(d * cap + slot) * 32 + cls] = pf[d];
+                fbt[slot * 32 + cls] = make_uint2(pbase, ptag);
+                pend = false;
+            }
+            cnt += min(__popc(arr), cap - cnt);
+            __syncwarp();
+            take = cnt > 0;
+            if (take) {
+#pragma unroll
+                for (int d = 0; d < NDIM; ++d) ex[d] = ff[(d * cap + head) * 32 + lane];
+                const uint2 bt = fbt[head * 32 + lane];
+                ebase = bt.x;
+                etag = bt.y;
+                head = (head + 1 >= cap) ? 0 : head + 1;
+                --cnt;
+            }
+            __syncwarp();
+        }
+        refill();
+        if (take) {
+            float b[NDIM][4];
+            bool isnan_q = false;
+            const bool oob = (ebase & SPL_UNI_OOB) != 0u;
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) {
+                spl_uni_weights_f32(ex[d], oob, b[d]);
+                isnan_q |= (ex[d] != ex[d]);
+            }
+            const float sum = spl_contract_at<NDIM, float>(tl, cf + (ebase & ~SPL_UNI_OOB), b) * scale;
+            ob[etag] = isnan_q ? 0.0f : sum;
+        }
+        if (done && !__any_sync(full, pend || cnt > 0)) break;
+    }
+}
+
+// How the REAL32 library evaluates a splfe batch in the uniform form (decided the same way by the scratch sizing and
+// by the launcher): extended float table in natural layout (plain kernel alone), or padded for the 32-class regrouping
+// kernel (order probe + both kernels, as the float64 path; SPLPAK_B200_EVAL=plain|regroup overrides).
+struct EvalRouteF32 {
+    bool ok = false, regroup = false, force_regroup = false;
+    TableLayout tl;
+    long long table_floats = 0;
+};
+static EvalRouteF32 eval_route_f32(const GridParams &gp, long long nq, int nsm, size_t smem_optin) {
+    EvalRouteF32 r;
+    const char *basis = getenv("SPLPAK_B200_BASIS");
+    const char *mode = getenv("SPLPAK_B200_EVAL");
+    if (basis && strcmp(basis, "exact") == 0) return r;
+    const long long ext = natural_doubles(gp, 2);                  // entries (rounded up to even)
+    const long long ext4 = (ext + 3) & ~3LL;                       // bulk copies move multiples of 16 bytes
+    if ((size_t)ext4 * sizeof(float) + 2048 > smem_optin) return r;
+    if (!(basis && strcmp(basis, "uniform") == 0) && nq * (long long)spl_ipow(4, gp.ndim) * 16 <= ext) return r;
+    r.ok = true;
+    r.tl = natural_layout(gp, 2);
+    r.table_floats = ext4;
+    const bool plain_only = mode && strcmp(mode, "plain") == 0;
+    r.force_regroup = mode && strcmp(mode, "regroup") == 0;
+    // measured per 1e9 scattered float queries, plain vs regrouped: 2-D 6.6 vs 13.5 ms (regroups only when forced),
+    // 3-D 25.2 vs 17.8 ms, 4-D 82.7 (float64 regrouping kernel) vs 46.4 ms
+    if (!plain_only && gp.ndim >= 2 && (r.force_regroup || (gp.ndim >= 3 && nq >= (1LL << 18))) &&
+        nq / (nsm > 0 ? nsm : 1) < (1LL << 32) - 1024) {
+        const RegroupPlan &pl = regroup_plan(gp, smem_optin, true, true);
+        if (pl.ok) {
+            r.regroup = true;
+            r.tl = pl.tl;
+            r.table_floats = pl.table_doubles;
+        }
+    }
+    return r;
+}
+// floats of scratch the uniform float path needs for this batch (table image + 4 for the order flag); 0: not applicable
+long long spl_eval_uni_f32_elems(const GridParams &gp, long long nq, int nsm, size_t smem_optin) {
+    const EvalRouteF32 r = eval_route_f32(gp, nq, nsm, smem_optin);
+    return r.ok ? r.table_floats + 4 : 0;
+}
+
+template <int NDIM>
+static int launch_eval_uni_f32(const GridParams &gp, const EvalRouteF32 &rt, const float *d_x, int l1x, long long nq,
+                               const float *d_coef, float *d_ext, float *d_out, cudaStream_t stream, int nsm,
+                               size_t smem_optin) {
+    {
+        long long blocks = (rt.table_floats + 255) / 256;
+        if (blocks > 1024) blocks = 1024;
+        spl_uni_table_kernel<float, float><<<(unsigned)blocks, 256, 0, stream>>>(gp, rt.tl, d_coef, d_ext, rt.table_floats);
+        ++g_spl_launches;
+    }
+    int *d_flag = nullptr;
+    if (rt.regroup) {
+        if constexpr (NDIM >= 2) {
+            const RegroupPlan &pl = regroup_plan(gp, smem_optin, true, true);
+            if (!rt.force_regroup) {
+                d_flag = reinterpret_cast<int *>(d_ext + rt.table_floats);
+                spl_eval_probe_kernel<NDIM, true, 32><<<1, 1024, 0, stream>>>(gp, pl.tl, d_x, l1x, nq, d_flag);
+                ++g_spl_launches;
+            }
+            auto kern = spl_eval_regroup_f32_kernel<NDIM, 16>;
+            SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+            long long grid = nsm;
+            const long long per_cta_min = 4096;
+            if (grid > (nq + per_cta_min - 1) / per_cta_min) grid = (nq + per_cta_min - 1) / per_cta_min;
+            if (grid < 1) grid = 1;
+            kern<<<(unsigned)grid, 16 * 32, pl.smem, stream>>>(gp, pl.tl, d_x, l1x, nq, d_ext, (unsigned)pl.table_doubles, pl.cap,
+                                                               d_out, d_flag);
+            ++g_spl_launches;
+            SPL_CUDA_TRY(cudaGetLastError());
+            if (rt.force_regroup) return SPLPAK_OK;
+        }
+    }
+    auto kern = spl_eval_uni_f32_kernel<NDIM>;
+    const size_t bytes = (size_t)rt.table_floats * sizeof(float);
+    SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    long long grid = nsm;
+    const long long per_cta_min = 8192;
+    if (grid > (nq + per_cta_min - 1) / per_cta_min) grid = (nq + per_cta_min - 1) / per_cta_min;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 1024, bytes, stream>>>(gp, rt.tl, d_x, l1x, nq, d_ext, (unsigned)rt.table_floats, d_out, d_flag);
+    ++g_spl_launches;
+    SPL_CUDA_TRY(cudaGetLastError());
+    return SPLPAK_OK;
+}
+
+// d_ext: scratch of spl_eval_uni_f32_elems() floats
+int spl_eval_uni_f32_launch(const GridParams &gp, const real_t *d_x, int l1x, long long nq, const real_t *d_coef,
+                            real_t *d_ext, real_t *d_out, cudaStream_t stream, int nsm, size_t smem_optin) {
+    if (nq <= 0) return SPLPAK_OK;
+    const EvalRouteF32 rt = eval_route_f32(gp, nq, nsm, smem_optin);
+    if (!rt.ok) return SPLPAK_ERR_HANDLE;
+    switch (gp.ndim) {
+    case 1: return launch_eval_uni_f32<1>(gp, rt, d_x, l1x, nq, d_coef, d_ext, d_out, stream, nsm, smem_optin);
+    case 2: return launch_eval_uni_f32<2>(gp, rt, d_x, l1x, nq, d_coef, d_ext, d_out, stream, nsm, smem_optin);
+    case 3: return launch_eval_uni_f32<3>(gp, rt, d_x, l1x, nq, d_coef, d_ext, d_out, stream, nsm, smem_optin);
+    case 4: return launch_eval_uni_f32<4>(gp, rt, d_x, l1x, nq, d_coef, d_ext, d_out, stream, nsm, smem_optin);
     }
     return SPLPAK_ERR_NDIM;
 }

@@ -165,10 +165,12 @@ def test_real32_library(oracle32):
 
 
 @pytest.mark.parametrize("ndim,nodes", [(1, [50]), (2, [8, 9]), (2, [64, 64]), (3, [24, 24, 24]), (3, [5, 4, 6]), (4, [5, 4, 6, 5])])
-def test_real32_splfe_runs_in_working_precision(oracle32, ndim, nodes):
-    """REAL32 library, splfe: float arithmetic like the reference built with -DREAL32 (src/splpak.F90:33-34).  The 1-D
-    basis values are bit-identical to the float oracle's (unfused float operations); only the summation order of the
-    4^ndim terms differs, so the tolerance is k * eps32 * sum |c_j phi_j| -- not round 1's fixed 2e-4."""
+def test_real32_splfe_runs_in_working_precision(oracle32, ndim, nodes, basis_mode):
+    """REAL32 library, splfe: float arithmetic like the reference built with -DREAL32 (src/splpak.F90:33-34).
+    SPLPAK_B200_BASIS=exact: the 1-D basis values are bit-identical to the float oracle's (unfused float operations); only
+    the summation order of the 4^ndim terms differs, so the tolerance is k * eps32 * sum |c_j phi_j| -- not round 1's fixed
+    2e-4.  Default: the uniform form with float weights and float contraction; it does not repeat the float oracle's
+    rounding of the node positions (eps32 * node index in u), hence the extra 4 eps32 sum(nodes) (see _tol)."""
     import os
 
     rng = np.random.default_rng(20 + ndim)
@@ -183,7 +185,8 @@ def test_real32_splfe_runs_in_working_precision(oracle32, ndim, nodes):
     assert ierr == 0 and got.dtype == np.float32
     eps32 = float(np.finfo(np.float32).eps)
     # worst-case rounding of two different summation orders of 4^ndim float terms (sequential in the oracle, nested here)
-    tol = np.maximum(8 * eps32 * np.abs(coef).max(), (2 * 4 ** ndim + 8) * eps32 * np.abs(bound))
+    knod = 0 if basis_mode == "exact" else 4 * int(np.sum(nodes))
+    tol = np.maximum(8 * eps32 * np.abs(coef).max(), (2 * 4 ** ndim + 8 + knod) * eps32 * np.abs(bound))
     assert (np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= tol).all(), np.abs(got - ref).max()
     # the float64-internal path of the same library (float I/O) agrees to float rounding of the result
     os.environ["SPLPAK_B200_R32"] = "f64"

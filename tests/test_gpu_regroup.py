@@ -25,11 +25,11 @@ def basis_mode(request, monkeypatch):
     return request.param
 
 
-def _eval(mode, ndim, q, coef, mn, mx, nodes, nderiv=None):
+def _eval(mode, ndim, q, coef, mn, mx, nodes, nderiv=None, real32=False):
     old = os.environ.get("SPLPAK_B200_EVAL")
     os.environ["SPLPAK_B200_EVAL"] = mode
     try:
-        out, ierr = sp.eval_batch(ndim, q, coef, mn, mx, nodes, nderiv=nderiv)
+        out, ierr = sp.eval_batch(ndim, q, coef, mn, mx, nodes, nderiv=nderiv, real32=real32)
     finally:
         if old is None:
             del os.environ["SPLPAK_B200_EVAL"]
@@ -130,3 +130,34 @@ def test_default_dispatch_probes_the_query_order():
     out, ierr = sp.eval_batch(3, g, coef, [0, 0, 0], [1, 1, 1], nodes)
     assert ierr == 0
     assert np.array_equal(out, _eval("plain", 3, g, coef, [0, 0, 0], [1, 1, 1], nodes))
+
+
+@pytest.mark.parametrize("ndim,nodes,nq", [
+    (2, [64, 64], 400_001), (3, [24, 24, 24], 600_003), (3, [5, 4, 6], 280_000),
+    (4, [12, 12, 12, 12], 300_000), (4, [4, 5, 4, 6], 270_000),
+])
+def test_real32_regroup_bit_identical_to_plain_and_matches_oracle(oracle32, basis_mode, ndim, nodes, nq):
+    """REAL32 library, uniform form: the 32-class float regrouping kernel (spl_eval_regroup_f32_kernel, one FIFO column
+    per lane) against the plain float kernel -- bit-identical for every ordering -- and against the float oracle."""
+    if basis_mode == "exact":
+        pytest.skip("the float regrouping kernel exists in the uniform form only")
+    rng = np.random.default_rng(7 * ndim + nodes[0])
+    coef = rng.standard_normal(int(np.prod(nodes))).astype(np.float32)
+    mn = np.zeros(ndim)
+    mx = np.ones(ndim)
+    for name, q in _orderings(rng, ndim, nq, mn, mx).items():
+        q = q.astype(np.float32)
+        a = _eval("plain", ndim, q, coef, mn, mx, nodes, real32=True)
+        b = _eval("regroup", ndim, q, coef, mn, mx, nodes, real32=True)
+        assert a.dtype == np.float32
+        assert np.array_equal(a, b, equal_nan=True), (name, np.nanmax(np.abs(a - b)), int((a != b).sum()))
+        if name == "random":
+            idx = rng.choice(len(q), 2000, replace=False)
+            ref, _ = oracle32.evaluate_batch(ndim, q[idx], coef, mn, mx, nodes)
+            bound, _ = oracle32.evaluate_batch(ndim, q[idx], np.abs(coef), mn, mx, nodes)
+            eps32 = float(np.finfo(np.float32).eps)
+            tol = np.maximum(8 * eps32 * np.abs(coef).max(),
+                             (2 * 4 ** ndim + 8 + 4 * int(np.sum(nodes))) * eps32 * np.abs(bound))
+            assert (np.abs(b[idx].astype(np.float64) - ref.astype(np.float64)) <= tol).all()
+            d = sp.eval_batch(ndim, q, coef, mn, mx, nodes, real32=True)[0]       # default dispatch (order probe)
+            assert np.array_equal(d, a, equal_nan=True)
