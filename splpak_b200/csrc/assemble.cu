@@ -112,17 +112,22 @@ template <int NDIM, bool SMEMH, bool CELL, bool SMEMC = false>
 __global__ void __launch_bounds__(SMEMC ? 1024 : 512, SMEMC ? 1 : 2)
 spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
                     const real_t *__restrict__ w, int weighted, long long n, int nbins,
-                    unsigned *__restrict__ wincount, int do_hist, double *__restrict__ cnt,
-                    double *__restrict__ totals, const real_t *__restrict__ y, double2 *__restrict__ yw) {
+                    unsigned *__restrict__ wincount, int do_hist, unsigned long long *__restrict__ hq,
+                    const double *__restrict__ qparams, double *__restrict__ totals, const real_t *__restrict__ y,
+                    double2 *__restrict__ yw) {
     extern __shared__ __align__(8) unsigned s_hist[];
-    double *s_cnt = reinterpret_cast<double *>(s_hist + ((nbins + 1) & ~1));     // SMEMC: gp.ncol doubles
+    unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(s_hist + ((nbins + 1) & ~1));   // SMEMC: gp.ncol x 8 bytes
     if (SMEMH) {
         for (int e = threadIdx.x; e < nbins; e += blockDim.x) s_hist[e] = 0u;
         if (SMEMC)
-            for (long long e = threadIdx.x; e < gp.ncol; e += blockDim.x) s_cnt[e] = 0.0;
+            for (long long e = threadIdx.x; e < gp.ncol; e += blockDim.x) s_cnt[e] = 0ULL;
         __syncthreads();
     }
-    double tot = 0.0;
+    // nearest-node histogram in FIXED POINT: q = rn(w * qscale) with qscale a power of two chosen from the chunk's
+    // largest |w| (spl_hist_prepare), accumulated with INTEGER atomics -- exact, hence independent of the order in which
+    // the atomics land: the sparse-node decision of :936 is reproducible run to run (a float64 atomic sum is not)
+    const double qscale = do_hist ? qparams[0] : 0.0;
+    long long totq = 0;
     double rows = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * BIN_U) {
@@ -153,9 +158,15 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
                 else atomicAdd(wincount + key, 1u);
                 rows += 1.0;
                 if (do_hist) {
-                    if (SMEMC) atomicAdd(s_cnt + spl_nearest_node<NDIM>(gp, xp[u]), wv[u]);
-                    else atomicAdd(cnt + spl_nearest_node<NDIM>(gp, xp[u]), wv[u]);
-                    tot += wv[u];
+                    const long long q = __double2ll_rn(wv[u] * qscale);
+                    const long long node = spl_nearest_node<NDIM>(gp, xp[u]);
+                    if (SMEMC) {
+                        atomicAdd(s_cnt + node, (unsigned long long)q);
+                    } else {
+                        atomicAdd(hq + 2 * node, (unsigned long long)(q & 0x7fffffffLL));
+                        atomicAdd(hq + 2 * node + 1, (unsigned long long)(q >> 31));
+                    }
+                    totq += q;
                 }
             }
         }
@@ -168,32 +179,129 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
         }
         if (SMEMC && do_hist)
             for (long long e = threadIdx.x; e < gp.ncol; e += blockDim.x) {
-                const double c = s_cnt[e];
-                if (c != 0.0) atomicAdd(cnt + e, c);
+                const long long c = (long long)s_cnt[e];             // this CTA's exact sum: two limbs into the global table
+                if (c != 0) {
+                    atomicAdd(hq + 2 * e, (unsigned long long)(c & 0x7fffffffLL));
+                    atomicAdd(hq + 2 * e + 1, (unsigned long long)(c >> 31));
+                }
             }
     }
-    // block reduction of totlwt and the row count
-    __shared__ double s_tot[32], s_rows[32];
+    // block reduction of totlwt (fixed point, exact) and the row count (integer-valued, exact)
+    __shared__ long long s_tot[32];
+    __shared__ double s_rows[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        totq += __shfl_xor_sync(0xffffffffu, totq, o);
         rows += __shfl_xor_sync(0xffffffffu, rows, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        s_tot[threadIdx.x >> 5] = tot;
+        s_tot[threadIdx.x >> 5] = totq;
         s_rows[threadIdx.x >> 5] = rows;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0, r = 0.0;
+        long long t = 0;
+        double r = 0.0;
         for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
             t += s_tot[k];
             r += s_rows[k];
         }
-        if (t != 0.0) atomicAdd(totals + 0, t);
+        if (do_hist && t != 0) {
+            atomicAdd(hq + 2 * gp.ncol, (unsigned long long)(t & 0x7fffffffLL));
+            atomicAdd(hq + 2 * gp.ncol + 1, (unsigned long long)(t >> 31));
+        }
         if (r != 0.0) atomicAdd(totals + 1, r);
     }
 }
+
+// ---- fixed-point histogram: scale selection before, conversion to float64 after the classify pass ----
+// largest finite |w| of the chunk (bit pattern: non-negative doubles order like integers)
+__global__ void __launch_bounds__(1024)
+spl_wmax_kernel(const real_t *__restrict__ w, long long n, unsigned long long *__restrict__ wmax_bits) {
+    unsigned long long m = 0ULL;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(fabs((double)w[i]));
+        if (b < 0x7ff0000000000000ULL && b > m) m = b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o);
+        m = v > m ? v : m;
+    }
+    __shared__ unsigned long long s_m[32];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) m = s_m[k] > m ? s_m[k] : m;
+        if (m) atomicMax(wmax_bits, m);
+    }
+}
+// qparams[0] = qscale = 2^-lsb_exp, qparams[1] = lsb_exp: |w| < 2^e  ->  |q| = |w| qscale < 2^bits
+__global__ void spl_qparams_kernel(const unsigned long long *__restrict__ wmax_bits, int bits, double *__restrict__ qparams) {
+    const double wmax = wmax_bits ? __longlong_as_double((long long)*wmax_bits) : 1.0;
+    int e = 0;
+    if (wmax > 0.0) frexp(wmax, &e);                     // wmax = m 2^e, 0.5 <= m < 1
+    int lsb_exp = e - bits;
+    lsb_exp = max(min(lsb_exp, 1000), -1000);
+    qparams[0] = ldexp(1.0, -lsb_exp);
+    qparams[1] = (double)lsb_exp;
+}
+// cnt[node] += exact chunk sum (two limbs) * lsb; totals[0] += the same for totlwt; the limbs are zeroed for the next chunk
+__global__ void __launch_bounds__(256)
+spl_hist_finalize_kernel(unsigned long long *__restrict__ hq, const double *__restrict__ qparams, long long ncol,
+                         double *__restrict__ cnt, double *__restrict__ totals) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > ncol) return;
+    const int lsb_exp = (int)qparams[1];
+    const long long lo = (long long)hq[2 * e], hi = (long long)hq[2 * e + 1];
+    hq[2 * e] = 0ULL;
+    hq[2 * e + 1] = 0ULL;
+    if (lo == 0 && hi == 0) return;
+    const double v = ldexp((double)hi, 31 + lsb_exp) + ldexp((double)lo, lsb_exp);
+    if (e < ncol) cnt[e] += v;
+    else totals[0] += v;
+}
+
+int spl_hist_scratch_init(const GridParams &gp, HistScratch &hs, cudaStream_t st) {
+    if (hs.hq) return SPLPAK_OK;
+    SPL_CUDA_TRY(cudaMalloc((void **)&hs.hq, sizeof(unsigned long long) * (size_t)(2 * gp.ncol + 2)));
+    SPL_CUDA_TRY(cudaMalloc((void **)&hs.qparams, sizeof(double) * 2));
+    SPL_CUDA_TRY(cudaMalloc((void **)&hs.wmax, sizeof(unsigned long long)));
+    SPL_CUDA_TRY(cudaMemsetAsync(hs.hq, 0, sizeof(unsigned long long) * (size_t)(2 * gp.ncol + 2), st));
+    return SPLPAK_OK;
+}
+void spl_hist_scratch_free(HistScratch &hs) {
+    if (hs.hq) cudaFree(hs.hq);
+    if (hs.qparams) cudaFree(hs.qparams);
+    if (hs.wmax) cudaFree(hs.wmax);
+    hs.hq = nullptr;
+    hs.qparams = nullptr;
+    hs.wmax = nullptr;
+}
+// before the classify pass of a chunk: per_acc = the largest number of points one integer accumulator can receive
+static int spl_hist_prepare(const HistScratch &hs, const real_t *d_w, int weighted, long long n, long long per_acc,
+                            cudaStream_t st, int nsm) {
+    int bits = 42;
+    while (bits > 8 && (per_acc >> (62 - bits)) != 0) --bits;         // per_acc * 2^bits < 2^62
+    if (weighted) {
+        SPL_CUDA_TRY(cudaMemsetAsync(hs.wmax, 0, sizeof(unsigned long long), st));
+        long long blocks = (n + 4095) / 4096;
+        if (blocks > 4LL * nsm) blocks = 4LL * nsm;
+        spl_wmax_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 1024, 0, st>>>(d_w, n, hs.wmax);
+        spl_qparams_kernel<<<1, 1, 0, st>>>(hs.wmax, bits, hs.qparams);
+        g_spl_launches += 2;
+    } else {
+        spl_qparams_kernel<<<1, 1, 0, st>>>(nullptr, bits, hs.qparams);
+        ++g_spl_launches;
+    }
+    return SPLPAK_OK;
+}
+static void spl_hist_finalize(const HistScratch &hs, const GridParams &gp, double *d_cnt, double *d_totals, cudaStream_t st) {
+    spl_hist_finalize_kernel<<<spl_div_up(gp.ncol + 1, 256), 256, 0, st>>>(hs.hq, hs.qparams, gp.ncol, d_cnt, d_totals);
+    ++g_spl_launches;
+}
+
 
 // Exclusive scan of the window counts (single CTA; nwindows is at most a few 10^5 in practice).
 // winstart[k] = first record of window k, itemstart[k] = first work item of window k,
@@ -733,7 +841,7 @@ int spl_assemble_scratch_init(const GridParams &gp, AssembleScratch &sc, cudaStr
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.wincursor, sizeof(unsigned) * (size_t)sc.nbins * sc.cursor_stride));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.itemstart, sizeof(unsigned) * (size_t)sc.nbins));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.meta, sizeof(unsigned) * 4));
-    return SPLPAK_OK;
+    return spl_hist_scratch_init(gp, sc.hist, st);
 }
 
 void spl_assemble_scratch_free(AssembleScratch &sc) {
@@ -744,6 +852,7 @@ void spl_assemble_scratch_free(AssembleScratch &sc) {
     if (sc.cellmom) cudaFree(sc.cellmom);
     sc.wincount = sc.winstart = sc.wincursor = sc.itemstart = sc.meta = nullptr;
     sc.celltab = sc.cellmom = nullptr;
+    spl_hist_scratch_free(sc.hist);
 }
 
 template <int NDIM, bool CELL>
@@ -773,22 +882,30 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
         // both histograms in shared memory: one 1024-thread CTA per SM
         const size_t both_bytes = sizeof(unsigned) * (size_t)((nbins + 1) & ~1LL) + sizeof(double) * (size_t)gp.ncol;
         const bool smemc = smemh && do_hist && both_bytes <= 200 * 1024 && !getenv("SPLPAK_B200_GLOBAL_HIST");
+        long long cb1 = (n + 1024LL * BIN_U - 1) / (1024LL * BIN_U);
+        const int cgrid1 = (int)(cb1 < nsm ? (cb1 < 1 ? 1 : cb1) : nsm);
+        if (do_hist) {
+            // points one shared-memory accumulator can receive (its CTA's share) -- the global limbs take 31-bit pieces
+            const long long per_acc = smemc ? (n + cgrid1 - 1) / cgrid1 + 1024LL * BIN_U : 1;
+            const int rh = spl_hist_prepare(sc.hist, d_w, weighted, n, per_acc, st, nsm);
+            if (rh != SPLPAK_OK) return rh;
+        }
         if (smemc) {
             auto kern = spl_classify_kernel<NDIM, true, CELL, true>;
             SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)both_bytes));
-            long long cb1 = (n + 1024LL * BIN_U - 1) / (1024LL * BIN_U);
-            const int cgrid1 = (int)(cb1 < nsm ? (cb1 < 1 ? 1 : cb1) : nsm);
             kern<<<cgrid1, 1024, both_bytes, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins, sc.wincount, do_hist,
-                                                   d_cnt, d_totals, d_y, yw);
+                                                   sc.hist.hq, sc.hist.qparams, d_totals, d_y, yw);
         } else if (smemh) {
             auto kern = spl_classify_kernel<NDIM, true, CELL>;
             SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
             kern<<<cgrid, 512, hist_bytes, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins, sc.wincount, do_hist,
-                                                 d_cnt, d_totals, d_y, yw);
+                                                 sc.hist.hq, sc.hist.qparams, d_totals, d_y, yw);
         } else {
             spl_classify_kernel<NDIM, false, CELL><<<cgrid, 512, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins,
-                                                                          sc.wincount, do_hist, d_cnt, d_totals, d_y, yw);
+                                                                          sc.wincount, do_hist, sc.hist.hq, sc.hist.qparams,
+                                                                          d_totals, d_y, yw);
         }
+        if (do_hist) spl_hist_finalize(sc.hist, gp, d_cnt, d_totals, st);
     }
     if (ev) cudaEventRecord(ev[1], st);
     spl_scan_kernel<<<1, 1024, 0, st>>>(sc.wincount, nbins, ch, sc.winstart, sc.itemstart, sc.meta);

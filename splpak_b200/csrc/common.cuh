@@ -45,6 +45,14 @@ __host__ __device__ __forceinline__ void spl_pair(int a, int &i, int &j) {
 
 __host__ __device__ constexpr int spl_ipow(int b, int e) { return e <= 0 ? 1 : b * spl_ipow(b, e - 1); }
 
+// Fixed-point nearest-node histogram (assemble.cu: spl_classify_kernel): two int64 limbs per node (+ one pair for
+// totlwt), the chunk's scale (qscale, lsb exponent) and the bit pattern of its largest |w|.
+struct HistScratch {
+    unsigned long long *hq = nullptr;
+    double *qparams = nullptr;
+    unsigned long long *wmax = nullptr;
+};
+
 // Scratch of the chunk pipeline of assemble.cu (owned by a fit handle, sized by spl_assemble_scratch_*).
 struct AssembleScratch {
     unsigned *wincount, *winstart, *wincursor, *itemstart, *item_win, *item_seg, *meta;
@@ -55,6 +63,7 @@ struct AssembleScratch {
     double *celltab;      // moment path: per-(dimension, cell) coefficient tables
     double *cellmom;      // moment path: per-cell moment sums of the chunk in flight (kept zero between chunks)
     int cursor_stride;    // 4-byte words between the per-bin cursors of the second binning pass
+    HistScratch hist;     // fixed-point histogram scratch
     double *yw;           // moment path: interleaved (y, w) copy of the chunk, 2 doubles per point (sized with perm)
 };
 
@@ -63,6 +72,7 @@ struct OrthoScratch {
     unsigned *wincount = nullptr, *winstart = nullptr, *wincursor = nullptr, *itemstart = nullptr, *meta = nullptr;
     unsigned *perm = nullptr;
     long long perm_cap = 0;
+    HistScratch hist;              // fixed-point histogram scratch
     double *Rw = nullptr;          // nwindows x ncw x (ncw + 1)
     unsigned *blist = nullptr;     // non-zero stage-2 blocks, in order; meta2[0] = their number
     unsigned *meta2 = nullptr;

@@ -459,6 +459,7 @@ void spl_ortho_free(OrthoScratch &os) {
                  os.Rb, os.progress, os.csol};
     for (void *q : p)
         if (q) cudaFree(q);
+    spl_hist_scratch_free(os.hist);
     os = OrthoScratch();
 }
 
@@ -524,8 +525,14 @@ static int ortho_add_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, c
     long long cb = (n + 512LL * BIN_U - 1) / (512LL * BIN_U);
     const long long ccap = (long long)nsm * 4;
     const int cgrid = (int)(cb < ccap ? (cb < 1 ? 1 : cb) : ccap);
+    if (do_hist) {
+        int rh = spl_hist_scratch_init(gp, os.hist, st);
+        if (rh == SPLPAK_OK) rh = spl_hist_prepare(os.hist, d_w, weighted, n, 1, st, nsm);
+        if (rh != SPLPAK_OK) return rh;
+    }
     spl_classify_kernel<NDIM, false, false><<<cgrid, 512, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins, os.wincount,
-                                                                   do_hist, d_cnt, d_totals, d_y, nullptr);
+                                                                   do_hist, os.hist.hq, os.hist.qparams, d_totals, d_y, nullptr);
+    if (do_hist) spl_hist_finalize(os.hist, gp, d_cnt, d_totals, st);
     spl_scan_kernel<<<1, 1024, 0, st>>>(os.wincount, nbins, 1u << 30, os.winstart, os.itemstart, os.meta);
     long long nb = (n + 255) / 256;
     const long long cap = (long long)nsm * 8;

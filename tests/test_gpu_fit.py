@@ -458,3 +458,45 @@ def test_ill_conditioned_fit_without_constraints(oracle):
         assert ierr == 0
         err = np.abs(got - ref).max() / np.abs(ref).max()
         assert err <= max(1e-11, 20 * np.finfo(float).eps * cond), (ndim, nodes, err, cond)
+
+
+@pytest.mark.parametrize("ndim,nodes,ndata,solver", [(1, [40], 200_000, None), (2, [30, 25], 400_000, None),
+                                                     (3, [24, 24, 24], 3_000_000, None), (3, [9, 8, 10], 300_000, "orthogonal"),
+                                                     (4, [6, 5, 6, 5], 300_000, None)])
+def test_weight_histogram_is_reproducible_bit_for_bit(ndim, nodes, ndata, solver):
+    """The nearest-node weight histogram and totlwt (src/splpak.F90:885-907) decide which nodes get derivative-constraint
+    rows (:936: cnt < 0.75 * expect).  They are accumulated in fixed point with integer atomics (spl_classify_kernel), so
+    they do not depend on the order in which the atomics land: repeated fits of the same weighted data give the SAME
+    histogram bit for bit -- in shared-memory, global and chunked accumulation alike -- and it equals the float64 sum to
+    rounding."""
+    rng = np.random.default_rng(40 + ndim)
+    x = rng.random((ndata, ndim))
+    y = rng.standard_normal(ndata)
+    w = np.exp(rng.standard_normal(ndata) * 3.0)            # weights over ~8 decades
+    w[rng.random(ndata) < 0.01] = 0.0
+    mn, mx = [0.0] * ndim, [1.0] * ndim
+    runs = []
+    for rep in range(3):
+        h = sp.FitHandle(ndim, mn, mx, nodes, 1.0, solver=solver)
+        if rep < 2:
+            h.add_points(x, y, w)
+        else:                                                # the same data in two chunks: still exact sums per chunk
+            half = ndata // 2
+            h.add_points(x[:half], y[:half], w[:half])
+            h.add_points(x[half:], y[half:], w[half:])
+        _, _, cnt, totlwt, nrows = h.normal_equations()
+        runs.append((cnt.copy(), totlwt, nrows))
+        h.destroy()
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1] and runs[0][2] == runs[1][2]
+    # against float64 sums of the same nearest-node assignment (all points are inside the grid here)
+    node = np.zeros(ndata, dtype=np.int64)
+    for d in reversed(range(ndim)):
+        node = node * nodes[d] + np.floor(x[:, d] * (nodes[d] - 1) + 0.5).astype(np.int64)
+    want = np.bincount(node, weights=w, minlength=int(np.prod(nodes)))
+    # quantisation: |w| < 2^e -> lsb <= wmax 2^-41 per point; float64 reference sum: ~eps per addition
+    npn = np.bincount(node).max()
+    assert np.abs(runs[0][0] - want).max() <= npn * np.abs(w).max() * 2.0 ** -40 + 1e-12 * want.max()
+    assert abs(runs[0][1] - w.sum()) <= 1e-11 * w.sum()
+    # chunking: every chunk is quantised with its own scale, so the sums agree to the quantisation bound
+    assert np.abs(runs[2][0] - runs[0][0]).max() <= npn * np.abs(w).max() * 2.0 ** -39 + 1e-12 * want.max()
+    assert runs[0][2] == float((w != 0).sum())
