@@ -170,8 +170,10 @@ class CopyPool {
             int hw = (int)std::thread::hardware_concurrency();
             int ranks = 1;
             if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
-            n = hw / ranks;
-            if (n > 8) n = 8;
+            // measured on the 16-core GPU box, 1e8 pageable points / queries (scripts/pageable_ab.py): 4 / 8 / 12 / 16 / 24
+            // threads -> fit 120 / 97 / 83 / 84 / 85 ms, evaluation 139 / 94 / 83 / 84 / 93 ms
+            n = (hw * 3 / 4) / ranks;
+            if (n > 12) n = 12;
         }
         if (n < 1) n = 1;
         nthr_ = n;
