@@ -953,7 +953,7 @@ extern "C" int splpak_b200_fit_create(int ndim, const real_t *xmin, const real_t
     ok = ok && cudaStreamCreateWithFlags(&h->st_aux, cudaStreamNonBlocking) == cudaSuccess;
     h->n_part = gp.ncol * gp.nsten + gp.ncol + gp.ncol + 2;
     ok = ok && cudaMalloc((void **)&h->d_part, sizeof(double) * (size_t)h->n_part) == cudaSuccess;
-    ok = ok && cudaMalloc((void **)&h->d_fail, 2 * sizeof(int)) == cudaSuccess;   // [failure flag, grid-barrier counter of the persistent factor kernel]
+    ok = ok && cudaMalloc((void **)&h->d_fail, SPL_FAIL_WORDS * sizeof(int)) == cudaSuccess;   // [failure flag, grid-barrier counter of the persistent kernels, ..., flags of the data-flow factor kernel from word 32]
     ok = ok && cudaMalloc((void **)&h->d_coef64, sizeof(double) * (size_t)(gp.ncol + 2)) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&h->d_dummy_tot, sizeof(double) * 4) == cudaSuccess;
     if (sizeof(real_t) != sizeof(double))
@@ -1319,7 +1319,7 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
     const int bw = spl_half_bandwidth(gp);
     const long long lda = spl_band_lda(bw);
     // element (i, j) lives at i + j*lda, so the last one, (n-1, n-1), is at (n-1)*(lda+1)
-    const long long band_elems = gp.ncol * (lda + 1) + 64;
+    const long long band_elems = (gp.ncol * (lda + 1) + 64 + 1) & ~1LL;     // even: the workspace behind stays 16-byte aligned
     const long long need = band_elems + spl_solve_workspace(gp);
     if (need > h->ab_elems) {
         if (h->d_AB) cudaFree(h->d_AB);
@@ -1535,7 +1535,7 @@ static int fit_refine_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_o
         }
         const int bw = spl_half_bandwidth(gp);
         const long long lda = spl_band_lda(bw);
-        const long long band_elems = gp.ncol * (lda + 1) + 64;
+        const long long band_elems = (gp.ncol * (lda + 1) + 64 + 1) & ~1LL;     // even: the workspace behind stays 16-byte aligned
         const long long need = band_elems + spl_solve_workspace(gp);
         if (need > h->ab_elems) rc = SPLPAK_ERR_HANDLE;               // compute allocated it
         if (rc == SPLPAK_OK) {

@@ -21,6 +21,7 @@ typedef splpak_real real_t;
 
 #define SPL_MAXDIM 4
 #define SPL_NSM_DEFAULT 148
+#define SPL_FAIL_WORDS 256      // ints behind a handle's failure flag: [0] flag, [1] barrier counter, [32..] data-flow flags
 
 struct GridParams {
     int ndim;

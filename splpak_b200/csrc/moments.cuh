@@ -27,8 +27,13 @@
 #define MOM_NM 343                    // moments of G per cell
 #define MOM_NR 64                     // moments of g per cell
 #define MOM_MG 408                    // doubles per cell of the moment array (407 used)
+#ifndef MOM_NT
 #define MOM_NT 128                    // threads per CTA of the moment kernel (thread = point when staging)
-#define MOM_PB 128                    // points per staged batch
+#endif
+#define MOM_PB MOM_NT                 // points per staged batch
+#ifndef MOM_MINB
+#define MOM_MINB 4                    // CTAs per SM the register allocation aims at
+#endif
 // staged record of one point (doubles):
 //   [0..7] P1[0..6], 0   [8..15] P2[0..6], 0   [16..23] A3[0..6] = w^2 P3, 0   [24..27] B3[0..3] = w^2 y P3
 // RS/2 odd: the 128-bit staging stores of neighbouring points do not collide; RS = 14 mod 16: the four points
@@ -122,7 +127,7 @@ __device__ __forceinline__ void spl_mom_dmma(double &c0, double &c1, double a, d
 //           loads per point -- the kernel is bound by the shared-memory pipe, not by FP64 issue.
 // Several CTAs are resident per SM, so one CTA's staging overlaps another's MMA stream.
 template <bool RHS_ONLY>
-__global__ void __launch_bounds__(MOM_NT, 4)
+__global__ void __launch_bounds__(MOM_NT, MOM_MINB)
 spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
                    const real_t *__restrict__ y, const double2 *__restrict__ yw,
                    const unsigned *__restrict__ perm, const unsigned *__restrict__ bincount,

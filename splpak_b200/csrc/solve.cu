@@ -328,6 +328,9 @@ spl_expand_band_kernel(const __grid_constant__ GridParams gp, const double *__re
 // panel: diagonal-block Cholesky + inverse (registers), rhs forward solve, TRSM as a DMMA GEMM
 // ------------------------------------------------------------------------------------------
 #define PANEL_THREADS 256
+// CTA barrier of the 256 working threads.  The pieces below run in 256-thread CTAs (where this IS __syncthreads) and in
+// the data-flow kernel, whose CTAs carry a ninth warp that must not take part.
+#define SPL_SYNC256() asm volatile("bar.sync 0, 256;" ::: "memory")
 #define TILE_LD 68      // 64 + 4: (t4*68 + g) hits 16 distinct 8-byte banks per half-warp (conflict-free LDS.64)
 
 __device__ __forceinline__ void spl_dmma_8x8x4(double &c0, double &c1, double a, double b) {
@@ -342,6 +345,45 @@ __device__ __forceinline__ void spl_cp_async8(double *smem_dst, const double *gs
 }
 __device__ __forceinline__ void spl_cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void spl_cp_async16(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc)
+                 : "memory");
+}
+// One 16-byte piece (two consecutive rows of one column) of an operand tile: cp.async when both rows are valid,
+// otherwise an 8-byte cp.async of the valid row (if any) and zeros.  The band leading dimension is even
+// (spl_band_lda) and tiles start at even rows, so every piece is 16-byte aligned on both sides.
+__device__ __forceinline__ void spl_tile_piece(double *dst, const double *src, const int valid, const bool kok) {
+    if (kok && valid >= 2) {
+        spl_cp_async16(dst, src);
+    } else if (kok && valid == 1) {
+        // (asynchronous too: a blocking load here cost a full L2 round trip per column in every tile of an edge row
+        // with an odd number of rows -- cfg3's half bandwidth is 1803 -- and those tiles' CTAs were the last at every
+        // barrier)
+        spl_cp_async8(dst, src);
+        dst[1] = 0.0;
+    } else {
+        *reinterpret_cast<double2 *>(dst) = make_double2(0.0, 0.0);
+    }
+}
+// 64 rows x 64 columns at src (column-major, leading dimension lda; `rows` of the rows and `nb` of the columns
+// exist, the rest reads as zero) -> shared memory s[column * TILE_LD + row], with PANEL_THREADS threads: 8 pieces per
+// thread, a warp covers the 64 rows of one column (512 contiguous bytes).  The caller commits the cp.async group.
+__device__ __forceinline__ void spl_tile_load16(double *s, const double *src, const long long lda, const int rows,
+                                                const int nb, const int t) {
+    const int r = 2 * (t & 31);
+    int k = t >> 5;
+    const double *gp = src + r + (long long)k * lda;
+    double *dp = s + k * TILE_LD + r;
+    const int valid = rows - r;
+    const long long gstep = 8 * lda;
+#pragma unroll
+    for (int q = 0; q < 8; ++q, k += 8) {
+        spl_tile_piece(dp, gp, valid, k < nb);
+        gp += gstep;
+        dp += 8 * TILE_LD;
+    }
 }
 
 #define PANEL_LDT 36    // 32 + 4, same bank argument as TILE_LD
@@ -370,7 +412,7 @@ __device__ __forceinline__ void spl_inv_level(const double *sL, double *sX, doub
         *reinterpret_cast<double2 *>(sT + (q * SZ + ti * 8 + gq) * PANEL_LDT + tj * 8 + 2 * t4) =
             make_double2(c0 + d0, c1 + d1);
     }
-    __syncthreads();
+    SPL_SYNC256();
     for (int tl = warp; tl < NTILE; tl += PANEL_THREADS / 32) {                  // X21 = -X22 T
         const int q = tl / TPI, rem = tl % TPI, ti = rem / TR, tj = rem % TR;
         const int rb = (2 * q + 1) * SZ, cb = 2 * q * SZ;
@@ -385,7 +427,211 @@ __device__ __forceinline__ void spl_inv_level(const double *sL, double *sX, doub
         *reinterpret_cast<double2 *>(sX + (rb + ti * 8 + gq) * TILE_LD + cb + tj * 8 + 2 * t4) =
             make_double2(-(c0 + d0), -(c1 + d1));
     }
-    __syncthreads();
+    SPL_SYNC256();
+}
+
+// ---- pieces of the diagonal-block chain, shared by spl_panel_body and the data-flow kernel's diagonal CTA ----
+// Thread (ri, rc) = (tid / 4, tid % 4) owns u[kk] = A11[ri][4 kk + rc], kk = 0..15 (lower triangle, identity padding).
+//
+// Right-looking Cholesky in the square-root-free form, one barrier per column.  Column j of the Schur complement is
+// published unscaled (u_ij); every thread forms 1/d_j itself (d_j = u_jj) and applies  u_ik -= (u_ij / d_j) u_kj  to its
+// 16 entries.  The dependent chain per pivot is publish -> barrier -> reciprocal -> one multiply -> one FMA (the entry
+// of column j+1), instead of a 4 x 4 block factorisation + two triangular solves per four pivots; L = U diag(d)^-1/2
+// is formed afterwards (spl_linv64).  s_rd[j] = d_j on return; *s_bad is set on a non-positive (or NaN) pivot.
+template <int JLO = 0, int JHI = 64>      // pivots [JLO, JHI): the caller may put work between two halves
+__device__ __forceinline__ void spl_chol64(double (&u)[16], double *s_col, double *s_rd, int *s_bad, const int tid) {
+    const int ri = tid >> 2, rc = tid & 3;
+#pragma unroll
+    for (int j = JLO; j < JHI; ++j) {
+        const int kj = j >> 2, cj = j & 3;
+        double *col = s_col + (j & 1) * 64;
+        if (rc == cj) col[ri] = u[kj];
+        SPL_SYNC256();
+        const double d = col[j];
+        // 1/d: hardware seed + one cubically convergent step: y0 (1 + e + e^2), e = 1 - d y0 ~ 2^-23 -> 2^-69 (three
+        // dependent operations; two Newton steps are four, and FP64 latency is what this loop is made of)
+        double ci;
+        {
+            double y0;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+            const double e = fma(-d, y0, 1.0);
+            const double e2 = fma(e, e, e);
+            // ci = col[ri] / d = t (1 + e2), t = col[ri] y0: t does not wait for e, so forming ci directly is
+            // one dependent FP64 operation shorter than rinv = y0 (1 + e2) followed by col[ri] * rinv
+            const double t = col[ri] * y0;
+            ci = fma(t, e2, t);
+        }
+        if (tid == 0) {
+            s_rd[j] = d;                                     // d_j for now; 1 / L_jj after spl_linv64
+            if (!(d > 0.0)) *s_bad = 1;                      // non-positive (or NaN) pivot -> 107
+        }
+#pragma unroll
+        for (int kk = kj; kk < 16; ++kk) {
+            const int k = 4 * kk + rc;
+            if (k > j) u[kk] = fma(-ci, col[k], u[kk]);
+        }
+    }
+    if (JHI == 64) SPL_SYNC256();
+}
+
+// 1 / L_jj = d_j^-1/2 (seed + two Goldschmidt steps), L11 = U diag(d)^-1/2 -> sX (row-major, stride TILE_LD), then
+// X = L11^-1 IN PLACE, blocked: the eight 8 x 8 diagonal blocks by forward substitution (64 threads, an 8-step chain
+// each), then three doubling levels  X21 = -X22 (L21 X11)  on the tensor cores.  One thread per column running the
+// whole 64-step substitution took 14.1k clocks.
+__device__ __forceinline__ void spl_linv64(const double (&u)[16], double *s_rd, double *sX, double *sT, const int tid) {
+    const int ri = tid >> 2, rc = tid & 3;
+    if (tid < 64) {
+        const double d = s_rd[tid];
+        double y0;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+        double gq2 = d * y0;
+        double hq = 0.5 * y0;
+#pragma unroll
+        for (int itn = 0; itn < 2; ++itn) {
+            const double rr = fma(-gq2, hq, 0.5);
+            gq2 = fma(gq2, rr, gq2);
+            hq = fma(hq, rr, hq);
+        }
+        s_rd[tid] = 2.0 * hq;
+    }
+    SPL_SYNC256();
+    double *sL = sX;
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+        const int k = 4 * kk + rc;
+        sL[ri * TILE_LD + k] = (k <= ri) ? u[kk] * s_rd[k] : 0.0;
+    }
+    SPL_SYNC256();
+    {
+        const int b0 = tid & 56, cj = tid & 7;            // threads >= 64 compute nothing
+        double Lb[8][8], X[8];
+        if (tid < 64) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int c = 0; c < i; ++c) Lb[i][c] = sL[(b0 + i) * TILE_LD + b0 + c];
+        }
+        SPL_SYNC256();                                  // the block is in registers: X may overwrite it
+        if (tid < 64) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < i; ++c) {
+                    if (c & 1) s1 = fma(Lb[i][c], X[c], s1);
+                    else s0 = fma(Lb[i][c], X[c], s0);
+                }
+                const double rhs = (i == cj) ? 1.0 : 0.0;
+                X[i] = (rhs - (s0 + s1)) * s_rd[b0 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sX[(b0 + i) * TILE_LD + b0 + cj] = X[i];
+        }
+    }
+    SPL_SYNC256();
+    spl_inv_level<8>(sL, sX, sT, tid);
+    spl_inv_level<16>(sL, sX, sT, tid);
+    spl_inv_level<32>(sL, sX, sT, tid);
+}
+
+// y1[ri] = sum_k Linv[ri][k] g1[k]: four threads per row (ri, rc), 16 products each (k = rc + 4 q: conflict-free),
+// combined with two shuffles; every thread of the row returns the sum.
+__device__ __forceinline__ double spl_y1_64(const double *sX, const double *s_g, const int tid) {
+    const int ri = tid >> 2, rc = tid & 3;
+    double y1c = 0.0, y1d = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; q += 2) {
+        y1c = fma(sX[ri * TILE_LD + rc + 4 * q], s_g[rc + 4 * q], y1c);
+        y1d = fma(sX[ri * TILE_LD + rc + 4 * q + 4], s_g[rc + 4 * q + 4], y1d);
+    }
+    y1c += y1d;
+    y1c += __shfl_xor_sync(0xffffffffu, y1c, 1);
+    y1c += __shfl_xor_sync(0xffffffffu, y1c, 2);
+    return y1c;
+}
+
+// L21 tile = A21 tile * Linv^T: out[r][c] = sum_k A21[r][k] Linv[c][k] for the 64 rows R0.. (relative to r0) whose A21
+// tile is in sA (k-major); stored into AB, and (WITH_G) the right-hand side below the block is updated: g2 -= L21 y1
+// (s_g = y1) with atomic adds into g -- the data-flow kernel's workers do that later from the tile left in sA
+// (spl_g_update), so that the diagonal CTA can publish L11^-1 before it has formed y1.
+// keep_l21: leave the L21 tile in sA, k-major, where the tile update expects its A operand.
+template <bool WITH_G = true>
+__device__ __forceinline__ void spl_l21_gemm(double *AB, long long lda, long long j0, int nb, int m, long long r0,
+                                             int R0, double *g, double *sA, const double *sX, const double *s_g,
+                                             const bool keep_l21, const int tid) {
+    // Linv is lower triangular: column block cb (8 columns) of the product needs k < 8 cb + 8 only.  A warp owns 16
+    // rows and the four column blocks cb = 2 ni + (warp & 1) -- interleaved, so the two warp classes do 64 and 80 of
+    // the 128 MMAs of the full product instead of 40 and 104.
+    const int warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, t4 = lane & 3;
+    const int wy = (warp >> 1) * 16, wodd = warp & 1;
+    double acc[2][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll 4
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+        double af[2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) af[mi] = sA[(k0 + t4) * TILE_LD + wy + mi * 8 + gq];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int cb = 2 * ni + wodd;
+            if (k0 < 8 * cb + 8) {                                                          // warp-uniform
+                const double bf = sX[(cb * 8 + gq) * TILE_LD + k0 + t4];                    // B[k][n] = Linv[n][k]
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf);
+            }
+        }
+    }
+    // store L21 and update the right-hand side below the block: g2 -= L21 y1
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+        const int r = R0 + wy + mi * 8 + gq;
+        double part = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = (2 * ni + wodd) * 8 + 2 * t4 + h;
+                const double v = acc[mi][ni][h];
+                if (r < m && c < nb) AB[(r0 + r) + (j0 + c) * lda] = v;
+                if (WITH_G) part = fma(v, s_g[c], part);
+            }
+        if (WITH_G) {
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (t4 == 0 && r < m && part != 0.0) atomicAdd(g + r0 + r, -part);
+        }
+    }
+    if (keep_l21) {
+        SPL_SYNC256();                                      // everyone is done reading sA (A21)
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    sA[((2 * ni + wodd) * 8 + 2 * t4 + h) * TILE_LD + wy + mi * 8 + gq] = acc[mi][ni][h];
+    }
+}
+
+// g2 -= L21 y1 for the 64 rows R0.. from the L21 tile in sA (k-major) and y1 in s_g: four threads per row (16
+// products each, conflict-free), two shuffles, one atomic add per row.
+__device__ __forceinline__ void spl_g_update(double *g, long long r0, int R0, int m, const double *sA, const double *s_g,
+                                             const int tid) {
+    const int ri = tid >> 2, rc = tid & 3;
+    double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; q += 2) {
+        p0 = fma(sA[(rc + 4 * q) * TILE_LD + ri], s_g[rc + 4 * q], p0);
+        p1 = fma(sA[(rc + 4 * q + 4) * TILE_LD + ri], s_g[rc + 4 * q + 4], p1);
+    }
+    p0 += p1;
+    p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+    p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+    if (rc == 0 && R0 + ri < m && p0 != 0.0) atomicAdd(g + r0 + R0 + ri, -p0);
 }
 
 // Every CTA factors the nb x nb diagonal block A11 = L11 L11^T (four threads per row, 16 entries each in
@@ -396,7 +642,7 @@ __device__ __forceinline__ void spl_inv_level(const double *sL, double *sX, doub
 // inverse, so no per-row substitution chain) and  g2 -= L21 y1.
 // CTA 0 stores L11^-1 (for the back-substitution) and y1.
 // cta / ncta: this CTA's index among the CTAs working on the panel and their number (the stand-alone kernel passes
-// blockIdx.x / gridDim.x; the persistent factor kernel its first CTAs).  failed: an earlier panel failed.
+// blockIdx.x / gridDim.x; the barrier-phased persistent kernel its first CTAs).  failed: an earlier panel failed.
 __device__ __forceinline__ void spl_panel_body(double *AB, long long lda, long long j0, int nb, int m, double *g,
                                                double *ysol, double *linv_blk, int *fail, long long *dbg,
                                                double *s_pan, const int cta, const int ncta, const int failed,
@@ -404,11 +650,10 @@ __device__ __forceinline__ void spl_panel_body(double *AB, long long lda, long l
 #define PANEL_STAMP(i) do { if (dbg && cta == 0 && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
     PANEL_STAMP(0);
     double *sA = s_pan;                          // [k][row]  A21 tile, 64 x TILE_LD
-    double *sX = s_pan + 64 * TILE_LD;           // [n][k]    L11^-1, row-major, stride TILE_LD
+    double *sX = s_pan + 64 * TILE_LD;           // [n][k]    L11, then L11^-1, row-major, stride TILE_LD
     double *s_col = sX + 64 * TILE_LD;           // 2 x 64   pivot column (double buffered)
     double *s_g = s_col + 128;                   // 64       g1, then y1
     double *s_rd = s_g + 64;                     // 64       d_k, then 1 / L11[k][k]
-    double *s_lfac = sX;                         // L11, row-major, inverted in place
     double *sT = s_rd + 64;                      // 32 x PANEL_LDT  L21 X11 of the current inversion level
     int *s_bad = reinterpret_cast<int *>(sT + 32 * PANEL_LDT);
     const int tid = threadIdx.x;
@@ -429,12 +674,7 @@ __device__ __forceinline__ void spl_panel_body(double *AB, long long lda, long l
     if (tid == 0) *s_bad = 0;
 
     // ---- start streaming this CTA's A21 tile into shared memory; it lands under the factorization ----
-    for (int e = tid; e < 64 * 64; e += PANEL_THREADS) {
-        const int k = e >> 6, r = e & 63;
-        double *dst = sA + k * TILE_LD + r;
-        if (k < nb && R0 + r < m) spl_cp_async8(dst, AB + (r0 + R0 + r) + (j0 + k) * lda);
-        else *dst = 0.0;
-    }
+    spl_tile_load16(sA, AB + (r0 + R0) + j0 * lda, lda, m - R0, nb, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (failed) {
         spl_cp_async_wait_all();
@@ -442,137 +682,25 @@ __device__ __forceinline__ void spl_panel_body(double *AB, long long lda, long l
     }
 
     PANEL_STAMP(1);
-    // ---- right-looking Cholesky in the square-root-free form, one barrier per column.
-    // Column j of the Schur complement is published unscaled (u_ij); every thread forms 1/d_j itself
-    // (d_j = u_jj) and applies  u_ik -= (u_ij / d_j) u_kj  to its 16 entries.  The dependent chain per pivot is
-    // publish -> barrier -> reciprocal -> one multiply -> one FMA (the entry of column j+1), instead of a 4 x 4
-    // block factorisation + two triangular solves per four pivots; L = U diag(d)^-1/2 is formed at the end. ----
-#pragma unroll
-    for (int j = 0; j < 64; ++j) {
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int kj = j >> 2, cj = j & 3;
-        double *col = s_col + (j & 1) * 64;
-        if (rc == cj) col[ri] = u[kj];
-        __syncthreads();
-        const double d = col[j];
-        // 1/d: hardware seed + two Newton steps (d > 0 and finite for a valid pivot)
-        double rinv;
-        {
-            double y0;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-            // one cubically convergent step: y0 (1 + e + e^2), e = 1 - d y0 ~ 2^-23 -> 2^-69 (three dependent
-            // operations; two Newton steps are four, and FP64 latency is what this loop is made of)
-            const double e = fma(-d, y0, 1.0);
-            const double e2 = fma(e, e, e);
-            // ci = col[ri] / d = t (1 + e2), t = col[ri] y0: t does not wait for e, so forming ci directly is
-            // one dependent FP64 operation shorter than rinv = y0 (1 + e2) followed by col[ri] * rinv
-            const double t = col[ri] * y0;
-            rinv = fma(t, e2, t);
-        }
-        if (tid == 0) {
-            s_rd[j] = d;                                     // d_j for now; 1/L_jj after the loop
-            if (!(d > 0.0)) *s_bad = 1;                      // non-positive (or NaN) pivot -> 107
-        }
-        const double ci = rinv;
-#pragma unroll
-        for (int kk = kj; kk < 16; ++kk) {
-            const int k = 4 * kk + rc;
-            if (k > j) u[kk] = fma(-ci, col[k], u[kk]);
-        }
-    }
-    __syncthreads();
+    spl_chol64(u, s_col, s_rd, s_bad, tid);
     PANEL_STAMP(2);
     if (*s_bad) {
         if (cta == 0 && tid == 0) *fail = 1;
         spl_cp_async_wait_all();
         return;
     }
-    // ---- 1 / L_jj = d_j^-1/2 (seed + two Goldschmidt steps), then L11 = U diag(d)^-1/2 -> shared memory ----
-    if (tid < 64) {
-        const double d = s_rd[tid];
-        double y0;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-        double gq2 = d * y0;
-        double hq = 0.5 * y0;
-#pragma unroll
-        for (int itn = 0; itn < 2; ++itn) {
-            const double rr = fma(-gq2, hq, 0.5);
-            gq2 = fma(gq2, rr, gq2);
-            hq = fma(hq, rr, hq);
-        }
-        s_rd[tid] = 2.0 * hq;
-    }
-    __syncthreads();
-    double *sL = s_lfac;
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-        const int k = 4 * kk + rc;
-        sL[ri * TILE_LD + k] = (k <= ri) ? u[kk] * s_rd[k] : 0.0;
-    }
-    __syncthreads();
-    // ---- X = L11^-1, blocked: the eight 8 x 8 diagonal blocks by forward substitution (64 threads, an 8-step
-    //      chain each), then three doubling levels  X21 = -X22 (L21 X11)  on the tensor cores.  One thread per
-    //      column running the whole 64-step substitution took 14.1k clocks. ----
+    spl_linv64(u, s_rd, sX, sT, tid);
+    // L11^-1 for the back-substitution: every CTA has it, each stores a slice of its rows
     {
-        PANEL_STAMP(7);
-        {
-            const int b0 = tid & 56, cj = tid & 7;            // threads >= 64 compute nothing
-            double Lb[8][8], X[8];
-            if (tid < 64) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int c = 0; c < i; ++c) Lb[i][c] = sL[(b0 + i) * TILE_LD + b0 + c];
-            }
-            __syncthreads();                                  // the block is in registers: X may overwrite it
-            if (tid < 64) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int c = 0; c < i; ++c) {
-                        if (c & 1) s1 = fma(Lb[i][c], X[c], s1);
-                        else s0 = fma(Lb[i][c], X[c], s0);
-                    }
-                    const double rhs = (i == cj) ? 1.0 : 0.0;
-                    X[i] = (rhs - (s0 + s1)) * s_rd[b0 + i];
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) sX[(b0 + i) * TILE_LD + b0 + cj] = X[i];
-            }
-        }
-        __syncthreads();
-        PANEL_STAMP(8);
-        spl_inv_level<8>(sL, sX, sT, tid);
-        spl_inv_level<16>(sL, sX, sT, tid);
-        spl_inv_level<32>(sL, sX, sT, tid);
-        PANEL_STAMP(9);
-        // L11^-1 for the back-substitution: every CTA has it, each stores a slice of its rows
-        {
-            const int rows = (64 + ncta - 1) / ncta;
-            const int rlo = cta * rows, rhi = min(64, rlo + rows);
-            for (int e = rlo * 64 + tid; e < rhi * 64; e += PANEL_THREADS) linv_blk[e] = sX[(e >> 6) * TILE_LD + (e & 63)];
-        }
+        const int rows = (64 + ncta - 1) / ncta;
+        const int rlo = cta * rows, rhi = min(64, rlo + rows);
+        for (int e = rlo * 64 + tid; e < rhi * 64; e += PANEL_THREADS) linv_blk[e] = sX[(e >> 6) * TILE_LD + (e & 63)];
     }
     PANEL_STAMP(3);
     spl_cp_async_wait_all();
     __syncthreads();
     PANEL_STAMP(4);
-    // y1[c] = sum_k Linv[c][k] g1[k]
-    // four threads per row (ri, rc): 16 products each (k = rc + 4 q: conflict-free), combined with two shuffles
-    double y1c = 0.0;
-    {
-        double y1d = 0.0;
-#pragma unroll
-        for (int q = 0; q < 16; q += 2) {
-            y1c = fma(sX[ri * TILE_LD + rc + 4 * q], s_g[rc + 4 * q], y1c);
-            y1d = fma(sX[ri * TILE_LD + rc + 4 * q + 4], s_g[rc + 4 * q + 4], y1d);
-        }
-        y1c += y1d;
-        y1c += __shfl_xor_sync(0xffffffffu, y1c, 1);
-        y1c += __shfl_xor_sync(0xffffffffu, y1c, 2);
-    }
+    const double y1c = spl_y1_64(sX, s_g, tid);
     __syncthreads();
     if (rc == 0) {
         s_g[ri] = y1c;
@@ -581,58 +709,7 @@ __device__ __forceinline__ void spl_panel_body(double *AB, long long lda, long l
     __syncthreads();
     PANEL_STAMP(5);
     if (m <= 0) return;
-
-    // ---- L21 tile = A21 tile * Linv^T: out[r][c] = sum_k A21[r][k] Linv[c][k] ----
-    const int warp = tid >> 5, lane = tid & 31;
-    const int gq = lane >> 2, t4 = lane & 3;
-    const int wy = (warp >> 1) * 16, wx = (warp & 1) * 32;
-    double acc[2][4][2];
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-#pragma unroll 4
-    for (int k0 = 0; k0 < 64; k0 += 4) {
-        double af[2], bf[4];
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi) af[mi] = sA[(k0 + t4) * TILE_LD + wy + mi * 8 + gq];
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) bf[ni] = sX[(wx + ni * 8 + gq) * TILE_LD + k0 + t4];   // B[k][n] = Linv[n][k]
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-    }
-    // store L21 and update the right-hand side below the block: g2 -= L21 y1
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-        const int r = R0 + wy + mi * 8 + gq;
-        double part = 0.0;
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = wx + ni * 8 + 2 * t4 + h;
-                const double v = acc[mi][ni][h];
-                if (r < m && c < nb) AB[(r0 + r) + (j0 + c) * lda] = v;
-                part = fma(v, s_g[c], part);
-            }
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        if (t4 == 0 && r < m && part != 0.0) atomicAdd(g + r0 + r, -part);
-    }
-    if (keep_l21) {
-        // leave this CTA's L21 tile in shared memory, k-major, where spl_syrk_tile expects its A operand: the
-        // persistent kernel's column-0 update of the same tile row then loads only the other operand
-        __syncthreads();                                      // everyone is done reading sA (A21)
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    sA[(wx + ni * 8 + 2 * t4 + h) * TILE_LD + wy + mi * 8 + gq] = acc[mi][ni][h];
-    }
+    spl_l21_gemm(AB, lda, j0, nb, m, r0, R0, g, sA, sX, s_g, keep_l21, tid);
     PANEL_STAMP(6);
 }
 
@@ -842,6 +919,147 @@ spl_syrk_kernel(double *__restrict__ AB, long long lda, long long r0, long long 
 }
 
 // ------------------------------------------------------------------------------------------
+// Update tile for 256 threads, split in two halves so that a CTA with a list of tiles can have the operands of the
+// next tile in flight under the MMA stream of the current one:
+//   spl_tile_issue   operands of tile (ti, tj) -> shared memory buffer (sA | sB), k-major, 16-byte cp.async, one
+//                    committed group;
+//   spl_tile_finish  C tile -> accumulators (128-bit loads), wait for the operands, 64 x 64 x 64 on the FP64 tensor
+//                    cores, 128-bit stores.  The product is formed TRANSPOSED (the MMA's rows are the tile's columns
+//                    J, the MMA's column pairs are consecutive rows I), so the two accumulators of a fragment are
+//                    adjacent in the column-major band matrix.
+// Warp w of 8: rows I in [32 (w & 1), +32), columns J in [16 (w >> 1), +16).
+// ------------------------------------------------------------------------------------------
+// half = -1: the whole tile; 0 / 1: its rows [32 half, +32) only (the last, partial round of a helper list is split
+// in row halves so that nobody carries a whole extra tile) -- the A operand then holds 32 rows, B all 64 even on the
+// diagonal, and the eight warps take 32 x 8 each (MJ = 1) instead of 32 x 16.
+template <bool A_READY>
+__device__ __forceinline__ void spl_tile_issue(const double *AB, long long lda, long long r0, long long j0, int nb,
+                                               int m, int ti, int tj, double *s_ab, const int half = -1) {
+    const int t = threadIdx.x;
+    const int I0 = ti * SYRK_TILE + (half > 0 ? 32 : 0), J0 = tj * SYRK_TILE;
+    if (!A_READY) {
+        int rows = m - I0;
+        if (half >= 0 && rows > 32) rows = 32;
+        spl_tile_load16(s_ab, AB + (r0 + I0) + j0 * lda, lda, rows, nb, t);
+    }
+    if (ti != tj || half >= 0) spl_tile_load16(s_ab + 64 * TILE_LD, AB + (r0 + J0) + j0 * lda, lda, m - J0, nb, t);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// C tile of (ti, tj) -> accumulators.  Thread layout, MJ = 2 (warp w of 8: rows I in [32 (w & 1), +32), columns J in
+// [16 (w >> 1), +16)) or MJ = 1 (half tile: rows [0, 32) of the half, columns [8 w, +8)):
+// accumulator (mj, ni, h) = C[I0 + wI + ni 8 + 2 t4 + h][J0 + wJ + mj 8 + g].
+template <int MJ>
+__device__ __forceinline__ void spl_tile_cload(double (&acc)[2][4][2], const double *AB, long long lda, long long r0,
+                                               int m, int ti, int tj, const int half = -1) {
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wI = (MJ == 2) ? (warp & 1) * 32 : 0, wJ = (MJ == 2) ? (warp >> 1) * 16 : warp * 8;
+    const int I0 = ti * SYRK_TILE + (half > 0 ? 32 : 0), J0 = tj * SYRK_TILE;
+    const double *pc = AB + (r0 + I0 + wI + 2 * t4) + (r0 + J0 + wJ + g) * lda;
+    const bool inside = ti != tj && I0 + (MJ == 2 ? 64 : 32) <= m && J0 + 64 <= m;   // no per-element tests
+    if (inside) {
+#pragma unroll
+        for (int mj = 0; mj < MJ; ++mj)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const double2 v = __ldcg(reinterpret_cast<const double2 *>(pc + ni * 8 + (long long)(mj * 8) * lda));
+                acc[mj][ni][0] = v.x;
+                acc[mj][ni][1] = v.y;
+            }
+    } else {
+#pragma unroll
+        for (int mj = 0; mj < MJ; ++mj)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    // raw, unconditional loads; spl_tile_mma_store masks them when it starts, i.e. when they have landed
+                    // (a conditional load becomes a branch per element, and a select right here would wait for the L2
+                    // round trip before the previous tile's MMA stream instead of under it).  The address of an element
+                    // outside the window or above the diagonal is still inside the band array: a column has
+                    // lda >= bw + 64 rows and the array 64 spare elements behind the last column.
+                    acc[mj][ni][h] = __ldcg(pc + ni * 8 + h + (long long)(mj * 8) * lda);
+                }
+    }
+}
+
+template <int PENDING, int MJ>   // PENDING: cp.async groups that may stay in flight (1: the next tile's operands)
+__device__ __forceinline__ void spl_tile_mma_store(double (&acc)[2][4][2], double *AB, long long lda, long long r0,
+                                                   int m, int ti, int tj, const double *s_ab, const int half = -1) {
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wI = (MJ == 2) ? (warp & 1) * 32 : 0, wJ = (MJ == 2) ? (warp >> 1) * 16 : warp * 8;
+    const int I0 = ti * SYRK_TILE + (half > 0 ? 32 : 0), J0 = tj * SYRK_TILE;
+    const bool diag = (ti == tj);
+    const double *sA = s_ab;
+    const double *sB = (diag && half < 0) ? s_ab : s_ab + 64 * TILE_LD;
+    double *pc = AB + (r0 + I0 + wI + 2 * t4) + (r0 + J0 + wJ + g) * lda;
+    const bool inside = !diag && I0 + (MJ == 2 ? 64 : 32) <= m && J0 + 64 <= m;
+    if (PENDING == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.wait_group 1;" ::: "memory");
+    SPL_SYNC256();
+    if (!inside) {
+#pragma unroll
+        for (int mj = 0; mj < MJ; ++mj)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int li = I0 + wI + ni * 8 + 2 * t4 + h;
+                    const int lj = J0 + wJ + mj * 8 + g;
+                    if (!(li < m && lj < m && li >= lj)) acc[mj][ni][h] = 0.0;
+                }
+    }
+#pragma unroll 4
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+        double a[MJ], b[4];
+#pragma unroll
+        for (int mj = 0; mj < MJ; ++mj) a[mj] = -sB[(k0 + t4) * TILE_LD + wJ + mj * 8 + g];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = sA[(k0 + t4) * TILE_LD + wI + ni * 8 + g];
+#pragma unroll
+        for (int mj = 0; mj < MJ; ++mj)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) spl_dmma_8x8x4(acc[mj][ni][0], acc[mj][ni][1], a[mj], b[ni]);
+    }
+    if (inside) {
+#pragma unroll
+        for (int mj = 0; mj < MJ; ++mj)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+                *reinterpret_cast<double2 *>(pc + ni * 8 + (long long)(mj * 8) * lda) =
+                    make_double2(acc[mj][ni][0], acc[mj][ni][1]);
+    } else {
+#pragma unroll
+        for (int mj = 0; mj < MJ; ++mj)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int li = I0 + wI + ni * 8 + 2 * t4 + h;
+                    const int lj = J0 + wJ + mj * 8 + g;
+                    if (li < m && lj < m && li >= lj) pc[ni * 8 + h + (long long)(mj * 8) * lda] = acc[mj][ni][h];
+                }
+    }
+}
+
+template <int PENDING>
+__device__ __forceinline__ void spl_tile_finish(double *AB, long long lda, long long r0, int m, int ti, int tj,
+                                                const double *s_ab) {
+    double acc[2][4][2];
+    spl_tile_cload<2>(acc, AB, lda, r0, m, ti, tj);
+    spl_tile_mma_store<PENDING, 2>(acc, AB, lda, r0, m, ti, tj, s_ab);
+}
+
+template <bool A_READY>
+__device__ __forceinline__ void spl_tile256(double *AB, long long lda, long long r0, long long j0, int nb, int m,
+                                            int ti, int tj, double *s_ab) {
+    spl_tile_issue<A_READY>(AB, lda, r0, j0, nb, m, ti, tj, s_ab);
+    spl_tile_finish<0>(AB, lda, r0, m, ti, tj, s_ab);
+}
+
+// ------------------------------------------------------------------------------------------
 // persistent factorisation: the whole right-looking loop in ONE cooperative kernel (one 256-thread CTA per SM),
 // phases separated by grid-wide barriers instead of kernel boundaries and cross-stream events:
 //   step kb, phase P:  CTAs [0, pblocks) run panel(kb)  ||  the other CTAs finish the trailing update of step kb-1
@@ -911,7 +1129,7 @@ spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, dou
             for (int u = me; u < nfull; u += helpers) {
                 int ti, tj;
                 spl_rest_tile(pfirst + u, ti, tj);
-                spl_syrk_tile<PANEL_THREADS>(AB, lda, pr0, pj0, pnb, pm, ti, tj, s_dyn_f);
+                spl_tile256<false>(AB, lda, pr0, pj0, pnb, pm, ti, tj, s_dyn_f);
                 __syncthreads();
             }
             if (2 * rem <= helpers) {
@@ -919,12 +1137,12 @@ spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, dou
                     int ti, tj;
                     spl_rest_tile(pfirst + nfull + (me >> 1), ti, tj);
                     if (ti != tj) spl_syrk_half_tile(AB, lda, pr0, pj0, pnb, pm, ti, tj, me & 1, s_dyn_f);
-                    else if ((me & 1) == 0) spl_syrk_tile<PANEL_THREADS>(AB, lda, pr0, pj0, pnb, pm, ti, tj, s_dyn_f);
+                    else if ((me & 1) == 0) spl_tile256<false>(AB, lda, pr0, pj0, pnb, pm, ti, tj, s_dyn_f);
                 }
             } else if (me < rem) {
                 int ti, tj;
                 spl_rest_tile(pfirst + nfull + me, ti, tj);
-                spl_syrk_tile<PANEL_THREADS>(AB, lda, pr0, pj0, pnb, pm, ti, tj, s_dyn_f);
+                spl_tile256<false>(AB, lda, pr0, pj0, pnb, pm, ti, tj, s_dyn_f);
             }
         }
         if (dbg && kb == nblk / 2 && cta == 0 && threadIdx.x == 0) dbg[12] = clock64();
@@ -938,14 +1156,14 @@ spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, dou
         if (m > 0) {
             if (cta < T) {
                 for (int ti = cta; ti < T; ti += G) {
-                    if (one_row_each && ti == cta) spl_syrk_tile<PANEL_THREADS, true>(AB, lda, r0, j0, nb, m, ti, 0, s_dyn_f);
-                    else spl_syrk_tile<PANEL_THREADS>(AB, lda, r0, j0, nb, m, ti, 0, s_dyn_f);
+                    if (one_row_each && ti == cta) spl_tile256<true>(AB, lda, r0, j0, nb, m, ti, 0, s_dyn_f);
+                    else spl_tile256<false>(AB, lda, r0, j0, nb, m, ti, 0, s_dyn_f);
                     __syncthreads();
                 }
             } else if (cta - T < ntiles) {
                 int ti, tj;
                 spl_rest_tile(cta - T, ti, tj);
-                spl_syrk_tile<PANEL_THREADS>(AB, lda, r0, j0, nb, m, ti, tj, s_dyn_f);
+                spl_tile256<false>(AB, lda, r0, j0, nb, m, ti, tj, s_dyn_f);
             }
             first = (G - T > 0) ? ((G - T < ntiles) ? G - T : ntiles) : 0;
         }
@@ -958,6 +1176,508 @@ spl_factor_persistent_kernel(double *AB, long long lda, long long n, int bw, dou
         if (dbg && kb == nblk / 2 && cta == 0 && threadIdx.x == 0) dbg[14] = clock64();
         spl_grid_barrier(bar, bar_target, (unsigned)G);
         if (dbg && kb == nblk / 2 && cta == 0 && threadIdx.x == 0) dbg[15] = clock64();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// DATA-FLOW factorisation (default where the panel chain dominates): one cooperative kernel, one CTA per SM, three
+// roles coupled by release/acquire flags instead of grid-wide phases.  The critical path of the right-looking loop is
+//   chol(k) -> L11^-1 -> L[k+1,k] -> update of block (k+1,k+1) -> chol(k+1);
+// the barrier-phased kernel above put two grid barriers, a global round trip of the diagonal block and the slowest
+// helper's tile on it (43k clocks per step at cfg3 for a 28k chain).  Here
+//   CTA 0 (diagonal)    eight compute warps run exactly that chain and touch shared memory only: the updated
+//                       diagonal block never leaves the SM.  A NINTH warp does everything that talks to the rest of
+//                       the GPU, coupled to the compute warps by named barriers: it waits for the two blocks the step
+//                       reads (flags T10, T11: one step behind) and streams them in under the factorization, stores
+//                       L11^-1 and y1 and raises LINV, stores L[k+1,k], forms this CTA's share of g2 -= L21 y1 and
+//                       raises L10 -- fences, flag polls and global stores are off the chain.
+//   CTAs 1 .. Tmax-1    tile rows 1.. of the panel: wait for LINV, L21 = A21 L11^-T, g2 -= L21 y1  | barrier B1 (all
+//   (panel workers)     workers) | column-0 tile of their row (A operand still in shared memory; B = L[k+1,k], flag
+//                       L10); CTA 1 raises T10 | barrier B2 (panel workers only: the next A21 tiles are final) | one
+//                       rest tile from the end of the list while the diagonal CTA factors the next block.
+//   the other CTAs      B1(k), then the rest tiles (ti >= tj >= 1) of update k as ONE list with the next tile's
+//   (helpers)           operands and C tile in flight under the current MMA stream; helper 0 starts with (1,1) and
+//                       raises T11.
+// Every spin gives up when the failure flag is set or after a watchdog interval (which sets it), so the kernel
+// cannot hang; a failure is reported as 107 like a non-positive pivot.
+// ------------------------------------------------------------------------------------------
+#define DF_THREADS 288                     // 8 working warps + the diagonal CTA's communication warp
+#define DF_FLAG_STRIDE 32                  // unsigneds between flags: one 128-byte line each
+enum { DF_B1 = 0, DF_B2 = 1, DF_LINV = 2, DF_L10 = 3, DF_T10 = 4, DF_T11 = 5, DF_NFLAGS = 6 };
+#define DF_WATCHDOG_CLOCKS (1LL << 32)     // ~2 s
+// named barriers of the diagonal CTA (all 288 threads: one side arrives, the other waits)
+#define DF_STR_(x) #x
+#define DF_STR(x) DF_STR_(x)
+#define DF_BAR_SYNC(id) asm volatile("bar.sync " DF_STR(id) ", 288;" ::: "memory")
+#define DF_BAR_ARRIVE(id) asm volatile("bar.arrive " DF_STR(id) ", 288;" ::: "memory")
+#define DF_NB_OPER 1        // comm -> compute: the flags of the two blocks this step reads are acquired (and the
+                            //                  communication warp is done with the previous step)
+#define DF_NB_LINV 2        // compute -> comm: L11^-1 stored
+#define DF_NB_L10 3         // compute -> comm: y1 and L[k+1,k] stored, L[k+1,k] also in sA (k-major), y1 in s_g
+
+__device__ __forceinline__ unsigned spl_ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread spins until *flag >= target: relaxed polls (an acquire load invalidates the SM's L1 every time, next
+// to warps whose shared-memory chain is the critical path), then ONE acquire load of the flag.  (Measured: relaxed polls
+// followed by a fence.acq_rel.gpu are slower, 33.4k -> 39k clocks per step -- the two-way fence waits for the CTA's
+// own stores and cp.async prefetches in flight, the one-way acquire load does not.)
+__device__ __forceinline__ unsigned spl_ld_relaxed(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int SLEEP_NS = 20>
+__device__ __forceinline__ void spl_df_spin(const unsigned *flag, const unsigned target, int *fail) {
+    if (spl_ld_acquire(flag) >= target) return;
+    const long long t0 = clock64();
+    unsigned it = 0;
+    while (spl_ld_relaxed(flag) < target) {
+        __nanosleep(SLEEP_NS);
+        if ((++it & 63u) == 0u) {
+            if (*reinterpret_cast<volatile int *>(fail)) return;
+            if (clock64() - t0 > DF_WATCHDOG_CLOCKS) {
+                *reinterpret_cast<volatile int *>(fail) = 2;
+                return;
+            }
+        }
+    }
+    (void)spl_ld_acquire(flag);
+}
+__device__ __forceinline__ void spl_df_wait(const unsigned *flag, const unsigned target, int *fail) {
+    if (threadIdx.x == 0) spl_df_spin(flag, target, fail);
+    SPL_SYNC256();
+}
+// the CTA's writes so far become visible to whoever acquires the flag
+__device__ __forceinline__ void spl_df_post(unsigned *flag, const unsigned value) {
+    SPL_SYNC256();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+// barrier among P CTAs on a monotonically increasing counter (every CTA keeps `target` in step, participant or not)
+__device__ __forceinline__ void spl_df_barrier(unsigned *counter, unsigned &target, const unsigned P, int *fail) {
+    SPL_SYNC256();
+    target += P;
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        spl_df_spin(counter, target, fail);
+    }
+    SPL_SYNC256();
+}
+
+#define DF_STAMP(i) do { if (stamp && (threadIdx.x & 255) == 0) dbg[i] = clock64(); } while (0)
+// nanoseconds on the device-wide timer: the only clock two CTAs can be compared on
+#define DF_STAMP_NS(i) do { if (stamp && (threadIdx.x & 255) == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[i] = (long long)t_; } } while (0)
+
+__global__ void __launch_bounds__(DF_THREADS, 1)
+spl_factor_dataflow_kernel(double *AB, long long lda, long long n, int bw, double *g, double *ysol, double *linv,
+                           int *fail, long long *dbg, unsigned *flags) {
+    extern __shared__ __align__(16) double s_df[];
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x, tid = threadIdx.x;
+    const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    const int Tmax = (bw + SYRK_TILE - 1) / SYRK_TILE > 1 ? (bw + SYRK_TILE - 1) / SYRK_TILE : 1;
+    unsigned *f_b1 = flags + DF_B1 * DF_FLAG_STRIDE, *f_b2 = flags + DF_B2 * DF_FLAG_STRIDE;
+    unsigned *f_linv = flags + DF_LINV * DF_FLAG_STRIDE, *f_l10 = flags + DF_L10 * DF_FLAG_STRIDE;
+    unsigned *f_t10 = flags + DF_T10 * DF_FLAG_STRIDE, *f_t11 = flags + DF_T11 * DF_FLAG_STRIDE;
+
+    if (cta == 0) {
+        // ================================ diagonal CTA ================================
+        double *sA = s_df;                           // [k][row]  A21 tile row 0, then L[k+1,k] (k-major)
+        double *sX = s_df + 64 * TILE_LD;            // L11, then L11^-1 (row-major)
+        double *sC = sX + 64 * TILE_LD;              // [col][row] the NEXT diagonal block
+        double *s_col = sC + 64 * TILE_LD;           // 2 x 64
+        double *s_g = s_col + 128;                   // 64  g1, then y1
+        double *s_rd = s_g + 64;                     // 64
+        double *s_gn = s_rd + 64;                    // 2 x 64  this CTA's own g2 -= L21 y1 for the next block
+        double *sT = s_gn + 128;                     // 32 x PANEL_LDT
+        int *s_bad = reinterpret_cast<int *>(sT + 32 * PANEL_LDT);     // [0] bad pivot, [1] quit, [2] see below
+        if (tid < 4) s_bad[tid] = 0;                                  // [2] step whose operands may be loaded
+        __syncthreads();                                              // all 288 threads
+        if (tid >= 256) {
+            // -------- communication warp --------
+            const int lane = tid - 256;
+            for (long long kb = 0; kb < nblk; ++kb) {
+                const bool stamp = dbg && kb == nblk / 2 && lane == 0;
+                const long long j0 = kb * SOLVE_NB;
+                const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
+                const long long r0 = j0 + nb;
+                long long mm = n - r0;
+                if (mm > bw) mm = bw;
+                const int m = (int)mm;
+                if (stamp) dbg[32] = clock64();
+                // the two blocks this step reads were last written by the workers during step kb-1
+                if (kb > 0) {
+                    long long pm = n - j0;                            // window of step kb-1
+                    if (pm > bw) pm = bw;
+                    if (pm > SYRK_TILE) {
+                        if (lane == 0) {
+                            spl_df_spin<200>(f_t10, (unsigned)kb, fail);
+                            spl_df_spin<200>(f_t11, (unsigned)kb, fail);
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (stamp) dbg[33] = clock64();
+                if (lane == 0) *reinterpret_cast<volatile int *>(s_bad + 2) = (int)kb + 1;    // seen by the mid-chol check
+                DF_BAR_ARRIVE(DF_NB_OPER);
+                if (stamp) dbg[34] = clock64();
+                DF_BAR_SYNC(DF_NB_LINV);                              // the compute warps have stored L11^-1
+                if (stamp) dbg[35] = clock64();
+                if (lane == 0) {
+                    if (s_bad[1]) *reinterpret_cast<volatile int *>(fail) = 1;
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f_linv), "r"((unsigned)(kb + 1)) : "memory");
+                }
+                if (s_bad[1]) return;                                 // the workers leave after B1
+                if (stamp) dbg[36] = clock64();
+                if (m <= 0) continue;
+                DF_BAR_SYNC(DF_NB_L10);                               // L[k+1,k] stored, and in sA (k-major)
+                if (stamp) dbg[37] = clock64();
+                if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f_l10), "r"((unsigned)(kb + 1)) : "memory");
+                {
+                    // this CTA's share of g2 -= L21 y1 for the next block: rows 2 lane, 2 lane + 1
+                    const int r = 2 * lane;
+                    double p[4][2];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) p[q][0] = p[q][1] = 0.0;
+#pragma unroll 4
+                    for (int c = 0; c < 64; c += 4) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double2 v = *reinterpret_cast<const double2 *>(sA + (c + q) * TILE_LD + r);
+                            const double y = s_g[c + q];
+                            p[q][0] = fma(v.x, y, p[q][0]);
+                            p[q][1] = fma(v.y, y, p[q][1]);
+                        }
+                    }
+                    double *gn = s_gn + ((kb + 1) & 1) * 64;
+                    gn[r] = -((p[0][0] + p[1][0]) + (p[2][0] + p[3][0]));
+                    gn[r + 1] = -((p[0][1] + p[1][1]) + (p[2][1] + p[3][1]));
+                }
+                if (stamp) dbg[38] = clock64();
+            }
+            return;
+        }
+        // -------- compute warps --------
+        const int ri = tid >> 2, rc = tid & 3;
+        if (tid < 128) s_gn[tid] = 0.0;
+        // block (0,0) -> sC
+        spl_tile_load16(sC, AB, lda, (int)(n < 64 ? n : 64), (int)(n < 64 ? n : 64), tid);
+        spl_cp_async_wait_all();
+        SPL_SYNC256();
+        for (long long kb = 0; kb < nblk; ++kb) {
+            const bool stamp = dbg && kb == nblk / 2;
+            const long long j0 = kb * SOLVE_NB;
+            const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
+            const long long r0 = j0 + nb;
+            long long mm = n - r0;
+            if (mm > bw) mm = bw;
+            const int m = (int)mm;
+            DF_STAMP(0);
+            DF_STAMP_NS(8);
+            double u[16];
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                const int k = 4 * kk + rc;
+                double v = (ri == k) ? 1.0 : 0.0;                 // identity padding when nb < 64
+                if (ri < nb && k < nb && k <= ri) v = sC[k * TILE_LD + ri];
+                u[kk] = v;
+            }
+            // the workers' shares of g1 are complete: they precede the flags the communication warp acquired one step ago
+            const double g1r = (tid < nb) ? __ldcg(g + j0 + tid) : 0.0;
+            // operands of this step (A21 tile row 0 -> sA, the next diagonal block -> sC): issued in the shadow of the
+            // (latency-bound) factorization as soon as the communication warp has acquired the workers' flags
+            const int nbn = (int)((n - r0 < SOLVE_NB) ? n - r0 : SOLVE_NB);
+            bool issued = false;
+            spl_chol64<0, 56>(u, s_col, s_rd, s_bad, tid);
+            if (tid == 0) s_bad[3] = *reinterpret_cast<volatile int *>(s_bad + 2) >= (int)kb + 1;
+            SPL_SYNC256();                                        // one thread decides for all
+            if (s_bad[3]) {
+                DF_BAR_SYNC(DF_NB_OPER);                          // (does not wait: the flag is written before the arrive)
+                if (m > 0) {
+                    spl_tile_load16(sA, AB + r0 + j0 * lda, lda, m, nb, tid);
+                    spl_tile_load16(sC, AB + r0 + r0 * lda, lda, nbn, nbn, tid);
+                }
+                issued = true;
+            }
+            spl_chol64<56, 64>(u, s_col, s_rd, s_bad, tid);
+            DF_STAMP(1);
+            if (s_bad[0]) {
+                if (tid == 0) s_bad[1] = 1;
+                if (!issued) DF_BAR_SYNC(DF_NB_OPER);             // (the communication warp arrives there first)
+                spl_cp_async_wait_all();
+                DF_BAR_ARRIVE(DF_NB_LINV);
+                return;
+            }
+            if (!issued) {
+                DF_BAR_SYNC(DF_NB_OPER);
+                if (m > 0) {
+                    spl_tile_load16(sA, AB + r0 + j0 * lda, lda, m, nb, tid);
+                    spl_tile_load16(sC, AB + r0 + r0 * lda, lda, nbn, nbn, tid);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            spl_linv64(u, s_rd, sX, sT, tid);
+            DF_STAMP(2);
+            {
+                double *lb = linv + kb * 4096;                    // (fire and forget: the communication warp fences)
+                for (int e = 2 * tid; e < 4096; e += 2 * PANEL_THREADS)
+                    *reinterpret_cast<double2 *>(lb + e) =
+                        *reinterpret_cast<const double2 *>(sX + (e >> 6) * TILE_LD + (e & 63));
+            }
+            DF_BAR_ARRIVE(DF_NB_LINV);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            SPL_SYNC256();
+            DF_STAMP(3);
+            if (tid < 64) {
+                double *gn = s_gn + (kb & 1) * 64;
+                s_g[tid] = g1r + gn[tid];
+            }
+            SPL_SYNC256();
+            const double y1c = spl_y1_64(sX, s_g, tid);
+            SPL_SYNC256();
+            if (rc == 0) {
+                s_g[ri] = y1c;
+                if (ri < nb) ysol[j0 + ri] = y1c;                 // visible with L10 (or, in the last step, at the kernel's end)
+            }
+            DF_STAMP(4);
+            if (m <= 0) continue;
+            // ---- L[k+1,k] = A21 tile row 0 * Linv^T, left in sA k-major (triangular product as in spl_l21_gemm) ----
+            {
+                const int warp = tid >> 5, lane = tid & 31;
+                const int gq = lane >> 2, t4 = lane & 3;
+                const int wy = (warp >> 1) * 16, wodd = warp & 1;
+                double acc[2][4][2];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll 4
+                for (int k0 = 0; k0 < 64; k0 += 4) {
+                    double af[2];
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi) af[mi] = sA[(k0 + t4) * TILE_LD + wy + mi * 8 + gq];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        const int cb = 2 * ni + wodd;
+                        if (k0 < 8 * cb + 8) {
+                            const double bf = sX[(cb * 8 + gq) * TILE_LD + k0 + t4];
+#pragma unroll
+                            for (int mi = 0; mi < 2; ++mi) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf);
+                        }
+                    }
+                }
+                SPL_SYNC256();                                    // everyone is done reading sA (A21)
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            sA[((2 * ni + wodd) * 8 + 2 * t4 + h) * TILE_LD + wy + mi * 8 + gq] = acc[mi][ni][h];
+            }
+            SPL_SYNC256();
+            {
+                // L[k+1,k] -> band matrix, from shared memory: a warp stores whole columns (512 contiguous bytes)
+                const int r = 2 * (tid & 31);
+                double *dst = AB + (r0 + r) + j0 * lda;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c = (tid >> 5) + 8 * q;
+                    if (c < nb) {
+                        const double2 v = *reinterpret_cast<const double2 *>(sA + c * TILE_LD + r);
+                        if (r + 1 < m) *reinterpret_cast<double2 *>(dst + (long long)c * lda) = v;
+                        else if (r < m) dst[(long long)c * lda] = v.x;
+                    }
+                }
+            }
+            DF_BAR_ARRIVE(DF_NB_L10);
+            DF_STAMP(5);
+            // ---- block (k+1,k+1) -= L10 L10^T in shared memory, lower triangle only: 36 of the 64 8 x 8 blocks.  Block
+            // rows ib = p and 7 - p hold 9 blocks together; warps 2p, 2p + 1 take 5 and 4 of them.  Transposed product
+            // as in spl_tile_mma_store: the MMA's rows are the block's columns. ----
+            {
+                const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
+                const int p = warp >> 1, q0 = (warp & 1) ? 5 : 0, nq = (warp & 1) ? 4 : 5;
+                double acc[5][2];
+                int ibq[5], jbq[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int qq = q0 + q;
+                    ibq[q] = (qq <= p) ? p : 7 - p;
+                    jbq[q] = (qq <= p) ? qq : qq - p - 1;
+                    if (q < nq) {
+                        const double2 v =
+                            *reinterpret_cast<const double2 *>(sC + (jbq[q] * 8 + gq) * TILE_LD + ibq[q] * 8 + 2 * t4);
+                        acc[q][0] = v.x;
+                        acc[q][1] = v.y;
+                    }
+                }
+#pragma unroll 4
+                for (int k0 = 0; k0 < 64; k0 += 4) {
+                    const double *row = sA + (k0 + t4) * TILE_LD + gq;
+                    const double b_lo = row[p * 8], b_hi = row[(7 - p) * 8];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+                        if (q < nq) {
+                            const double a = -row[jbq[q] * 8];
+                            spl_dmma_8x8x4(acc[q][0], acc[q][1], a, (ibq[q] == p) ? b_lo : b_hi);
+                        }
+                }
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    if (q < nq)
+                        *reinterpret_cast<double2 *>(sC + (jbq[q] * 8 + gq) * TILE_LD + ibq[q] * 8 + 2 * t4) =
+                            make_double2(acc[q][0], acc[q][1]);
+            }
+            SPL_SYNC256();
+            DF_STAMP(6);
+        }
+        return;
+    }
+
+    // ================================ workers ================================
+    if (tid >= 256) return;                                       // only the diagonal CTA has a ninth warp
+    const unsigned nwork = (unsigned)(G - 1);
+    unsigned tgt1 = 0, tgt2 = 0;
+    const bool panel_worker = cta < Tmax;
+    const int NH = G - Tmax, me = cta - Tmax;                     // helpers
+    double *sA = s_df, *sX = s_df + 64 * TILE_LD;
+    double *s_g = s_df + 4 * 64 * TILE_LD;                        // behind the helpers' two operand buffers
+    int *s_flag = reinterpret_cast<int *>(s_g + 64);
+    for (long long kb = 0; kb < nblk; ++kb) {
+        const bool stamp = dbg && kb == nblk / 2 && (cta == 1 || cta == Tmax);
+        const long long j0 = kb * SOLVE_NB;
+        const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
+        const long long r0 = j0 + nb;
+        long long mm = n - r0;
+        if (mm > bw) mm = bw;
+        const int m = (int)mm;
+        const int T = (m + SYRK_TILE - 1) / SYRK_TILE;
+        const int ntiles = (T > 1) ? (T - 1) * T / 2 : 0;
+        const int npw = 0;              // rest tiles the panel workers take from the end of the list (measured: none --
+                                        // a panel worker that is late for LINV delays B1 for everybody)
+        const int nth = ntiles - npw;                             // the helpers' list
+        const bool active = panel_worker && cta < T;
+        const int sbase = (cta == 1) ? 16 : 24;
+        DF_STAMP(sbase + 0);
+        DF_STAMP_NS(sbase + 6);
+        bool b_issued = false;
+        if (active) {
+            // ---- tile row `cta` of the panel ----
+            spl_tile_load16(sA, AB + (r0 + (long long)cta * 64) + j0 * lda, lda, m - cta * 64, nb, tid);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            spl_df_wait(f_linv, (unsigned)(kb + 1), fail);
+            DF_STAMP(sbase + 1);
+            {
+                const double *lb = linv + kb * 4096;
+                for (int e = 2 * tid; e < 4096; e += 2 * PANEL_THREADS)
+                    spl_cp_async16(sX + (e >> 6) * TILE_LD + (e & 63), lb + e);
+            }
+            spl_cp_async_wait_all();
+            SPL_SYNC256();
+            spl_l21_gemm<false>(AB, lda, j0, nb, m, r0, cta * 64, g, sA, sX, s_g, true, tid);
+            // L[k+1,k] is usually there by now: start the column-0 tile's B operand before the barrier
+            if (tid == 0) *s_flag = spl_ld_acquire(f_l10) >= (unsigned)(kb + 1);
+            SPL_SYNC256();
+            if (*s_flag) {
+                spl_tile_issue<true>(AB, lda, r0, j0, nb, m, cta, 0, s_df);
+                b_issued = true;
+            }
+            DF_STAMP(sbase + 2);
+        }
+        if (dbg && kb == nblk / 2 && tid == 0) {                  // arrival of every worker at B1, device-wide timer
+            unsigned long long t_;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+            dbg[64 + cta] = (long long)t_;
+        }
+        spl_df_barrier(f_b1, tgt1, nwork, fail);
+        DF_STAMP(sbase + 3);
+        DF_STAMP_NS(sbase + 7);
+        if (*reinterpret_cast<volatile int *>(fail)) {            // uniform: written before the flag B1 chains from
+            spl_cp_async_wait_all();
+            return;
+        }
+        if (active) {
+            // ---- column-0 tile of the same row: A operand = the L21 tile left in sA, B = L[k+1,k] ----
+            if (!b_issued) {
+                spl_df_wait(f_l10, (unsigned)(kb + 1), fail);
+                spl_tile_issue<true>(AB, lda, r0, j0, nb, m, cta, 0, s_df);
+            }
+            // g2 -= L21 y1 for this tile row (y1 is published with L[k+1,k]), under the B operand's flight
+            if (tid < 64) s_g[tid] = (tid < nb) ? __ldcg(ysol + j0 + tid) : 0.0;
+            SPL_SYNC256();
+            spl_g_update(g, r0, cta * 64, m, sA, s_g, tid);
+            spl_tile_finish<0>(AB, lda, r0, m, cta, 0, s_df);
+            if (cta == 1) spl_df_post(f_t10, (unsigned)(kb + 1));
+            DF_STAMP(sbase + 4);
+        }
+        if (panel_worker) {
+            if (active) spl_df_barrier(f_b2, tgt2, (unsigned)(T - 1), fail);
+            else if (T > 1) tgt2 += (unsigned)(T - 1);
+            DF_STAMP(sbase + 5);
+            if (active && cta - 1 < npw) {
+                // one rest tile from the end of the list while the diagonal CTA factors the next block
+                int ti, tj;
+                spl_rest_tile(ntiles - 1 - (cta - 1), ti, tj);
+                spl_tile256<false>(AB, lda, r0, j0, nb, m, ti, tj, s_df);
+                SPL_SYNC256();
+            }
+        } else if (me < nth) {
+            // ---- rest tiles of update kb: me, me + NH, .. with the next tile's operands and C tile in flight; the tiles
+            // of the last, partial round are split in row halves when that gives everybody half a tile instead of some a
+            // whole one (the barrier B1 waits for the longest list) ----
+            const int base = nth / NH, rem = nth - base * NH;
+            const bool halves = base >= 1 && 2 * rem <= NH;
+            const int nfull = base + ((!halves && me < rem) ? 1 : 0);
+            const int cnt = nfull + ((halves && me < 2 * rem) ? 1 : 0);
+            auto item = [&](const int idx, int &ti_, int &tj_, int &half_) {
+                if (idx < nfull) {
+                    spl_rest_tile(me + NH * idx, ti_, tj_);
+                    half_ = -1;
+                } else {
+                    spl_rest_tile(base * NH + (me >> 1), ti_, tj_);
+                    half_ = me & 1;
+                }
+            };
+            int cur = 0, ti, tj, half;
+            double accn[2][4][2];
+            item(0, ti, tj, half);
+            spl_tile_issue<false>(AB, lda, r0, j0, nb, m, ti, tj, s_df, half);
+            if (half < 0) spl_tile_cload<2>(accn, AB, lda, r0, m, ti, tj);
+            else spl_tile_cload<1>(accn, AB, lda, r0, m, ti, tj, half);
+            for (int idx = 0; idx < cnt; ++idx) {
+                double *bcur = s_df + cur * (2 * 64 * TILE_LD);
+                double acc[2][4][2];
+#pragma unroll
+                for (int mj = 0; mj < 2; ++mj)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        acc[mj][ni][0] = accn[mj][ni][0];
+                        acc[mj][ni][1] = accn[mj][ni][1];
+                    }
+                if (idx + 1 < cnt) {
+                    int tin, tjn, halfn;
+                    item(idx + 1, tin, tjn, halfn);
+                    spl_tile_issue<false>(AB, lda, r0, j0, nb, m, tin, tjn, s_df + (cur ^ 1) * (2 * 64 * TILE_LD), halfn);
+                    if (halfn < 0) spl_tile_cload<2>(accn, AB, lda, r0, m, tin, tjn);
+                    else spl_tile_cload<1>(accn, AB, lda, r0, m, tin, tjn, halfn);
+                    if (half < 0) spl_tile_mma_store<1, 2>(acc, AB, lda, r0, m, ti, tj, bcur);
+                    else spl_tile_mma_store<1, 1>(acc, AB, lda, r0, m, ti, tj, bcur, half);
+                    ti = tin;
+                    tj = tjn;
+                    half = halfn;
+                } else {
+                    if (half < 0) spl_tile_mma_store<0, 2>(acc, AB, lda, r0, m, ti, tj, bcur);
+                    else spl_tile_mma_store<0, 1>(acc, AB, lda, r0, m, ti, tj, bcur, half);
+                }
+                if (me == 0 && idx == 0) spl_df_post(f_t11, (unsigned)(kb + 1));      // tile (1,1), always whole
+                else SPL_SYNC256();                                // buffer `cur` is refilled by the next issue
+                if (idx == 0) DF_STAMP(sbase + 4);
+                cur ^= 1;
+            }
+            DF_STAMP(sbase + 5);
+        }
     }
 }
 
@@ -1222,7 +1942,9 @@ spl_forwardsolve_persistent_kernel(const double *__restrict__ AB, long long lda,
 // ------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------
-long long spl_band_lda(int bw) { return (long long)bw + SOLVE_NB; }
+// even: columns of the band matrix then start at 16-byte boundaries, which the 16-byte cp.async of the operand tiles
+// and the 128-bit accesses of the update tiles need
+long long spl_band_lda(int bw) { return ((long long)bw + SOLVE_NB + 1) & ~1LL; }
 
 int spl_half_bandwidth(const GridParams &gp) {
     long long b = 0, stride = 1;
@@ -1276,7 +1998,8 @@ static long long *spl_panel_dbg_buffer() {
     if (!tried) {
         tried = true;
         if (getenv("SPLPAK_B200_PANELCLK")) {
-            if (cudaMalloc((void **)&buf, 128) != cudaSuccess) buf = nullptr;
+            if (cudaMalloc((void **)&buf, 512 * sizeof(long long)) != cudaSuccess) buf = nullptr;
+            else cudaMemset(buf, 0, 512 * sizeof(long long));
         }
     }
     return buf;
@@ -1399,6 +2122,30 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         const long long helpers = (long long)pgrid - T;
         if (helpers <= 0 || (T - 1) * T / 2 > 4 * helpers) persistent_factor = false;
     }
+    // Data-flow kernel (default) or the barrier-phased one (SPLPAK_B200_SOLVER=barrier) for the persistent factor loop
+    const size_t df_smem = sizeof(double) * (4 * 64 * TILE_LD + 64 + 2);
+    bool dataflow = false;
+    int dfgrid = 1;
+    if (persistent_factor) {
+        const char *mode = getenv("SPLPAK_B200_SOLVER");
+        int per_sm = 0;
+        if (!(mode && strcmp(mode, "barrier") == 0) &&
+            cudaFuncSetAttribute(spl_factor_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)df_smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spl_factor_dataflow_kernel, DF_THREADS,
+                                                          df_smem) == cudaSuccess &&
+            per_sm >= 1) {
+            const long long T = ((long long)bw + SYRK_TILE - 1) / SYRK_TILE;
+            if (T >= 2) {
+                const long long want = T + (T - 1) * T / 2;      // diagonal + panel workers + one helper per rest tile
+                dfgrid = (int)(want < pgrid ? want : pgrid);
+                dataflow = dfgrid >= T + 1;
+            } else {
+                dataflow = true;                                  // half bandwidth <= 64: the diagonal CTA alone
+            }
+        }
+        cudaGetLastError();
+    }
     const size_t back_smem = sizeof(double) * (2 * 4096 + 128);
     int back_grid = 0;
     if (persistent) {
@@ -1464,7 +2211,30 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     }
     if (ev) cudaEventRecord(ev[1], st);
     long long nl = 0;
-    if (persistent_factor) {
+    bool df_done = false;
+    if (persistent_factor && dataflow) {
+        double *a_AB = d_AB, *a_g = d_g, *a_y = d_ysol, *a_li = d_linv;
+        long long a_lda = lda, a_n = n;
+        int a_bw = bw;
+        int *a_fail = d_fail;
+        long long *a_dbg = spl_panel_dbg_buffer();
+        // flags behind the failure flag and the barrier counter of the other persistent kernels (SPL_FAIL_WORDS ints)
+        unsigned *a_flags = reinterpret_cast<unsigned *>(d_fail) + DF_FLAG_STRIDE;
+        SPL_CUDA_TRY(cudaMemsetAsync(a_flags, 0, sizeof(unsigned) * DF_NFLAGS * DF_FLAG_STRIDE, st));
+        void *args[] = {&a_AB, &a_lda, &a_n, &a_bw, &a_g, &a_y, &a_li, &a_fail, &a_dbg, &a_flags};
+        const cudaError_t ce = cudaLaunchCooperativeKernel((const void *)spl_factor_dataflow_kernel, dim3(dfgrid),
+                                                           dim3(DF_THREADS), args, df_smem, st);
+        if (ce == cudaSuccess) {
+            nl = 1;
+            df_done = true;
+        } else {
+            fprintf(stderr, "splpak_b200: cooperative launch of the data-flow factor kernel failed (%s)\n",
+                    cudaGetErrorString(ce));
+            cudaGetLastError();
+        }
+    }
+    if (df_done) {
+    } else if (persistent_factor) {
         double *a_AB = d_AB, *a_g = d_g, *a_y = d_ysol, *a_li = d_linv;
         long long a_lda = lda, a_n = n;
         int a_bw = bw;
@@ -1493,16 +2263,43 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     }
     g_spl_launches += nl;
     if (spl_panel_dbg_buffer()) {
-        long long hst[16];
+        long long hst[512];
         cudaStreamSynchronize(st);
         cudaMemcpy(hst, spl_panel_dbg_buffer(), sizeof(hst), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "persistent step (CTA 0): panel body %lld, barrier 1 %lld, column-0 tile %lld, barrier 2 %lld\n",
-                hst[12] - hst[0], hst[13] - hst[12], hst[14] - hst[13], hst[15] - hst[14]);
-        fprintf(stderr, "inverse phases: scale+L %lld base %lld levels %lld store %lld\n", hst[7] - hst[2],
-                hst[8] - hst[7], hst[9] - hst[8], hst[3] - hst[9]);
-        fprintf(stderr, "panel (mid) clocks: load %lld chol %lld inverse %lld wait %lld y1 %lld gemm+store %lld total %lld\n",
-                hst[1] - hst[0], hst[2] - hst[1], hst[3] - hst[2], hst[4] - hst[3], hst[5] - hst[4], hst[6] - hst[5],
-                hst[6] - hst[0]);
+        if (df_done) {
+            fprintf(stderr, "data-flow step (diagonal CTA, compute warps): chol %lld, inverse %lld, store Linv + operand wait %lld, y1 %lld, "
+                            "L10 product %lld, diagonal update %lld, total %lld\n",
+                    hst[1] - hst[0], hst[2] - hst[1], hst[3] - hst[2], hst[4] - hst[3], hst[5] - hst[4], hst[6] - hst[5],
+                    hst[6] - hst[0]);
+            fprintf(stderr, "  communication warp: wait T10/T11 %lld, arrive %lld, wait Linv %lld, post Linv %lld, "
+                            "wait L10 %lld, post L10 + g share %lld\n",
+                    hst[33] - hst[32], hst[34] - hst[33], hst[35] - hst[34], hst[36] - hst[35], hst[37] - hst[36],
+                    hst[38] - hst[37]);
+            fprintf(stderr, "  panel worker 1: wait Linv %lld, L21 gemm %lld, B1 %lld, column-0 tile %lld, B2 %lld (step start %+lld ns, B1 passed %+lld ns after the diagonal CTA's step start)\n",
+                    hst[17] - hst[16], hst[18] - hst[17], hst[19] - hst[18], hst[20] - hst[19], hst[21] - hst[20],
+                    hst[22] - hst[8], hst[23] - hst[8]);
+            {
+                // the five last arrivals at B1 of the stamped step (ns after the diagonal CTA's step start)
+                int order[512], nw = 0;
+                for (int c = 1; c < dfgrid && c < 448; ++c) order[nw++] = c;
+                for (int a = 0; a < nw; ++a)
+                    for (int b2 = a + 1; b2 < nw; ++b2)
+                        if (hst[64 + order[b2]] > hst[64 + order[a]]) { const int t_ = order[a]; order[a] = order[b2]; order[b2] = t_; }
+                fprintf(stderr, "  B1 arrivals (ns after the diagonal CTA's step start): last");
+                for (int a = 0; a < 6 && a < nw; ++a) fprintf(stderr, " cta %d %+lld", order[a], hst[64 + order[a]] - hst[8]);
+                fprintf(stderr, " .. median cta %d %+lld, first cta %d %+lld\n", order[nw / 2], hst[64 + order[nw / 2]] - hst[8],
+                        order[nw - 1], hst[64 + order[nw - 1]] - hst[8]);
+            }
+            fprintf(stderr, "  helper 0: B1 %lld, first tile %lld, rest of its list %lld (B1 passed %+lld ns after the diagonal CTA's step start)\n",
+                    hst[27] - hst[24], hst[28] - hst[27], hst[29] - hst[28], hst[31] - hst[8]);
+        } else if (persistent_factor) {
+            fprintf(stderr, "persistent step (CTA 0): panel body %lld, barrier 1 %lld, column-0 tile %lld, barrier 2 %lld\n",
+                    hst[12] - hst[0], hst[13] - hst[12], hst[14] - hst[13], hst[15] - hst[14]);
+        }
+        if (!df_done)
+            fprintf(stderr, "panel (mid) clocks: load %lld chol %lld inverse %lld wait %lld y1 %lld gemm+store %lld total %lld\n",
+                    hst[1] - hst[0], hst[2] - hst[1], hst[3] - hst[2], hst[4] - hst[3], hst[5] - hst[4], hst[6] - hst[5],
+                    hst[6] - hst[0]);
     }
     if (ev) cudaEventRecord(ev[2], st);
     if (persistent && back_grid > 0) {

@@ -185,15 +185,16 @@ def test_solver_failures_map_to_107(oracle):
 @pytest.mark.parametrize("ndim,nodes,ndata", [(3, [9, 8, 10], 6000), (2, [24, 20], 5000), (1, [300], 5000)])
 def test_solver_paths_agree(oracle, monkeypatch, ndim, nodes, ndata):
     """The factorisation / back-substitution run as persistent cooperative kernels where the panel chain dominates
-    and as one kernel per phase (CUDA graph, two streams) otherwise; SPLPAK_B200_SOLVER=graph forces the latter.
+    (the data-flow kernel by default, the barrier-phased one with SPLPAK_B200_SOLVER=barrier) and as one kernel per phase
+    (CUDA graph, two streams) otherwise; SPLPAK_B200_SOLVER=graph forces the latter.
     Same normal equations -> coefficients equal to the solver's own run-to-run spread, and both at oracle parity."""
     x, y, w, mn, mx = make_problem(ndim, nodes, ndata, seed=ndim + ndata)
     ref, ierr = oracle.initialize(ndim, x, y, w, mn, mx, nodes, 0.0)     # xtrap = 0: no constraint rows, no refinement
     assert ierr == 0
     got = {}
-    for mode in ("persistent", "graph"):
-        if mode == "graph":
-            monkeypatch.setenv("SPLPAK_B200_SOLVER", "graph")
+    for mode in ("persistent", "barrier", "graph"):
+        if mode != "persistent":
+            monkeypatch.setenv("SPLPAK_B200_SOLVER", mode)
         else:
             monkeypatch.delenv("SPLPAK_B200_SOLVER", raising=False)
         h = sp.FitHandle(ndim, mn, mx, nodes, 0.0)
@@ -206,6 +207,7 @@ def test_solver_paths_agree(oracle, monkeypatch, ndim, nodes, ndata):
         np.testing.assert_allclose(c, ref, rtol=0, atol=tol * np.abs(ref).max(), err_msg=f"{mode}, cond {cond:.2e}")
         h.destroy()
     np.testing.assert_allclose(got["persistent"], got["graph"], rtol=0, atol=tol * np.abs(ref).max())
+    np.testing.assert_allclose(got["barrier"], got["graph"], rtol=0, atol=tol * np.abs(ref).max())
 
 
 def test_solver_failure_is_reported_by_both_paths(monkeypatch):
@@ -214,9 +216,9 @@ def test_solver_failure_is_reported_by_both_paths(monkeypatch):
     rng = np.random.default_rng(3)
     x = rng.random((20, 3)) * 0.1                      # 20 points in one corner of a 6^3 grid
     y = rng.random(20)
-    for mode in ("persistent", "graph"):
-        if mode == "graph":
-            monkeypatch.setenv("SPLPAK_B200_SOLVER", "graph")
+    for mode in ("persistent", "barrier", "graph"):
+        if mode != "persistent":
+            monkeypatch.setenv("SPLPAK_B200_SOLVER", mode)
         else:
             monkeypatch.delenv("SPLPAK_B200_SOLVER", raising=False)
         coef, ierr = sp.splcc(3, x, 3, y, len(x), [0] * 3, [1] * 3, [6] * 3, 0.0, quiet=True)
