@@ -16,7 +16,7 @@ echo "full capture eval rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:spl_moments -s 3 -c 1 -f -o $OUT/prof_r02_accumulate \
     $CMD > $OUT/ncu_r02_accumulate.log 2>&1
 echo "full capture accumulate rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:spl_factor_persistent -s 3 -c 1 -f -o $OUT/prof_r02_factor \
+ncu --set full --clock-control none --import-source on -k regex:"spl_factor_(dataflow|persistent)" -s 3 -c 1 -f -o $OUT/prof_r02_factor \
     $CMD > $OUT/ncu_r02_factor.log 2>&1
 echo "full capture factor rc=$?"
 ls -la $OUT | grep r02

@@ -555,36 +555,46 @@ __device__ __forceinline__ double spl_y1_64(const double *sX, const double *s_g,
 // (s_g = y1) with atomic adds into g -- the data-flow kernel's workers do that later from the tile left in sA
 // (spl_g_update), so that the diagonal CTA can publish L11^-1 before it has formed y1.
 // keep_l21: leave the L21 tile in sA, k-major, where the tile update expects its A operand.
-template <bool WITH_G = true>
-__device__ __forceinline__ void spl_l21_gemm(double *AB, long long lda, long long j0, int nb, int m, long long r0,
-                                             int R0, double *g, double *sA, const double *sX, const double *s_g,
-                                             const bool keep_l21, const int tid) {
-    // Linv is lower triangular: column block cb (8 columns) of the product needs k < 8 cb + 8 only.  A warp owns 16
-    // rows and the four column blocks cb = 2 ni + (warp & 1) -- interleaved, so the two warp classes do 64 and 80 of
-    // the 128 MMAs of the full product instead of 40 and 104.
-    const int warp = tid >> 5, lane = tid & 31;
-    const int gq = lane >> 2, t4 = lane & 3;
-    const int wy = (warp >> 1) * 16, wodd = warp & 1;
-    double acc[2][4][2];
+// acc = A21 tile * Linv^T for the calling warp's 16 rows (wy..) and its four column blocks cb = 2 ni + wodd (8 columns
+// each; interleaved over the two warp classes so that both do the same work).  Linv is lower triangular: column block
+// cb needs k < 8 cb + 8 only, so the k range is cut in four segments of 16 and segment s feeds the blocks ni >= s --
+// 80 of the 128 MMAs of the full product, in straight-line code (a test per block and k step made the loop
+// latency-bound: 4.4k clocks for 64 MMAs).
+__device__ __forceinline__ void spl_l21_mma(double (&acc)[2][4][2], const double *sA, const double *sX, const int wy,
+                                            const int wodd, const int gq, const int t4) {
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-#pragma unroll 4
-    for (int k0 = 0; k0 < 64; k0 += 4) {
-        double af[2];
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi) af[mi] = sA[(k0 + t4) * TILE_LD + wy + mi * 8 + gq];
+    for (int sgm = 0; sgm < 4; ++sgm) {
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int cb = 2 * ni + wodd;
-            if (k0 < 8 * cb + 8) {                                                          // warp-uniform
-                const double bf = sX[(cb * 8 + gq) * TILE_LD + k0 + t4];                    // B[k][n] = Linv[n][k]
+        for (int k0 = 16 * sgm; k0 < 16 * sgm + 16; k0 += 4) {
+            double af[2], bf[4];
 #pragma unroll
-                for (int mi = 0; mi < 2; ++mi) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf);
-            }
+            for (int mi = 0; mi < 2; ++mi) af[mi] = sA[(k0 + t4) * TILE_LD + wy + mi * 8 + gq];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+                if (ni >= sgm) bf[ni] = sX[((2 * ni + wodd) * 8 + gq) * TILE_LD + k0 + t4];    // B[k][n] = Linv[n][k]
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+                if (ni >= sgm) {
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                }
         }
     }
+}
+
+template <bool WITH_G = true>
+__device__ __forceinline__ void spl_l21_gemm(double *AB, long long lda, long long j0, int nb, int m, long long r0,
+                                             int R0, double *g, double *sA, const double *sX, const double *s_g,
+                                             const bool keep_l21, const int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, t4 = lane & 3;
+    const int wy = (warp >> 1) * 16, wodd = warp & 1;
+    double acc[2][4][2];
+    spl_l21_mma(acc, sA, sX, wy, wodd, gq, t4);
     // store L21 and update the right-hand side below the block: g2 -= L21 y1
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) {
@@ -1059,6 +1069,23 @@ __device__ __forceinline__ void spl_tile256(double *AB, long long lda, long long
     spl_tile_finish<0>(AB, lda, r0, m, ti, tj, s_ab);
 }
 
+// The same tile launch with the 256-thread tile (16-byte cp.async operands, 128-bit C accesses): the kernel-per-phase
+// driver's trailing update (SPLPAK_B200_SYRK=128 selects the older 128-thread tile for A/B).
+__global__ void __launch_bounds__(PANEL_THREADS, 3)
+spl_syrk256_kernel(double *__restrict__ AB, long long lda, long long r0, long long j0, int nb, int m,
+                   const int *__restrict__ fail, int part) {
+    extern __shared__ __align__(16) double s_ab[];
+    if (*fail) return;
+    int ti, tj;
+    if (part == 0) {
+        ti = blockIdx.x;
+        tj = 0;
+    } else {
+        spl_rest_tile((int)blockIdx.x, ti, tj);
+    }
+    spl_tile256<false>(AB, lda, r0, j0, nb, m, ti, tj, s_ab);
+}
+
 // ------------------------------------------------------------------------------------------
 // persistent factorisation: the whole right-looking loop in ONE cooperative kernel (one 256-thread CTA per SM),
 // phases separated by grid-wide barriers instead of kernel boundaries and cross-stream events:
@@ -1442,32 +1469,16 @@ spl_factor_dataflow_kernel(double *AB, long long lda, long long n, int bw, doubl
             }
             DF_STAMP(4);
             if (m <= 0) continue;
-            // ---- L[k+1,k] = A21 tile row 0 * Linv^T, left in sA k-major (triangular product as in spl_l21_gemm) ----
+            // ---- L[k+1,k] = A21 tile row 0 * Linv^T (spl_l21_mma), left in sA k-major ----
             {
                 const int warp = tid >> 5, lane = tid & 31;
                 const int gq = lane >> 2, t4 = lane & 3;
                 const int wy = (warp >> 1) * 16, wodd = warp & 1;
                 double acc[2][4][2];
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-#pragma unroll 4
-                for (int k0 = 0; k0 < 64; k0 += 4) {
-                    double af[2];
-#pragma unroll
-                    for (int mi = 0; mi < 2; ++mi) af[mi] = sA[(k0 + t4) * TILE_LD + wy + mi * 8 + gq];
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) {
-                        const int cb = 2 * ni + wodd;
-                        if (k0 < 8 * cb + 8) {
-                            const double bf = sX[(cb * 8 + gq) * TILE_LD + k0 + t4];
-#pragma unroll
-                            for (int mi = 0; mi < 2; ++mi) spl_dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf);
-                        }
-                    }
-                }
+                spl_l21_mma(acc, sA, sX, wy, wodd, gq, t4);
+                DF_STAMP(40);
                 SPL_SYNC256();                                    // everyone is done reading sA (A21)
+                DF_STAMP(41);
 #pragma unroll
                 for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -1477,6 +1488,7 @@ spl_factor_dataflow_kernel(double *AB, long long lda, long long n, int bw, doubl
                             sA[((2 * ni + wodd) * 8 + 2 * t4 + h) * TILE_LD + wy + mi * 8 + gq] = acc[mi][ni][h];
             }
             SPL_SYNC256();
+            DF_STAMP(42);
             {
                 // L[k+1,k] -> band matrix, from shared memory: a warp stores whole columns (512 contiguous bytes)
                 const int r = 2 * (tid & 31);
@@ -2009,6 +2021,8 @@ static cudaError_t enqueue_factor(long long n, int bw, long long lda, double *d_
                                   double *d_linv, int *d_fail, cudaStream_t st, cudaStream_t st_aux,
                                   size_t panel_smem, size_t syrk_smem, long long *nlaunch) {
     const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    const char *syrk_mode = getenv("SPLPAK_B200_SYRK");
+    const bool syrk256 = !(syrk_mode && strcmp(syrk_mode, "128") == 0);
     cudaEvent_t ev_panel = nullptr, ev_rest = nullptr;
     cudaError_t e;
     if ((e = cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -2033,12 +2047,14 @@ static cudaError_t enqueue_factor(long long n, int bw, long long lda, double *d_
             if (T > 1) {
                 if ((e = cudaEventRecord(ev_panel, st)) != cudaSuccess) break;
                 if ((e = cudaStreamWaitEvent(st_aux, ev_panel, 0)) != cudaSuccess) break;
-                spl_syrk_kernel<<<(T - 1) * T / 2, SYRK_THREADS, syrk_smem, st_aux>>>(d_AB, lda, r0, j0, nb, m, d_fail, 1);
+                if (syrk256) spl_syrk256_kernel<<<(T - 1) * T / 2, PANEL_THREADS, syrk_smem, st_aux>>>(d_AB, lda, r0, j0, nb, m, d_fail, 1);
+                else spl_syrk_kernel<<<(T - 1) * T / 2, SYRK_THREADS, syrk_smem, st_aux>>>(d_AB, lda, r0, j0, nb, m, d_fail, 1);
                 ++count;
             }
             if (rest_pending && (e = cudaStreamWaitEvent(st, ev_rest, 0)) != cudaSuccess) break;   // rest(k-1) done
             rest_pending = false;
-            spl_syrk_kernel<<<T, SYRK_THREADS, syrk_smem, st>>>(d_AB, lda, r0, j0, nb, m, d_fail, 0);
+            if (syrk256) spl_syrk256_kernel<<<T, PANEL_THREADS, syrk_smem, st>>>(d_AB, lda, r0, j0, nb, m, d_fail, 0);
+            else spl_syrk_kernel<<<T, SYRK_THREADS, syrk_smem, st>>>(d_AB, lda, r0, j0, nb, m, d_fail, 0);
             ++count;
             if (T > 1) {
                 if ((e = cudaEventRecord(ev_rest, st_aux)) != cudaSuccess) break;
@@ -2088,6 +2104,7 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     const size_t syrk_smem = sizeof(double) * 2 * 64 * TILE_LD;
     const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 64 + 64 + 32 * PANEL_LDT + 2);
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
+    SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
 
     // The factor loop runs as ONE persistent cooperative kernel when the device can keep one CTA per SM resident
@@ -2271,6 +2288,8 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
                             "L10 product %lld, diagonal update %lld, total %lld\n",
                     hst[1] - hst[0], hst[2] - hst[1], hst[3] - hst[2], hst[4] - hst[3], hst[5] - hst[4], hst[6] - hst[5],
                     hst[6] - hst[0]);
+            fprintf(stderr, "  L10 product: MMA loop (warp 0) %lld, barrier %lld, transposition + barrier %lld, store %lld\n",
+                    hst[40] - hst[4], hst[41] - hst[40], hst[42] - hst[41], hst[5] - hst[42]);
             fprintf(stderr, "  communication warp: wait T10/T11 %lld, arrive %lld, wait Linv %lld, post Linv %lld, "
                             "wait L10 %lld, post L10 + g share %lld\n",
                     hst[33] - hst[32], hst[34] - hst[33], hst[35] - hst[34], hst[36] - hst[35], hst[37] - hst[36],
