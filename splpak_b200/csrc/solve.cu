@@ -1756,99 +1756,182 @@ spl_backsolve_kernel(const double *__restrict__ AB, long long lda, long long j0,
 // read with ld.global.cg (other CTAs wrote it).
 // ------------------------------------------------------------------------------------------
 #define BACKP_THREADS 256
-#define BACKP_NC 8                                // columns per warp and step: grid = ceil(bw / (8 warps x 8))
+#define BACKP_NC 8                                // columns per warp and step: grid = ceil((bw + 64) / (8 warps x 8))
+#define BACKP_LBP 66                              // pitch of the staged L[k,k-1] block: 16-byte pieces, 2-way conflicts at most
+#define BACKP_SMEM_DOUBLES (2 * 2 * 4096 + 2 * 64 * BACKP_LBP + 256)
+// Two blocks per grid barrier: every CTA forms c_k = L11(k)^-T y_k, then y'_{k-1} = y_{k-1} - L[k,k-1]^T c_k and
+// c_{k-1} = L11(k-1)^-T y'_{k-1} itself (the 64 x 64 block L[k,k-1] rides along with the two inverses), and
+// eliminates BOTH from its columns of the bw columns in front of block k-1.  The barrier, the y round trip and the
+// reductions are paid once per 128 columns: 216 x 3.6 us -> 108 x 4.2 us at cfg3.
 __global__ void __launch_bounds__(BACKP_THREADS, 1)
 spl_backsolve_persistent_kernel(const double *__restrict__ AB, long long lda, long long n, int bw,
                                 const double *__restrict__ linv, double *ysol, double *__restrict__ csol,
                                 const int *__restrict__ fail, unsigned *bar) {
     extern __shared__ __align__(16) double s_bk[];
-    double *s_li = s_bk;                        // 2 x 64 x 64  block inverse, row-major [r][c]
-    double *s_y = s_bk + 2 * 4096;              // 64
-    double *s_c = s_y + 64;                     // 64
+    double *s_li = s_bk;                        // 2 buffers x {top, bottom} x 64 x 64  block inverses, row-major [r][c]
+    double *s_lb = s_bk + 4 * 4096;             // 2 buffers x 64 x LBP  L[k,k-1], [c][r]: c = column in block k-1, r = row in block k
+    double *s_y = s_lb + 2 * 64 * BACKP_LBP;    // 128: y_k | y_{k-1}
+    double *s_c = s_y + 128;                    // 128: c_k | c_{k-1}
     const int t = threadIdx.x, lane = t & 31;
     const unsigned G = gridDim.x;
     const int gw = (int)blockIdx.x * (BACKP_THREADS / 32) + (t >> 5), nw = (int)G * (BACKP_THREADS / 32);
     unsigned target = 0;
     if (*fail) return;                          // uniform across the grid
     const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
-    auto fetch_inv = [&](long long kb, int buf) {
-        const double *src = linv + kb * 4096;
-        double *dst = s_li + buf * 4096;
-        for (int e = t; e < 4096; e += BACKP_THREADS) spl_cp_async8(dst + e, src + e);
+    // step with top block kb: pair (kb, kb-1) when kb >= 1, else block 0 alone.  jt / jb: first column of the top / of the
+    // lowest block of the step; the step eliminates from the columns [max(0, jb - bw), jb).
+    double colr[BACKP_NC][4];                   // rows l, l+32 of the lowest block | rows l, l+32 of the top block (pairs)
+    auto fetch = [&](long long kb, int buf) {
+        const bool pair = kb >= 1;
+        const long long jt = kb * SOLVE_NB, jb = pair ? jt - SOLVE_NB : jt;
+        const int nbt = (int)((n - jt < SOLVE_NB) ? n - jt : SOLVE_NB);
+        {
+            const double *src = linv + kb * 4096;
+            double *dst = s_li + buf * 8192;
+            for (int e = 2 * t; e < 4096; e += 2 * BACKP_THREADS) spl_cp_async16(dst + e, src + e);
+            if (pair) {
+                const double *src2 = linv + (kb - 1) * 4096;
+                for (int e = 2 * t; e < 4096; e += 2 * BACKP_THREADS) spl_cp_async16(dst + 4096 + e, src2 + e);
+                // L[k,k-1], column by column (rows contiguous) in 16-byte pieces; outside the band -- half bandwidth
+                // < 127 -- the address would run into the next column, so those entries are zeros written here
+                double *lb = s_lb + buf * (64 * BACKP_LBP);
+                for (int e = t; e < 2048; e += BACKP_THREADS) {
+                    const int c = e >> 5, r = 2 * (e & 31);
+                    double *dst = lb + c * BACKP_LBP + r;
+                    const double *src = AB + (jt + r) + (jb + c) * lda;
+                    const bool ok0 = r < nbt && SOLVE_NB + r - c <= bw;
+                    const bool ok1 = r + 1 < nbt && SOLVE_NB + r + 1 - c <= bw;
+                    if (ok0 && ok1) {
+                        spl_cp_async16(dst, src);
+                    } else {
+                        if (ok0) spl_cp_async8(dst, src);
+                        else dst[0] = 0.0;
+                        dst[1] = 0.0;
+                    }
+                }
+            }
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    // warp gw eliminates from the columns jlo + gw, jlo + gw + nw, ..: a column's 64 entries of the block rows are
-    // contiguous, lane l holds rows l and l + 32 (two coalesced 256-byte loads per column)
-    double colr[BACKP_NC][2];
-    auto fetch_col = [&](long long kb) {
-        const long long j0 = kb * SOLVE_NB;
-        const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
-        const long long jlo = (j0 - bw > 0) ? j0 - bw : 0;
+        const long long jlo = (jb - bw > 0) ? jb - bw : 0;
 #pragma unroll
         for (int q = 0; q < BACKP_NC; ++q) {
             const long long j = jlo + gw + (long long)q * nw;
-            colr[q][0] = colr[q][1] = 0.0;
-            if (j < j0) {
-                const double *col = AB + j0 + j * lda;
-                if (lane < nb) colr[q][0] = col[lane];
-                if (lane + 32 < nb) colr[q][1] = col[lane + 32];
+            colr[q][0] = colr[q][1] = colr[q][2] = colr[q][3] = 0.0;
+            if (j < jb) {
+                const double *col = AB + jb + j * lda;                // rows of the lowest block: always inside the band
+                const int nbb = pair ? SOLVE_NB : nbt;
+                if (lane < nbb) colr[q][0] = col[lane];
+                if (lane + 32 < nbb) colr[q][1] = col[lane + 32];
+                if (pair && j >= jt - bw) {                           // rows of the top block, where the band reaches them
+                    if (lane < nbt) colr[q][2] = col[64 + lane];
+                    if (lane + 32 < nbt) colr[q][3] = col[64 + lane + 32];
+                }
             }
         }
     };
-    fetch_inv(nblk - 1, (int)((nblk - 1) & 1));
-    fetch_col(nblk - 1);
-    for (long long kb = nblk - 1; kb >= 0; --kb) {
-        const long long j0 = kb * SOLVE_NB;
-        const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
-        const long long jlo = (j0 - bw > 0) ? j0 - bw : 0;
-        const double *li = s_li + (kb & 1) * 4096;
-        if (t < 64) s_y[t] = (t < nb) ? __ldcg(ysol + j0 + t) : 0.0;
+    // c[i] = sum_r Linv[r][i] y[r]: thread (i, part) sums r = part, part + 4, ..; every thread of the row returns it
+    auto matvec_t = [&](const double *li, const double *y) {
+        const int i = t >> 2, part = t & 3;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) {
+            c0 = fma(li[(part + 4 * q) * 64 + i], y[part + 4 * q], c0);
+            c1 = fma(li[(part + 4 * q + 4) * 64 + i], y[part + 4 * q + 4], c1);
+        }
+        double c = c0 + c1;
+        c += __shfl_xor_sync(0xffffffffu, c, 1);
+        c += __shfl_xor_sync(0xffffffffu, c, 2);
+        return c;
+    };
+    fetch(nblk - 1, 0);
+    int buf = 0;
+    for (long long kb = nblk - 1; kb >= 0;) {
+        const bool pair = kb >= 1;
+        const long long jt = kb * SOLVE_NB, jb = pair ? jt - SOLVE_NB : jt;
+        const int nbt = (int)((n - jt < SOLVE_NB) ? n - jt : SOLVE_NB);
+        const long long jlo = (jb - bw > 0) ? jb - bw : 0;
+        const double *li = s_li + buf * 8192;
+        if (t < 64) s_y[t] = (t < nbt) ? __ldcg(ysol + jt + t) : 0.0;
+        else if (t < 128 && pair) s_y[t] = __ldcg(ysol + jb + (t - 64));
         // the entries this warp will update, fetched now (other CTAs wrote them before the barrier)
         double yold = 0.0;
         if (lane < BACKP_NC) {
             const long long j = jlo + gw + (long long)lane * nw;
-            if (j < j0) yold = __ldcg(ysol + j);
+            if (j < jb) yold = __ldcg(ysol + j);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        // c_k = L11^-T y_k:  c[i] = sum_r Linv[r][i] y[r]; thread (i, part) sums r = part, part + 4, ..
         {
-            const int i = t >> 2, part = t & 3;
-            double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-            for (int q = 0; q < 16; q += 2) {
-                c0 = fma(li[(part + 4 * q) * 64 + i], s_y[part + 4 * q], c0);
-                c1 = fma(li[(part + 4 * q + 4) * 64 + i], s_y[part + 4 * q + 4], c1);
-            }
-            double c = c0 + c1;
-            c += __shfl_xor_sync(0xffffffffu, c, 1);
-            c += __shfl_xor_sync(0xffffffffu, c, 2);
-            if (part == 0) {
+            const double c = matvec_t(li, s_y);                    // c_k
+            const int i = t >> 2;
+            if ((t & 3) == 0) {
                 s_c[i] = c;
-                if (blockIdx.x == 0 && i < nb) csol[j0 + i] = c;
+                if (blockIdx.x == 0 && i < nbt) csol[jt + i] = c;
             }
         }
         __syncthreads();
-        // eliminate c_k from the bw preceding unknowns: y[j] -= sum_i L[i][j] c[i], i in the block
+        if (pair) {
+            // (L[k,k-1]^T c_k)[column i of block k-1]: thread (i, part) sums the rows part, part + 4, ..
+            const int i = t >> 2, part = t & 3;
+            double tc;
+            {
+                const double *lcol = s_lb + buf * (64 * BACKP_LBP) + i * BACKP_LBP;
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < 16; q += 2) {
+                    c0 = fma(lcol[part + 4 * q], s_c[part + 4 * q], c0);
+                    c1 = fma(lcol[part + 4 * q + 4], s_c[part + 4 * q + 4], c1);
+                }
+                tc = c0 + c1;
+                tc += __shfl_xor_sync(0xffffffffu, tc, 1);
+                tc += __shfl_xor_sync(0xffffffffu, tc, 2);
+            }
+            if ((t & 3) == 0) s_y[64 + i] -= tc;                   // (nobody reads y_{k-1} in this phase)
+            __syncthreads();
+            const double c = matvec_t(li + 4096, s_y + 64);        // c_{k-1}
+            if ((t & 3) == 0) {
+                s_c[64 + i] = c;
+                if (blockIdx.x == 0) csol[jb + i] = c;
+            }
+            __syncthreads();
+        }
+        // eliminate from the bw columns in front of the lowest block: y[j] -= sum_i L[i][j] c[i]
         {
-            const double ca = s_c[lane], cb = s_c[lane + 32];
+            const double *cl = pair ? s_c + 64 : s_c;              // c of the lowest block
+            const double ca = cl[lane], cb = cl[lane + 32];
+            const double ta = pair ? s_c[lane] : 0.0, tb = pair ? s_c[lane + 32] : 0.0;
             double mine = 0.0;
 #pragma unroll
             for (int q = 0; q < BACKP_NC; ++q) {
                 double v = fma(colr[q][0], ca, colr[q][1] * cb);
+                v = fma(colr[q][2], ta, fma(colr[q][3], tb, v));
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (lane == q) mine = v;
             }
             if (lane < BACKP_NC) {
                 const long long j = jlo + gw + (long long)lane * nw;
-                if (j < j0) ysol[j] = yold - mine;
+                if (j < jb) ysol[j] = yold - mine;
             }
         }
-        if (kb > 0) {
-            fetch_inv(kb - 1, (int)((kb - 1) & 1));
-            fetch_col(kb - 1);
-            spl_grid_barrier(bar, target, G);
+        kb -= pair ? 2 : 1;
+        if (kb >= 0) {
+            // grid barrier with the next step's prefetch between the arrive and the wait: issued in front of the
+            // release, the fence of the arrive would wait for the 96 KB in flight
+            buf ^= 1;
+            __syncthreads();
+            if (t == 0) {
+                target += G;
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+            }
+            fetch(kb, buf);
+            if (t == 0) {
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+                } while (v < target);
+            }
+            __syncthreads();
         }
     }
 }
@@ -2163,11 +2246,11 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
         }
         cudaGetLastError();
     }
-    const size_t back_smem = sizeof(double) * (2 * 4096 + 128);
+    const size_t back_smem = sizeof(double) * BACKP_SMEM_DOUBLES;
     int back_grid = 0;
     if (persistent) {
         const long long per_cta = (BACKP_THREADS / 32) * BACKP_NC;      // columns a CTA covers per step
-        const long long need = ((long long)bw + per_cta - 1) / per_cta;
+        const long long need = ((long long)bw + SOLVE_NB + per_cta - 1) / per_cta;     // bw columns in front of a pair of blocks
         if (need >= 1 && need <= pgrid &&
             cudaFuncSetAttribute(spl_backsolve_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)back_smem) == cudaSuccess)
@@ -2374,10 +2457,10 @@ int spl_resolve_launch(const GridParams &gp, const double *d_AB, double *d_g, do
         return SPLPAK_ERR_HANDLE;
     }
     const int pgrid = nsm > 0 ? nsm : SPL_NSM_DEFAULT;
-    const size_t back_smem = sizeof(double) * (2 * 4096 + 128);
+    const size_t back_smem = sizeof(double) * BACKP_SMEM_DOUBLES;
     const size_t fwd_smem = sizeof(double) * (2 * 64 * FWDP_LD + 128 + 8 * 32);
     const long long per_cta = (BACKP_THREADS / 32) * BACKP_NC;
-    const long long back_grid = ((long long)bw + per_cta - 1) / per_cta;
+    const long long back_grid = ((long long)bw + SOLVE_NB + per_cta - 1) / per_cta;
     long long fwd_grid = ((((long long)bw + 31) / 32) * 2 + FWDP_THREADS / 32 - 1) / (FWDP_THREADS / 32);
     if (fwd_grid < 1) fwd_grid = 1;
     if (back_grid < 1 || back_grid > pgrid || fwd_grid > pgrid) return SPLPAK_ERR_HANDLE;
