@@ -182,7 +182,13 @@ def test_solver_failures_map_to_107(oracle):
     assert sp.splcc(1, xh, 1, xh[:, 0], 80, [0.0], [1.0], [20], 0.0, **a)[1] == 107
 
 
-@pytest.mark.parametrize("ndim,nodes,ndata", [(3, [9, 8, 10], 6000), (2, [24, 20], 5000), (1, [300], 5000)])
+@pytest.mark.parametrize("ndim,nodes,ndata", [
+    (3, [9, 8, 10], 6000), (2, [24, 20], 5000), (1, [300], 5000),
+    # shapes at the edges of the blocked solvers: one 64-column block exactly / one column more / an odd number of
+    # blocks (the back-substitution pairs them), half bandwidth 63 and 64 +- (one tile row, no helpers), n = 64 in 2-D,
+    # a last block of one column under a two-tile-row band
+    (1, [64], 3000), (1, [65], 3000), (1, [129], 4000), (1, [192], 4000), (2, [8, 8], 3000), (2, [13, 5], 3000),
+    (3, [4, 4, 5], 4000), (3, [4, 5, 4], 4000), (3, [5, 5, 5], 5000), (2, [21, 31], 6000), (3, [6, 6, 9], 8000)])
 def test_solver_paths_agree(oracle, monkeypatch, ndim, nodes, ndata):
     """The factorisation / back-substitution run as persistent cooperative kernels where the panel chain dominates
     (the data-flow kernel by default, the barrier-phased one with SPLPAK_B200_SOLVER=barrier) and as one kernel per phase
