@@ -47,6 +47,11 @@ def run(name, ndim, nodes, n, nq, weighted, xtrap, hole=False, nderiv=None):
 
 print("| config | ndim | nodes | points | fit ms | Gpoints/s | refinement step ms | queries | eval ms | Gq/s | fit stages (ms, incl. refinement pass) |")
 print("|---|---|---|---:|---:|---:|---:|---:|---:|---:|---|")
+only = sys.argv[1:]          # e.g. "cfg4": just that row
+_run = run
+def run(name, *a, **k):
+    if not only or any(name.startswith(o) for o in only):
+        _run(name, *a, **k)
 run("cfg1 splcw", 1, [50], 10_000, 100_000, True, 1.0)
 run("cfg2 splcc + hole, splde d/dx", 2, [64, 64], 1_000_000, 10_000_000, False, 1.0, hole=True, nderiv=[1, 0])
 run("cfg3 splcw", 3, [24, 24, 24], 100_000_000, 1_000_000_000, True, 1.0)

@@ -294,33 +294,42 @@ int spl_constraints_launch(const GridParams &gp, double xtrap, const double *d_c
 // ------------------------------------------------------------------------------------------
 // S (orthant stencil) -> lower band storage
 // ------------------------------------------------------------------------------------------
+// One CTA per column j (grid-stride): the column's node index is decomposed once, the threads walk the 7^ndim signed
+// offset tuples (d_1..d_n), d in -3..3, of the stencil -- base 7 with constant divisors -- and keep those inside the grid
+// with i = j + sum d_d stride_d >= j (the lower band).  The first version ran one thread per (column, band offset)
+// pair with two runtime 64-bit divisions per dimension for every one of the n (b + 1) pairs, 58 % of which hold no
+// entry in 4-D: 1.39 ms at cfg4 (12^4 nodes, b = 5,655), 0.25 ms at cfg3.
 __global__ void __launch_bounds__(256)
 spl_expand_band_kernel(const __grid_constant__ GridParams gp, const double *__restrict__ S,
                        double *__restrict__ AB, long long lda, int bw) {
-    // one thread per (column j, band offset off in 0..bw)
-    const long long total = gp.ncol * (long long)(bw + 1);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const long long j = e / (bw + 1);
-        const int off = (int)(e - j * (bw + 1));
-        const long long i = j + off;
-        if (i >= gp.ncol) continue;
-        long long ki = i, kj = j, node = 0, nstride = 1;
-        int sten = 0, sstride = 1;
-        bool inside = true;
-        for (int d = 0; d < gp.ndim; ++d) {
-            const int id = (int)(ki % gp.nodes[d]);
-            const int jd = (int)(kj % gp.nodes[d]);
-            ki /= gp.nodes[d];
-            kj /= gp.nodes[d];
-            const int del = id > jd ? id - jd : jd - id;
-            if (del > 3) inside = false;
-            node += (long long)(id < jd ? id : jd) * nstride;
-            sten += del * sstride;
-            nstride *= gp.nodes[d];
-            sstride *= 4;
+    int ncombo = 1;
+    for (int d = 0; d < gp.ndim; ++d) ncombo *= 7;
+    for (long long j = blockIdx.x; j < gp.ncol; j += gridDim.x) {
+        int jd[SPL_MAXDIM];
+        {
+            long long kj = j;
+            for (int d = 0; d < gp.ndim; ++d) {
+                jd[d] = (int)(kj % gp.nodes[d]);
+                kj /= gp.nodes[d];
+            }
         }
-        if (inside) AB[i + j * lda] = S[node * gp.nsten + sten];
+        for (int c = threadIdx.x; c < ncombo; c += blockDim.x) {
+            int cc = c, sten = 0, sstride = 1;
+            long long off = 0, node = 0, nstride = 1;
+            bool inside = true;
+            for (int d = 0; d < gp.ndim; ++d) {
+                const int dd = cc % 7 - 3;
+                cc /= 7;
+                const int id = jd[d] + dd;
+                if (id < 0 || id >= gp.nodes[d]) inside = false;
+                off += (long long)dd * nstride;
+                node += (long long)(dd < 0 ? id : jd[d]) * nstride;
+                sten += (dd < 0 ? -dd : dd) * sstride;
+                nstride *= gp.nodes[d];
+                sstride *= 4;
+            }
+            if (inside && off >= 0 && off <= bw) AB[(j + off) + j * lda] = S[node * gp.nsten + sten];
+        }
     }
 }
 
@@ -1084,6 +1093,189 @@ spl_syrk256_kernel(double *__restrict__ AB, long long lda, long long r0, long lo
         spl_rest_tile((int)blockIdx.x, ti, tj);
     }
     spl_tile256<false>(AB, lda, r0, j0, nb, m, ti, tj, s_ab);
+}
+
+// ------------------------------------------------------------------------------------------
+// Two-level blocking for the update-bound shape (cfg4: half bandwidth 5,655 = 89 tile rows, 3,916 update tiles per
+// panel).  With one 64-column panel per trailing update every 64 x 64 tile of the 128 MB band window is read and
+// written once per 64 x 64 x 64 product: 8 flops per byte of C traffic plus the operand tiles, and the kernel-per-phase
+// loop ran at 51 % of the DMMA peak.  Here KB (8; SPLPAK_B200_KBLOCK) panels form an outer block: inside the block a panel's update only
+// touches the block's own remaining columns (spl_syrk_cols_kernel: <= KB - 1 tile columns, the existing K = 64 tile),
+// and the trailing matrix beyond the block gets ONE update with K = 64 KB (spl_syrk_kblock_kernel): the C tile stays in
+// the accumulators while the 2 KB operand half-chunks (32 columns of one panel) stream through a double-buffered
+// 2 x 34.8 KB staging area -- a quarter of the C traffic, and the tile's prologue / epilogue amortised over 4x the MMAs.
+// The band windows of the block's panels differ (panel p reaches KB - 1 - p tile rows less far than the last one):
+// rows beyond a panel's window are zero-filled by the operand loader, and half-chunks whose window ends above the
+// tile are skipped.  Same arithmetic as the unblocked loop (every C element receives the panels' contributions in
+// panel order), so the two agree to the rounding of the MMA's internal order.
+// ------------------------------------------------------------------------------------------
+#define KBLOCK_MAX 8
+
+// NK (32) k-columns of an operand tile: like spl_tile_load16 with every column present; 4 pieces per thread
+template <int NK>
+__device__ __forceinline__ void spl_tile_loadk(double *s, const double *src, const long long lda, const int rows,
+                                               const int t) {
+    const int r = 2 * (t & 31);
+    const int k = t >> 5;
+    const double *gp = src + r + (long long)k * lda;
+    double *dp = s + k * TILE_LD + r;
+    const int valid = rows - r;
+    const long long gstep = 8 * lda;
+#pragma unroll
+    for (int q = 0; q < NK / 8; ++q) {
+        spl_tile_piece(dp, gp, valid, true);
+        gp += gstep;
+        dp += 8 * TILE_LD;
+    }
+}
+
+// Update of the block's own columns by panel (j0, nb): tiles (ti = blockIdx.x, tj = blockIdx.y < gridDim.y), ti >= tj.
+__global__ void __launch_bounds__(PANEL_THREADS, 3)
+spl_syrk_cols_kernel(double *__restrict__ AB, long long lda, long long r0, long long j0, int nb, int m,
+                     const int *__restrict__ fail) {
+    extern __shared__ __align__(16) double s_ab[];
+    const int ti = blockIdx.x, tj = blockIdx.y;
+    if (ti < tj || *fail) return;
+    spl_tile256<false>(AB, lda, r0, j0, nb, m, ti, tj, s_ab);
+}
+
+// Trailing update by the np panels of the outer block that starts at column jb (all 64 wide; R0 = jb + 64 np is the
+// first trailing row / column).  part 0: tile columns [0, c0) (what the next outer block factors: the critical path),
+// grid (T, c0); part 1: tile columns >= c0, the lower triangle enumerated linearly.
+__global__ void __launch_bounds__(PANEL_THREADS, 3)
+spl_syrk_kblock_kernel(double *__restrict__ AB, long long lda, long long jb, int np, long long n, int bw,
+                       const int *__restrict__ fail, int part, int c0) {
+    extern __shared__ __align__(16) double s_ab[];
+    constexpr int HALF = 32 * TILE_LD;            // one operand half-chunk (32 k-columns)
+    constexpr int BUF = 2 * HALF;                 // A | B
+    int ti, tj;
+    if (part == 0) {
+        ti = blockIdx.x;
+        tj = blockIdx.y;
+        if (ti < tj) return;
+    } else {
+        spl_rest_tile((int)blockIdx.x, ti, tj);
+        ti += c0 - 1;
+        tj += c0 - 1;
+    }
+    if (*fail) return;
+    const long long R0 = jb + (long long)np * SOLVE_NB;
+    const int M = (int)((n - R0 < bw) ? n - R0 : bw);             // window of the last panel = the update's extent
+    const int I0 = ti * SYRK_TILE, J0 = tj * SYRK_TILE;
+    if (I0 >= M) return;
+    const bool diag = (ti == tj);
+    const int t = threadIdx.x;
+    // window of panel p in R0-relative rows: Mp = min(bw, n - r0_p) - 64 (np - 1 - p), non-decreasing in p
+    int pfirst = 0;
+    while (pfirst < np - 1) {
+        const long long r0p = jb + (long long)(pfirst + 1) * SOLVE_NB;
+        const long long mp = (n - r0p < bw) ? n - r0p : bw;
+        if (mp - (long long)SOLVE_NB * (np - 1 - pfirst) > I0) break;
+        ++pfirst;
+    }
+    const int h0 = 2 * pfirst, H = 2 * np;
+    // window (R0-relative rows) of the first contributing panel: when it covers the whole tile row, every operand
+    // piece of every half-chunk is a full 16-byte cp.async and the loads are pointer bumps without tests
+    int Mfirst;
+    {
+        const long long r0p = jb + (long long)(pfirst + 1) * SOLVE_NB;
+        const long long mp = (n - r0p < bw) ? n - r0p : bw;
+        Mfirst = (int)(mp - (long long)SOLVE_NB * (np - 1 - pfirst));
+    }
+    const bool full = I0 + 64 <= Mfirst;
+    const int lr = 2 * (t & 31), lk = t >> 5;
+    const double *ga = AB + (R0 + I0 + lr) + (jb + 32LL * h0 + lk) * lda;      // half-chunk h0, this thread's first piece
+    const double *gb = AB + (R0 + J0 + lr) + (jb + 32LL * h0 + lk) * lda;
+    const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(s_ab + lk * TILE_LD + lr);
+    const long long gstep = 8 * lda;
+    auto issue = [&](int h) {
+        if (full) {
+            const uint32_t d = sdst + (uint32_t)((h & 1) * BUF * sizeof(double));
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)(q * 8 * TILE_LD * sizeof(double))),
+                             "l"(ga + q * gstep) : "memory");
+            if (!diag) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)((HALF + q * 8 * TILE_LD) * sizeof(double))),
+                                 "l"(gb + q * gstep) : "memory");
+            }
+            ga += 4 * gstep;
+            gb += 4 * gstep;
+        } else {
+            const int p = h >> 1;
+            const long long j0p = jb + (long long)p * SOLVE_NB + 32 * (h & 1);
+            const long long r0p = jb + (long long)(p + 1) * SOLVE_NB;
+            const long long mp = (n - r0p < bw) ? n - r0p : bw;
+            const int Mp = (int)(mp - (long long)SOLVE_NB * (np - 1 - p));
+            double *buf = s_ab + (h & 1) * BUF;
+            spl_tile_loadk<32>(buf, AB + (R0 + I0) + j0p * lda, lda, Mp - I0, t);
+            if (!diag) spl_tile_loadk<32>(buf + HALF, AB + (R0 + J0) + j0p * lda, lda, Mp - J0, t);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(h0);
+    double acc[2][4][2];
+    spl_tile_cload<2>(acc, AB, lda, R0, M, ti, tj);
+
+    const int warp = t >> 5, lane = t & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wI = (warp & 1) * 32, wJ = (warp >> 1) * 16;
+    const bool inside = !diag && I0 + 64 <= M && J0 + 64 <= M;
+    for (int h = h0; h < H; ++h) {
+        // one barrier per half-chunk: behind it every warp has finished the MMAs of h - 1, so their buffer is free for
+        // h + 1, and everybody's pieces of h have landed
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (h + 1 < H) issue(h + 1);
+        if (h == h0 && !inside) {
+#pragma unroll
+            for (int mj = 0; mj < 2; ++mj)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int li = I0 + wI + ni * 8 + 2 * t4 + hh;
+                        const int lj = J0 + wJ + mj * 8 + g;
+                        if (!(li < M && lj < M && li >= lj)) acc[mj][ni][hh] = 0.0;
+                    }
+        }
+        const double *sA = s_ab + (h & 1) * BUF;
+        const double *sB = diag ? sA : sA + HALF;
+#pragma unroll 4
+        for (int k0 = 0; k0 < 32; k0 += 4) {
+            double a[2], b[4];
+#pragma unroll
+            for (int mj = 0; mj < 2; ++mj) a[mj] = -sB[(k0 + t4) * TILE_LD + wJ + mj * 8 + g];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = sA[(k0 + t4) * TILE_LD + wI + ni * 8 + g];
+#pragma unroll
+            for (int mj = 0; mj < 2; ++mj)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) spl_dmma_8x8x4(acc[mj][ni][0], acc[mj][ni][1], a[mj], b[ni]);
+        }
+    }
+    double *pc = AB + (R0 + I0 + wI + 2 * t4) + (R0 + J0 + wJ + g) * lda;
+    if (inside) {
+#pragma unroll
+        for (int mj = 0; mj < 2; ++mj)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+                *reinterpret_cast<double2 *>(pc + ni * 8 + (long long)(mj * 8) * lda) =
+                    make_double2(acc[mj][ni][0], acc[mj][ni][1]);
+    } else {
+#pragma unroll
+        for (int mj = 0; mj < 2; ++mj)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int li = I0 + wI + ni * 8 + 2 * t4 + hh;
+                    const int lj = J0 + wJ + mj * 8 + g;
+                    if (li < M && lj < M && li >= lj) pc[ni * 8 + hh + (long long)(mj * 8) * lda] = acc[mj][ni][hh];
+                }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2069,6 +2261,7 @@ struct SolveGraphs {
     int bw = 0;
     long long nfactor = 0, nback = 0;     // kernel nodes
     bool persistent = false;              // the factor loop is the cooperative kernel: no factor graph
+    int kblock = 0;                       // panels per outer block the factor graph was captured with
 };
 
 void spl_solve_cache_free(void *cache) {
@@ -2153,6 +2346,101 @@ static cudaError_t enqueue_factor(long long n, int bw, long long lda, double *d_
     return e;
 }
 
+// Two-level blocked factor loop (see spl_syrk_kblock_kernel): outer blocks of KB panels.
+//   st     : [panel(p) -> block-column update(p)] p = 0..np-1 -> [wait rest(k-1)] -> K-blocked update, tile columns
+//            of the next block (k) -> next block ...
+//   st_aux : [wait the block's last panel] -> K-blocked update, every other tile column (k)
+// so the latency chain of the next block's KB panels runs under the bulk of update k, as in enqueue_factor.
+static int spl_kblock() {
+    const char *s = getenv("SPLPAK_B200_KBLOCK");
+    int kb = s ? atoi(s) : KBLOCK_MAX;
+    if (kb < 1) kb = 1;
+    if (kb > KBLOCK_MAX) kb = KBLOCK_MAX;
+    return kb;
+}
+
+static cudaError_t enqueue_factor_blocked(long long n, int bw, long long lda, double *d_AB, double *d_g, double *d_ysol,
+                                          double *d_linv, int *d_fail, cudaStream_t st, cudaStream_t st_aux,
+                                          size_t panel_smem, size_t syrk_smem, int KB, long long *nlaunch) {
+    const long long nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    cudaEvent_t ev_panel = nullptr, ev_rest = nullptr;
+    cudaError_t e;
+    if ((e = cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ev_rest, cudaEventDisableTiming)) != cudaSuccess) return e;
+    bool rest_pending = false;
+    long long count = 0;
+    for (long long ob = 0; ob < nblk && e == cudaSuccess; ob += KB) {
+        const int np = (int)((nblk - ob < KB) ? nblk - ob : KB);
+        const long long jb = ob * SOLVE_NB;
+        for (int p = 0; p < np; ++p) {
+            const long long kb = ob + p;
+            const long long j0 = kb * SOLVE_NB;
+            const int nb = (int)((n - j0 < SOLVE_NB) ? n - j0 : SOLVE_NB);
+            const long long r0 = j0 + nb;
+            long long mm = n - r0;
+            if (mm > bw) mm = bw;
+            const int m = (int)mm;
+            int pblocks = (m + 63) / 64;
+            if (pblocks < 1) pblocks = 1;
+            spl_panel_kernel<<<pblocks, PANEL_THREADS, panel_smem, st>>>(d_AB, lda, j0, nb, m, d_g, d_ysol,
+                                                                         d_linv + kb * 4096, d_fail,
+                                                                         kb == nblk / 2 ? spl_panel_dbg_buffer() : nullptr);
+            ++count;
+            const int T = (m + SYRK_TILE - 1) / SYRK_TILE;
+            int cols = np - 1 - p;
+            if (cols > T) cols = T;
+            if (m > 0 && cols > 0) {
+                spl_syrk_cols_kernel<<<dim3(T, cols), PANEL_THREADS, syrk_smem, st>>>(d_AB, lda, r0, j0, nb, m, d_fail);
+                ++count;
+            }
+        }
+        const long long R0 = jb + (long long)np * SOLVE_NB;
+        long long MM = n - R0;
+        if (MM > bw) MM = bw;
+        if (MM > 0) {
+            const int T = (int)((MM + SYRK_TILE - 1) / SYRK_TILE);
+            long long next_np = nblk - (ob + np);
+            if (next_np > KB) next_np = KB;
+            int c0 = (int)next_np;
+            if (c0 > T) c0 = T;
+            if (c0 < 1) c0 = 1;
+            const int TR = T - c0;                                 // tile columns of the rest
+            if (TR > 0) {
+                if ((e = cudaEventRecord(ev_panel, st)) != cudaSuccess) break;
+                if ((e = cudaStreamWaitEvent(st_aux, ev_panel, 0)) != cudaSuccess) break;
+                spl_syrk_kblock_kernel<<<TR * (TR + 1) / 2, PANEL_THREADS, syrk_smem, st_aux>>>(d_AB, lda, jb, np, n, bw,
+                                                                                                 d_fail, 1, c0);
+                ++count;
+            }
+            if (rest_pending && (e = cudaStreamWaitEvent(st, ev_rest, 0)) != cudaSuccess) break;   // rest(k-1) done
+            rest_pending = false;
+            spl_syrk_kblock_kernel<<<dim3(T, c0), PANEL_THREADS, syrk_smem, st>>>(d_AB, lda, jb, np, n, bw, d_fail, 0, c0);
+            ++count;
+            if (TR > 0) {
+                if ((e = cudaEventRecord(ev_rest, st_aux)) != cudaSuccess) break;
+                rest_pending = true;
+            }
+        }
+    }
+    if (e == cudaSuccess && rest_pending) e = cudaStreamWaitEvent(st, ev_rest, 0);   // join st_aux
+    cudaEventDestroy(ev_panel);
+    cudaEventDestroy(ev_rest);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    *nlaunch = count;
+    return e;
+}
+
+// kernel-per-phase factor loop: two-level blocked (default) or one trailing update per panel (SPLPAK_B200_KBLOCK=1)
+static cudaError_t enqueue_factor_phases(long long n, int bw, long long lda, double *d_AB, double *d_g, double *d_ysol,
+                                         double *d_linv, int *d_fail, cudaStream_t st, cudaStream_t st_aux,
+                                         size_t panel_smem, size_t syrk_smem, long long *nlaunch) {
+    const int KB = spl_kblock();
+    if (KB > 1)
+        return enqueue_factor_blocked(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux, panel_smem, syrk_smem, KB,
+                                      nlaunch);
+    return enqueue_factor(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux, panel_smem, syrk_smem, nlaunch);
+}
+
 static cudaError_t enqueue_back(long long n, int bw, long long lda, const double *d_AB, const double *d_linv,
                                 double *d_ysol, double *d_csol, const int *d_fail, cudaStream_t st,
                                 long long *nlaunch) {
@@ -2188,6 +2476,8 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     const size_t panel_smem = sizeof(double) * (2 * 64 * TILE_LD + 128 + 64 + 64 + 32 * PANEL_LDT + 2);
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
+    SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
+    SPL_CUDA_TRY(cudaFuncSetAttribute(spl_syrk_kblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
     SPL_CUDA_TRY(cudaFuncSetAttribute(spl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
 
     // The factor loop runs as ONE persistent cooperative kernel when the device can keep one CTA per SM resident
@@ -2260,16 +2550,18 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
     (void)spl_panel_dbg_buffer();        // allocate (if asked for) outside stream capture
     // (re)build the graphs when the buffers or the problem changed
     SolveGraphs *sg = cache ? static_cast<SolveGraphs *>(*cache) : nullptr;
-    if (cache && (!sg || sg->key_AB != d_AB || sg->key_g != d_g || sg->n != n || sg->bw != bw || sg->persistent != persistent_factor)) {
+    if (cache && (!sg || sg->key_AB != d_AB || sg->key_g != d_g || sg->n != n || sg->bw != bw || sg->persistent != persistent_factor ||
+                  sg->kblock != spl_kblock())) {
         spl_solve_cache_free(sg);
         sg = new (std::nothrow) SolveGraphs();
         *cache = sg;
         if (sg) {
             cudaGraph_t gr = nullptr;
             sg->persistent = persistent_factor;
+            sg->kblock = spl_kblock();
             cudaError_t e = persistent_factor ? cudaSuccess : cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
             if (e == cudaSuccess && !persistent_factor) {
-                const cudaError_t eq = enqueue_factor(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux,
+                const cudaError_t eq = enqueue_factor_phases(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux,
                                                       panel_smem, syrk_smem, &sg->nfactor);
                 e = cudaStreamEndCapture(st, &gr);
                 if (eq != cudaSuccess) e = eq;
@@ -2303,8 +2595,7 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
 
     if (ev) cudaEventRecord(ev[0], st);
     {
-        const long long total = n * (long long)(bw + 1);
-        long long blocks = (total + 255) / 256;
+        long long blocks = n;
         if (blocks > 148LL * 32) blocks = 148LL * 32;
         spl_expand_band_kernel<<<(unsigned)blocks, 256, 0, st>>>(gp, d_S, d_AB, lda, bw);
         ++g_spl_launches;
@@ -2353,13 +2644,13 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
             fprintf(stderr, "splpak_b200: cooperative launch of the factor kernel failed (%s); launching per phase\n",
                     cudaGetErrorString(ce));
             cudaGetLastError();
-            SPL_CUDA_TRY(enqueue_factor(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux, panel_smem, syrk_smem, &nl));
+            SPL_CUDA_TRY(enqueue_factor_phases(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux, panel_smem, syrk_smem, &nl));
         }
     } else if (sg && sg->factor) {
         SPL_CUDA_TRY(cudaGraphLaunch(sg->factor, st));
         nl = sg->nfactor;
     } else {
-        SPL_CUDA_TRY(enqueue_factor(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux, panel_smem, syrk_smem, &nl));
+        SPL_CUDA_TRY(enqueue_factor_phases(n, bw, lda, d_AB, d_g, d_ysol, d_linv, d_fail, st, st_aux, panel_smem, syrk_smem, &nl));
     }
     g_spl_launches += nl;
     if (spl_panel_dbg_buffer()) {

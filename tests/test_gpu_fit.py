@@ -188,19 +188,25 @@ def test_solver_failures_map_to_107(oracle):
     # blocks (the back-substitution pairs them), half bandwidth 63 and 64 +- (one tile row, no helpers), n = 64 in 2-D,
     # a last block of one column under a two-tile-row band
     (1, [64], 3000), (1, [65], 3000), (1, [129], 4000), (1, [192], 4000), (2, [8, 8], 3000), (2, [13, 5], 3000),
-    (3, [4, 4, 5], 4000), (3, [4, 5, 4], 4000), (3, [5, 5, 5], 5000), (2, [21, 31], 6000), (3, [6, 6, 9], 8000)])
+    (3, [4, 4, 5], 4000), (3, [4, 5, 4], 4000), (3, [5, 5, 5], 5000), (2, [21, 31], 6000), (3, [6, 6, 9], 8000),
+    # more tile rows (8) than panels per outer block: the K-blocked trailing update has a rest part on the second stream
+    (3, [12, 12, 6], 12000)])
 def test_solver_paths_agree(oracle, monkeypatch, ndim, nodes, ndata):
     """The factorisation / back-substitution run as persistent cooperative kernels where the panel chain dominates
     (the data-flow kernel by default, the barrier-phased one with SPLPAK_B200_SOLVER=barrier) and as one kernel per phase
-    (CUDA graph, two streams) otherwise; SPLPAK_B200_SOLVER=graph forces the latter.
-    Same normal equations -> coefficients equal to the solver's own run-to-run spread, and both at oracle parity."""
+    (CUDA graph, two streams) otherwise; SPLPAK_B200_SOLVER=graph forces the latter, whose trailing update is blocked
+    over SPLPAK_B200_KBLOCK panels (default 4; 1 = one update per panel, 3 = blocks that do not divide the panel count).
+    Same normal equations -> coefficients equal to the solver's own run-to-run spread, and all at oracle parity."""
     x, y, w, mn, mx = make_problem(ndim, nodes, ndata, seed=ndim + ndata)
     ref, ierr = oracle.initialize(ndim, x, y, w, mn, mx, nodes, 0.0)     # xtrap = 0: no constraint rows, no refinement
     assert ierr == 0
     got = {}
-    for mode in ("persistent", "barrier", "graph"):
+    for mode in ("persistent", "barrier", "graph", "graph-kb1", "graph-kb3"):
+        monkeypatch.delenv("SPLPAK_B200_KBLOCK", raising=False)
         if mode != "persistent":
-            monkeypatch.setenv("SPLPAK_B200_SOLVER", mode)
+            monkeypatch.setenv("SPLPAK_B200_SOLVER", mode.split("-")[0])
+            if "-kb" in mode:
+                monkeypatch.setenv("SPLPAK_B200_KBLOCK", mode[-1])
         else:
             monkeypatch.delenv("SPLPAK_B200_SOLVER", raising=False)
         h = sp.FitHandle(ndim, mn, mx, nodes, 0.0)
@@ -214,6 +220,8 @@ def test_solver_paths_agree(oracle, monkeypatch, ndim, nodes, ndata):
         h.destroy()
     np.testing.assert_allclose(got["persistent"], got["graph"], rtol=0, atol=tol * np.abs(ref).max())
     np.testing.assert_allclose(got["barrier"], got["graph"], rtol=0, atol=tol * np.abs(ref).max())
+    np.testing.assert_allclose(got["graph-kb1"], got["graph"], rtol=0, atol=tol * np.abs(ref).max())
+    np.testing.assert_allclose(got["graph-kb3"], got["graph"], rtol=0, atol=tol * np.abs(ref).max())
 
 
 def test_solver_failure_is_reported_by_both_paths(monkeypatch):
