@@ -812,18 +812,26 @@ int spl_acc_chunk_points(int ndim, int moments) {
 // SPLPAK_B200_ASSEMBLY=direct keeps 3-D on the direct orthant-stencil accumulation (A/B tests).
 int spl_assemble_scratch_init(const GridParams &gp, AssembleScratch &sc, cudaStream_t st) {
     const char *mode = getenv("SPLPAK_B200_ASSEMBLY");
-    sc.moments = (gp.ndim == 3 && !(mode && strcmp(mode, "direct") == 0)) ? 1 : 0;
+    sc.moments = ((gp.ndim == 3 || gp.ndim == 4) && !(mode && strcmp(mode, "direct") == 0)) ? 1 : 0;
     sc.nbins = gp.nwindows;
     if (sc.moments) {
-        sc.nbins = 1;
-        long long ntab = 0;
+        long long ncell = 1, ntab = 0;
         for (int d = 0; d < gp.ndim; ++d) {
-            sc.nbins *= gp.nodes[d] + 1;
+            ncell *= gp.nodes[d] + 1;
             ntab += gp.nodes[d] + 1;
         }
+        // 4-D: 21 KB of moments per cell; beyond 2^31 cells-bytes / 16 GB the direct accumulation is used instead
+        const size_t per_cell = gp.ndim == 4 ? MOM4_MG : MOM_MG;
+        if (ncell > 0x7fffffffLL || (double)ncell * per_cell * sizeof(double) > 16e9) sc.moments = 0;
+        if (sc.moments) sc.nbins = ncell;
+    }
+    if (sc.moments) {
+        long long ntab = 0;
+        for (int d = 0; d < gp.ndim; ++d) ntab += gp.nodes[d] + 1;
+        const size_t per_cell = gp.ndim == 4 ? MOM4_MG : MOM_MG;
         SPL_CUDA_TRY(cudaMalloc((void **)&sc.celltab, sizeof(double) * (size_t)ntab * MOM_CW));
-        SPL_CUDA_TRY(cudaMalloc((void **)&sc.cellmom, sizeof(double) * (size_t)sc.nbins * MOM_MG));
-        SPL_CUDA_TRY(cudaMemsetAsync(sc.cellmom, 0, sizeof(double) * (size_t)sc.nbins * MOM_MG, st));
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.cellmom, sizeof(double) * (size_t)sc.nbins * per_cell));
+        SPL_CUDA_TRY(cudaMemsetAsync(sc.cellmom, 0, sizeof(double) * (size_t)sc.nbins * per_cell, st));
         spl_cell_tables_kernel<<<spl_div_up(ntab, 128), 128, 0, st>>>(gp, sc.celltab);
         ++g_spl_launches;
         SPL_CUDA_TRY(cudaGetLastError());
@@ -915,8 +923,24 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
                                                              sc.item_seg);
     if (ev) cudaEventRecord(ev[2], st);
     const long long max_items = nbins + n / ch + 1;
-    if constexpr (CELL) {
-        static_assert(NDIM == 3, "the moment path is 3-D");
+    if constexpr (CELL && NDIM == 4) {
+        const size_t smem = sizeof(double) * (size_t)MOM4_PB * MOM4_RS;
+        const size_t tsmem = sizeof(double) * (size_t)MOM4_TSMEM;
+        auto kern = rhs_only ? spl_moments4_kernel<true> : spl_moments4_kernel<false>;
+        auto tkern = rhs_only ? spl_cell_transform4_kernel<true> : spl_cell_transform4_kernel<false>;
+        SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPL_CUDA_TRY(cudaFuncSetAttribute(tkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        int per_sm = 1;
+        SPL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MOM4_NT, smem));
+        if (per_sm < 1) per_sm = 1;
+        long long agrid = (long long)nsm * per_sm;
+        if (agrid > max_items) agrid = max_items;
+        kern<<<(unsigned)agrid, MOM4_NT, smem, st>>>(gp, d_x, l1x, d_y, yw, sc.perm, sc.wincount, sc.winstart,
+                                                     sc.item_win, sc.item_seg, sc.meta, sc.cellmom);
+        tkern<<<(unsigned)nbins, 256, tsmem, st>>>(gp, sc.wincount, sc.celltab, sc.cellmom, d_S, d_g);
+        g_spl_launches += 6;
+    } else if constexpr (CELL) {
+        static_assert(NDIM == 3, "the moment path is 3-D and 4-D");
         const size_t smem = sizeof(double) * (size_t)MOM_PB * MOM_RS;
         auto kern = rhs_only ? spl_moments_kernel<true> : spl_moments_kernel<false>;
         SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -960,7 +984,9 @@ int spl_assemble_chunk(const GridParams &gp, const real_t *d_x, int l1x, const r
     case 3:
         if (sc.moments) return assemble_chunk_t<3, true>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
         return assemble_chunk_t<3, false>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
-    case 4: return assemble_chunk_t<4, false>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+    case 4:
+        if (sc.moments) return assemble_chunk_t<4, true>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
+        return assemble_chunk_t<4, false>(gp, d_x, l1x, d_y, d_w, weighted, n, do_hist, rhs_only, sc, d_S, d_g, d_cnt, d_totals, st, nsm, ev);
     }
     return SPLPAK_ERR_NDIM;
 }

@@ -390,3 +390,336 @@ spl_cell_transform_kernel(const __grid_constant__ GridParams gp, const unsigned 
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// 4-D: the same construction with one more factor (round 2).
+//     M[e4][e3][e2][e1] = sum_p w^2   P_e4(t4) P_e3(t3) P_e2(t2) P_e1(t1),   e = 0..6   (2,401 values)
+//     R[f4][f3][f2][f1] = sum_p w^2 y P_f4(t4) P_f3(t3) P_f2(t2) P_f1(t1),   f = 0..3   (  256 values)
+// i.e. 2,657 FMAs per point against the 10^4 + 4^4 of the direct orthant-stencil accumulation.  As a GEMM over the
+// points: rows (e4, e3, e2), columns e1, k = 4 points per DMMA.8x8x4 -- 49 m-tiles (e4, e3) with rows e2 plus 8 tiles
+// (f4, f3 half) with rows (f3, f2) for the right-hand side, 57 DMMA per 4 points.  114 accumulator doubles do not fit
+// one warp, so the M dimension is split over the CTA's eight warps and EVERY warp walks all the points of the batch:
+// warp e4 < 7 owns the seven tiles (e4, e3 = 0..6), warp 7 the eight right-hand-side tiles (14 + 14 + 14 + 15 DMMA per
+// 4 points on the four SM sub-partitions).  Nothing is reduced across warps; a work item ends with each warp adding
+// its own fragment entries to the cell's moment array.
+// Staged record of one point (doubles):
+//   [0..7] P1, 0   [8..15] P2, 0   [16..23] P3, 0   [24..31] A4 = w^2 P4, 0   [32..35] B4 = w^2 y P4[0..3]
+// MOM4_RS = 46: RS/2 odd and RS = 14 mod 16, the bank argument of MOM_RS.
+// ------------------------------------------------------------------------------------------
+#define MOM4_NM 2401
+#define MOM4_NR 256
+#define MOM4_MG 2664                  // doubles per cell (2,657 used)
+#define MOM4_NT 256
+#define MOM4_PB 256
+#define MOM4_RS 46
+#define MOM4_OFF_P2 8
+#define MOM4_OFF_P3 16
+#define MOM4_OFF_A4 24
+#define MOM4_OFF_B4 32
+
+template <bool RHS_ONLY>
+__global__ void __launch_bounds__(MOM4_NT, 2)
+spl_moments4_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
+                    const real_t *__restrict__ y, const double2 *__restrict__ yw,
+                    const unsigned *__restrict__ perm, const unsigned *__restrict__ bincount,
+                    const unsigned *__restrict__ binstart, const unsigned *__restrict__ item_bin,
+                    const unsigned *__restrict__ item_seg, unsigned *__restrict__ meta,
+                    double *__restrict__ MG) {
+    extern __shared__ __align__(16) double s_pts[];          // MOM4_PB x MOM4_RS
+    __shared__ unsigned s_item;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;                // MMA fragment coordinates of this lane
+    const int frr = fr & 3, frh = fr >> 2;
+    const unsigned nitems = meta[0];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(meta + 2, 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= nitems) break;
+        const unsigned cell = item_bin[item];
+        const unsigned seg = item_seg[item];
+        const long long first = (long long)binstart[cell] + (long long)seg * MOM_CH;
+        const int npts = (int)min((unsigned)MOM_CH, bincount[cell] - seg * (unsigned)MOM_CH);
+        const int nbatch = (npts + MOM4_PB - 1) / MOM4_PB;
+        double xc[4];                                        // left end of the cell per dimension (:246 form)
+        {
+            unsigned c = cell;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const unsigned ncd = (unsigned)(gp.nodes[d] + 1);
+                const int cd = (int)(c % ncd);
+                c /= ncd;
+                xc[d] = spl_add(gp.xmin[d], spl_mul((double)(cd - 1), gp.dx[d]));
+            }
+        }
+        double acc[8][2];                                    // warps 0..6: tiles e3 = 0..6; warp 7: tiles (f4, half)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e][0] = acc[e][1] = 0.0;
+
+        unsigned pn;
+        double px[4], py, pw;
+        auto load_perm = [&](int b) {
+            const int p = b * MOM4_PB + tid;
+            pn = (b < nbatch && p < npts) ? perm[first + p] : 0xffffffffu;
+        };
+        auto load_data = [&](unsigned pc) {
+            px[0] = px[1] = px[2] = px[3] = 0.0;
+            py = 0.0;
+            pw = 0.0;
+            if (pc != 0xffffffffu) {
+                const long long i = pc;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) px[d] = (double)x[i * (long long)l1x + d];
+                if (yw) {                                    // weighted: interleaved (y, w) copy written by classify
+                    const double2 v = __ldg(yw + i);
+                    py = v.x;
+                    pw = v.y;
+                } else {
+                    py = (double)y[i];
+                    pw = 1.0;
+                }
+            }
+        };
+        load_perm(0);
+        load_data(pn);
+        load_perm(1);
+        for (int b = 0; b < nbatch; ++b) {
+            const int nb = min(MOM4_PB, npts - b * MOM4_PB);
+            // ---- stage ----
+            if (tid < nb) {
+                double P[MOM_NE];
+                double *rec = s_pts + tid * MOM4_RS;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    spl_legendre<MOM_NE>(spl_mul(gp.dxin[d], spl_sub(px[d], xc[d])), P);
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2)
+                        *reinterpret_cast<double2 *>(rec + 8 * d + e) = make_double2(P[e], e + 1 < MOM_NE ? P[e + 1] : 0.0);
+                }
+                spl_legendre<MOM_NE>(spl_mul(gp.dxin[3], spl_sub(px[3], xc[3])), P);
+                const double w2 = pw * pw;                       // row = w*phi, rhs = w*y (:806, :837)
+                const double w2y = w2 * py;
+                if (!RHS_ONLY) {
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2)
+                        *reinterpret_cast<double2 *>(rec + MOM4_OFF_A4 + e) =
+                            make_double2(w2 * P[e], e + 1 < MOM_NE ? w2 * P[e + 1] : 0.0);
+                }
+                *reinterpret_cast<double2 *>(rec + MOM4_OFF_B4) = make_double2(w2y * P[0], w2y * P[1]);
+                *reinterpret_cast<double2 *>(rec + MOM4_OFF_B4 + 2) = make_double2(w2y * P[2], w2y * P[3]);
+            } else if (tid < ((nb + 7) & ~7)) {
+                // the MMA consumes whole groups of 8 points: pad the last group with zero records
+                double *rec = s_pts + tid * MOM4_RS;
+#pragma unroll
+                for (int e = 0; e < 36; e += 2) *reinterpret_cast<double2 *>(rec + e) = make_double2(0.0, 0.0);
+            }
+            __syncthreads();
+            {
+                const unsigned pc = pn;
+                load_perm(b + 2);                                // permutation two batches ahead
+                if (b + 1 < nbatch) load_data(pc);               // gathers of the next batch fly under the MMAs
+            }
+            // ---- accumulate: every warp walks all the points ----
+            if (warp < 7) {
+                if (!RHS_ONLY) {
+                    for (int p0 = 0; p0 < nb; p0 += 8) {
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const double *rec = s_pts + (p0 + half + 2 * fk) * MOM4_RS;   // point of this lane's k
+                            const double bfrag = rec[fr];                                  // B[k][n = fr] = P1[fr]
+                            const double a4p2 = rec[MOM4_OFF_A4 + warp] * rec[MOM4_OFF_P2 + fr];
+                            double p3[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const double2 v = *reinterpret_cast<const double2 *>(rec + MOM4_OFF_P3 + e);
+                                p3[e] = v.x;
+                                p3[e + 1] = v.y;
+                            }
+#pragma unroll
+                            for (int e = 0; e < MOM_NE; ++e) spl_mom_dmma(acc[e][0], acc[e][1], a4p2 * p3[e], bfrag);
+                        }
+                    }
+                }
+            } else {
+                for (int p0 = 0; p0 < nb; p0 += 8) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const double *rec = s_pts + (p0 + half + 2 * fk) * MOM4_RS;
+                        const double bfrag = rec[fr];
+                        const double p2r = rec[MOM4_OFF_P2 + frr];
+                        const double q0 = rec[MOM4_OFF_P3 + frh] * p2r;              // rows (f3 = frh, f2 = frr)
+                        const double q1 = rec[MOM4_OFF_P3 + 2 + frh] * p2r;          // rows (f3 = 2 + frh, f2 = frr)
+                        const double2 b01 = *reinterpret_cast<const double2 *>(rec + MOM4_OFF_B4);
+                        const double2 b23 = *reinterpret_cast<const double2 *>(rec + MOM4_OFF_B4 + 2);
+                        spl_mom_dmma(acc[0][0], acc[0][1], b01.x * q0, bfrag);
+                        spl_mom_dmma(acc[1][0], acc[1][1], b01.x * q1, bfrag);
+                        spl_mom_dmma(acc[2][0], acc[2][1], b01.y * q0, bfrag);
+                        spl_mom_dmma(acc[3][0], acc[3][1], b01.y * q1, bfrag);
+                        spl_mom_dmma(acc[4][0], acc[4][1], b23.x * q0, bfrag);
+                        spl_mom_dmma(acc[5][0], acc[5][1], b23.x * q1, bfrag);
+                        spl_mom_dmma(acc[6][0], acc[6][1], b23.y * q0, bfrag);
+                        spl_mom_dmma(acc[7][0], acc[7][1], b23.y * q1, bfrag);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- flush: C fragment rows fr, columns 2 fk + {0, 1}; every warp owns its moments ----
+        double *dst = MG + (long long)cell * MOM4_MG;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = 2 * fk + j;
+            if (warp < 7) {
+                if (!RHS_ONLY && fr < MOM_NE && col < MOM_NE) {
+#pragma unroll
+                    for (int e = 0; e < MOM_NE; ++e) {
+                        const double v = acc[e][j];
+                        if (v != 0.0) atomicAdd(dst + ((warp * MOM_NE + e) * MOM_NE + fr) * MOM_NE + col, v);
+                    }
+                }
+            } else if (col < MOM_NF) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int f4 = t >> 1, f3 = 2 * (t & 1) + frh;
+                    const double v = acc[t][j];
+                    if (v != 0.0) atomicAdd(dst + MOM4_NM + ((f4 * 4 + f3) * 4 + frr) * MOM_NF + col, v);
+                }
+            }
+        }
+    }
+}
+
+// One CTA per non-empty cell: four 1-D changes of basis 2401 -> 343 x 10 -> 49 x 100 -> 7 x 1000 -> 10^4 (+ 256 -> 256
+// for g), added into S / g; the cell's moments are zeroed after they are read.
+// Shared memory (doubles): R1 [7000]: the moments (2,657) and T1 (3,430), later T3 (7,000) | R2 [4900]: T2 |
+// coefficient tables 4 x MOM_CW | U [3 x 256].
+#define MOM4_R1 7000
+#define MOM4_R2 4900
+#define MOM4_TSMEM (MOM4_R1 + MOM4_R2 + 4 * MOM_CW + 3 * 256)
+template <bool RHS_ONLY>
+__global__ void __launch_bounds__(256)
+spl_cell_transform4_kernel(const __grid_constant__ GridParams gp, const unsigned *__restrict__ bincount,
+                           const double *__restrict__ tab, double *__restrict__ MG, double *__restrict__ S,
+                           double *__restrict__ g) {
+    const unsigned cell = blockIdx.x;
+    if (bincount[cell] == 0u) return;
+    extern __shared__ __align__(16) double s_t4[];
+    double *s_M = s_t4;                       // [2657]
+    double *s_T1 = s_t4 + 2664;               // [343][10]
+    double *s_T3 = s_t4;                      // [7][1000]   (over M and T1, both dead by then)
+    double *s_T2 = s_t4 + MOM4_R1;            // [49][100]
+    double *s_C = s_T2 + MOM4_R2;             // [4][MOM_CW]
+    double *s_U1 = s_C + 4 * MOM_CW, *s_U2 = s_U1 + 256, *s_U3 = s_U2 + 256;
+    const int tid = threadIdx.x;
+    int ws[4];
+    {
+        unsigned c = cell;
+        long long toff = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const unsigned ncd = (unsigned)(gp.nodes[d] + 1);
+            const int cd = (int)(c % ncd);
+            c /= ncd;
+            ws[d] = min(max(cd - 2, 0), gp.nodes[d] - 4);
+            const double *src = tab + toff + (long long)cd * MOM_CW;
+            for (int k = tid; k < MOM_CW; k += blockDim.x) s_C[d * MOM_CW + k] = src[k];
+            toff += (long long)(gp.nodes[d] + 1) * MOM_CW;
+        }
+    }
+    double *mg = MG + (long long)cell * MOM4_MG;
+    for (int k = (RHS_ONLY ? MOM4_NM : 0) + tid; k < MOM4_NM + MOM4_NR; k += blockDim.x) {
+        s_M[k] = mg[k];
+        mg[k] = 0.0;
+    }
+    __syncthreads();
+    // a zero coefficient must skip its moment (it may be inf/NaN for a far exterior point)
+    auto mac = [](double cf, double m, double s) { return cf != 0.0 ? fma(cf, m, s) : s; };
+    // right-hand side: U1[(f4,f3,f2)][i1], U2[(f4,f3)][i2][i1], U3[f4][i3][i2][i1], g[i4][i3][i2][i1]
+    {
+        const int ro = tid >> 2, i1 = tid & 3;
+        double s = 0.0;
+#pragma unroll
+        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[70 + i1 * MOM_NF + f], s_M[MOM4_NM + ro * MOM_NF + f], s);
+        s_U1[tid] = s;
+    }
+    if (!RHS_ONLY) {
+        for (int k = tid; k < 3430; k += blockDim.x) {           // T1[o = (e4,e3,e2)][a1]
+            const int o = k / 10, a1 = k - o * 10;
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[a1 * MOM_NE + e], s_M[o * MOM_NE + e], s);
+            s_T1[k] = s;
+        }
+    }
+    __syncthreads();
+    {
+        const int o = tid >> 4, i2 = (tid >> 2) & 3, i1 = tid & 3;   // o = (f4, f3)
+        double s = 0.0;
+#pragma unroll
+        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[MOM_CW + 70 + i2 * MOM_NF + f], s_U1[(o * 4 + f) * 4 + i1], s);
+        s_U2[tid] = s;
+    }
+    if (!RHS_ONLY) {
+        for (int k = tid; k < 4900; k += blockDim.x) {           // T2[o = (e4,e3)][a2][a1]
+            const int o = k / 100, r = k - o * 100, a2 = r / 10, a1 = r - a2 * 10;
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[MOM_CW + a2 * MOM_NE + e], s_T1[(o * MOM_NE + e) * 10 + a1], s);
+            s_T2[k] = s;
+        }
+    }
+    __syncthreads();
+    {
+        const int f4 = tid >> 6, i3 = (tid >> 4) & 3, r = tid & 15;
+        double s = 0.0;
+#pragma unroll
+        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[2 * MOM_CW + 70 + i3 * MOM_NF + f], s_U2[(f4 * 4 + f) * 16 + r], s);
+        s_U3[tid] = s;
+    }
+    if (!RHS_ONLY) {
+        for (int k = tid; k < 7000; k += blockDim.x) {           // T3[e4][a3][a2 a1]
+            const int e4 = k / 1000, r = k - e4 * 1000, a3 = r / 100, r2 = r - a3 * 100;
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[2 * MOM_CW + a3 * MOM_NE + e], s_T2[(e4 * MOM_NE + e) * 100 + r2], s);
+            s_T3[k] = s;
+        }
+    }
+    __syncthreads();
+    {
+        const int i4 = tid >> 6, r = tid & 63;
+        double s = 0.0;
+#pragma unroll
+        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[3 * MOM_CW + 70 + i4 * MOM_NF + f], s_U3[f * 64 + r], s);
+        if (s != 0.0) {
+            const long long node = (long long)(ws[0] + (r & 3)) + (long long)(ws[1] + ((r >> 2) & 3)) * gp.nodes[0] +
+                                   (long long)(ws[2] + (r >> 4)) * gp.nodes[0] * gp.nodes[1] +
+                                   (long long)(ws[3] + i4) * gp.nodes[0] * gp.nodes[1] * gp.nodes[2];
+            atomicAdd(g + node, s);
+        }
+    }
+    if (!RHS_ONLY) {
+        for (int k = tid; k < 10000; k += blockDim.x) {          // S[a4][a3][a2][a1]
+            const int a4 = k / 1000, r = k - a4 * 1000;
+            double s = 0.0;
+#pragma unroll
+            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[3 * MOM_CW + a4 * MOM_NE + e], s_T3[e * 1000 + r], s);
+            if (s != 0.0) {
+                const int a[4] = {r % 10, (r / 10) % 10, r / 100, a4};
+                long long node = 0, nstride = 1;
+                int sten = 0, sstride = 1;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    int i, j;
+                    spl_pair(a[d], i, j);
+                    node += (long long)(ws[d] + i) * nstride;
+                    sten += (j - i) * sstride;
+                    nstride *= gp.nodes[d];
+                    sstride *= 4;
+                }
+                atomicAdd(S + node * gp.nsten + sten, s);
+            }
+        }
+    }
+}

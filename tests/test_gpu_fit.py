@@ -274,25 +274,42 @@ def test_3d_moment_and_direct_assembly_agree(oracle, monkeypatch, nodes, ndata, 
     """3-D assembles through per-cell Legendre moments (csrc/moments.cuh); SPLPAK_B200_ASSEMBLY=direct keeps the
     per-point orthant-stencil accumulation.  Both against the oracle's rows, and against each other at the
     rounding level of the re-associated sums; points exactly on nodes / box faces included."""
+    _moment_vs_direct(oracle, monkeypatch, nodes, ndata, outside, lo, hi)
+
+
+@pytest.mark.parametrize("nodes,ndata,outside,lo,hi", [
+    ([4, 4, 4, 4], 6000, 0.3, 0.0, 1.0),        # every cell touches an edge
+    ([5, 4, 6, 5], 20000, 0.25, 0.0, 1.0),
+    ([6, 5, 4, 5], 12000, 0.5, -3.0, 7.5),      # far exterior points
+    ([4, 5, 4, 4], 60000, 0.0, 0.0, 1.0),       # several 256-point batches per cell
+])
+def test_4d_moment_and_direct_assembly_agree(oracle, monkeypatch, nodes, ndata, outside, lo, hi):
+    """4-D (round 2): 7^4 + 4^4 moments per cell, the GEMM's M dimension split over the CTA's eight warps
+    (spl_moments4_kernel), four 1-D changes of basis per cell (spl_cell_transform4_kernel)."""
+    _moment_vs_direct(oracle, monkeypatch, nodes, ndata, outside, lo, hi)
+
+
+def _moment_vs_direct(oracle, monkeypatch, nodes, ndata, outside, lo, hi):
+    nd = len(nodes)
     rng = np.random.default_rng(nodes[0] * 100 + ndata)
-    x, y, w, mn, mx = make_problem(3, nodes, ndata, seed=nodes[1] + ndata, weighted=True, outside=outside)
+    x, y, w, mn, mx = make_problem(nd, nodes, ndata, seed=nodes[1] + ndata, weighted=True, outside=outside)
     span = np.asarray(mx) - np.asarray(mn)
-    x = lo + (x - np.asarray(mn)) / span * (hi - lo)         # same relative positions in the box [lo, hi]^3
-    mn, mx = [lo] * 3, [hi] * 3
+    x = lo + (x - np.asarray(mn)) / span * (hi - lo)         # same relative positions in the box [lo, hi]^nd
+    mn, mx = [lo] * nd, [hi] * nd
     dx = (hi - lo) / (np.asarray(nodes) - 1)
-    x[:40] = lo + rng.integers(0, np.asarray(nodes), (40, 3)) * dx      # exactly on nodes (cell boundaries)
-    x[40] = [lo, lo, lo]
-    x[41] = [hi, hi, hi]
+    x[:40] = lo + rng.integers(0, np.asarray(nodes), (40, nd)) * dx      # exactly on nodes (cell boundaries)
+    x[40] = [lo] * nd
+    x[41] = [hi] * nd
     w[5::23] = 0.0
     res = {}
     for mode in ("direct", "moments"):
         monkeypatch.setenv("SPLPAK_B200_ASSEMBLY", mode)
-        h = sp.FitHandle(3, mn, mx, nodes, 1.0)
+        h = sp.FitHandle(nd, mn, mx, nodes, 1.0)
         assert h.add_points(x, y, w) == 0
         S, g, cnt, totlwt, nrows = h.normal_equations()
         res[mode] = (dense_from_stencil(S, nodes), g, cnt, totlwt, nrows)
         h.destroy()
-    Gref, gref, A, r = _gram_from_oracle(oracle, 3, x, y, w, mn, mx, nodes, 0.0)
+    Gref, gref, A, r = _gram_from_oracle(oracle, nd, x, y, w, mn, mx, nodes, 0.0)
     scale = np.abs(np.diag(Gref)).max()
     gs = np.abs(gref).max()
     for mode, (G, g, cnt, totlwt, nrows) in res.items():
@@ -310,7 +327,8 @@ def test_refinement_recovers_orthogonal_solver_accuracy(oracle):
     """Handle path: compute() alone is accurate to eps*cond(G); one refinement pass over the same points
     (fit_refine_*) brings the coefficients to eps*cond(A), where the reference's QR (suprls) works."""
     eps = np.finfo(float).eps
-    for ndim, nodes, n, seed in ((1, [30], 400, 1), (2, [20, 20], 20000, 3), (3, [8, 7, 8], 20000, 4)):
+    for ndim, nodes, n, seed in ((1, [30], 400, 1), (2, [20, 20], 20000, 3), (3, [8, 7, 8], 20000, 4),
+                                 (4, [5, 4, 5, 4], 20000, 5)):      # 4-D: the right-hand-side-only moment kernel
         x, y, w, mn, mx = make_problem(ndim, nodes, n, seed=seed, weighted=True, hole=True)
         ref, ie = oracle.initialize(ndim, x, y, w, mn, mx, nodes, 1.0)
         A, r = oracle.rows(ndim, x, y, w, mn, mx, nodes, 1.0)
