@@ -1,0 +1,8 @@
+#!/bin/bash
+# 4-D cell transform with plain FMAs: moment tests, cfg4 row, launch list of the assembly
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_fit.py -x -q -m gpu -k "moment or refinement or normal_equations or streaming" > gpurun_out/r5h_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/r5h_tests.log
+timeout 600 python -m pytest tests/test_gpu_scale.py -x -q -m gpu -k cfg4 > gpurun_out/r5h_tests_cfg4.log 2>&1; echo "cfg4 test rc=$?"; tail -2 gpurun_out/r5h_tests_cfg4.log
+timeout 600 python scripts/config_times.py cfg4 2>&1 | tail -1 | tee gpurun_out/r5h_cfg4.md
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"spl_(moments4|cell_transform4|classify|perm)" -c 8 --csv --log-file gpurun_out/r5h_launches.csv python scripts/cfg4_fit_once.py 1e7 1 > gpurun_out/r5h_ncu_launch.log 2>&1
+python scripts/launch_shares.py gpurun_out/r5h_launches.csv | head -12

@@ -314,9 +314,23 @@ spl_cell_transform_kernel(const __grid_constant__ GridParams gp, const unsigned 
         toff += (long long)(gp.nodes[d] + 1) * MOM_CW;
     }
     double *mg = MG + (long long)cell * MOM_MG;
-    for (int k = (RHS_ONLY ? MOM_NM : 0) + tid; k < MOM_NM + MOM_NR; k += blockDim.x) {
-        s_M[k] = mg[k];
-        mg[k] = 0.0;
+    {
+        // the thread's four moments in flight together (a load / store-zero loop made one DRAM round trip per element)
+        constexpr int NL = (MOM_NM + MOM_NR + 127) / 128;
+        double v[NL];
+#pragma unroll
+        for (int q = 0; q < NL; ++q) {
+            const int k = tid + 128 * q;
+            v[q] = (k < MOM_NM + MOM_NR && (!RHS_ONLY || k >= MOM_NM)) ? __ldcg(mg + k) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < NL; ++q) {
+            const int k = tid + 128 * q;
+            if (k < MOM_NM + MOM_NR && (!RHS_ONLY || k >= MOM_NM)) {
+                __stcg(mg + k, 0.0);
+                s_M[k] = v[q];
+            }
+        }
     }
     __syncthreads();
     // a zero coefficient must skip its moment (it may be inf/NaN for a far exterior point)
@@ -612,7 +626,7 @@ spl_cell_transform4_kernel(const __grid_constant__ GridParams gp, const unsigned
     double *s_C = s_T2 + MOM4_R2;             // [4][MOM_CW]
     double *s_U1 = s_C + 4 * MOM_CW, *s_U2 = s_U1 + 256, *s_U3 = s_U2 + 256;
     const int tid = threadIdx.x;
-    int ws[4];
+    int ws[4], ext = 0;                       // ext: bit d set when the cell is an exterior half-line in dimension d
     {
         unsigned c = cell;
         long long toff = 0;
@@ -622,103 +636,135 @@ spl_cell_transform4_kernel(const __grid_constant__ GridParams gp, const unsigned
             const int cd = (int)(c % ncd);
             c /= ncd;
             ws[d] = min(max(cd - 2, 0), gp.nodes[d] - 4);
+            if (cd == 0 || cd == gp.nodes[d]) ext |= 1 << d;
             const double *src = tab + toff + (long long)cd * MOM_CW;
             for (int k = tid; k < MOM_CW; k += blockDim.x) s_C[d * MOM_CW + k] = src[k];
             toff += (long long)(gp.nodes[d] + 1) * MOM_CW;
         }
     }
+    // Moments of a degree the cell's table has no coefficient for (exterior half-lines: degrees > 2 of G, > 1 of g; they may
+    // be inf / NaN for a far exterior point) are dropped HERE, so the changes of basis below are plain FMAs.  The first
+    // version tested every coefficient for zero inside the sums: 89k warp instructions per cell for 5.5k of FMAs, 3.5 ms at
+    // cfg4 (ncu: issue-bound).
     double *mg = MG + (long long)cell * MOM4_MG;
-    for (int k = (RHS_ONLY ? MOM4_NM : 0) + tid; k < MOM4_NM + MOM4_NR; k += blockDim.x) {
-        s_M[k] = mg[k];
-        mg[k] = 0.0;
+    {
+        // all of the thread's moments in flight at once: a load / store-zero loop ran one DRAM round trip per element
+        // (the moments of 14,641 cells, 312 MB, do not stay in L2) -- 29 % of the kernel's stall samples
+        constexpr int NL = (MOM4_NM + MOM4_NR + 255) / 256;
+        double v[NL];
+#pragma unroll
+        for (int q = 0; q < NL; ++q) {
+            const int k = tid + 256 * q;
+            v[q] = (k < MOM4_NM + MOM4_NR && (!RHS_ONLY || k >= MOM4_NM)) ? __ldcg(mg + k) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < NL; ++q) {
+            const int k = tid + 256 * q;
+            if (k < MOM4_NM + MOM4_NR && (!RHS_ONLY || k >= MOM4_NM)) {
+                __stcg(mg + k, 0.0);
+                double val = v[q];
+                if (ext) {
+                    if (k < MOM4_NM) {
+                        const int e1 = k % 7, e2 = (k / 7) % 7, e3 = (k / 49) % 7, e4 = k / 343;
+                        if (((ext & 1) && e1 > 2) || ((ext & 2) && e2 > 2) || ((ext & 4) && e3 > 2) || ((ext & 8) && e4 > 2)) val = 0.0;
+                    } else {
+                        const int qq = k - MOM4_NM;
+                        if (((ext & 1) && (qq & 3) > 1) || ((ext & 2) && ((qq >> 2) & 3) > 1) || ((ext & 4) && ((qq >> 4) & 3) > 1) ||
+                            ((ext & 8) && (qq >> 6) > 1))
+                            val = 0.0;
+                    }
+                }
+                s_M[k] = val;
+            }
+        }
     }
     __syncthreads();
-    // a zero coefficient must skip its moment (it may be inf/NaN for a far exterior point)
-    auto mac = [](double cf, double m, double s) { return cf != 0.0 ? fma(cf, m, s) : s; };
+    // One change of basis: out[o][a][r] = sum_e C[a][e] in[o][e][r], a = 0..9 (pairs) -- a work item (o, r) loads its seven
+    // inputs once and forms the ten outputs with warp-uniform coefficient loads.
+    auto basis_g = [&](const double *C, const double *in, double *out, int no, int nr) {
+        for (int it = tid; it < no * nr; it += blockDim.x) {
+            const int o = it / nr, r = it - o * nr;
+            double v[MOM_NE];
+#pragma unroll
+            for (int e = 0; e < MOM_NE; ++e) v[e] = in[(o * MOM_NE + e) * nr + r];
+#pragma unroll
+            for (int a = 0; a < 10; ++a) {
+                double sum = 0.0;
+#pragma unroll
+                for (int e = 0; e < MOM_NE; ++e) sum = fma(C[a * MOM_NE + e], v[e], sum);
+                out[(o * 10 + a) * nr + r] = sum;
+            }
+        }
+    };
     // right-hand side: U1[(f4,f3,f2)][i1], U2[(f4,f3)][i2][i1], U3[f4][i3][i2][i1], g[i4][i3][i2][i1]
     {
         const int ro = tid >> 2, i1 = tid & 3;
-        double s = 0.0;
+        double sum = 0.0;
 #pragma unroll
-        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[70 + i1 * MOM_NF + f], s_M[MOM4_NM + ro * MOM_NF + f], s);
-        s_U1[tid] = s;
+        for (int f = 0; f < MOM_NF; ++f) sum = fma(s_C[70 + i1 * MOM_NF + f], s_M[MOM4_NM + ro * MOM_NF + f], sum);
+        s_U1[tid] = sum;
     }
-    if (!RHS_ONLY) {
-        for (int k = tid; k < 3430; k += blockDim.x) {           // T1[o = (e4,e3,e2)][a1]
-            const int o = k / 10, a1 = k - o * 10;
-            double s = 0.0;
-#pragma unroll
-            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[a1 * MOM_NE + e], s_M[o * MOM_NE + e], s);
-            s_T1[k] = s;
-        }
-    }
+    if (!RHS_ONLY) basis_g(s_C, s_M, s_T1, 343, 1);                      // T1[(e4,e3,e2)][a1]
     __syncthreads();
     {
         const int o = tid >> 4, i2 = (tid >> 2) & 3, i1 = tid & 3;   // o = (f4, f3)
-        double s = 0.0;
+        double sum = 0.0;
 #pragma unroll
-        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[MOM_CW + 70 + i2 * MOM_NF + f], s_U1[(o * 4 + f) * 4 + i1], s);
-        s_U2[tid] = s;
+        for (int f = 0; f < MOM_NF; ++f) sum = fma(s_C[MOM_CW + 70 + i2 * MOM_NF + f], s_U1[(o * 4 + f) * 4 + i1], sum);
+        s_U2[tid] = sum;
     }
-    if (!RHS_ONLY) {
-        for (int k = tid; k < 4900; k += blockDim.x) {           // T2[o = (e4,e3)][a2][a1]
-            const int o = k / 100, r = k - o * 100, a2 = r / 10, a1 = r - a2 * 10;
-            double s = 0.0;
-#pragma unroll
-            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[MOM_CW + a2 * MOM_NE + e], s_T1[(o * MOM_NE + e) * 10 + a1], s);
-            s_T2[k] = s;
-        }
-    }
+    if (!RHS_ONLY) basis_g(s_C + MOM_CW, s_T1, s_T2, 49, 10);            // T2[(e4,e3)][a2][a1]
     __syncthreads();
     {
         const int f4 = tid >> 6, i3 = (tid >> 4) & 3, r = tid & 15;
-        double s = 0.0;
+        double sum = 0.0;
 #pragma unroll
-        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[2 * MOM_CW + 70 + i3 * MOM_NF + f], s_U2[(f4 * 4 + f) * 16 + r], s);
-        s_U3[tid] = s;
+        for (int f = 0; f < MOM_NF; ++f) sum = fma(s_C[2 * MOM_CW + 70 + i3 * MOM_NF + f], s_U2[(f4 * 4 + f) * 16 + r], sum);
+        s_U3[tid] = sum;
     }
-    if (!RHS_ONLY) {
-        for (int k = tid; k < 7000; k += blockDim.x) {           // T3[e4][a3][a2 a1]
-            const int e4 = k / 1000, r = k - e4 * 1000, a3 = r / 100, r2 = r - a3 * 100;
-            double s = 0.0;
-#pragma unroll
-            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[2 * MOM_CW + a3 * MOM_NE + e], s_T2[(e4 * MOM_NE + e) * 100 + r2], s);
-            s_T3[k] = s;
-        }
-    }
+    if (!RHS_ONLY) basis_g(s_C + 2 * MOM_CW, s_T2, s_T3, 7, 100);        // T3[e4][a3][a2 a1]
     __syncthreads();
     {
         const int i4 = tid >> 6, r = tid & 63;
-        double s = 0.0;
+        double sum = 0.0;
 #pragma unroll
-        for (int f = 0; f < MOM_NF; ++f) s = mac(s_C[3 * MOM_CW + 70 + i4 * MOM_NF + f], s_U3[f * 64 + r], s);
-        if (s != 0.0) {
+        for (int f = 0; f < MOM_NF; ++f) sum = fma(s_C[3 * MOM_CW + 70 + i4 * MOM_NF + f], s_U3[f * 64 + r], sum);
+        if (sum != 0.0) {
             const long long node = (long long)(ws[0] + (r & 3)) + (long long)(ws[1] + ((r >> 2) & 3)) * gp.nodes[0] +
                                    (long long)(ws[2] + (r >> 4)) * gp.nodes[0] * gp.nodes[1] +
                                    (long long)(ws[3] + i4) * gp.nodes[0] * gp.nodes[1] * gp.nodes[2];
-            atomicAdd(g + node, s);
+            atomicAdd(g + node, sum);
         }
     }
     if (!RHS_ONLY) {
-        for (int k = tid; k < 10000; k += blockDim.x) {          // S[a4][a3][a2][a1]
-            const int a4 = k / 1000, r = k - a4 * 1000;
-            double s = 0.0;
+        // S[a4][a3][a2][a1]: a work item r = (a3, a2, a1) loads T3[0..6][r] and adds its ten entries
+        const long long st3 = (long long)gp.nodes[0] * gp.nodes[1] * gp.nodes[2];
+        for (int r = tid; r < 1000; r += blockDim.x) {
+            double v[MOM_NE];
 #pragma unroll
-            for (int e = 0; e < MOM_NE; ++e) s = mac(s_C[3 * MOM_CW + a4 * MOM_NE + e], s_T3[e * 1000 + r], s);
-            if (s != 0.0) {
-                const int a[4] = {r % 10, (r / 10) % 10, r / 100, a4};
-                long long node = 0, nstride = 1;
-                int sten = 0, sstride = 1;
+            for (int e = 0; e < MOM_NE; ++e) v[e] = s_T3[e * 1000 + r];
+            const int a[3] = {r % 10, (r / 10) % 10, r / 100};
+            long long node = 0, nstride = 1;
+            int sten = 0, sstride = 1;
 #pragma unroll
-                for (int d = 0; d < 4; ++d) {
+            for (int d = 0; d < 3; ++d) {
+                int i, j;
+                spl_pair(a[d], i, j);
+                node += (long long)(ws[d] + i) * nstride;
+                sten += (j - i) * sstride;
+                nstride *= gp.nodes[d];
+                sstride *= 4;
+            }
+#pragma unroll
+            for (int a4 = 0; a4 < 10; ++a4) {
+                double sum = 0.0;
+#pragma unroll
+                for (int e = 0; e < MOM_NE; ++e) sum = fma(s_C[3 * MOM_CW + a4 * MOM_NE + e], v[e], sum);
+                if (sum != 0.0) {
                     int i, j;
-                    spl_pair(a[d], i, j);
-                    node += (long long)(ws[d] + i) * nstride;
-                    sten += (j - i) * sstride;
-                    nstride *= gp.nodes[d];
-                    sstride *= 4;
+                    spl_pair(a4, i, j);
+                    atomicAdd(S + (node + (long long)(ws[3] + i) * st3) * gp.nsten + sten + (j - i) * 64, sum);
                 }
-                atomicAdd(S + node * gp.nsten + sten, s);
             }
         }
     }
