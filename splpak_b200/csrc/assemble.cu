@@ -470,7 +470,7 @@ __device__ __forceinline__ void spl_flush_g(const GridParams &gp, const int *ws,
         ad = o % 10;
         o /= 10;
     }
-    atomicAdd(S + node * gp.nsten + sten, v);
+    spl_add_S(gp, S, node * gp.nsten + sten, v);
 }
 
 // rhs accumulator e = (i_N..i_1) in base 4, i_1 fastest -> g
@@ -485,7 +485,7 @@ __device__ __forceinline__ void spl_flush_rhs(const GridParams &gp, const int *w
         nstride *= gp.nodes[d];
         e >>= 2;
     }
-    atomicAdd(g + node, v);
+    spl_add_g(gp, g, node, v);
 }
 
 // named barriers (id 0 is __syncthreads): FULL/EMPTY per staging buffer, one for the consumer warps
@@ -794,6 +794,146 @@ spl_accumulate_kernel(const __grid_constant__ GridParams gp, const real_t *__res
 }
 
 // ------------------------------------------------------------------------------------------
+// deterministic mode (opt-in; GridParams::fxS): the reference is a serial program and gives the same coefficients every run;
+// here the order of the points inside a bin (returning atomics of spl_perm_kernel) and the order in which work items and
+// cells add their sums into S / g (FP64 atomics) change from run to run, and the coefficients with them at the level of
+// eps * cond(G).  With SPLPAK_B200_DETERMINISTIC=1
+//   * every bin's segment of the permutation is sorted (spl_segsort_kernel), so a work item always holds the same points in
+//     the same order; on the moment path a work item is a whole cell, so every moment receives exactly one addition;
+//   * the sums that several CTAs add to one entry of S / g go through fixed-point limbs with integer atomics
+//     (common.cuh: spl_add_S / spl_add_g), in two passes: the first finds the largest |partial sum| (the scale), the
+//     second adds; spl_fx_finalize_kernel then adds the exact limb sums to S / g, one rounding per entry and chunk.
+// Integer addition commutes, so S, g and -- with the solver's single add per row and panel -- the coefficients are
+// bit-for-bit reproducible (tests/test_gpu_fit.py::test_deterministic_mode_is_bit_reproducible).
+// ------------------------------------------------------------------------------------------
+// In-place ascending sort of every bin's segment of perm (distinct point indices < 2^(8 passes)): LSD radix sort, 8-bit
+// digits, one CTA per bin (grid-stride), tiles of 1024 elements ranked stably: match.any inside the warp, per-warp digit
+// counts, one scan over the warps per digit.
+__global__ void __launch_bounds__(1024)
+spl_segsort_kernel(unsigned *__restrict__ perm, unsigned *__restrict__ tmp, const unsigned *__restrict__ binstart,
+                   const unsigned *__restrict__ bincount, long long nbins, int passes) {
+    __shared__ unsigned s_base[256];
+    __shared__ unsigned s_wc[32][256];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (long long bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
+        const unsigned c = bincount[bin];
+        if (c < 2) continue;
+        unsigned *src = perm + binstart[bin], *dst = tmp + binstart[bin];
+        for (int pass = 0; pass < passes; ++pass) {
+            const int shift = 8 * pass;
+            __syncthreads();
+            if (tid < 256) s_base[tid] = 0;
+            __syncthreads();
+            for (unsigned i = tid; i < c; i += 1024) atomicAdd(&s_base[(src[i] >> shift) & 255u], 1u);
+            __syncthreads();
+            if (warp == 0) {                                    // exclusive scan of the 256 digit counts
+                unsigned v[8], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    v[q] = s_base[lane * 8 + q];
+                    sum += v[q];
+                }
+                unsigned incl = sum;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += o;
+                }
+                unsigned run = incl - sum;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    s_base[lane * 8 + q] = run;
+                    run += v[q];
+                }
+            }
+            __syncthreads();
+            for (unsigned t0 = 0; t0 < c; t0 += 1024) {
+                const unsigned i = t0 + tid;
+                const bool valid = i < c;
+                const unsigned key = valid ? src[i] : 0u;
+                const unsigned d = valid ? ((key >> shift) & 255u) : 256u;
+                for (int e = tid; e < 32 * 256; e += 1024) (&s_wc[0][0])[e] = 0;
+                __syncthreads();
+                const unsigned mask = __match_any_sync(0xffffffffu, d);
+                const unsigned rank = __popc(mask & ((1u << lane) - 1u));
+                if (valid && rank == 0) s_wc[warp][d] = __popc(mask);
+                __syncthreads();
+                if (tid < 256) {
+                    unsigned run = s_base[tid];
+#pragma unroll 8
+                    for (int w = 0; w < 32; ++w) {
+                        const unsigned cnt = s_wc[w][tid];
+                        s_wc[w][tid] = run;
+                        run += cnt;
+                    }
+                    s_base[tid] = run;
+                }
+                __syncthreads();
+                if (valid) dst[s_wc[warp][d] + rank] = key;
+                __syncthreads();
+            }
+            unsigned *sw = src;
+            src = dst;
+            dst = sw;
+        }
+        if (passes & 1) {                                        // the sorted segment is in tmp
+            __syncthreads();
+            for (unsigned i = tid; i < c; i += 1024) dst[i] = src[i];
+        }
+    }
+}
+
+// fxe[k] = exponent bound of the pass's partial sums: |v| < 2^fxe for every v recorded in fxmax[k]
+__global__ void spl_fx_exponent_kernel(const unsigned long long *__restrict__ fxmax, int *__restrict__ fxe) {
+    const int k = threadIdx.x;
+    if (k < 2) {
+        const double m = __longlong_as_double((long long)fxmax[k]);
+        fxe[k] = (m > 0.0 && m < 1.7e308) ? ilogb(m) + 1 : 0;     // inf / NaN sums: any scale, they are dropped as zeros
+    }
+}
+
+// dst[i] += exact limb sum (one rounding), limbs cleared for the next pass
+__global__ void __launch_bounds__(256)
+spl_fx_finalize_kernel(double *__restrict__ dst, unsigned long long *__restrict__ limbs, long long n,
+                       const int *__restrict__ fxe, int which) {
+    const int e = fxe[which];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        unsigned long long *l = limbs + 3 * i;
+        if (l[0] | l[1] | l[2]) {
+            dst[i] += spl_fx_value(l, e);
+            l[0] = l[1] = l[2] = 0ull;
+        }
+    }
+}
+
+// zero limbs + maxima before a deterministic pass pair; exponent between the passes; finalize after them
+int spl_fx_begin(const GridParams &gp, cudaStream_t st) {
+    SPL_CUDA_TRY(cudaMemsetAsync(gp.fxmax, 0, 2 * sizeof(unsigned long long), st));
+    return SPLPAK_OK;
+}
+int spl_fx_scale(const GridParams &gp, int *fxe, cudaStream_t st) {
+    spl_fx_exponent_kernel<<<1, 32, 0, st>>>(gp.fxmax, fxe);
+    ++g_spl_launches;
+    SPL_CUDA_TRY(cudaGetLastError());
+    return SPLPAK_OK;
+}
+int spl_fx_finish(const GridParams &gp, double *d_S, double *d_g, cudaStream_t st) {
+    if (d_S) {
+        const long long n = gp.ncol * gp.nsten;
+        spl_fx_finalize_kernel<<<(unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16), 256, 0, st>>>(d_S, gp.fxS, n, gp.fxe, 0);
+        ++g_spl_launches;
+    }
+    if (d_g) {
+        const long long n = gp.ncol;
+        spl_fx_finalize_kernel<<<(unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16), 256, 0, st>>>(d_g, gp.fxg, n, gp.fxe, 1);
+        ++g_spl_launches;
+    }
+    SPL_CUDA_TRY(cudaGetLastError());
+    return SPLPAK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side launch of the chunk pipeline
 // ------------------------------------------------------------------------------------------
 #include "moments.cuh"
@@ -849,6 +989,20 @@ int spl_assemble_scratch_init(const GridParams &gp, AssembleScratch &sc, cudaStr
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.wincursor, sizeof(unsigned) * (size_t)sc.nbins * sc.cursor_stride));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.itemstart, sizeof(unsigned) * (size_t)sc.nbins));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.meta, sizeof(unsigned) * 4));
+    {
+        // opt-in deterministic accumulation (see spl_segsort_kernel): limb arrays for S and g, exponents, maxima
+        const char *e = getenv("SPLPAK_B200_DETERMINISTIC");
+        sc.deterministic = (e && atoi(e) != 0) ? 1 : 0;
+        if (sc.deterministic) {
+            const size_t nl = 3 * (size_t)(gp.ncol * gp.nsten + gp.ncol);
+            SPL_CUDA_TRY(cudaMalloc((void **)&sc.fxS, sizeof(unsigned long long) * nl));
+            SPL_CUDA_TRY(cudaMemsetAsync(sc.fxS, 0, sizeof(unsigned long long) * nl, st));
+            sc.fxg = sc.fxS + 3 * (size_t)(gp.ncol * gp.nsten);
+            SPL_CUDA_TRY(cudaMalloc((void **)&sc.fxmax, sizeof(unsigned long long) * 2));
+            SPL_CUDA_TRY(cudaMalloc((void **)&sc.fxe, sizeof(int) * 2));
+            SPL_CUDA_TRY(cudaMemsetAsync(sc.fxe, 0, sizeof(int) * 2, st));
+        }
+    }
     return spl_hist_scratch_init(gp, sc.hist, st);
 }
 
@@ -858,6 +1012,11 @@ void spl_assemble_scratch_free(AssembleScratch &sc) {
         if (p) cudaFree(p);
     if (sc.celltab) cudaFree(sc.celltab);
     if (sc.cellmom) cudaFree(sc.cellmom);
+    if (sc.fxS) cudaFree(sc.fxS);
+    if (sc.fxmax) cudaFree(sc.fxmax);
+    if (sc.fxe) cudaFree(sc.fxe);
+    sc.fxS = sc.fxg = sc.fxmax = nullptr;
+    sc.fxe = nullptr;
     sc.wincount = sc.winstart = sc.wincursor = sc.itemstart = sc.meta = nullptr;
     sc.celltab = sc.cellmom = nullptr;
     spl_hist_scratch_free(sc.hist);
@@ -871,7 +1030,11 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
     using T = AccTraits<NDIM>;
     using D = AccDerived<NDIM>;
     const long long nbins = sc.nbins;
-    const unsigned ch = CELL ? (unsigned)MOM_CH : (unsigned)T::CH;
+    const bool det = gp.fxS != nullptr;
+    // deterministic mode, moment path: a work item is a whole cell (every moment then receives exactly one addition)
+    const unsigned ch = CELL ? (det ? 0x7fffffffu : (unsigned)MOM_CH) : (unsigned)T::CH;
+    GridParams gp1 = gp;                       // deterministic mode: scale-finding pass
+    gp1.fxpass = 1;
     SPL_CUDA_TRY(cudaMemsetAsync(sc.wincount, 0, sizeof(unsigned) * nbins, st));
     SPL_CUDA_TRY(cudaMemsetAsync(sc.wincursor, 0, sizeof(unsigned) * nbins * sc.cursor_stride, st));
     long long nb = (n + 255) / 256;
@@ -921,6 +1084,15 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
                                                       sc.cursor_stride, sc.perm);
     spl_items_kernel<<<spl_div_up(nbins, 256), 256, 0, st>>>(sc.wincount, sc.itemstart, nbins, ch, sc.item_win,
                                                              sc.item_seg);
+    if (det) {
+        int passes = 1;
+        while (passes < 4 && (n - 1) >> (8 * passes)) ++passes;
+        long long sgrid = nbins < (long long)nsm * 2 ? nbins : (long long)nsm * 2;
+        spl_segsort_kernel<<<(unsigned)sgrid, 1024, 0, st>>>(sc.perm, sc.perm2, sc.winstart, sc.wincount, nbins, passes);
+        ++g_spl_launches;
+        const int rf = spl_fx_begin(gp, st);
+        if (rf != SPLPAK_OK) return rf;
+    }
     if (ev) cudaEventRecord(ev[2], st);
     const long long max_items = nbins + n / ch + 1;
     if constexpr (CELL && NDIM == 4) {
@@ -936,7 +1108,13 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
         long long agrid = (long long)nsm * per_sm;
         if (agrid > max_items) agrid = max_items;
         kern<<<(unsigned)agrid, MOM4_NT, smem, st>>>(gp, d_x, l1x, d_y, yw, sc.perm, sc.wincount, sc.winstart,
-                                                     sc.item_win, sc.item_seg, sc.meta, sc.cellmom);
+                                                     sc.item_win, sc.item_seg, sc.meta, sc.cellmom, ch);
+        if (det) {
+            tkern<<<(unsigned)nbins, 256, tsmem, st>>>(gp1, sc.wincount, sc.celltab, sc.cellmom, d_S, d_g);
+            const int rf = spl_fx_scale(gp, sc.fxe, st);
+            if (rf != SPLPAK_OK) return rf;
+            ++g_spl_launches;
+        }
         tkern<<<(unsigned)nbins, 256, tsmem, st>>>(gp, sc.wincount, sc.celltab, sc.cellmom, d_S, d_g);
         g_spl_launches += 6;
     } else if constexpr (CELL) {
@@ -950,11 +1128,15 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
         long long agrid = (long long)nsm * per_sm;
         if (agrid > max_items) agrid = max_items;
         kern<<<(unsigned)agrid, MOM_NT, smem, st>>>(gp, d_x, l1x, d_y, yw, sc.perm, sc.wincount, sc.winstart,
-                                                    sc.item_win, sc.item_seg, sc.meta, sc.cellmom);
-        if (rhs_only)
-            spl_cell_transform_kernel<true><<<(unsigned)nbins, 128, 0, st>>>(gp, sc.wincount, sc.celltab, sc.cellmom, d_S, d_g);
-        else
-            spl_cell_transform_kernel<false><<<(unsigned)nbins, 128, 0, st>>>(gp, sc.wincount, sc.celltab, sc.cellmom, d_S, d_g);
+                                                    sc.item_win, sc.item_seg, sc.meta, sc.cellmom, ch);
+        auto tkern = rhs_only ? spl_cell_transform_kernel<true> : spl_cell_transform_kernel<false>;
+        if (det) {
+            tkern<<<(unsigned)nbins, 128, 0, st>>>(gp1, sc.wincount, sc.celltab, sc.cellmom, d_S, d_g);
+            const int rf = spl_fx_scale(gp, sc.fxe, st);
+            if (rf != SPLPAK_OK) return rf;
+            ++g_spl_launches;
+        }
+        tkern<<<(unsigned)nbins, 128, 0, st>>>(gp, sc.wincount, sc.celltab, sc.cellmom, d_S, d_g);
         g_spl_launches += 6;
     } else {
         const size_t smem = sizeof(double) * (2 * (size_t)T::PB * T::RS + (size_t)D::LPGW * (T::R * 10 + D::APL));
@@ -965,9 +1147,21 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
         if (per_sm < 1) per_sm = 1;
         long long agrid = (long long)nsm * per_sm;
         if (agrid > max_items) agrid = max_items;
+        if (det) {
+            kern<<<(unsigned)agrid, T::NT + D::NP, smem, st>>>(gp1, d_x, l1x, d_y, d_w, weighted, sc.perm, sc.wincount,
+                                                               sc.winstart, sc.item_win, sc.item_seg, sc.meta, d_S, d_g);
+            const int rf = spl_fx_scale(gp, sc.fxe, st);
+            if (rf != SPLPAK_OK) return rf;
+            SPL_CUDA_TRY(cudaMemsetAsync(sc.meta + 2, 0, sizeof(unsigned), st));      // work counter of the second pass
+            ++g_spl_launches;
+        }
         kern<<<(unsigned)agrid, T::NT + D::NP, smem, st>>>(gp, d_x, l1x, d_y, d_w, weighted, sc.perm, sc.wincount,
                                                            sc.winstart, sc.item_win, sc.item_seg, sc.meta, d_S, d_g);
         g_spl_launches += 5;
+    }
+    if (det) {
+        const int rf = spl_fx_finish(gp, rhs_only ? nullptr : d_S, d_g, st);
+        if (rf != SPLPAK_OK) return rf;
     }
     if (ev) cudaEventRecord(ev[3], st);
     SPL_CUDA_TRY(cudaGetLastError());

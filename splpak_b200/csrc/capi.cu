@@ -884,7 +884,7 @@ static void free_handle(splpak_b200_fit_t h) {
     if (!h) return;
     if (h->d_part) cudaFree(h->d_part);
     if (h->sc.yw) cudaFree(h->sc.yw);
-    unsigned *u[] = {h->sc.item_win, h->sc.item_seg, h->sc.perm};
+    unsigned *u[] = {h->sc.item_win, h->sc.item_seg, h->sc.perm, h->sc.perm2};
     for (unsigned *p : u)
         if (p) cudaFree(p);
     spl_assemble_scratch_free(h->sc);
@@ -997,9 +997,11 @@ extern "C" int splpak_b200_fit_reset(splpak_b200_fit_t h) {
 
 static int ensure_scratch(splpak_b200_fit_t h, long long n) {
     if (n <= h->chunk_cap) return SPLPAK_OK;
-    const GridParams &gp = h->gp;
+    GridParams &gp = h->gp;
     AssembleScratch &sc = h->sc;
     if (sc.perm) cudaFree(sc.perm);
+    if (sc.perm2) cudaFree(sc.perm2);
+    sc.perm2 = nullptr;
     if (sc.yw) cudaFree(sc.yw);
     sc.yw = nullptr;
     if (sc.item_win) cudaFree(sc.item_win);
@@ -1014,6 +1016,15 @@ static int ensure_scratch(splpak_b200_fit_t h, long long n) {
     const int ch = spl_acc_chunk_points(gp.ndim, sc.moments);
     sc.max_items = sc.nbins + n / ch + 2;
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.perm, sizeof(unsigned) * (size_t)n));
+    if (sc.deterministic) {
+        // SPLPAK_B200_DETERMINISTIC=1: second permutation buffer of the per-bin sort; the kernels find the limb arrays in gp
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.perm2, sizeof(unsigned) * (size_t)n));
+        gp.fxS = sc.fxS;
+        gp.fxg = sc.fxg;
+        gp.fxmax = sc.fxmax;
+        gp.fxe = sc.fxe;
+        gp.fxpass = 0;
+    }
     if (sc.moments) SPL_CUDA_TRY(cudaMalloc((void **)&sc.yw, 2 * sizeof(double) * (size_t)n));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_win, sizeof(unsigned) * (size_t)sc.max_items));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_seg, sizeof(unsigned) * (size_t)sc.max_items));

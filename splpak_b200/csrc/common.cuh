@@ -33,7 +33,54 @@ struct GridParams {
     long long ncol;                // product of nodes
     long long nwindows;            // product of nwin
     int nsten;                     // 4^ndim
+    // Deterministic accumulation (opt-in, SPLPAK_B200_DETERMINISTIC=1; null otherwise): every partial sum that several
+    // CTAs add to the same entry of S / g goes into three 40-bit fixed-point limbs with INTEGER atomics (integer addition
+    // commutes, so the sums do not depend on the order in which the CTAs arrive), scaled by 2^(fxe - 116):
+    //   fxS [3 * ncol * nsten], fxg [3 * ncol], fxe[0] / fxe[1] = exponent bound of any S / g partial sum of the pass.
+    // A pass runs twice: fxpass = 1 records the largest |partial sum| (bit pattern, atomicMax) in fxmax[0] / fxmax[1], from
+    // which the scale is taken; fxpass = 0 adds.  Both passes compute the same values (sorted permutation, fixed item order).
+    unsigned long long *fxS, *fxg, *fxmax;
+    const int *fxe;
+    int fxpass;
 };
+
+// ---- deterministic accumulation: 120-bit fixed point in three int64 limbs (see GridParams) ----
+// v = t * 2^(e - 116), |t| < 2^116 (+ 23 bits of head-room in the top limb); limbs hold bits [0, 40), [40, 80), [80, ..)
+// of trunc(t); the splits are exact in double arithmetic (each remainder is a suffix of t's 53-bit mantissa), bits below
+// 2^(e - 116) are dropped -- 60 binary digits below the rounding of any entry within 2^-60 of the bound.
+__device__ __forceinline__ void spl_fx_add(unsigned long long *limb, double v, int e) {
+    const double t = scalbn(v, 116 - e);
+    const double h2 = trunc(t * 0x1p-80);
+    const double r1 = fma(-h2, 0x1p80, t);
+    const double h1 = trunc(r1 * 0x1p-40);
+    const double h0 = trunc(fma(-h1, 0x1p40, r1));
+    if (h2 != 0.0) atomicAdd(limb + 2, (unsigned long long)(long long)h2);
+    if (h1 != 0.0) atomicAdd(limb + 1, (unsigned long long)(long long)h1);
+    if (h0 != 0.0) atomicAdd(limb, (unsigned long long)(long long)h0);
+}
+__device__ __forceinline__ double spl_fx_value(const unsigned long long *limb, int e) {
+    const __int128 tot = ((__int128)(long long)limb[2] << 80) + ((__int128)(long long)limb[1] << 40) + (__int128)(long long)limb[0];
+    const long long hi = (long long)(tot >> 64);
+    const unsigned long long lo = (unsigned long long)tot;
+    return scalbn(fma((double)hi, 0x1p64, (double)lo), e - 116);
+}
+// scale-finding pass: largest |v| as a bit pattern.  The current maximum is read first -- almost every value is below it,
+// and one atomicMax per value on a single address serialised the pass (cfg4: 1.5e8 values, 70 ms)
+__device__ __forceinline__ void spl_fx_max(unsigned long long *m, double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
+    if (b > *reinterpret_cast<volatile unsigned long long *>(m)) atomicMax(m, b);
+}
+// one contribution to S[idx] / g[idx]
+__device__ __forceinline__ void spl_add_S(const GridParams &gp, double *S, long long idx, double v) {
+    if (!gp.fxS) atomicAdd(S + idx, v);
+    else if (gp.fxpass) spl_fx_max(gp.fxmax, v);
+    else spl_fx_add(gp.fxS + 3 * idx, v, gp.fxe[0]);
+}
+__device__ __forceinline__ void spl_add_g(const GridParams &gp, double *g, long long idx, double v) {
+    if (!gp.fxS) atomicAdd(g + idx, v);
+    else if (gp.fxpass) spl_fx_max(gp.fxmax + 1, v);
+    else spl_fx_add(gp.fxg + 3 * idx, v, gp.fxe[1]);
+}
 
 // 10 symmetric pairs (i <= j) of the 4 window-local node indices of one dimension.
 __host__ __device__ __forceinline__ void spl_pair(int a, int &i, int &j) {
@@ -66,6 +113,11 @@ struct AssembleScratch {
     int cursor_stride;    // 4-byte words between the per-bin cursors of the second binning pass
     HistScratch hist;     // fixed-point histogram scratch
     double *yw;           // moment path: interleaved (y, w) copy of the chunk, 2 doubles per point (sized with perm)
+    // deterministic mode (GridParams::fxS): limb arrays, exponents, bound scratch, second permutation buffer of the sort
+    int deterministic;
+    unsigned long long *fxS, *fxg, *fxmax;   // fxS and fxg are one allocation (3 (ncol nsten + ncol) limbs), fxmax 2 words
+    int *fxe;
+    unsigned *perm2;
 };
 
 // Scratch of the orthogonal fit path (ortho.cuh), owned by a fit handle.

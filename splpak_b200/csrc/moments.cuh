@@ -133,7 +133,8 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
                    const unsigned *__restrict__ perm, const unsigned *__restrict__ bincount,
                    const unsigned *__restrict__ binstart, const unsigned *__restrict__ item_bin,
                    const unsigned *__restrict__ item_seg, unsigned *__restrict__ meta,
-                   double *__restrict__ MG) {
+                   double *__restrict__ MG, const unsigned ch) {
+    // ch: points per work item (MOM_CH; deterministic mode: a whole cell, so that every moment receives ONE addition)
     extern __shared__ __align__(16) double s_pts[];          // MOM_PB x MOM_RS, reused for the reduction
     __shared__ unsigned s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,8 +150,8 @@ spl_moments_kernel(const __grid_constant__ GridParams gp, const real_t *__restri
         if (item >= nitems) break;
         const unsigned cell = item_bin[item];
         const unsigned seg = item_seg[item];
-        const long long first = (long long)binstart[cell] + (long long)seg * MOM_CH;
-        const int npts = (int)min((unsigned)MOM_CH, bincount[cell] - seg * (unsigned)MOM_CH);
+        const long long first = (long long)binstart[cell] + (long long)seg * ch;
+        const int npts = (int)min(ch, bincount[cell] - seg * ch);
         const int nbatch = (npts + MOM_PB - 1) / MOM_PB;
         double xc[3];                                        // left end of the cell per dimension (:246 form)
         {
@@ -327,7 +328,7 @@ spl_cell_transform_kernel(const __grid_constant__ GridParams gp, const unsigned 
         for (int q = 0; q < NL; ++q) {
             const int k = tid + 128 * q;
             if (k < MOM_NM + MOM_NR && (!RHS_ONLY || k >= MOM_NM)) {
-                __stcg(mg + k, 0.0);
+                if (!gp.fxpass) __stcg(mg + k, 0.0);      // (the scale-finding pass of the deterministic mode reads only)
                 s_M[k] = v[q];
             }
         }
@@ -388,7 +389,7 @@ spl_cell_transform_kernel(const __grid_constant__ GridParams gp, const unsigned 
                     nstride *= gp.nodes[d];
                     sstride *= 4;
                 }
-                atomicAdd(S + node * gp.nsten + sten, s);
+                spl_add_S(gp, S, node * gp.nsten + sten, s);
             }
         }
     }
@@ -400,7 +401,7 @@ spl_cell_transform_kernel(const __grid_constant__ GridParams gp, const unsigned 
         if (s != 0.0) {
             const long long node = (long long)(ws[0] + (r & 3)) + (long long)(ws[1] + (r >> 2)) * gp.nodes[0] +
                                    (long long)(ws[2] + i3) * gp.nodes[0] * gp.nodes[1];
-            atomicAdd(g + node, s);
+            spl_add_g(gp, g, node, s);
         }
     }
 }
@@ -438,7 +439,7 @@ spl_moments4_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
                     const unsigned *__restrict__ perm, const unsigned *__restrict__ bincount,
                     const unsigned *__restrict__ binstart, const unsigned *__restrict__ item_bin,
                     const unsigned *__restrict__ item_seg, unsigned *__restrict__ meta,
-                    double *__restrict__ MG) {
+                    double *__restrict__ MG, const unsigned ch) {
     extern __shared__ __align__(16) double s_pts[];          // MOM4_PB x MOM4_RS
     __shared__ unsigned s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -453,8 +454,8 @@ spl_moments4_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
         if (item >= nitems) break;
         const unsigned cell = item_bin[item];
         const unsigned seg = item_seg[item];
-        const long long first = (long long)binstart[cell] + (long long)seg * MOM_CH;
-        const int npts = (int)min((unsigned)MOM_CH, bincount[cell] - seg * (unsigned)MOM_CH);
+        const long long first = (long long)binstart[cell] + (long long)seg * ch;
+        const int npts = (int)min(ch, bincount[cell] - seg * ch);
         const int nbatch = (npts + MOM4_PB - 1) / MOM4_PB;
         double xc[4];                                        // left end of the cell per dimension (:246 form)
         {
@@ -661,7 +662,7 @@ spl_cell_transform4_kernel(const __grid_constant__ GridParams gp, const unsigned
         for (int q = 0; q < NL; ++q) {
             const int k = tid + 256 * q;
             if (k < MOM4_NM + MOM4_NR && (!RHS_ONLY || k >= MOM4_NM)) {
-                __stcg(mg + k, 0.0);
+                if (!gp.fxpass) __stcg(mg + k, 0.0);      // (the scale-finding pass of the deterministic mode reads only)
                 double val = v[q];
                 if (ext) {
                     if (k < MOM4_NM) {
@@ -733,7 +734,7 @@ spl_cell_transform4_kernel(const __grid_constant__ GridParams gp, const unsigned
             const long long node = (long long)(ws[0] + (r & 3)) + (long long)(ws[1] + ((r >> 2) & 3)) * gp.nodes[0] +
                                    (long long)(ws[2] + (r >> 4)) * gp.nodes[0] * gp.nodes[1] +
                                    (long long)(ws[3] + i4) * gp.nodes[0] * gp.nodes[1] * gp.nodes[2];
-            atomicAdd(g + node, sum);
+            spl_add_g(gp, g, node, sum);
         }
     }
     if (!RHS_ONLY) {
@@ -763,7 +764,7 @@ spl_cell_transform4_kernel(const __grid_constant__ GridParams gp, const unsigned
                 if (sum != 0.0) {
                     int i, j;
                     spl_pair(a4, i, j);
-                    atomicAdd(S + (node + (long long)(ws[3] + i) * st3) * gp.nsten + sten + (j - i) * 64, sum);
+                    spl_add_S(gp, S, (node + (long long)(ws[3] + i) * st3) * gp.nsten + sten + (j - i) * 64, sum);
                 }
             }
         }

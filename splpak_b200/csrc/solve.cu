@@ -136,11 +136,11 @@ spl_constraints_kernel(const __grid_constant__ GridParams gp, double xtrap,
                         nstride *= gp.nodes[d];
                         sstride *= 4;
                     }
-                    if (ok && v != 0.0) atomicAdd(S + nd * gp.nsten + sten, v);
+                    if (ok && v != 0.0) spl_add_S(gp, S, nd * gp.nsten + sten, v);
                 }
             }
         }
-        if (lane == 0) atomicAdd(totals_out + 1, (double)NPAIR);   // constraint rows count as rows
+        if (lane == 0 && !gp.fxpass) atomicAdd(totals_out + 1, (double)NPAIR);   // constraint rows count as rows (integers: exact in any order)
     }
 }
 
@@ -251,10 +251,28 @@ spl_constraints_residual_kernel(const __grid_constant__ GridParams gp, double xt
                 const double scale = -(rowwt * rowwt) * v;
 #pragma unroll
                 for (int e = 0; e < PER; ++e)
-                    if (b[e] != 0.0) atomicAdd(g + col[e], scale * b[e]);
+                    if (b[e] != 0.0) spl_add_g(gp, g, col[e], scale * b[e]);
             }
         }
     }
+}
+
+// deterministic mode (assemble.cu): scale-finding pass, exponent, adding pass, limb sums -> S / g
+int spl_fx_begin(const GridParams &gp, cudaStream_t st);
+int spl_fx_scale(const GridParams &gp, int *fxe, cudaStream_t st);
+int spl_fx_finish(const GridParams &gp, double *d_S, double *d_g, cudaStream_t st);
+
+template <int NDIM>
+static void constraints_residual_once(const GridParams &gp, unsigned blocks, double xtrap, const double *d_cnt,
+                                      const double *d_totals_in, const double *d_coef, double *d_g, cudaStream_t st) {
+    spl_constraints_residual_kernel<NDIM><<<blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_coef, d_g);
+    ++g_spl_launches;
+}
+template <int NDIM>
+static void constraints_once(const GridParams &gp, unsigned blocks, double xtrap, const double *d_cnt,
+                             const double *d_totals_in, double *d_S, double *d_totals_out, cudaStream_t st) {
+    spl_constraints_kernel<NDIM><<<blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_S, d_totals_out);
+    ++g_spl_launches;
 }
 
 int spl_constraints_residual_launch(const GridParams &gp, double xtrap, const double *d_cnt,
@@ -262,14 +280,30 @@ int spl_constraints_residual_launch(const GridParams &gp, double xtrap, const do
                                     cudaStream_t st, int nsm) {
     long long blocks = (gp.ncol + 3) / 4;
     if (blocks > (long long)nsm * 16) blocks = (long long)nsm * 16;
-    switch (gp.ndim) {
-    case 1: spl_constraints_residual_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_coef, d_g); break;
-    case 2: spl_constraints_residual_kernel<2><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_coef, d_g); break;
-    case 3: spl_constraints_residual_kernel<3><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_coef, d_g); break;
-    case 4: spl_constraints_residual_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_coef, d_g); break;
-    default: return SPLPAK_ERR_NDIM;
+    const bool det = gp.fxS != nullptr;
+    GridParams gpp = gp;
+    if (det) {
+        const int rf = spl_fx_begin(gp, st);
+        if (rf != SPLPAK_OK) return rf;
     }
-    ++g_spl_launches;
+    for (int pass = det ? 1 : 0; pass >= 0; --pass) {
+        gpp.fxpass = pass;
+        switch (gp.ndim) {
+        case 1: constraints_residual_once<1>(gpp, (unsigned)blocks, xtrap, d_cnt, d_totals_in, d_coef, d_g, st); break;
+        case 2: constraints_residual_once<2>(gpp, (unsigned)blocks, xtrap, d_cnt, d_totals_in, d_coef, d_g, st); break;
+        case 3: constraints_residual_once<3>(gpp, (unsigned)blocks, xtrap, d_cnt, d_totals_in, d_coef, d_g, st); break;
+        case 4: constraints_residual_once<4>(gpp, (unsigned)blocks, xtrap, d_cnt, d_totals_in, d_coef, d_g, st); break;
+        default: return SPLPAK_ERR_NDIM;
+        }
+        if (pass == 1) {
+            const int rf = spl_fx_scale(gp, const_cast<int *>(gp.fxe), st);
+            if (rf != SPLPAK_OK) return rf;
+        }
+    }
+    if (det) {
+        const int rf = spl_fx_finish(gp, nullptr, d_g, st);
+        if (rf != SPLPAK_OK) return rf;
+    }
     SPL_CUDA_TRY(cudaGetLastError());
     return SPLPAK_OK;
 }
@@ -279,14 +313,30 @@ int spl_constraints_launch(const GridParams &gp, double xtrap, const double *d_c
                            cudaStream_t st, int nsm) {
     long long blocks = (gp.ncol + 3) / 4;
     if (blocks > (long long)nsm * 16) blocks = (long long)nsm * 16;
-    switch (gp.ndim) {
-    case 1: spl_constraints_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_S, d_totals_out); break;
-    case 2: spl_constraints_kernel<2><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_S, d_totals_out); break;
-    case 3: spl_constraints_kernel<3><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_S, d_totals_out); break;
-    case 4: spl_constraints_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(gp, xtrap, d_cnt, d_totals_in, d_S, d_totals_out); break;
-    default: return SPLPAK_ERR_NDIM;
+    const bool det = gp.fxS != nullptr;
+    GridParams gpp = gp;
+    if (det) {
+        const int rf = spl_fx_begin(gp, st);
+        if (rf != SPLPAK_OK) return rf;
     }
-    ++g_spl_launches;
+    for (int pass = det ? 1 : 0; pass >= 0; --pass) {
+        gpp.fxpass = pass;
+        switch (gp.ndim) {
+        case 1: constraints_once<1>(gpp, (unsigned)blocks, xtrap, d_cnt, d_totals_in, d_S, d_totals_out, st); break;
+        case 2: constraints_once<2>(gpp, (unsigned)blocks, xtrap, d_cnt, d_totals_in, d_S, d_totals_out, st); break;
+        case 3: constraints_once<3>(gpp, (unsigned)blocks, xtrap, d_cnt, d_totals_in, d_S, d_totals_out, st); break;
+        case 4: constraints_once<4>(gpp, (unsigned)blocks, xtrap, d_cnt, d_totals_in, d_S, d_totals_out, st); break;
+        default: return SPLPAK_ERR_NDIM;
+        }
+        if (pass == 1) {
+            const int rf = spl_fx_scale(gp, const_cast<int *>(gp.fxe), st);
+            if (rf != SPLPAK_OK) return rf;
+        }
+    }
+    if (det) {
+        const int rf = spl_fx_finish(gp, d_S, nullptr, st);
+        if (rf != SPLPAK_OK) return rf;
+    }
     SPL_CUDA_TRY(cudaGetLastError());
     return SPLPAK_OK;
 }
@@ -603,6 +653,7 @@ __device__ __forceinline__ void spl_l21_gemm(double *AB, long long lda, long lon
     const int gq = lane >> 2, t4 = lane & 3;
     const int wy = (warp >> 1) * 16, wodd = warp & 1;
     double acc[2][4][2];
+    double gpart[2] = {0.0, 0.0};
     spl_l21_mma(acc, sA, sX, wy, wodd, gq, t4);
     // store L21 and update the right-hand side below the block: g2 -= L21 y1
 #pragma unroll
@@ -621,7 +672,24 @@ __device__ __forceinline__ void spl_l21_gemm(double *AB, long long lda, long lon
         if (WITH_G) {
             part += __shfl_xor_sync(0xffffffffu, part, 1);
             part += __shfl_xor_sync(0xffffffffu, part, 2);
-            if (t4 == 0 && r < m && part != 0.0) atomicAdd(g + r0 + r, -part);
+            gpart[mi] = part;
+        }
+    }
+    if (WITH_G) {
+        // the two warps that hold the column halves of a row combine their shares in a fixed order and the row gets ONE
+        // addition per panel (two atomics per row made g -- and the coefficients -- depend on which warp arrived first)
+        __shared__ double s_gpart[64];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+            if (wodd && t4 == 0) s_gpart[wy + mi * 8 + gq] = gpart[mi];
+        SPL_SYNC256();
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+            const int r = R0 + wy + mi * 8 + gq;
+            if (!wodd && t4 == 0 && r < m) {
+                const double both = gpart[mi] + s_gpart[wy + mi * 8 + gq];
+                if (both != 0.0) atomicAdd(g + r0 + r, -both);
+            }
         }
     }
     if (keep_l21) {

@@ -534,3 +534,54 @@ def test_weight_histogram_is_reproducible_bit_for_bit(ndim, nodes, ndata, solver
     # chunking: every chunk is quantised with its own scale, so the sums agree to the quantisation bound
     assert np.abs(runs[2][0] - runs[0][0]).max() <= npn * np.abs(w).max() * 2.0 ** -39 + 1e-12 * want.max()
     assert runs[0][2] == float((w != 0).sum())
+
+
+@pytest.mark.parametrize("ndim,nodes,ndata,solver_mode,assembly", [
+    (1, [300], 200_000, None, None), (2, [30, 25], 300_000, None, None), (3, [9, 8, 10], 300_000, None, None),
+    (3, [9, 8, 10], 300_000, "graph", None),          # kernel-per-phase solver: one rhs addition per row and panel
+    (3, [7, 8, 6], 200_000, None, "direct"),          # direct orthant-stencil accumulation in 3-D
+    (4, [6, 5, 6, 5], 300_000, None, None)])
+def test_deterministic_mode_is_bit_reproducible(oracle, monkeypatch, ndim, nodes, ndata, solver_mode, assembly):
+    """SPLPAK_B200_DETERMINISTIC=1 (the reference is a serial program): the permutation is sorted
+    inside every bin, partial sums that several CTAs add to one entry of S / g go through fixed-point limbs with integer
+    atomics, the solver adds once per row and panel.  Repeated fits of the same data then give the SAME normal equations
+    and the SAME coefficients bit for bit (incl. constraint rows and the refinement of the one-shot call), and they agree
+    with the default mode to its own run-to-run spread."""
+    x, y, w, mn, mx = make_problem(ndim, nodes, ndata, seed=70 + ndim, weighted=True, hole=True, outside=0.05)
+    if solver_mode:
+        monkeypatch.setenv("SPLPAK_B200_SOLVER", solver_mode)
+    if assembly:
+        monkeypatch.setenv("SPLPAK_B200_ASSEMBLY", assembly)
+
+    def run(chunks=1):
+        h = sp.FitHandle(ndim, mn, mx, nodes, 1.0)
+        step = (len(x) + chunks - 1) // chunks
+        for lo in range(0, len(x), step):
+            assert h.add_points(x[lo:lo + step], y[lo:lo + step], w[lo:lo + step]) == 0
+        S, g, cnt, totlwt, nrows = h.normal_equations()
+        c, ierr = h.compute()
+        assert ierr == 0
+        h.destroy()
+        return S.copy(), g.copy(), c.copy()
+
+    default = run()
+    monkeypatch.setenv("SPLPAK_B200_DETERMINISTIC", "1")
+    runs = [run() for _ in range(4)]
+    for r in runs[1:]:
+        assert np.array_equal(r[0], runs[0][0]), "S differs between deterministic runs"
+        assert np.array_equal(r[1], runs[0][1]), "g differs between deterministic runs"
+        assert np.array_equal(r[2], runs[0][2]), "coefficients differ between deterministic runs"
+    two = [run(chunks=2) for _ in range(2)]                  # chunked: reproducible as well (another summation order)
+    assert np.array_equal(two[0][0], two[1][0]) and np.array_equal(two[0][2], two[1][2])
+    # same numbers as the default mode up to the re-association of the sums
+    scale = np.abs(default[0]).max()
+    np.testing.assert_allclose(runs[0][0], default[0], rtol=0, atol=1e-13 * scale)
+    np.testing.assert_allclose(runs[0][1], default[1], rtol=0, atol=1e-13 * np.abs(default[1]).max())
+    np.testing.assert_allclose(two[0][0], runs[0][0], rtol=0, atol=1e-13 * scale)
+    tol, cond = coef_tolerance(dense_from_stencil(default[0], nodes))
+    if np.isfinite(tol):
+        np.testing.assert_allclose(runs[0][2], default[2], rtol=0, atol=tol * np.abs(default[2]).max())
+    # the one-shot call (constraint rows fire -> refinement passes) is reproducible too
+    one = [sp.splcw(ndim, x, ndim, y, w, len(x), mn, mx, nodes, 1.0, quiet=True) for _ in range(3)]
+    assert all(o[1] == 0 for o in one)
+    assert np.array_equal(one[0][0], one[1][0]) and np.array_equal(one[0][0], one[2][0])
