@@ -22,9 +22,14 @@ def _ngpu():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs on one box (gpurun --gpus 2)")
-def test_c_abi_allreduce_two_devices(oracle):
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_c_abi_allreduce_two_devices(oracle, monkeypatch, deterministic):
     import torch
 
+    if deterministic:
+        # SPLPAK_B200_DETERMINISTIC=1: every rank's partial buffer is order-independent, the all-reduce hands every rank the
+        # same sums and the constraint rows go through integer limbs -> the replicated solves agree BITWISE
+        monkeypatch.setenv("SPLPAK_B200_DETERMINISTIC", "1")
     lib = sp.load()
     ndim, nodes = 2, [9, 8]
     x, y, w, mn, mx = make_problem(ndim, nodes, 20000, seed=71, hole=True)
@@ -75,8 +80,10 @@ def test_c_abi_allreduce_two_devices(oracle):
     scale = np.abs(ref).max()
     for r in range(2):
         assert np.abs(coefs[r] - ref).max() <= 1e-10 * scale, np.abs(coefs[r] - ref).max() / scale
-    # the replicated solves add their constraint rows with unordered atomics: the replicas agree to ~eps*cond, not bitwise
+    # default: the replicated solves add their constraint rows with unordered atomics: the replicas agree to ~eps*cond
     assert np.abs(coefs[0] - coefs[1]).max() <= 3e-10 * scale
+    if deterministic:
+        assert np.array_equal(coefs[0], coefs[1]), np.abs(coefs[0] - coefs[1]).max() / scale
     for r in range(2):
         torch.cuda.set_device(r)
         handles[r].destroy()
