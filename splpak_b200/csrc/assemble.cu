@@ -990,10 +990,11 @@ int spl_assemble_scratch_init(const GridParams &gp, AssembleScratch &sc, cudaStr
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.itemstart, sizeof(unsigned) * (size_t)sc.nbins));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.meta, sizeof(unsigned) * 4));
     {
-        // opt-in deterministic accumulation (see spl_segsort_kernel): limb arrays for S and g, exponents, maxima
+        // limb arrays for S and g, exponents, maxima: always for the constraint rows, for the assembly in the opt-in
+        // deterministic mode (see spl_segsort_kernel)
         const char *e = getenv("SPLPAK_B200_DETERMINISTIC");
         sc.deterministic = (e && atoi(e) != 0) ? 1 : 0;
-        if (sc.deterministic) {
+        {
             const size_t nl = 3 * (size_t)(gp.ncol * gp.nsten + gp.ncol);
             SPL_CUDA_TRY(cudaMalloc((void **)&sc.fxS, sizeof(unsigned long long) * nl));
             SPL_CUDA_TRY(cudaMemsetAsync(sc.fxS, 0, sizeof(unsigned long long) * nl, st));

@@ -835,6 +835,7 @@ extern "C" real_t splpak_b200_splfe(int ndim, const real_t *x, const real_t *coe
 #define NTIMER 7
 
 struct splpak_b200_fit_s {
+    GridParams gp_fx;             // gp with the fixed-point limb arrays: the constraint kernels ALWAYS accumulate through them
     unsigned magic;
     GridParams gp;
     DeviceInfo di;
@@ -1016,14 +1017,21 @@ static int ensure_scratch(splpak_b200_fit_t h, long long n) {
     const int ch = spl_acc_chunk_points(gp.ndim, sc.moments);
     sc.max_items = sc.nbins + n / ch + 2;
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.perm, sizeof(unsigned) * (size_t)n));
+    // The constraint rows always go through the fixed-point limbs (tiny work): after an all-reduce every rank holds the
+    // same S, adds the same rows in an order-independent way and -- the solver being deterministic -- gets the SAME
+    // coefficients, bit for bit.  With unordered FP64 atomics the replicas differed by ~eps cond(G), every rank formed the
+    // residual of its shard with its own coefficients, and a multi-GPU refinement stalled at that difference.
+    h->gp_fx = gp;
+    h->gp_fx.fxS = sc.fxS;
+    h->gp_fx.fxg = sc.fxg;
+    h->gp_fx.fxmax = sc.fxmax;
+    h->gp_fx.fxe = sc.fxe;
+    h->gp_fx.fxpass = 0;
     if (sc.deterministic) {
-        // SPLPAK_B200_DETERMINISTIC=1: second permutation buffer of the per-bin sort; the kernels find the limb arrays in gp
+        // SPLPAK_B200_DETERMINISTIC=1: the assembly too (second permutation buffer of the per-bin sort; the assembly
+        // kernels find the limb arrays in gp)
         SPL_CUDA_TRY(cudaMalloc((void **)&sc.perm2, sizeof(unsigned) * (size_t)n));
-        gp.fxS = sc.fxS;
-        gp.fxg = sc.fxg;
-        gp.fxmax = sc.fxmax;
-        gp.fxe = sc.fxe;
-        gp.fxpass = 0;
+        gp = h->gp_fx;
     }
     if (sc.moments) SPL_CUDA_TRY(cudaMalloc((void **)&sc.yw, 2 * sizeof(double) * (size_t)n));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_win, sizeof(unsigned) * (size_t)sc.max_items));
@@ -1361,7 +1369,7 @@ static int fit_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_on_devic
     FC_TRY(cudaMemcpyAsync(h->d_dummy_tot + 2, h->d_totals + 1, sizeof(double), cudaMemcpyDeviceToDevice, st));
     FC_TRY(cudaEventRecord(h->ev[4], st));
     if (h->xtrap != 0.0) {
-        rc = spl_constraints_launch(gp, h->xtrap, h->d_cnt, h->d_totals, h->d_S, h->d_totals, st, h->di.nsm);
+        rc = spl_constraints_launch(h->gp_fx.fxS ? h->gp_fx : gp, h->xtrap, h->d_cnt, h->d_totals, h->d_S, h->d_totals, st, h->di.nsm);
         if (rc != SPLPAK_OK) {
             h->finalized = 1;
             if (ierror) *ierror = rc;
@@ -1538,7 +1546,7 @@ static int fit_refine_compute_impl(splpak_b200_fit_t h, real_t *coef, int coef_o
     } while (0)
     if (sizeof(real_t) == sizeof(double)) {
         if (h->xtrap != 0.0) {
-            rc = spl_constraints_residual_launch(gp, h->xtrap, h->d_cnt, h->d_totals, h->d_coef64, h->d_g, st, h->di.nsm);
+            rc = spl_constraints_residual_launch(h->gp_fx.fxS ? h->gp_fx : gp, h->xtrap, h->d_cnt, h->d_totals, h->d_coef64, h->d_g, st, h->di.nsm);
             if (rc != SPLPAK_OK) {
                 if (ierror) *ierror = rc;
                 return rc;

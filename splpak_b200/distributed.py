@@ -62,9 +62,10 @@ def fit_sharded(handle, x, y, w, weighted=True, device_resident=False, l1x=None,
                 broadcast_coef=False):
     """Every rank adds ITS shard to `handle`, the partial sums are all-reduced, every rank solves.
     Returns (coef, ierror).  The all-reduce is ordered against the handle's stream (see _on_handle_stream), so no
-    host synchronisation is needed around it.  The replicated solves see identical inputs; their constraint rows
-    are added with unordered FP64 atomics, so coefficients may differ by ~eps*cond(G) between ranks unless the handle
-    is deterministic or `broadcast_coef` is set (rank 0's coefficients are then broadcast, 8*ncol bytes)."""
+    host synchronisation is needed around it.  The replicated solves see identical inputs (the all-reduce hands every
+    rank the same sums), add their constraint rows through order-independent integer limbs and solve deterministically,
+    so the coefficients are bitwise identical on all ranks (tests/test_gpu_multi.py); `broadcast_coef` additionally
+    broadcasts rank 0's coefficients (8*ncol bytes) for hosts that want to rule out any divergence, e.g. mixed GPU types."""
     import torch
     import torch.distributed as dist
 
