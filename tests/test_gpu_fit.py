@@ -381,23 +381,26 @@ def test_emulated_ranks_sum_to_single_rank(oracle):
     full.destroy()
 
 
-def test_real32_fit(oracle32):
-    x, y, w, mn, mx = make_problem(2, [6, 6], 1500, seed=55)
-    ref, ie = oracle32.initialize(2, x, y, w, mn, mx, [6, 6], 1.0)
-    got, ierr = sp.splcw(2, x.astype(np.float32), 2, y.astype(np.float32), w.astype(np.float32), len(x),
-                         mn, mx, [6, 6], 1.0, quiet=True, real32=True)
+@pytest.mark.parametrize("ndim,nodes,ndata", [(2, [6, 6], 1500), (3, [6, 5, 6], 6000), (4, [5, 4, 5, 4], 12000)])
+def test_real32_fit(oracle32, ndim, nodes, ndata):
+    """REAL32 library (the reference built with -DREAL32): float arrays in and out, float64 accumulation -- in 3-D / 4-D
+    through the cell-moment kernels, which read the float coordinates directly."""
+    x, y, w, mn, mx = make_problem(ndim, nodes, ndata, seed=55)
+    ref, ie = oracle32.initialize(ndim, x, y, w, mn, mx, nodes, 1.0)
+    got, ierr = sp.splcw(ndim, x.astype(np.float32), ndim, y.astype(np.float32), w.astype(np.float32), len(x),
+                         mn, mx, nodes, 1.0, quiet=True, real32=True)
     assert ie == 0 and ierr == 0 and got.dtype == np.float32
     # The real32 library rounds inputs and outputs to float32 and computes in float64; the real32 ORACLE does the whole
     # QR in float32, so the difference is the oracle's own rounding, ~eps32 * cond(A): the tolerance is derived from
     # that instead of a fixed 5e-3.
     from oracle import Oracle
-    A, _ = Oracle().rows(2, x, y, w, mn, mx, [6, 6], 1.0)
+    A, _ = Oracle().rows(ndim, x, y, w, mn, mx, nodes, 1.0)
     tol = max(1e-5, 20.0 * float(np.finfo(np.float32).eps) * np.linalg.cond(A))
     np.testing.assert_allclose(got, ref, rtol=0, atol=tol * np.abs(ref).max())
     # and against the real64 oracle on the float32-rounded inputs: only the rounding of the outputs and of the grid
     # spacing (dx is formed in working precision, :747) is left -- 100 eps32, 400x tighter than round 1's 5e-3
     x32, y32, w32 = (a.astype(np.float32).astype(np.float64) for a in (x, y, w))
-    ref64, _ = Oracle().initialize(2, x32, y32, w32, mn, mx, [6, 6], 1.0)
+    ref64, _ = Oracle().initialize(ndim, x32, y32, w32, mn, mx, nodes, 1.0)
     np.testing.assert_allclose(got, ref64, rtol=0, atol=100.0 * float(np.finfo(np.float32).eps) * np.abs(ref64).max())
 
 
