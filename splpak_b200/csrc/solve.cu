@@ -36,6 +36,8 @@
 #include <string.h>
 #include <new>
 
+#include <vector>
+
 #include "basis.cuh"
 
 #define SOLVE_NB 64
@@ -2498,6 +2500,39 @@ static cudaError_t enqueue_factor_blocked(long long n, int bw, long long lda, do
     return e;
 }
 
+// Per-node priorities of the captured factor graph: the kernels of the latency chain (panels, block-column updates, the
+// tile columns the next block factors: `part` == 0) get the highest priority, the bulk of the trailing update (the
+// look-ahead branch) the lowest, and the graph is instantiated with cudaGraphInstantiateFlagUseNodePriority.  Without it
+// every node runs at the priority of the stream the graph is launched into, the CTAs of a bulk update -- all queued before
+// the next chain's kernels -- take every free SM slot first, and the chain only overlaps the bulk's last wave.
+// SPLPAK_B200_GRAPHPRIO=0 disables (A/B).
+static cudaError_t spl_graph_priorities(cudaGraph_t gr) {
+    const char *env = getenv("SPLPAK_B200_GRAPHPRIO");
+    if (env && atoi(env) == 0) return cudaErrorNotSupported;
+    int least = 0, greatest = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (e != cudaSuccess || greatest >= least) return e != cudaSuccess ? e : cudaErrorNotSupported;
+    size_t nn = 0;
+    if ((e = cudaGraphGetNodes(gr, nullptr, &nn)) != cudaSuccess) return e;
+    std::vector<cudaGraphNode_t> nodes(nn);
+    if (nn && (e = cudaGraphGetNodes(gr, nodes.data(), &nn)) != cudaSuccess) return e;
+    for (size_t k = 0; k < nn; ++k) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[k], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        if (cudaGraphKernelNodeGetParams(nodes[k], &kp) != cudaSuccess) continue;
+        bool chain = kp.func == (void *)spl_panel_kernel || kp.func == (void *)spl_syrk_cols_kernel;
+        if (kp.func == (void *)spl_syrk_kblock_kernel || kp.func == (void *)spl_syrk256_kernel ||
+            kp.func == (void *)spl_syrk_kernel)
+            chain = kp.kernelParams && *static_cast<int *>(kp.kernelParams[7]) == 0;     // argument 7: `part`
+        cudaKernelNodeAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.priority = chain ? greatest : least;
+        if ((e = cudaGraphKernelNodeSetAttribute(nodes[k], cudaKernelNodeAttributePriority, &v)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // kernel-per-phase factor loop: two-level blocked (default) or one trailing update per panel (SPLPAK_B200_KBLOCK=1)
 static cudaError_t enqueue_factor_phases(long long n, int bw, long long lda, double *d_AB, double *d_g, double *d_ysol,
                                          double *d_linv, int *d_fail, cudaStream_t st, cudaStream_t st_aux,
@@ -2634,7 +2669,10 @@ int spl_solve_launch(const GridParams &gp, const double *d_S, double *d_AB, doub
                 e = cudaStreamEndCapture(st, &gr);
                 if (eq != cudaSuccess) e = eq;
             }
-            if (e == cudaSuccess && !persistent_factor) e = cudaGraphInstantiate(&sg->factor, gr, 0);
+            unsigned long long inst_flags = 0;
+            if (e == cudaSuccess && !persistent_factor && spl_graph_priorities(gr) == cudaSuccess)
+                inst_flags = cudaGraphInstantiateFlagUseNodePriority;
+            if (e == cudaSuccess && !persistent_factor) e = cudaGraphInstantiateWithFlags(&sg->factor, gr, inst_flags);
             if (gr) cudaGraphDestroy(gr);
             gr = nullptr;
             if (e == cudaSuccess) e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
