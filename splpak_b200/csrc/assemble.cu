@@ -108,13 +108,15 @@ __device__ __forceinline__ long long spl_nearest_node(const GridParams &gp, cons
 // 1024-thread CTA per SM, shared-memory f64 atomic adds, one flush of the non-zero entries per CTA): with one
 // red.global.add.f64 per point the pass was bound by the L2 atomic units (1.45 ms per 1e8 points for 0.5 ms of HBM
 // traffic).  Used when both tables fit (launcher decides).
-template <int NDIM, bool SMEMH, bool CELL, bool SMEMC = false>
+template <int NDIM, bool SMEMH, bool CELL, bool SMEMC = false, bool KEYS = false>
 __global__ void __launch_bounds__(SMEMC ? 1024 : 512, SMEMC ? 1 : 2)
 spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict__ x, int l1x,
                     const real_t *__restrict__ w, int weighted, long long n, int nbins,
                     unsigned *__restrict__ wincount, int do_hist, unsigned long long *__restrict__ hq,
                     const double *__restrict__ qparams, double *__restrict__ totals, const real_t *__restrict__ y,
-                    double2 *__restrict__ yw) {
+                    double2 *__restrict__ yw, unsigned *__restrict__ keys = nullptr) {
+    // keys (two-level partition): the bin key of every point (0xffffffff for a zero-weight point), so that the partition
+    // pass reads 4 bytes per point instead of the coordinates and the weight again
     extern __shared__ __align__(8) unsigned s_hist[];
     unsigned long long *s_cnt = reinterpret_cast<unsigned long long *>(s_hist + ((nbins + 1) & ~1));   // SMEMC: gp.ncol x 8 bytes
     if (SMEMH) {
@@ -152,8 +154,10 @@ spl_classify_kernel(const __grid_constant__ GridParams gp, const real_t *__restr
         }
 #pragma unroll
         for (int u = 0; u < BIN_U; ++u) {
+            if (KEYS && wv[u] == 0.0 && i0 + u * stride < n) __stcs(keys + i0 + u * stride, 0xffffffffu);
             if (wv[u] != 0.0) {                                  // zero-weight points are skipped (:796-800)
                 const unsigned key = spl_bin_key<NDIM, CELL>(gp, xp[u]);
+                if (KEYS) __stcs(keys + i0 + u * stride, key);
                 if (SMEMH) atomicAdd(s_hist + key, 1u);
                 else atomicAdd(wincount + key, 1u);
                 rows += 1.0;
@@ -388,6 +392,175 @@ spl_perm_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict_
 #pragma unroll
         for (int u = 0; u < BIN_U; ++u)
             if (key[u] != 0xffffffffu) perm[(long long)ws0[u] + pos[u]] = (unsigned)(i0 + u * stride);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Two-level partition (round 2; cell path, large chunks) in place of spl_perm_kernel's one returning L2 atomic per point
+// (1e8 atomics in 1.9 ms: bound by the L2 atomic units, not by HBM).  The bins are grouped into <= 64 BUCKETS of 2^shift
+// consecutive cells.
+//   pass 1 (spl_part1_kernel)  tiles of 8,192 points: bin key, rank inside (tile, bucket) from a shared-memory counter, ONE
+//                              global reservation per (tile, bucket); (key, index) pairs land bucket-sorted in `pairs`,
+//                              each tile writing <= 64 contiguous runs;
+//   pass 2 (spl_part2_kernel)  tiles of 8,192 pairs (a tile spans few buckets): rank inside (tile, cell) from a shared-memory
+//                              histogram over the tile's key range, one global reservation per (tile, non-empty cell) --
+//                              ~13 points per reservation at cfg3 -- then the point indices go to their cell's segment.
+// The write frontiers of pass 2 are the cells of the buckets in flight (a few MB), which stay in L2; ranking whole chunks
+// per CTA without the bucket level kept 148 x 15,625 partly written sectors alive and lost (experiments/ranked_binning_r02).
+// The order of the points inside a cell is as arbitrary as before.
+// ------------------------------------------------------------------------------------------
+#define PART_TILE 8192                 // pairs per tile of pass 2 (1024 threads x 8)
+#define PART_U (PART_TILE / 1024)
+#define PART1_NT 512                   // pass 1: 512 threads x 8 points, several CTAs per SM
+#define PART1_U 8
+#define PART1_TILE (PART1_NT * PART1_U)
+
+// exclusive scan of s[0..n) in place (n <= 2 * blockDim.x, blockDim.x = 32 * nw <= 1024), total returned to every thread;
+// s_w: nw + 1 words of scratch.  Contains barriers: all threads of the CTA call it.
+__device__ __forceinline__ unsigned spl_block_exscan2(unsigned *s, int n, unsigned *s_w) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const unsigned v0 = (2 * tid < n) ? s[2 * tid] : 0u, v1 = (2 * tid + 1 < n) ? s[2 * tid + 1] : 0u;
+    unsigned incl = v0 + v1;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += o;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned t = (lane < nw) ? s_w[lane] : 0u, ti = t;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, ti, off);
+            if (lane >= off) ti += o;
+        }
+        if (lane < nw) s_w[lane] = ti - t;
+        if (lane == 31) s_w[nw] = ti;
+    }
+    __syncthreads();
+    const unsigned ex = s_w[warp] + incl - v0 - v1;
+    if (2 * tid < n) s[2 * tid] = ex;
+    if (2 * tid + 1 < n) s[2 * tid + 1] = ex + v0;
+    const unsigned total = s_w[nw];
+    __syncthreads();
+    return total;
+}
+
+// Both passes sort their tile LOCALLY in shared memory first and write it out in position order, so that the lanes of a
+// warp store to consecutive addresses inside a run: storing every pair straight to its run (32 lanes, 32 runs) made
+// 1e8 partial-sector writes, which the L2 handles no faster than the 1e8 atomics they were meant to replace (1.2 ms).
+__global__ void __launch_bounds__(PART1_NT, 3)
+spl_part1_kernel(const unsigned *__restrict__ keys, long long n, const unsigned *__restrict__ winstart,
+                 int shift, int nbuckets, unsigned *__restrict__ cursor1, uint2 *__restrict__ pairs) {
+    // per-WARP bucket counters (the 512 threads of a CTA hitting <= 64 shared counters serialised on them), turned into
+    // the warps' offsets inside the tile's run of every bucket by one scan over the warps per bucket
+    __shared__ unsigned s_cnt[PART1_NT / 32][64];
+    __shared__ unsigned s_base[64], s_toff[64], s_w[PART1_NT / 32 + 1];
+    __shared__ uint2 s_stage[PART1_TILE];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long ntiles = (n + PART1_TILE - 1) / PART1_TILE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int e = tid; e < (PART1_NT / 32) * 64; e += PART1_NT) (&s_cnt[0][0])[e] = 0;
+        __syncthreads();
+        unsigned key[PART1_U], rank[PART1_U];
+#pragma unroll
+        for (int u = 0; u < PART1_U; ++u) {
+            const long long i = tile * PART1_TILE + u * PART1_NT + tid;
+            key[u] = (i < n) ? __ldcs(keys + i) : 0xffffffffu;     // written by spl_classify_kernel
+            rank[u] = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < PART1_U; ++u)
+            if (key[u] != 0xffffffffu) rank[u] = atomicAdd(&s_cnt[warp][key[u] >> shift], 1u);
+        __syncthreads();
+        if (tid < 64) {
+            unsigned run = 0;
+#pragma unroll
+            for (int q = 0; q < PART1_NT / 32; ++q) {
+                const unsigned c = s_cnt[q][tid];
+                s_cnt[q][tid] = run;
+                run += c;
+            }
+            s_toff[tid] = run;
+            s_base[tid] = (run && tid < nbuckets) ? winstart[(unsigned)tid << shift] + atomicAdd(cursor1 + tid, run) : 0u;
+        }
+        __syncthreads();
+        const unsigned count = spl_block_exscan2(s_toff, 64, s_w);          // tile-local start of every bucket's run
+#pragma unroll
+        for (int u = 0; u < PART1_U; ++u)
+            if (key[u] != 0xffffffffu) {
+                const unsigned b = key[u] >> shift;
+                s_stage[s_toff[b] + s_cnt[warp][b] + rank[u]] =
+                    make_uint2(key[u], (unsigned)(tile * PART1_TILE + u * PART1_NT + tid));
+            }
+        __syncthreads();
+        for (unsigned p = tid; p < count; p += PART1_NT) {
+            const uint2 pr = s_stage[p];
+            const unsigned b = pr.x >> shift;
+            pairs[s_base[b] + (p - s_toff[b])] = pr;
+        }
+        __syncthreads();
+    }
+}
+
+// span: cells per group (a multiple of the bucket size, <= 2048: spl_block_exscan2); meta[1] = number of pairs.
+// Shared memory: [span] counts -> tile-local offsets | [span] global bases | [PART_TILE] staged (cell - g0, index).
+__global__ void __launch_bounds__(1024, 2)
+spl_part2_kernel(const uint2 *__restrict__ pairs, const unsigned *__restrict__ meta, const unsigned *__restrict__ winstart,
+                 unsigned *__restrict__ wincursor, int cstride, int shift, int span, long long nbins,
+                 unsigned *__restrict__ perm) {
+    extern __shared__ unsigned s_part[];
+    __shared__ unsigned s_lo, s_hi, s_w[33];
+    unsigned *s_h = s_part, *s_b = s_part + span;
+    uint2 *s_stage = reinterpret_cast<uint2 *>(s_part + 2 * span);
+    const int tid = threadIdx.x;
+    const long long nrec = meta[1];
+    const long long ntiles = (nrec + PART_TILE - 1) / PART_TILE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long t0 = tile * PART_TILE;
+        const long long tend = (t0 + PART_TILE < nrec) ? t0 + PART_TILE : nrec;
+        // the pairs are bucket-sorted: the tile's keys lie between the bucket of its first and of its last pair
+        if (tid == 0) {
+            s_lo = (pairs[t0].x >> shift) << shift;
+            s_hi = pairs[tend - 1].x | ((1u << shift) - 1u);
+        }
+        __syncthreads();
+        const unsigned klo = s_lo, khi = s_hi;
+        for (unsigned g0 = klo; g0 <= khi; g0 += (unsigned)span) {
+            for (int e = tid; e < span; e += 1024) s_h[e] = 0;
+            __syncthreads();
+            // (the pairs are read twice, the second time from L2, instead of being held in registers: two CTAs per SM)
+            unsigned rank[PART_U];
+#pragma unroll
+            for (int u = 0; u < PART_U; ++u) {
+                const long long pos = t0 + u * 1024 + tid;
+                const unsigned k = (pos < tend) ? __ldcg(&pairs[pos].x) : 0xffffffffu;
+                rank[u] = 0;
+                if (k - g0 < (unsigned)span) rank[u] = atomicAdd(&s_h[k - g0], 1u);
+            }
+            __syncthreads();
+            for (int e = tid; e < span; e += 1024) {
+                const unsigned c = s_h[e];
+                if (c && (long long)g0 + e < nbins)
+                    s_b[e] = winstart[g0 + e] + atomicAdd(wincursor + (size_t)(g0 + e) * cstride, c);
+            }
+            const unsigned count = spl_block_exscan2(s_h, span, s_w);        // counts -> tile-local offsets
+#pragma unroll
+            for (int u = 0; u < PART_U; ++u) {
+                const long long pos = t0 + u * 1024 + tid;
+                if (pos < tend) {
+                    const uint2 pr = __ldcg(pairs + pos);
+                    if (pr.x - g0 < (unsigned)span) s_stage[s_h[pr.x - g0] + rank[u]] = make_uint2(pr.x - g0, pr.y);
+                }
+            }
+            __syncthreads();
+            for (unsigned p = tid; p < count; p += 1024) {
+                const uint2 st = s_stage[p];
+                perm[(long long)s_b[st.x] + (p - s_h[st.x])] = st.y;
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -989,6 +1162,7 @@ int spl_assemble_scratch_init(const GridParams &gp, AssembleScratch &sc, cudaStr
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.wincursor, sizeof(unsigned) * (size_t)sc.nbins * sc.cursor_stride));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.itemstart, sizeof(unsigned) * (size_t)sc.nbins));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.meta, sizeof(unsigned) * 4));
+    if (sc.moments) SPL_CUDA_TRY(cudaMalloc((void **)&sc.cursor1, sizeof(unsigned) * 64));
     {
         // limb arrays for S and g, exponents, maxima: always for the constraint rows, for the assembly in the opt-in
         // deterministic mode (see spl_segsort_kernel)
@@ -1013,6 +1187,8 @@ void spl_assemble_scratch_free(AssembleScratch &sc) {
         if (p) cudaFree(p);
     if (sc.celltab) cudaFree(sc.celltab);
     if (sc.cellmom) cudaFree(sc.cellmom);
+    if (sc.cursor1) cudaFree(sc.cursor1);
+    sc.cursor1 = nullptr;
     if (sc.fxS) cudaFree(sc.fxS);
     if (sc.fxmax) cudaFree(sc.fxmax);
     if (sc.fxe) cudaFree(sc.fxe);
@@ -1043,6 +1219,15 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
     const int grid = (int)(nb < cap ? nb : cap);
 
     double2 *yw = (CELL && weighted) ? reinterpret_cast<double2 *>(sc.yw) : nullptr;
+    bool twolevel = false;
+    if constexpr (CELL) {
+        // two-level partition for large chunks of many cells (SPLPAK_B200_BINNING=atomic keeps the per-point atomics)
+        const char *bm = getenv("SPLPAK_B200_BINNING");
+        // (beyond ~1e5 cells a tile of 8,192 points holds less than one point per cell of its buckets: nothing to aggregate)
+        twolevel = sc.pairs && sc.keys && n >= (1LL << 21) && nbins >= 2048 && nbins <= 48 * 2048 &&
+                   !(bm && strcmp(bm, "atomic") == 0);
+    }
+    unsigned *keys = twolevel ? sc.keys : nullptr;
     if (ev) cudaEventRecord(ev[0], st);
     {
         // two 512-thread CTAs per SM when the histogram is in shared memory (<= 2 x 96 KB), else 4
@@ -1063,26 +1248,47 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
             if (rh != SPLPAK_OK) return rh;
         }
         if (smemc) {
-            auto kern = spl_classify_kernel<NDIM, true, CELL, true>;
+            auto kern = keys ? spl_classify_kernel<NDIM, true, CELL, true, CELL> : spl_classify_kernel<NDIM, true, CELL, true>;
             SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)both_bytes));
             kern<<<cgrid1, 1024, both_bytes, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins, sc.wincount, do_hist,
-                                                   sc.hist.hq, sc.hist.qparams, d_totals, d_y, yw);
+                                                   sc.hist.hq, sc.hist.qparams, d_totals, d_y, yw, keys);
         } else if (smemh) {
-            auto kern = spl_classify_kernel<NDIM, true, CELL>;
+            auto kern = keys ? spl_classify_kernel<NDIM, true, CELL, false, CELL> : spl_classify_kernel<NDIM, true, CELL>;
             SPL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
             kern<<<cgrid, 512, hist_bytes, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins, sc.wincount, do_hist,
-                                                 sc.hist.hq, sc.hist.qparams, d_totals, d_y, yw);
+                                                 sc.hist.hq, sc.hist.qparams, d_totals, d_y, yw, keys);
         } else {
-            spl_classify_kernel<NDIM, false, CELL><<<cgrid, 512, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins,
+            auto kern = keys ? spl_classify_kernel<NDIM, false, CELL, false, CELL> : spl_classify_kernel<NDIM, false, CELL>;
+            kern<<<cgrid, 512, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, (int)nbins,
                                                                           sc.wincount, do_hist, sc.hist.hq, sc.hist.qparams,
-                                                                          d_totals, d_y, yw);
+                                                                          d_totals, d_y, yw, keys);
         }
         if (do_hist) spl_hist_finalize(sc.hist, gp, d_cnt, d_totals, st);
     }
     if (ev) cudaEventRecord(ev[1], st);
     spl_scan_kernel<<<1, 1024, 0, st>>>(sc.wincount, nbins, ch, sc.winstart, sc.itemstart, sc.meta);
-    spl_perm_kernel<NDIM, CELL><<<grid, 256, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.winstart, sc.wincursor,
-                                                      sc.cursor_stride, sc.perm);
+    if (twolevel) {
+        int shift = 0;
+        while (((nbins + (1LL << shift) - 1) >> shift) > 48) ++shift;
+        const int nbuckets = (int)((nbins + (1LL << shift) - 1) >> shift);
+        int span = 4 << shift;
+        while (span > 2048) span >>= 1;                       // spl_block_exscan2: <= 2 counters per thread
+        const size_t psmem = sizeof(unsigned) * 2 * (size_t)span + sizeof(uint2) * PART_TILE;
+        SPL_CUDA_TRY(cudaMemsetAsync(sc.cursor1, 0, sizeof(unsigned) * 64, st));
+        const long long ntiles1 = (n + PART1_TILE - 1) / PART1_TILE;
+        const int pgrid1 = (int)(ntiles1 < (long long)nsm * 3 ? ntiles1 : (long long)nsm * 3);
+        const long long ntiles = (n + PART_TILE - 1) / PART_TILE;
+        const int pgrid = (int)(ntiles < (long long)nsm * 2 ? ntiles : (long long)nsm * 2);
+        spl_part1_kernel<<<pgrid1, PART1_NT, 0, st>>>(sc.keys, n, sc.winstart, shift, nbuckets, sc.cursor1,
+                                                      reinterpret_cast<uint2 *>(sc.pairs));
+        SPL_CUDA_TRY(cudaFuncSetAttribute(spl_part2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        spl_part2_kernel<<<pgrid, 1024, psmem, st>>>(reinterpret_cast<const uint2 *>(sc.pairs), sc.meta, sc.winstart,
+                                                     sc.wincursor, sc.cursor_stride, shift, span, nbins, sc.perm);
+        ++g_spl_launches;
+    } else {
+        spl_perm_kernel<NDIM, CELL><<<grid, 256, 0, st>>>(gp, d_x, l1x, d_w, weighted, n, sc.winstart, sc.wincursor,
+                                                          sc.cursor_stride, sc.perm);
+    }
     spl_items_kernel<<<spl_div_up(nbins, 256), 256, 0, st>>>(sc.wincount, sc.itemstart, nbins, ch, sc.item_win,
                                                              sc.item_seg);
     if (det) {

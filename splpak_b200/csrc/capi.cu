@@ -885,6 +885,8 @@ static void free_handle(splpak_b200_fit_t h) {
     if (!h) return;
     if (h->d_part) cudaFree(h->d_part);
     if (h->sc.yw) cudaFree(h->sc.yw);
+    if (h->sc.pairs) cudaFree(h->sc.pairs);
+    if (h->sc.keys) cudaFree(h->sc.keys);
     unsigned *u[] = {h->sc.item_win, h->sc.item_seg, h->sc.perm, h->sc.perm2};
     for (unsigned *p : u)
         if (p) cudaFree(p);
@@ -1003,6 +1005,10 @@ static int ensure_scratch(splpak_b200_fit_t h, long long n) {
     if (sc.perm) cudaFree(sc.perm);
     if (sc.perm2) cudaFree(sc.perm2);
     sc.perm2 = nullptr;
+    if (sc.pairs) cudaFree(sc.pairs);
+    sc.pairs = nullptr;
+    if (sc.keys) cudaFree(sc.keys);
+    sc.keys = nullptr;
     if (sc.yw) cudaFree(sc.yw);
     sc.yw = nullptr;
     if (sc.item_win) cudaFree(sc.item_win);
@@ -1034,6 +1040,10 @@ static int ensure_scratch(splpak_b200_fit_t h, long long n) {
         gp = h->gp_fx;
     }
     if (sc.moments) SPL_CUDA_TRY(cudaMalloc((void **)&sc.yw, 2 * sizeof(double) * (size_t)n));
+    if (sc.moments && n >= (1LL << 21)) {
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.pairs, sizeof(unsigned long long) * (size_t)n));
+        SPL_CUDA_TRY(cudaMalloc((void **)&sc.keys, sizeof(unsigned) * (size_t)n));
+    }
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_win, sizeof(unsigned) * (size_t)sc.max_items));
     SPL_CUDA_TRY(cudaMalloc((void **)&sc.item_seg, sizeof(unsigned) * (size_t)sc.max_items));
     h->chunk_cap = n;

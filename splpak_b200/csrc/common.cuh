@@ -118,6 +118,11 @@ struct AssembleScratch {
     unsigned long long *fxS, *fxg, *fxmax;   // fxS and fxg are one allocation (3 (ncol nsten + ncol) limbs), fxmax 2 words
     int *fxe;
     unsigned *perm2;
+    // two-level partition of the cell path (spl_part1_kernel / spl_part2_kernel): bucket-sorted (key, index) pairs of the
+    // chunk (8 bytes per point, sized with perm) and the <= 64 bucket cursors
+    unsigned long long *pairs;
+    unsigned *cursor1;
+    unsigned *keys;       // bin key per point of the chunk, written by the classify pass (4 bytes per point)
 };
 
 // Scratch of the orthogonal fit path (ortho.cuh), owned by a fit handle.
