@@ -11,15 +11,19 @@
 //                            nearest-node histogram (with the :899 quirk), totlwt, row count
 //   2. spl_scan_kernel       exclusive scan of the counts -> window segment starts + work items
 //   3. spl_perm_kernel       second pass: counting sort of the point INDICES by window (4 bytes per
-//                            point; scattering 40-byte records instead was LSU-bound)
+//                            point; scattering 40-byte records instead was LSU-bound);
+//      spl_part1/2_kernel    cell path, large chunks: two-level partition (buckets of cells, then cells), every tile
+//                            sorted locally in shared memory and written in position order -- one global reservation
+//                            per (tile, bucket) / (tile, cell) instead of one returning L2 atomic per point
+//      spl_segsort_kernel    SPLPAK_B200_DETERMINISTIC=1 only: every bin's segment of the permutation sorted
 //   4. spl_items_kernel      work-item table (window, segment of <= CH points)
-//   5. accumulate            3-D: spl_moments_kernel + spl_cell_transform_kernel (moments.cuh: per-cell Legendre
-//                            moments as an FP64 tensor-core GEMM over the points, then one change of basis per
-//                            cell); 1-D / 2-D / 4-D (and 3-D under SPLPAK_B200_ASSEMBLY=direct):
+//   5. accumulate            3-D / 4-D: spl_moments[4]_kernel + spl_cell_transform[4]_kernel (moments.cuh: per-cell
+//                            Legendre moments as an FP64 tensor-core GEMM over the points, then one change of basis
+//                            per cell); 1-D / 2-D (and 3-D / 4-D under SPLPAK_B200_ASSEMBLY=direct):
 //      spl_accumulate_kernel persistent CTAs; per work item the points are gathered through the
 //                            permutation (prefetched two batches ahead, hidden under the FP64 work),
 //                            the window-local block of G is accumulated in REGISTERS and flushed once
-//                            with red.global.add.f64
+//                            with red.global.add.f64 (deterministic mode: fixed-point limbs, integer atomics)
 //
 // The per-point outer product of a tensor-product basis has only 10^ndim distinct entries
 // (10 symmetric pairs per dimension), not 4^ndim(4^ndim+1)/2: G is symmetric under swapping the row
