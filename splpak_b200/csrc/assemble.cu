@@ -413,8 +413,11 @@ spl_perm_kernel(const __grid_constant__ GridParams gp, const real_t *__restrict_
 // per CTA without the bucket level kept 148 x 15,625 partly written sectors alive and lost (experiments/ranked_binning_r02).
 // The order of the points inside a cell is as arbitrary as before.
 // ------------------------------------------------------------------------------------------
-#define PART_TILE 8192                 // pairs per tile of pass 2 (1024 threads x 8)
-#define PART_U (PART_TILE / 1024)
+#ifndef PART2_NT
+#define PART2_NT 1024                  // pass 2: threads per CTA (2048 / PART2_NT CTAs per SM)
+#endif
+#define PART_U 8
+#define PART_TILE (PART2_NT * PART_U)  // pairs per tile of pass 2
 #define PART1_NT 512                   // pass 1: 512 threads x 8 points, several CTAs per SM
 #define PART1_U 8
 #define PART1_TILE (PART1_NT * PART1_U)
@@ -510,7 +513,7 @@ spl_part1_kernel(const unsigned *__restrict__ keys, long long n, const unsigned 
 
 // span: cells per group (a multiple of the bucket size, <= 2048: spl_block_exscan2); meta[1] = number of pairs.
 // Shared memory: [span] counts -> tile-local offsets | [span] global bases | [PART_TILE] staged (cell - g0, index).
-__global__ void __launch_bounds__(1024, 2)
+__global__ void __launch_bounds__(PART2_NT, 2048 / PART2_NT)
 spl_part2_kernel(const uint2 *__restrict__ pairs, const unsigned *__restrict__ meta, const unsigned *__restrict__ winstart,
                  unsigned *__restrict__ wincursor, int cstride, int shift, int span, long long nbins,
                  unsigned *__restrict__ perm) {
@@ -532,19 +535,19 @@ spl_part2_kernel(const uint2 *__restrict__ pairs, const unsigned *__restrict__ m
         __syncthreads();
         const unsigned klo = s_lo, khi = s_hi;
         for (unsigned g0 = klo; g0 <= khi; g0 += (unsigned)span) {
-            for (int e = tid; e < span; e += 1024) s_h[e] = 0;
+            for (int e = tid; e < span; e += PART2_NT) s_h[e] = 0;
             __syncthreads();
             // (the pairs are read twice, the second time from L2, instead of being held in registers: two CTAs per SM)
             unsigned rank[PART_U];
 #pragma unroll
             for (int u = 0; u < PART_U; ++u) {
-                const long long pos = t0 + u * 1024 + tid;
+                const long long pos = t0 + u * PART2_NT + tid;
                 const unsigned k = (pos < tend) ? __ldcg(&pairs[pos].x) : 0xffffffffu;
                 rank[u] = 0;
                 if (k - g0 < (unsigned)span) rank[u] = atomicAdd(&s_h[k - g0], 1u);
             }
             __syncthreads();
-            for (int e = tid; e < span; e += 1024) {
+            for (int e = tid; e < span; e += PART2_NT) {
                 const unsigned c = s_h[e];
                 if (c && (long long)g0 + e < nbins)
                     s_b[e] = winstart[g0 + e] + atomicAdd(wincursor + (size_t)(g0 + e) * cstride, c);
@@ -552,14 +555,14 @@ spl_part2_kernel(const uint2 *__restrict__ pairs, const unsigned *__restrict__ m
             const unsigned count = spl_block_exscan2(s_h, span, s_w);        // counts -> tile-local offsets
 #pragma unroll
             for (int u = 0; u < PART_U; ++u) {
-                const long long pos = t0 + u * 1024 + tid;
+                const long long pos = t0 + u * PART2_NT + tid;
                 if (pos < tend) {
                     const uint2 pr = __ldcg(pairs + pos);
                     if (pr.x - g0 < (unsigned)span) s_stage[s_h[pr.x - g0] + rank[u]] = make_uint2(pr.x - g0, pr.y);
                 }
             }
             __syncthreads();
-            for (unsigned p = tid; p < count; p += 1024) {
+            for (unsigned p = tid; p < count; p += PART2_NT) {
                 const uint2 st = s_stage[p];
                 perm[(long long)s_b[st.x] + (p - s_h[st.x])] = st.y;
             }
@@ -1276,17 +1279,18 @@ static int assemble_chunk_t(const GridParams &gp, const real_t *d_x, int l1x, co
         while (((nbins + (1LL << shift) - 1) >> shift) > 48) ++shift;
         const int nbuckets = (int)((nbins + (1LL << shift) - 1) >> shift);
         int span = 4 << shift;
-        while (span > 2048) span >>= 1;                       // spl_block_exscan2: <= 2 counters per thread
+        while (span > 2 * PART2_NT) span >>= 1;               // spl_block_exscan2: <= 2 counters per thread
         const size_t psmem = sizeof(unsigned) * 2 * (size_t)span + sizeof(uint2) * PART_TILE;
         SPL_CUDA_TRY(cudaMemsetAsync(sc.cursor1, 0, sizeof(unsigned) * 64, st));
         const long long ntiles1 = (n + PART1_TILE - 1) / PART1_TILE;
         const int pgrid1 = (int)(ntiles1 < (long long)nsm * 3 ? ntiles1 : (long long)nsm * 3);
         const long long ntiles = (n + PART_TILE - 1) / PART_TILE;
-        const int pgrid = (int)(ntiles < (long long)nsm * 2 ? ntiles : (long long)nsm * 2);
+        const long long pcap = (long long)nsm * (2048 / PART2_NT);
+        const int pgrid = (int)(ntiles < pcap ? ntiles : pcap);
         spl_part1_kernel<<<pgrid1, PART1_NT, 0, st>>>(sc.keys, n, sc.winstart, shift, nbuckets, sc.cursor1,
                                                       reinterpret_cast<uint2 *>(sc.pairs));
         SPL_CUDA_TRY(cudaFuncSetAttribute(spl_part2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        spl_part2_kernel<<<pgrid, 1024, psmem, st>>>(reinterpret_cast<const uint2 *>(sc.pairs), sc.meta, sc.winstart,
+        spl_part2_kernel<<<pgrid, PART2_NT, psmem, st>>>(reinterpret_cast<const uint2 *>(sc.pairs), sc.meta, sc.winstart,
                                                      sc.wincursor, sc.cursor_stride, shift, span, nbins, sc.perm);
         ++g_spl_launches;
     } else {
